@@ -1,0 +1,178 @@
+"""ctypes bindings for oracle/build/liboracle.so (O1 functional oracle + O2 RTL cycle model).
+
+Test infrastructure only: the product (libtrialign) never loads this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+LIB_PATH = os.path.join(ORACLE_DIR, "build", "liboracle.so")
+
+u8p = C.POINTER(C.c_uint8)
+i32p = C.POINTER(C.c_int32)
+i64p = C.POINTER(C.c_int64)
+
+
+class RtlCfg(C.Structure):
+    _fields_ = [
+        ("variant", C.c_int),
+        ("pe_len", C.c_int),
+        ("score_bits", C.c_int),
+        ("a_total_len", C.c_int),
+        ("sram_addr_bits", C.c_int),
+        ("strict", C.c_int),
+        ("max_cycles", C.c_int64),
+    ]
+
+
+RTL_OK, RTL_EARG, RTL_EDOMAIN, RTL_ETIMEOUT, RTL_EX = 0, -1, -2, -3, -4
+
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the oracle with its Makefile (gcc/g++ only)."""
+    if force or not os.path.exists(LIB_PATH):
+        subprocess.run(["make", "-C", ORACLE_DIR], check=True, capture_output=True)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB_PATH)
+        L.oracle_score.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, i32p, i32p, i32p]
+        L.oracle_score.restype = C.c_int
+        L.oracle_score_mt.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, i32p, i32p]
+        L.oracle_score_mt.restype = C.c_int
+        L.oracle_score_batch.argtypes = [u8p, u8p, u8p, C.c_int64, C.c_int, C.c_int, C.c_int, i32p]
+        L.oracle_score_batch.restype = C.c_int
+        L.oracle_cube.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, i32p]
+        L.oracle_cube.restype = C.c_int
+        L.oracle_synth.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, u8p]
+        L.oracle_synth.restype = None
+        L.oracle_hw_threads.restype = C.c_int
+        L.rtl_default_cfg.argtypes = [C.POINTER(RtlCfg), C.c_int]
+        L.rtl_model_run.argtypes = [C.POINTER(RtlCfg), u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, i32p, i32p, i64p]
+        L.rtl_model_run.restype = C.c_int
+        L.rtl_cycle_formula.argtypes = [C.c_int] * 5
+        L.rtl_cycle_formula.restype = C.c_int64
+        L.rtl_model_run_batch.argtypes = [C.POINTER(RtlCfg), u8p, u8p, u8p, C.c_int64, C.c_int, C.c_int, i32p, i64p]
+        L.rtl_model_run_batch.restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def _u8(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint8))
+
+
+def _ptr(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def score(a, b, c, score_bits: int = 12, want_range: bool = False):
+    """-> (score, final_states[7]) or (score, final_states, (lo, hi))."""
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    s = C.c_int32()
+    fin = np.zeros(7, np.int32)
+    rng = np.zeros(2, np.int32)
+    rc = lib().oracle_score(_ptr(a, u8p), len(a), _ptr(b, u8p), len(b), _ptr(c, u8p), len(c), score_bits,
+                            C.byref(s), _ptr(fin, i32p), _ptr(rng, i32p))
+    if rc:
+        raise ValueError(f"oracle_score rc={rc}")
+    if want_range:
+        return int(s.value), fin, (int(rng[0]), int(rng[1]))
+    return int(s.value), fin
+
+
+def score_mt(a, b, c, score_bits: int = 12, threads: int = 0):
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    s = C.c_int32()
+    fin = np.zeros(7, np.int32)
+    rc = lib().oracle_score_mt(_ptr(a, u8p), len(a), _ptr(b, u8p), len(b), _ptr(c, u8p), len(c), score_bits,
+                               threads, C.byref(s), _ptr(fin, i32p))
+    if rc:
+        raise ValueError(f"oracle_score_mt rc={rc}")
+    return int(s.value), fin
+
+
+def score_batch(a, b, c, score_bits: int = 12, threads: int = 0) -> np.ndarray:
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    assert a.ndim == 2 and a.shape == b.shape == c.shape
+    n, ln = a.shape
+    out = np.zeros(n, np.int32)
+    rc = lib().oracle_score_batch(_ptr(a, u8p), _ptr(b, u8p), _ptr(c, u8p), n, ln, score_bits, threads,
+                                  _ptr(out, i32p))
+    if rc:
+        raise ValueError(f"oracle_score_batch rc={rc}")
+    return out
+
+
+def cube(a, b, c, score_bits: int = 12) -> np.ndarray:
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    out = np.zeros((len(a) + 1, len(b) + 1, len(c) + 1, 7), np.int32)
+    rc = lib().oracle_cube(_ptr(a, u8p), len(a), _ptr(b, u8p), len(b), _ptr(c, u8p), len(c), score_bits,
+                           _ptr(out, i32p))
+    if rc:
+        raise ValueError(f"oracle_cube rc={rc}")
+    return out
+
+
+def synth(seed: int, triple: int, which: int, length: int) -> np.ndarray:
+    out = np.zeros(length, np.uint8)
+    lib().oracle_synth(C.c_uint64(seed), triple, which, length, _ptr(out, u8p))
+    return out
+
+
+def synth_batch(seed: int, first: int, n: int, length: int):
+    a = np.stack([synth(seed, first + t, 0, length) for t in range(n)])
+    b = np.stack([synth(seed, first + t, 1, length) for t in range(n)])
+    c = np.stack([synth(seed, first + t, 2, length) for t in range(n)])
+    return a, b, c
+
+
+def rtl_run(a, b, c, variant: int = 1, score_bits: int = 12, pe_len: int = 8, strict: bool = True,
+            a_total_len: int = 0, sram_addr_bits: int = 0, max_cycles: int = 0):
+    """-> (rc, score, final_states[7], cycles)."""
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    cfg = RtlCfg()
+    lib().rtl_default_cfg(C.byref(cfg), variant)
+    cfg.score_bits, cfg.pe_len, cfg.strict = score_bits, pe_len, int(strict)
+    cfg.a_total_len, cfg.sram_addr_bits, cfg.max_cycles = a_total_len, sram_addr_bits, max_cycles
+    s = C.c_int32(0)
+    fin = np.zeros(7, np.int32)
+    cyc = C.c_int64(0)
+    rc = lib().rtl_model_run(C.byref(cfg), _ptr(a, u8p), len(a), _ptr(b, u8p), len(b), _ptr(c, u8p), len(c),
+                             C.byref(s), _ptr(fin, i32p), C.byref(cyc))
+    return rc, int(s.value), fin, int(cyc.value)
+
+
+def rtl_cycle_formula(variant: int, pe_len: int, la: int, lb: int, lc: int) -> int:
+    return int(lib().rtl_cycle_formula(variant, pe_len, la, lb, lc))
+
+
+def read_dat(path: str) -> np.ndarray:
+    """dat/*_seq.dat: one decimal digit 0-3 per line, CRLF or LF."""
+    with open(path, "rb") as f:
+        txt = f.read().decode("ascii")
+    return np.array([int(t) for t in txt.split()], dtype=np.uint8)
+
+
+def mutated_triple(rng: np.random.Generator, length: int, rate: float = 0.15):
+    """A random; B, C = A with `rate` substitutions (exercises large values)."""
+    a = rng.integers(0, 4, length, dtype=np.uint8)
+    out = [a]
+    for _ in range(2):
+        m = a.copy()
+        mask = rng.random(length) < rate
+        m[mask] = rng.integers(0, 4, int(mask.sum()), dtype=np.uint8)
+        out.append(m)
+    return out
