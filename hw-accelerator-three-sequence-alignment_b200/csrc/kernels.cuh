@@ -1,0 +1,20 @@
+// kernels.cuh -- entry points of the CUDA kernel families behind the C ABI (all pointers are device memory).
+#pragma once
+
+#include <climits>
+#include <cstdint>
+
+#include "common.cuh"
+
+namespace trialign {
+
+// KL: literal plane-sweep kernel, exact for any score_bits in [2,32] (literal_kernel.cu).
+// d_a/d_b/d_c are [n][la] / [n][lb] / [n][lc]; d_scores [n]; d_finals [n][7] or nullptr.
+int literal_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals);
+
+// synthetic generator on the device (synth_kernel.cu)
+int synth_run(cudaStream_t st, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a, uint8_t *d_b,
+              uint8_t *d_c);
+
+}  // namespace trialign

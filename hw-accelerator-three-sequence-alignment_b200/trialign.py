@@ -1,0 +1,272 @@
+"""Host-side mirror of the reference's only interface to this path: the ``TRIALIGN`` module port list
+(/root/reference/src/TriAlign_1cyc.v:1-22) as the testbench drives it (src/TriAlign_tb.sv:204-262).
+
+    reference                                   here
+    ------------------------------------------  -----------------------------------------------
+    parameter SCORE_BITS                        TriAlign(score_bits=...)
+    A_idx / B_idx / C_idx + symbol RAMs         TriAlign.align(A, B, C)  (lengths = len of each)
+    start_align pulse ... finish                the call itself
+    Score (signed SCORE_BITS)                   return value
+    no error signalling at all                  TriAlignError with the C ABI's code
+
+All work happens in ``lib/libtrialign.so``; if it is missing or no CUDA device is present the calls raise --
+there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "lib", "libtrialign.so")
+
+BACKEND_AUTO, BACKEND_GPU, BACKEND_GPU_LITERAL, BACKEND_GPU_FAST = 0, 4, 5, 6
+PATH_NAMES = {0: "none", 1: "literal", 2: "fast_batch", 3: "fast_long", 4: "fast_then_literal"}
+
+_u8p = C.POINTER(C.c_uint8)
+_i32p = C.POINTER(C.c_int32)
+
+
+class TriAlignError(RuntimeError):
+    def __init__(self, rc: int, what: str):
+        self.rc = rc
+        detail = ""
+        try:
+            msg = library().trialign_strerror(rc).decode()
+            cuda = library().trialign_last_cuda_error().decode()
+            detail = f": {msg}" + (f" [{cuda}]" if cuda and rc in (-2, -3, -7) else "")
+        except Exception:  # pragma: no cover - library itself unavailable
+            pass
+        super().__init__(f"{what} failed with rc={rc}{detail}")
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def library_path() -> str:
+    return _LIB
+
+
+def build_library(force: bool = False) -> str:
+    """Compile lib/libtrialign.so for sm_100a with the package Makefile (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", _HERE, "clean"], check=True, capture_output=True)
+    proc = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("building libtrialign.so failed:\n" + proc.stdout[-4000:] + proc.stderr[-4000:])
+    return _LIB
+
+
+def library() -> C.CDLL:
+    """Load the C-ABI library; raises if it has not been built (no silent fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise FileNotFoundError(f"{_LIB} is missing: run __graft_entry__.build() (make -C {_HERE}) first")
+    L = C.CDLL(_LIB)
+    L.trialign_version.restype = C.c_int
+    L.trialign_strerror.argtypes = [C.c_int]
+    L.trialign_strerror.restype = C.c_char_p
+    L.trialign_last_cuda_error.restype = C.c_char_p
+    L.trialign_device_count.restype = C.c_int
+    L.trialign_score.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p, _i32p]
+    L.trialign_score.restype = C.c_int
+    L.trialign_score_batch.argtypes = [_u8p, _u8p, _u8p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p]
+    L.trialign_score_batch.restype = C.c_int
+    L.trialign_score_batch_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                           C.c_int, C.c_void_p, C.c_void_p]
+    L.trialign_score_batch_dev.restype = C.c_int
+    L.trialign_score_dev.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_void_p]
+    L.trialign_score_dev.restype = C.c_int
+    L.trialign_read_seq_dat.argtypes = [C.c_char_p, _u8p, C.c_int, C.POINTER(C.c_int)]
+    L.trialign_read_seq_dat.restype = C.c_int
+    L.trialign_write_seq_dat.argtypes = [C.c_char_p, _u8p, C.c_int, C.c_int]
+    L.trialign_write_seq_dat.restype = C.c_int
+    L.trialign_write_scores.argtypes = [C.c_char_p, _i32p, C.c_int64]
+    L.trialign_write_scores.restype = C.c_int
+    L.trialign_read_scores.argtypes = [C.c_char_p, _i32p, C.c_int64, C.POINTER(C.c_int64)]
+    L.trialign_read_scores.restype = C.c_int
+    L.trialign_synth.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, _u8p]
+    L.trialign_synth.restype = None
+    L.trialign_synth_batch_dev.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_void_p]
+    L.trialign_synth_batch_dev.restype = C.c_int
+    L.trialign_last_timing.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.trialign_last_timing.restype = C.c_int
+    L.trialign_last_path.restype = C.c_int
+    L.trialign_launch_count.restype = C.c_int64
+    _lib = L
+    return L
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise TriAlignError(rc, what)
+
+
+def _u8(x) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(x, dtype=np.uint8))
+
+
+def _p(a: np.ndarray, t):
+    return a.ctypes.data_as(t)
+
+
+def version() -> int:
+    return int(library().trialign_version())
+
+
+def device_count() -> int:
+    return int(library().trialign_device_count())
+
+
+def launch_count() -> int:
+    return int(library().trialign_launch_count())
+
+
+def last_path() -> str:
+    return PATH_NAMES.get(int(library().trialign_last_path()), "?")
+
+
+def last_timing() -> Tuple[float, float]:
+    """(kernel seconds, cells) of the last host-pointer compute call of this thread."""
+    s, c = C.c_double(), C.c_double()
+    library().trialign_last_timing(C.byref(s), C.byref(c))
+    return float(s.value), float(c.value)
+
+
+def _devmask(devices: Optional[Sequence[int]]) -> int:
+    if not devices:
+        return 0
+    m = 0
+    for d in devices:
+        m |= 1 << int(d)
+    return m
+
+
+class TriAlign:
+    """One configured aligner, the counterpart of a ``TRIALIGN #(.SCORE_BITS(W))`` instance."""
+
+    def __init__(self, score_bits: int = 12, backend: int = BACKEND_AUTO, devices: Optional[Sequence[int]] = None):
+        self.score_bits = int(score_bits)
+        self.backend = int(backend)
+        self.devices = list(devices) if devices else None
+
+    # -- host-memory entry points (these are what the reference-side binding would call) --
+    def align(self, A, B, C_, return_states: bool = False):
+        a, b, c = _u8(A), _u8(B), _u8(C_)
+        s = C.c_int32(0)
+        fin = np.zeros(7, np.int32)
+        rc = library().trialign_score(_p(a, _u8p), a.size, _p(b, _u8p), b.size, _p(c, _u8p), c.size,
+                                      self.score_bits, self.backend, _devmask(self.devices), C.byref(s),
+                                      _p(fin, _i32p))
+        _check(rc, "trialign_score")
+        return (int(s.value), fin) if return_states else int(s.value)
+
+    def align_batch(self, A, B, C_) -> np.ndarray:
+        a, b, c = _u8(A), _u8(B), _u8(C_)
+        if a.ndim != 2 or a.shape != b.shape or a.shape != c.shape:
+            raise ValueError("align_batch wants three [n][len] arrays of identical shape")
+        n, ln = a.shape
+        out = np.zeros(n, np.int32)
+        rc = library().trialign_score_batch(_p(a, _u8p), _p(b, _u8p), _p(c, _u8p), n, ln, self.score_bits,
+                                            self.backend, _devmask(self.devices), _p(out, _i32p))
+        _check(rc, "trialign_score_batch")
+        return out
+
+    # -- device-memory entry points: torch CUDA tensors (uint8 [n][len]) in, int32 tensor out --
+    def align_batch_cuda(self, A, B, C_, out=None, stream=None):
+        import torch
+
+        if not (A.is_cuda and B.is_cuda and C_.is_cuda):
+            raise ValueError("align_batch_cuda wants CUDA tensors")
+        if A.dtype != torch.uint8 or A.dim() != 2 or A.shape != B.shape or A.shape != C_.shape:
+            raise ValueError("align_batch_cuda wants three uint8 [n][len] tensors of identical shape")
+        A, B, C_ = A.contiguous(), B.contiguous(), C_.contiguous()
+        n, ln = A.shape
+        if out is None:
+            out = torch.empty(n, dtype=torch.int32, device=A.device)
+        st = stream if stream is not None else torch.cuda.current_stream(A.device)
+        rc = library().trialign_score_batch_dev(A.device.index or 0, A.data_ptr(), B.data_ptr(), C_.data_ptr(), n, ln,
+                                                self.score_bits, self.backend, out.data_ptr(), st.cuda_stream)
+        _check(rc, "trialign_score_batch_dev")
+        return out
+
+    def align_cuda(self, A, B, C_, out=None, stream=None):
+        """One triple resident on the GPU -> int32[8] tensor (score, then the 7 final states)."""
+        import torch
+
+        A, B, C_ = A.contiguous(), B.contiguous(), C_.contiguous()
+        if out is None:
+            out = torch.empty(8, dtype=torch.int32, device=A.device)
+        st = stream if stream is not None else torch.cuda.current_stream(A.device)
+        rc = library().trialign_score_dev(A.device.index or 0, A.data_ptr(), A.numel(), B.data_ptr(), B.numel(),
+                                          C_.data_ptr(), C_.numel(), self.score_bits, self.backend, out.data_ptr(),
+                                          st.cuda_stream)
+        _check(rc, "trialign_score_dev")
+        return out
+
+
+# ---- file formats of the reference's dat/ directory ----
+def read_seq_dat(path: str, cap: int = 1 << 20) -> np.ndarray:
+    buf = np.zeros(cap, np.uint8)
+    n = C.c_int(0)
+    _check(library().trialign_read_seq_dat(os.fsencode(path), _p(buf, _u8p), cap, C.byref(n)), "trialign_read_seq_dat")
+    return buf[: n.value].copy()
+
+
+def write_seq_dat(path: str, seq, crlf: bool = True) -> None:
+    s = _u8(seq)
+    _check(library().trialign_write_seq_dat(os.fsencode(path), _p(s, _u8p), s.size, int(crlf)), "trialign_write_seq_dat")
+
+
+def write_scores(path: str, scores) -> None:
+    s = np.ascontiguousarray(np.asarray(scores, dtype=np.int32))
+    _check(library().trialign_write_scores(os.fsencode(path), _p(s, _i32p), s.size), "trialign_write_scores")
+
+
+def read_scores(path: str, cap: int = 1 << 22) -> np.ndarray:
+    buf = np.zeros(cap, np.int32)
+    n = C.c_int64(0)
+    _check(library().trialign_read_scores(os.fsencode(path), _p(buf, _i32p), cap, C.byref(n)), "trialign_read_scores")
+    return buf[: n.value].copy()
+
+
+# ---- synthetic inputs ----
+def synth(seed: int, triple: int, which: int, length: int) -> np.ndarray:
+    out = np.zeros(max(length, 0), np.uint8)
+    library().trialign_synth(C.c_uint64(seed), triple, which, length, _p(out, _u8p))
+    return out
+
+
+def synth_batch(seed: int, first: int, n: int, length: int):
+    """Host arrays [n][len] for A, B, C (slow path; benchmarks generate on the device instead)."""
+    a = np.zeros((n, length), np.uint8)
+    b = np.zeros((n, length), np.uint8)
+    c = np.zeros((n, length), np.uint8)
+    L = library()
+    for t in range(n):
+        L.trialign_synth(C.c_uint64(seed), first + t, 0, length, _p(a[t], _u8p))
+        L.trialign_synth(C.c_uint64(seed), first + t, 1, length, _p(b[t], _u8p))
+        L.trialign_synth(C.c_uint64(seed), first + t, 2, length, _p(c[t], _u8p))
+    return a, b, c
+
+
+def synth_batch_cuda(seed: int, first: int, n: int, length: int, device=0, stream=None):
+    import torch
+
+    dev = torch.device("cuda", device) if isinstance(device, int) else device
+    a = torch.empty((n, length), dtype=torch.uint8, device=dev)
+    b = torch.empty_like(a)
+    c = torch.empty_like(a)
+    st = stream if stream is not None else torch.cuda.current_stream(dev)
+    rc = library().trialign_synth_batch_dev(dev.index or 0, C.c_uint64(seed), first, n, length, a.data_ptr(),
+                                            b.data_ptr(), c.data_ptr(), st.cuda_stream)
+    _check(rc, "trialign_synth_batch_dev")
+    return a, b, c

@@ -1,0 +1,123 @@
+/*
+ * trialign.h -- C ABI of libtrialign, the B200-native engine for the three-sequence alignment score
+ * that the reference RTL (TRIALIGN / PE / MAX7) computes.
+ *
+ * The reference has no host-language layer and no FFI (its .gitignore withholds the host scripts); the only
+ * interface its hot path sits behind is the TRIALIGN module port list, driven by the testbench:
+ *
+ *   reference interface                                      replaced here by
+ *   -------------------------------------------------------  ------------------------------------------
+ *   TRIALIGN ports  A_idx/B_idx/C_idx, A/B/C_symbol,          trialign_score(): lengths + symbol arrays in,
+ *     A/B/C_addr, start_align, finish, Score                  Score out (signed, SCORE_BITS wide)
+ *     (src/TriAlign_1cyc.v:9-22, src/TriAlign_tb.sv:204-262)
+ *   parameter SCORE_BITS (src/TriAlign_1cyc.v:6)              the score_bits argument (run-time)
+ *   parameter PE_LEN / SRAM_ADDR_BITS / *_TOTAL_LEN           none: array size, face depth and slicing are
+ *     (src/TriAlign_1cyc.v:1-8)                               internal to the CUDA kernels
+ *   dat/A_seq.dat, B_seq.dat, C_seq.dat (one digit per line)   trialign_read_seq_dat()
+ *   `$display("TriAlign Score: %d")` (TriAlign_tb.sv:339-341)  trialign_write_scores(): "%d" per line,
+ *     and dat/Pattern1.dat's one-integer-per-line layout       '\n'-joined, no trailing newline
+ *   tb symbol codes A=0,T=1,C=2,G=3,N=4 (TriAlign_tb.sv:42-46) bytes; only bits [1:0] are used
+ *     and the PE's 2-bit truncation (src/PE_1cyc.v:63-66)       (N aliases to A exactly as in the RTL)
+ *
+ * Semantics (bit-exact with the RTL): 7 states per cell (M,Ix,Iy,Iz,Ixy,Iyz,Ixz), scoring constants of
+ * src/PE_1cyc.v:55-61, substitution scores of :159-162 (including the operator-precedence quirk of temp_ABC),
+ * all-zero boundary planes (src/TriAlign_1cyc.v:156-181), every candidate wrapped to score_bits two's complement
+ * before the signed max (src/PE_1cyc.v:127-133), Score = max of the 7 states of cell (la,lb,lc).
+ *
+ * Conventions: C linkage, plain pointers and sizes, no exceptions cross the boundary, every function returns
+ * TRIALIGN_OK (0) or a negative error and never aborts.  Host-pointer entry points copy to the GPU and back
+ * themselves; *_dev entry points take device pointers and enqueue on the given CUDA stream.  There is no CPU
+ * fallback: without a usable CUDA device every compute entry point returns TRIALIGN_ENODEVICE.
+ */
+#ifndef TRIALIGN_H
+#define TRIALIGN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRIALIGN_VERSION 0x00010000 /* major<<16 | minor<<8 | patch */
+
+enum trialign_rc {
+    TRIALIGN_OK = 0,
+    TRIALIGN_EINVAL = -1,       /* bad pointer, negative length, score_bits outside [2,32], ... */
+    TRIALIGN_ENOMEM = -2,       /* host or device allocation failed */
+    TRIALIGN_ECUDA = -3,        /* a CUDA call failed; see trialign_last_cuda_error() */
+    TRIALIGN_EIO = -4,          /* file could not be opened / read / written */
+    TRIALIGN_EPARSE = -5,       /* dat file holds something other than digits 0-3 and line ends */
+    TRIALIGN_EUNSUPPORTED = -6, /* backend not part of the product (CPU checkers live under oracle/) */
+    TRIALIGN_ENODEVICE = -7,    /* no usable CUDA device */
+    TRIALIGN_ECAPACITY = -8,    /* output buffer too small */
+    TRIALIGN_EINEXACT = -9      /* TRIALIGN_BACKEND_GPU_FAST forced, but wrap-freedom could not be established */
+};
+
+enum trialign_backend {
+    TRIALIGN_BACKEND_AUTO = 0,        /* GPU: fast kernels where provably bit-exact, literal kernel otherwise */
+    TRIALIGN_BACKEND_CPU_ORACLE = 1,  /* reserved numbers of the survey's boundary; not in the product */
+    TRIALIGN_BACKEND_RTL_1CYC = 2,
+    TRIALIGN_BACKEND_RTL_2CYC = 3,
+    TRIALIGN_BACKEND_GPU = 4,         /* same as AUTO */
+    TRIALIGN_BACKEND_GPU_LITERAL = 5, /* force the literal 49-add/42-max kernel (any score_bits in [2,32]) */
+    TRIALIGN_BACKEND_GPU_FAST = 6     /* force the factored packed-16-bit kernels; EINEXACT if a wrap was possible */
+};
+
+/* Which kernel family served the last call on this thread (trialign_last_path). */
+enum trialign_path {
+    TRIALIGN_PATH_NONE = 0,
+    TRIALIGN_PATH_LITERAL = 1,        /* plane-sweep literal kernel */
+    TRIALIGN_PATH_FAST_BATCH = 2,     /* K1: batched systolic kernel, two triples per 32-bit lane */
+    TRIALIGN_PATH_FAST_LONG = 3,      /* K2: block-dataflow kernel for one long triple */
+    TRIALIGN_PATH_FAST_THEN_LITERAL = 4 /* fast kernel ran, its range check failed, literal kernel re-ran */
+};
+
+int trialign_version(void);
+const char *trialign_strerror(int rc);
+const char *trialign_last_cuda_error(void); /* thread-local text of the last CUDA failure, "" if none */
+int trialign_device_count(void);            /* 0 when no driver / no device; never negative */
+
+/* One triple.  a/b/c: host bytes.  score_bits in [2,32].  devices: bitmask of CUDA ordinals (0 = device 0).
+ * final_states (may be NULL) receives the 7 states of cell (la,lb,lc) in the order M,Ix,Iy,Iz,Ixy,Iyz,Ixz.
+ * Any zero length gives score 0 (the cell lies on a zero boundary plane). */
+int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                   int backend, unsigned devices, int32_t *score, int32_t final_states[7]);
+
+/* Uniform-length batch, structure of arrays: a/b/c are [n][len] row-major host bytes, scores is [n].
+ * With several bits set in `devices` the batch is split contiguously across those GPUs (no exchange). */
+int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len, int score_bits,
+                         int backend, unsigned devices, int32_t *scores);
+
+/* Device-resident variants: every pointer is device memory on CUDA ordinal `device`, work is enqueued on
+ * `stream` (a cudaStream_t; NULL = legacy default stream) and the call returns without synchronising unless
+ * the range check of the fast path forces a literal re-run.  d_scores is [n] int32. */
+int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c, int64_t n,
+                             int len, int score_bits, int backend, int32_t *d_scores, void *stream);
+/* d_out: int32[8] = score followed by the 7 final states. */
+int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
+                       int lc, int score_bits, int backend, int32_t *d_out, void *stream);
+
+/* dat/{A,B,C}_seq.dat reader: one decimal digit 0-3 per line, CRLF or LF, optional trailing newline.
+ * Writes at most cap symbols into buf, *n = symbols in the file (ECAPACITY if *n > cap). */
+int trialign_read_seq_dat(const char *path, uint8_t *buf, int cap, int *n);
+/* Writer for the same format (CRLF line ends like the reference's files when crlf != 0). */
+int trialign_write_seq_dat(const char *path, const uint8_t *buf, int n, int crlf);
+/* Score list in dat/Pattern1.dat's layout: ASCII signed decimals joined by '\n', no trailing newline. */
+int trialign_write_scores(const char *path, const int32_t *s, int64_t n);
+int trialign_read_scores(const char *path, int32_t *s, int64_t cap, int64_t *n);
+
+/* Synthetic symbols: sym = mix(seed ^ ((3*triple+which) << 32) ^ p) >> 62, splitmix64 finaliser. */
+void trialign_synth(uint64_t seed, int64_t triple, int which, int len, uint8_t *out);
+/* Same generator on the GPU: fills d_a/d_b/d_c [n][len] for triples first..first+n-1. */
+int trialign_synth_batch_dev(int device, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a,
+                             uint8_t *d_b, uint8_t *d_c, void *stream);
+
+/* Bookkeeping of the last compute call made by this thread. */
+int trialign_last_timing(double *seconds, double *cells); /* device time of the kernels only, cells = sum la*lb*lc */
+int trialign_last_path(void);                             /* enum trialign_path */
+int64_t trialign_launch_count(void);                      /* kernels launched by this process so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRIALIGN_H */

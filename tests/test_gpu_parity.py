@@ -1,0 +1,139 @@
+"""Parity tests proper (-m gpu): every call goes through the C ABI of lib/libtrialign.so and is compared with the
+golden vectors / the CPU oracle on the same inputs.  Bar: bit-exact (integer scores and states)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+BACKENDS = {"auto": 0, "literal": 5}
+
+
+def _abc(case):
+    return (np.array(case[k], np.uint8) for k in ("a", "b", "c"))
+
+
+@pytest.mark.parametrize("backend", list(BACKENDS))
+def test_golden_cases_single_triple(gpu_ta, golden, backend):
+    for case in golden["cases"]:
+        a, b, c = _abc(case)
+        eng = gpu_ta.TriAlign(score_bits=case["score_bits"], backend=BACKENDS[backend])
+        s, fin = eng.align(a, b, c, return_states=True)
+        assert s == case["score"], (case["name"], backend, gpu_ta.last_path())
+        assert fin.tolist() == case["final_states"], (case["name"], backend, gpu_ta.last_path())
+
+
+def test_dat_triple_and_tb_as_shipped(gpu_ta, golden):
+    d = golden["dat"]
+    eng = gpu_ta.TriAlign(score_bits=12)
+    assert eng.align(d["A"], d["B"], d["C"]) == 1
+    z = np.zeros(64, np.uint8)
+    assert eng.align(z, z, z) == 192
+
+
+def test_zero_and_ragged_lengths(gpu_ta, ob):
+    eng = gpu_ta.TriAlign()
+    a = np.array([0, 1, 2, 3, 1], np.uint8)
+    e = np.zeros(0, np.uint8)
+    for x, y, z in ((e, a, a), (a, e, a), (a, a, e), (e, e, e)):
+        s, fin = eng.align(x, y, z, return_states=True)
+        assert s == 0 and fin.tolist() == [0] * 7
+    rng = np.random.default_rng(7)
+    for (la, lb, lc) in [(1, 1, 1), (1, 40, 3), (70, 2, 9), (33, 65, 17), (5, 5, 130)]:
+        x, y, z = (rng.integers(0, 4, n, dtype=np.uint8) for n in (la, lb, lc))
+        s, fin = eng.align(x, y, z, return_states=True)
+        es, efin = ob.score(x, y, z, 12)
+        assert s == es and fin.tolist() == efin.tolist(), (la, lb, lc)
+
+
+@pytest.mark.parametrize("backend", list(BACKENDS))
+def test_synthetic_batch_config2_prefix(gpu_ta, golden, backend):
+    ent = next(e for e in golden["synth"] if e["config"] == 2)
+    n = len(ent["scores"])
+    a, b, c = gpu_ta.synth_batch(ent["seed"], 0, n, ent["len"])
+    got = gpu_ta.TriAlign(ent["score_bits"], backend=BACKENDS[backend]).align_batch(a, b, c)
+    assert got.tolist() == ent["scores"]
+
+
+def test_batch_against_oracle_random_and_mutated(gpu_ta, ob):
+    rng = np.random.default_rng(99)
+    for L, n in ((8, 65), (24, 33), (64, 130), (100, 9)):
+        a = rng.integers(0, 4, (n, L), dtype=np.uint8)
+        b = rng.integers(0, 4, (n, L), dtype=np.uint8)
+        c = rng.integers(0, 4, (n, L), dtype=np.uint8)
+        for t in range(0, n, 2):  # every other triple is a mutated copy so large values are exercised
+            ma, mb, mc = ob.mutated_triple(rng, L)
+            a[t], b[t], c[t] = ma, mb, mc
+        for w in (12, 16, 8):
+            want = ob.score_batch(a, b, c, w)
+            got = gpu_ta.TriAlign(w).align_batch(a, b, c)
+            assert got.tolist() == want.tolist(), (L, n, w, gpu_ta.last_path())
+
+
+def test_wrap_semantics_small_score_bits(gpu_ta, ob):
+    rng = np.random.default_rng(5)
+    for w in (2, 3, 5, 7, 9):
+        for L in (12, 40):
+            a, b, c = ob.mutated_triple(rng, L, rate=0.05)
+            s, fin = gpu_ta.TriAlign(w).align(a, b, c, return_states=True)
+            es, efin = ob.score(a, b, c, w)
+            assert s == es and fin.tolist() == efin.tolist(), (w, L)
+
+
+def test_wide_score_bits(gpu_ta, ob):
+    rng = np.random.default_rng(6)
+    a, b, c = ob.mutated_triple(rng, 90)
+    for w in (17, 24, 32):
+        s, fin = gpu_ta.TriAlign(w).align(a, b, c, return_states=True)
+        es, efin = ob.score(a, b, c, w)
+        assert s == es and fin.tolist() == efin.tolist(), w
+
+
+def test_long_single_triple_golden(gpu_ta, golden):
+    for ent in golden["synth"]:
+        if not ent.get("single"):
+            continue
+        L = ent["len"]
+        a, b, c = (gpu_ta.synth(ent["seed"], 0, s, L) for s in range(3))
+        s, fin = gpu_ta.TriAlign(ent["score_bits"]).align(a, b, c, return_states=True)
+        assert s == ent["score"] and fin.tolist() == ent["final_states"], (L, ent["score_bits"], gpu_ta.last_path())
+
+
+def test_device_resident_entry_points_match_host_ones(gpu_ta, ob):
+    import torch
+
+    n, L = 257, 48
+    a, b, c = gpu_ta.synth_batch(0x5EED0002, 1000, n, L)
+    da, db, dc = gpu_ta.trialign.synth_batch_cuda(0x5EED0002, 1000, n, L)
+    torch.cuda.synchronize()
+    assert da.cpu().numpy().tolist() == a.tolist() and dc.cpu().numpy().tolist() == c.tolist()
+    eng = gpu_ta.TriAlign(12)
+    got = eng.align_batch_cuda(da, db, dc)
+    torch.cuda.synchronize()
+    want = ob.score_batch(a, b, c, 12)
+    assert got.cpu().numpy().tolist() == want.tolist()
+    one = eng.align_cuda(da[3], db[3], dc[3])
+    torch.cuda.synchronize()
+    es, efin = ob.score(a[3], b[3], c[3], 12)
+    assert one.cpu().numpy().tolist() == [es] + efin.tolist()
+
+
+def test_properties_at_scale(gpu_ta):
+    """Size-independent properties on inputs too big for the oracle: identical sequences score 3L (W=16),
+    and a batch made of repeats of one triple returns one repeated score."""
+    eng16 = gpu_ta.TriAlign(16)
+    for L in (256, 700):
+        x = gpu_ta.synth(0x5EED0003, 5, 0, L)
+        assert eng16.align(x, x, x) == 3 * L
+    a, b, c = gpu_ta.synth_batch(0x5EED0004, 0, 1, 256)
+    n = 64
+    got = gpu_ta.TriAlign(12).align_batch(np.repeat(a, n, 0), np.repeat(b, n, 0), np.repeat(c, n, 0))
+    assert len(set(got.tolist())) == 1
+    assert got[0] == gpu_ta.TriAlign(12).align(a[0], b[0], c[0])
+
+
+def test_launches_are_counted(gpu_ta):
+    before = gpu_ta.launch_count()
+    gpu_ta.TriAlign().align([0, 1, 2, 3], [0, 1, 2, 3], [0, 1, 2, 3])
+    assert gpu_ta.launch_count() > before
+    sec, cells = gpu_ta.last_timing()
+    assert sec > 0 and cells == 64

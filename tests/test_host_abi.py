@@ -1,0 +1,137 @@
+"""CPU-side tests of libtrialign's C ABI: the library loads, exports every symbol include/trialign.h declares,
+file formats round-trip, argument errors come back as codes, and no compute happens without a GPU."""
+import ctypes as C
+import hashlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    with open(os.path.join(ROOT, "include", "trialign.h")) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(trialign_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(ta):
+    names = _declared_functions()
+    assert len(names) >= 15
+    lib = C.CDLL(ta.library_path())
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/trialign.h but not exported"
+
+
+def test_version_and_strerror(ta):
+    assert ta.version() == 0x00010000
+    L = ta.library()
+    assert L.trialign_strerror(0) == b"ok"
+    for rc in range(-9, 0):
+        assert len(L.trialign_strerror(rc)) > 3
+    assert L.trialign_strerror(-99) == b"unknown error"
+
+
+def test_seq_dat_roundtrip_crlf_and_lf(ta, golden, tmp_path):
+    A = np.array(golden["dat"]["A"], np.uint8)
+    p = str(tmp_path / "A_seq.dat")
+    ta.write_seq_dat(p, A, crlf=True)
+    raw = open(p, "rb").read()
+    assert len(raw) == 192 and raw[:3] == b"3\r\n"
+    # byte-identical to the reference's dat/A_seq.dat
+    assert hashlib.sha256(raw).hexdigest() == golden["dat"]["A_seq_sha256"]
+    assert ta.read_seq_dat(p).tolist() == A.tolist()
+    ta.write_seq_dat(p, A, crlf=False)
+    assert ta.read_seq_dat(p).tolist() == A.tolist()
+    # no trailing newline is fine too
+    open(p, "wb").write(b"0\n1\n2\n3")
+    assert ta.read_seq_dat(p).tolist() == [0, 1, 2, 3]
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/dat/A_seq.dat"), reason="reference only in the build container")
+def test_reads_reference_dat_files_directly(ta, golden):
+    for nm in "ABC":
+        got = ta.read_seq_dat(f"/root/reference/dat/{nm}_seq.dat")
+        assert got.tolist() == golden["dat"][nm]
+    assert ta.read_scores("/root/reference/dat/Pattern1.dat").tolist() == golden["pattern1"]
+
+
+def test_seq_dat_errors(ta, tmp_path):
+    L = ta.library()
+    n = C.c_int(0)
+    buf = (C.c_uint8 * 8)()
+    assert L.trialign_read_seq_dat(b"/nonexistent/file.dat", buf, 8, C.byref(n)) == -4  # EIO
+    p = str(tmp_path / "bad.dat")
+    open(p, "wb").write(b"0\n4\n")
+    assert L.trialign_read_seq_dat(p.encode(), buf, 8, C.byref(n)) == -5  # EPARSE: digit outside 0-3
+    open(p, "wb").write(b"01\n")
+    assert L.trialign_read_seq_dat(p.encode(), buf, 8, C.byref(n)) == -5  # two symbols on a line
+    open(p, "wb").write(b"0\n1\n2\n3\n0\n1\n2\n3\n0\n")
+    assert L.trialign_read_seq_dat(p.encode(), buf, 8, C.byref(n)) == -8 and n.value == 9  # ECAPACITY
+    assert L.trialign_read_seq_dat(None, buf, 8, C.byref(n)) == -1
+
+
+def test_scores_writer_reproduces_pattern1_layout(ta, golden, tmp_path):
+    vals = np.array(golden["pattern1"], np.int32)
+    assert len(vals) == 572
+    p = str(tmp_path / "Pattern1.dat")
+    ta.write_scores(p, vals)
+    raw = open(p, "rb").read()
+    assert len(raw) == 1147 and not raw.endswith(b"\n") and b"\r" not in raw
+    assert hashlib.sha256(raw).hexdigest() == golden["dat"]["Pattern1_sha256"]
+    assert ta.read_scores(p).tolist() == vals.tolist()
+    ta.write_scores(p, np.array([-5, 0, 2047, -2048], np.int32))
+    assert open(p, "rb").read() == b"-5\n0\n2047\n-2048"
+    ta.write_scores(p, np.zeros(0, np.int32))
+    assert open(p, "rb").read() == b""
+
+
+def test_synth_matches_oracle_generator(ta, ob, golden):
+    for seed, t, s, n in ((0x5EED0002, 0, 0, 64), (0x5EED0004, 123456, 2, 256), (0x5EED0005, 0, 1, 1000)):
+        assert ta.synth(seed, t, s, n).tolist() == ob.synth(seed, t, s, n).tolist()
+    ent = golden["synth"][0]
+    assert ta.synth(ent["seed"], 0, 0, 16).tolist() == ent["first_symbols"]["A"]
+
+
+def test_argument_errors_are_codes_not_crashes(ta):
+    L = ta.library()
+    s = C.c_int32(7)
+    a = (C.c_uint8 * 4)(0, 1, 2, 3)
+    assert L.trialign_score(a, 4, a, 4, a, 4, 12, 0, 0, None, None) == -1
+    assert L.trialign_score(a, -1, a, 4, a, 4, 12, 0, 0, C.byref(s), None) == -1
+    assert L.trialign_score(a, 4, a, 4, a, 4, 1, 0, 0, C.byref(s), None) == -1    # score_bits < 2
+    assert L.trialign_score(a, 4, a, 4, a, 4, 33, 0, 0, C.byref(s), None) == -1   # score_bits > 32
+    assert L.trialign_score(None, 4, a, 4, a, 4, 12, 0, 0, C.byref(s), None) == -1
+    assert L.trialign_score(a, 4, a, 4, a, 4, 12, 77, 0, C.byref(s), None) == -1  # unknown backend
+    # the CPU checkers are deliberately not reachable through the product library
+    for backend in (1, 2, 3):
+        assert L.trialign_score(a, 4, a, 4, a, 4, 12, backend, 0, C.byref(s), None) == -6
+    assert L.trialign_score_batch(a, a, a, -1, 4, 12, 0, 0, None) == -1
+
+
+def test_no_cpu_fallback_without_a_gpu(ta):
+    if ta.device_count() > 0:
+        pytest.skip("a GPU is present; covered by the gpu tests")
+    with pytest.raises(ta.TriAlignError) as ei:
+        ta.TriAlign().align([0, 1, 2], [0, 1, 2], [0, 1, 2])
+    assert ei.value.rc == -7  # ENODEVICE, not a silently computed score
+    with pytest.raises(ta.TriAlignError):
+        ta.TriAlign().align_batch(np.zeros((2, 4), np.uint8), np.zeros((2, 4), np.uint8), np.zeros((2, 4), np.uint8))
+    assert ta.launch_count() == 0
+
+
+def test_product_does_not_link_the_oracle(ta):
+    import subprocess
+
+    out = subprocess.run(["nm", "-D", "--defined-only", ta.library_path()], capture_output=True, text=True).stdout
+    assert "oracle_" not in out and "rtl_model" not in out
+    srcs = os.path.join(ROOT, "hw-accelerator-three-sequence-alignment_b200")
+    for dirpath, _, files in os.walk(srcs):
+        for fn in files:
+            if fn.endswith((".cu", ".cuh", ".cpp", ".h", ".py")):
+                text = open(os.path.join(dirpath, fn)).read()
+                for needle in ("liboracle", "trialign_oracle.h", "rtl_model.h", "oracle_bindings", "oracle_score"):
+                    assert needle not in text, f"{fn} references the test oracle ({needle})"

@@ -1,0 +1,122 @@
+"""CPU tests of the checkers themselves: O1 (functional oracle) against the frozen golden vectors and against
+O2 (cycle-accurate RTL model), plus the survey-derived known answers of SURVEY.md 8(c)."""
+import numpy as np
+import pytest
+
+
+def _abc(case):
+    return (np.array(case[k], np.uint8) for k in ("a", "b", "c"))
+
+
+def test_known_answers_of_survey(golden, ob):
+    by = {c["name"]: c for c in golden["cases"]}
+    assert by["dat_triple"]["score"] == 1
+    assert by["dat_triple"]["final_states"] == [-1, 1, -4, -5, 1, -7, -2]
+    assert by["dat_triple"]["range"] == [-19, 17]
+    assert by["dat_triple"]["rtl_1cyc_cycles"] == 9282
+    assert by["tb_as_shipped_allA_64"]["score"] == 192
+    assert by["tb_as_shipped_allA_64"]["final_states"] == [192, 185, 185, 185, 188, 188, 188]
+    assert [by[f"dat_prefix_{L}"]["score"] for L in range(8, 65, 8)] == [-3, -5, -2, 1, -1, 5, 2, 1]
+    assert by["dat_prefix_16"]["final_states"] == [-5, -6, -6, -7, -5, -6, -5]
+    assert by["dat_prefix_16"]["rtl_1cyc_cycles"] == 390
+    assert [by[f"dat_perm_{p}"]["score"] for p in ("ACB", "BAC", "BCA", "CAB", "CBA")] == [0, 1, -4, 0, -4]
+    assert by["wrap_W7_allA_24"]["score"] == 62 and by["wrap_W7_allA_24"]["rtl_1cyc_cycles"] == 947
+    assert by["wrap_W8_allA_48"]["score"] == 125 and by["wrap_W8_allA_48"]["rtl_1cyc_cycles"] == 4646
+
+
+def test_oracle_reproduces_golden(golden, ob):
+    for case in golden["cases"]:
+        a, b, c = _abc(case)
+        s, fin, rng = ob.score(a, b, c, case["score_bits"], want_range=True)
+        assert s == case["score"], case["name"]
+        assert fin.tolist() == case["final_states"], case["name"]
+        assert list(rng) == case["range"], case["name"]
+
+
+def test_wavefront_oracle_equals_serial(golden, ob):
+    for case in golden["cases"][:25]:
+        a, b, c = _abc(case)
+        s, fin = ob.score_mt(a, b, c, case["score_bits"], threads=3)
+        assert s == case["score"] and fin.tolist() == case["final_states"], case["name"]
+
+
+def test_identical_sequences_score_3L(ob):
+    rng = np.random.default_rng(3)
+    for L in (1, 7, 40, 100):
+        a = rng.integers(0, 4, L, dtype=np.uint8)
+        assert ob.score(a, a, a, 16)[0] == 3 * L
+
+
+def test_zero_length_is_zero(ob):
+    a = np.array([1, 2, 3], np.uint8)
+    e = np.zeros(0, np.uint8)
+    assert ob.score(e, a, a)[0] == 0
+    assert ob.score(a, e, a)[0] == 0
+    assert ob.score(a, a, e)[0] == 0
+
+
+def test_temp_abc_precedence_quirk(ob):
+    # A==B!=C scores 0, A!=B scores -3 even when A==C or B==C (PE_1cyc.v:162); single-cell problems expose it
+    cube = ob.cube([0], [0], [1])
+    assert cube[1, 1, 1, 0] == 0
+    assert ob.cube([0], [1], [0])[1, 1, 1, 0] == -3
+    assert ob.cube([1], [0], [0])[1, 1, 1, 0] == -3
+    assert ob.cube([2], [2], [2])[1, 1, 1, 0] == 3
+
+
+def test_rtl_model_equals_oracle_random(ob):
+    rng = np.random.default_rng(11)
+    for (la, lb, lc) in [(8, 8, 8), (16, 16, 16), (40, 16, 16), (24, 16, 8), (48, 40, 32), (64, 64, 64), (72, 64, 56)]:
+        for mutated in (False, True):
+            if mutated:
+                a, b, c = ob.mutated_triple(rng, max(la, lb, lc))
+                a, b, c = a[:la], b[:lb], c[:lc]
+            else:
+                a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in (la, lb, lc))
+            s, fin = ob.score(a, b, c, 12)
+            rc, rs, rfin, cyc = ob.rtl_run(a, b, c, 1)
+            assert rc == ob.RTL_OK
+            assert rs == s and rfin.tolist() == fin.tolist()
+            assert cyc == ob.rtl_cycle_formula(1, 8, la, lb, lc)
+
+
+def test_rtl_model_wrap_order_is_observable(ob):
+    # all-A L=24 at W=7: true score 72 > 63; the RTL gives 62, not wrap(72) -- candidates wrap before the max
+    z = np.zeros(24, np.uint8)
+    rc, rs, rfin, _ = ob.rtl_run(z, z, z, 1, score_bits=7)
+    assert rc == ob.RTL_OK and rs == 62 and rfin.tolist() == [62, 59, 59, 59, 62, 62, 62]
+    assert ob.score(z, z, z, 7)[0] == 62
+
+
+def test_rtl_model_domain_guard(ob):
+    rng = np.random.default_rng(5)
+    a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in (16, 24, 24))
+    assert ob.rtl_run(a, b, c, 1)[0] == ob.RTL_EDOMAIN      # A_idx < B_idx with C_idx > P
+    assert ob.rtl_run(a[:10], b[:12], c[:8], 1)[0] == ob.RTL_EDOMAIN  # B not a multiple of PE_LEN
+    # outside the domain the raw model reproduces the RTL's own mis-computation instead of the recurrence
+    rc, rs, _, cyc = ob.rtl_run(a, b, c, 1, strict=False)
+    assert rc in (ob.RTL_OK, ob.RTL_EX) and cyc == ob.rtl_cycle_formula(1, 8, 16, 24, 24)
+
+
+def test_rtl_model_counter_width_hang(ob):
+    # input_counter is SCORE_BITS wide: at W<7 it can never reach P*P=64 and the FSM stays in INITIAL
+    z = np.zeros(8, np.uint8)
+    rc = ob.rtl_run(z, z, z, 1, score_bits=6, strict=False, max_cycles=5000)[0]
+    assert rc == ob.RTL_ETIMEOUT
+
+
+def test_synth_generator_properties(golden, ob):
+    for ent in golden["synth"]:
+        if "first_symbols" in ent:
+            for s, nm in enumerate("ABC"):
+                assert ob.synth(ent["seed"], 0, s, 16).tolist() == ent["first_symbols"][nm]
+    x = ob.synth(0x5EED0002, 12345, 1, 4096)
+    assert set(np.unique(x)) == {0, 1, 2, 3}
+    assert abs(np.bincount(x, minlength=4) / 4096 - 0.25).max() < 0.05
+
+
+def test_batch_oracle_matches_golden(golden, ob):
+    ent = next(e for e in golden["synth"] if e["config"] == 2)
+    n = len(ent["scores"])
+    a, b, c = ob.synth_batch(ent["seed"], 0, n, ent["len"])
+    assert ob.score_batch(a, b, c, ent["score_bits"]).tolist() == ent["scores"]
