@@ -117,10 +117,14 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
                    int32_t *d_finals)
 {
     ThreadState &ts = tls();
-    if (backend == TRIALIGN_BACKEND_GPU_FAST) {
-        // the fast kernels land in a later milestone of this round; until then the forced-fast request is refused
-        return TRIALIGN_EINEXACT;
+    const bool want_fast = backend != TRIALIGN_BACKEND_GPU_LITERAL;
+    // fast paths are used only where they are provably bit-exact: no candidate can wrap at score_bits
+    if (want_fast && !d_finals && la == lb && lb == lc && fast_batch_supports(la) &&
+        provably_wrap_free(la, lb, lc, score_bits)) {
+        ts.last_path = TRIALIGN_PATH_FAST_BATCH;
+        return fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
     }
+    if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
     ts.last_path = TRIALIGN_PATH_LITERAL;
     return literal_run(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals);
 }

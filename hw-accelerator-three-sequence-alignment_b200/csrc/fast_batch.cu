@@ -1,0 +1,74 @@
+// fast_batch.cu -- K1 launcher: CTA-wide systolic kernel for batches of short triples (see fast_batch.cuh).
+#include "fast_batch.cuh"
+#include "kernels.cuh"
+
+namespace trialign {
+
+namespace {
+
+using Cfg = fast::BatchCfg<4, 4, 16, 16>;
+
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
+    const int tid = threadIdx.x;
+    const long long pair_base = (long long)blockIdx.x * A.pairs_per_cta;
+    long long left = A.pairs_total - pair_base;
+    if (left <= 0) return;
+    const int P = left < A.pairs_per_cta ? (int)left : A.pairs_per_cta;
+    int tj, tk;
+    fast::thread_pos<Cfg>(tid, tj, tk);
+
+    fast::load_pair_sequences<Cfg>(S, A, tid, pair_base, 0);
+    __syncthreads();
+    fast::build_pair_tables<Cfg>(S, tid, 0);
+    __syncthreads();
+
+    fast::BatchRegs<Cfg> R;
+    const int steps = fast::batch_total_steps<Cfg>(P);
+#pragma unroll 1
+    for (int s = 0; s <= steps; ++s) {
+        fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
+        fast::batch_thread_step<Cfg>(R, S, A, tj, tk, s, P, pair_base);
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+bool fast_batch_supports(int len) { return len >= 1 && len <= 64; }
+
+int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                   int64_t n, int len, int32_t *d_scores)
+{
+    if (n <= 0) return TRIALIGN_OK;
+    static_assert(sizeof(fast::BatchSmem<Cfg>) <= 227 * 1024, "shared memory budget");
+    const size_t smem = sizeof(fast::BatchSmem<Cfg>);
+    static bool attr_set[kMaxDevices] = {};
+    if (!attr_set[ctx->device]) {
+        TA_CUDA(cudaFuncSetAttribute(fast_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[ctx->device] = true;
+    }
+    fast::BatchArgs A;
+    A.a = d_a; A.b = d_b; A.c = d_c;
+    A.n = n; A.len = len; A.scores = d_scores;
+    A.pairs_total = (n + 1) / 2;
+    // one persistent CTA per SM slot; contiguous chunks so that the fill/drain is paid once per CTA
+    int occ = 1;
+    TA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_batch_kernel, Cfg::NT, smem));
+    if (occ < 1) occ = 1;
+    const long long slots = (long long)ctx->sm_count * occ;
+    long long ppc = (A.pairs_total + slots - 1) / slots;
+    if (ppc < 1) ppc = 1;
+    if (ppc > (1 << 20)) ppc = 1 << 20;  // keep the step counter far from int overflow
+    A.pairs_per_cta = (int)ppc;
+    A.base = 2 * 64 + 32;  // >= 2*min(len)+8 plus the "-1" headroom of the reductions (common.cuh envelope)
+    const long long grid = (A.pairs_total + ppc - 1) / ppc;
+    fast_batch_kernel<<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+}  // namespace trialign

@@ -1,0 +1,280 @@
+// fast_batch.cuh -- K1: the batched kernel for many short triples (len <= 64), as one CTA-wide systolic array.
+//
+// Mapping (the GPU counterpart of the RTL's P x P PE array, src/TriAlign_1cyc.v:116-125, with P = 16 threads x 4
+// cells per side and the whole 64x64 (j,k) plane resident, so no slicing / face SRAM is needed at this length):
+//   * one CTA = TJ x TK threads; thread (tj,tk) owns the RJ x RK cells j in (tj*RJ, tj*RJ+RJ], k likewise, for ALL i;
+//   * the plane-(i-1) state of those cells (all, wX, u1, u3 -- see fast_core.cuh) lives in registers;
+//   * thread (tj,tk) works on plane i at global step s = i + tj + tk (wavefront skew, like PE(j,k) at step i+j+k);
+//   * neighbours exchange tile edges through shared memory, double buffered, one __syncthreads per step
+//     (the counterpart of the PE-to-PE wires; the RTL's _d1/_d2 delay registers are the "old" values published
+//     one step late);
+//   * two triples ride in the two 16-bit halves of every word; consecutive pairs of triples stream through the array
+//     back to back, so the (TJ+TK-2)-step fill/drain is paid once per CTA, not once per triple.
+// Per-pair score tables (a vs b, a vs c for all 16 combinations of the two a symbols) are rebuilt in shared memory
+// while the previous pair is still in flight.
+#pragma once
+
+#include "fast_core.cuh"
+
+namespace trialign {
+namespace fast {
+
+template <int RJ_, int RK_, int TJ_, int TK_>
+struct BatchCfg {
+    static constexpr int RJ = RJ_, RK = RK_, TJ = TJ_, TK = TK_;
+    static constexpr int BJ = RJ * TJ, BK = RK * TK, NT = TJ * TK;
+    static constexpr int L = 64;                 // planes per pair (sequences are padded to 64)
+    static constexpr int COL_STRIDE = BJ + 4;    // +16 B: conflict-free 128-bit column reads
+    static constexpr int TAB_STRIDE = 68;
+    static constexpr int SKEW = TJ + TK - 2;
+    static_assert(BJ == 64 && BK == 64, "K1 keeps the whole 64x64 (j,k) plane in one CTA");
+    static_assert(RJ == 4 && RK == 4, "edge exchange is written for 4-word (128-bit) groups");
+};
+
+struct BatchArgs {
+    const uint8_t *a, *b, *c;  // [n][len] device
+    long long n;               // triples
+    int len;                   // <= 64
+    int32_t *scores;           // [n]
+    long long pairs_total;     // ceil(n/2)
+    int pairs_per_cta;         // contiguous chunk per CTA
+    int base;                  // potential base (common.cuh envelope), < 2^15
+};
+
+template <class C>
+struct BatchSmem {
+    uint32_t row[2][4][C::TJ][C::BK];          // [slot][wY,u2,u1(old),all(old)][tj][k]   bottom rows
+    uint32_t col[2][4][C::TK][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk][j]   right columns
+    uint32_t corner[2][2][C::TJ][C::TK];       // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
+    uint32_t tabAB[2][16][C::TAB_STRIDE];      // [buf][a code][j]  pair constant {4,2}
+    uint32_t tabMB[2][16][C::TAB_STRIDE];      // [buf][a code][j]  0xFFFF where a == b
+    uint32_t tabAC[2][16][C::TAB_STRIDE];      // [buf][a code][k]
+    uint8_t seq[2][3][2][64];                  // [buf][A,B,C][half][pos]
+    uint8_t acode[2][64];                      // a_lo | a_hi << 2
+};
+
+template <class C>
+struct BatchRegs {
+    uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
+    uint32_t cBC[C::RJ][C::RK], U[C::RJ][C::RK];                                       // per-cell constants
+};
+
+// thread id -> position in the TJ x TK thread grid.  A quarter-warp holds 8 consecutive tk of one tj
+// (conflict-free 128-bit shared-memory accesses); a warp spans 4 tj x 8 tk (11 distinct skews).
+template <class C>
+TA_HD void thread_pos(int tid, int &tj, int &tk)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    tk = (lane & 7) + 8 * (warp & 1);
+    tj = (lane >> 3) + 4 * (warp >> 1);
+}
+
+TA_HD uint32_t phi(const BatchArgs &A, int i, int jl, int kl) { return rep((uint32_t)(A.base + 2 * (i + jl + kl))); }
+
+// ---- CTA-uniform actions, executed by every thread at fixed global steps ----
+template <class C>
+TA_HD void load_pair_sequences(BatchSmem<C> &S, const BatchArgs &A, int tid, long long pair, int buf)
+{
+    for (int e = tid; e < 3 * 2 * 64; e += C::NT) {
+        const int which = e >> 7, half = (e >> 6) & 1, pos = e & 63;
+        const long long t = 2 * pair + half;
+        const uint8_t *src = which == 0 ? A.a : (which == 1 ? A.b : A.c);
+        uint8_t v = 0;
+        if (t < A.n && pos < A.len) v = src[t * A.len + pos] & 3;  // PE keeps bits [1:0] (src/PE_1cyc.v:63-66)
+        S.seq[buf][which][half][pos] = v;
+    }
+}
+
+template <class C>
+TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf)
+{
+    for (int e = tid; e < 16 * 64; e += C::NT) {
+        const int code = e >> 6, p = e & 63;
+        const uint32_t ap = (uint32_t)(code & 3) | ((uint32_t)(code >> 2) << 16);
+        const uint32_t bp = (uint32_t)S.seq[buf][1][0][p] | ((uint32_t)S.seq[buf][1][1][p] << 16);
+        const uint32_t cp = (uint32_t)S.seq[buf][2][0][p] | ((uint32_t)S.seq[buf][2][1][p] << 16);
+        const uint32_t nab = neq_flag(ap, bp), nac = neq_flag(ap, cp);
+        S.tabAB[buf][code][p] = pair_const(nab);
+        S.tabMB[buf][code][p] = eq_mask(nab);
+        S.tabAC[buf][code][p] = pair_const(nac);
+    }
+    for (int p = tid; p < 64; p += C::NT) S.acode[buf][p] = (uint8_t)(S.seq[buf][0][0][p] | (S.seq[buf][0][1][p] << 2));
+}
+
+// ---- one wavefront step of one thread ----
+template <class C>
+TA_HD void batch_thread_step(BatchRegs<C> &R, BatchSmem<C> &S, const BatchArgs &A, int tj, int tk, int s, int P,
+                             long long pair_base)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    const int u = s - (tj + tk);
+    const int p = u >> 6;          // pair index within this CTA's chunk (negative while the pipeline fills)
+    const int i = (u & 63) + 1;    // plane 1..64
+    const int buf = p & 1;
+    const int j0 = tj * RJ, k0 = tk * RK;  // block-local index of the cell left/above the tile
+
+    if (i == 1) {
+        // new pair enters this thread: plane 0 is the all-zero border (src/PE_1cyc.v:164-178 override), and the
+        // tile's (b,c) constants change
+        uint32_t bp[RJ], cp[RK];
+#pragma unroll
+        for (int r = 0; r < RJ; ++r)
+            bp[r] = (uint32_t)S.seq[buf][1][0][j0 + r] | ((uint32_t)S.seq[buf][1][1][j0 + r] << 16);
+#pragma unroll
+        for (int c = 0; c < RK; ++c)
+            cp[c] = (uint32_t)S.seq[buf][2][0][k0 + c] | ((uint32_t)S.seq[buf][2][1][k0 + c] << 16);
+#pragma unroll
+        for (int r = 0; r < RJ; ++r)
+#pragma unroll
+            for (int c = 0; c < RK; ++c) {
+                const uint32_t z = phi(A, 0, j0 + r + 1, k0 + c + 1);
+                R.all[r][c] = z; R.wX[r][c] = z; R.u1[r][c] = z; R.u3[r][c] = z;
+                const uint32_t nbc = neq_flag(bp[r], cp[c]);
+                R.cBC[r][c] = pair_const(nbc);
+                R.U[r][c] = triple_u(nbc);
+            }
+    }
+
+    // per-step constants: a_i against the tile's rows / columns
+    const int code = S.acode[buf][i - 1];
+    uint32_t cAB[RJ], mAB[RJ], cAC[RK];
+#pragma unroll
+    for (int r = 0; r < RJ; ++r) {
+        cAB[r] = S.tabAB[buf][code][j0 + r];
+        mAB[r] = S.tabMB[buf][code][j0 + r];
+    }
+#pragma unroll
+    for (int c = 0; c < RK; ++c) cAC[c] = S.tabAC[buf][code][k0 + c];
+
+    // halos: top = bottom row of thread (tj-1,tk), left = right column of (tj,tk-1), both published at step s-1.
+    // T_u2/T_all[c] belong to column k0+c (c = 0 is the corner cell, c = RK the cell above-right of the tile);
+    // L_u2/L_all[r] belong to row j0+r.  The corner cell belongs to thread (tj-1,tk-1), which is TWO steps ahead,
+    // so its value is relayed by the left neighbour (which read it one step ago as its own T_*[RK]).
+    const int rs = (s - 1) & 1, ws = s & 1;
+    uint32_t T_wY[RK], T_u1[RK], T_u2[RK + 1], T_all[RK + 1], L_wZ[RJ], L_u3[RJ], L_u2[RJ], L_all[RJ];
+    if (tj > 0) {
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            T_wY[c] = S.row[rs][0][tj - 1][k0 + c];
+            T_u1[c] = S.row[rs][2][tj - 1][k0 + c];
+            T_u2[c + 1] = S.row[rs][1][tj - 1][k0 + c];
+            T_all[c + 1] = S.row[rs][3][tj - 1][k0 + c];
+        }
+        if (tk > 0) {
+            T_u2[0] = S.corner[rs][0][tj][tk - 1];
+            T_all[0] = S.corner[rs][1][tj][tk - 1];
+        } else {  // corner lies on the k = 0 border plane
+            T_u2[0] = phi(A, i, j0, 0);
+            T_all[0] = phi(A, i - 1, j0, 0);
+        }
+    } else {  // j = 0 border plane (src/TriAlign_1cyc.v:156-165: all 7 states are 0 -> every reduced value is phi)
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            T_wY[c] = phi(A, i, 0, k0 + c + 1);
+            T_u1[c] = phi(A, i - 1, 0, k0 + c + 1);
+        }
+#pragma unroll
+        for (int c = 0; c <= RK; ++c) {
+            T_u2[c] = phi(A, i, 0, k0 + c);
+            T_all[c] = phi(A, i - 1, 0, k0 + c);
+        }
+    }
+    if (tk > 0) {
+#pragma unroll
+        for (int r = 0; r < RJ; ++r) {
+            L_wZ[r] = S.col[rs][0][tk - 1][j0 + r];
+            L_u3[r] = S.col[rs][2][tk - 1][j0 + r];
+        }
+#pragma unroll
+        for (int r = 1; r < RJ; ++r) {
+            L_u2[r] = S.col[rs][1][tk - 1][j0 + r - 1];
+            L_all[r] = S.col[rs][3][tk - 1][j0 + r - 1];
+        }
+    } else {  // k = 0 border plane (src/TriAlign_1cyc.v:166-174)
+#pragma unroll
+        for (int r = 0; r < RJ; ++r) {
+            L_wZ[r] = phi(A, i, j0 + r + 1, 0);
+            L_u3[r] = phi(A, i - 1, j0 + r + 1, 0);
+            L_u2[r] = phi(A, i, j0 + r, 0);
+            L_all[r] = phi(A, i - 1, j0 + r, 0);
+        }
+    }
+    L_u2[0] = T_u2[0];
+    L_all[0] = T_all[0];
+    S.corner[ws][0][tj][tk] = T_u2[RK];
+    S.corner[ws][1][tj][tk] = T_all[RK];
+
+    // the tile, row-major (within a plane a cell needs its j-1, k-1 and (j-1,k-1) neighbours)
+    uint32_t n_all[RJ][RK], n_wX[RJ][RK], n_u1[RJ][RK], n_u3[RJ][RK], n_wY[RJ][RK], n_wZ[RJ][RK], n_u2[RJ][RK];
+#pragma unroll
+    for (int r = 0; r < RJ; ++r)
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            const uint32_t p_all = (r > 0 && c > 0) ? R.all[r - 1][c - 1] : (r == 0 ? T_all[c] : L_all[r]);
+            const uint32_t p_wY = r > 0 ? n_wY[r - 1][c] : T_wY[c];
+            const uint32_t p_wZ = c > 0 ? n_wZ[r][c - 1] : L_wZ[r];
+            const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
+            const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
+            const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
+            const uint32_t cM = triple_const(mAB[r], R.U[r][c]);
+            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, cAB[r],
+                                                 R.cBC[r][c], cAC[c], nullptr);
+            n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
+            n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
+        }
+
+    // publish the tile's bottom row and right column for step s+1 (old = plane i-1 values, see header)
+#pragma unroll
+    for (int c = 0; c < RK; ++c) {
+        S.row[ws][0][tj][k0 + c] = n_wY[RJ - 1][c];
+        S.row[ws][1][tj][k0 + c] = n_u2[RJ - 1][c];
+        S.row[ws][2][tj][k0 + c] = R.u1[RJ - 1][c];
+        S.row[ws][3][tj][k0 + c] = R.all[RJ - 1][c];
+    }
+#pragma unroll
+    for (int r = 0; r < RJ; ++r) {
+        S.col[ws][0][tk][j0 + r] = n_wZ[r][RK - 1];
+        S.col[ws][1][tk][j0 + r] = n_u2[r][RK - 1];
+        S.col[ws][2][tk][j0 + r] = R.u3[r][RK - 1];
+        S.col[ws][3][tk][j0 + r] = R.all[r][RK - 1];
+    }
+
+    // Score = max of the 7 states of cell (len,len,len) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
+    if (i == A.len && u >= 0 && p < P && tj == (A.len - 1) / RJ && tk == (A.len - 1) / RK) {
+        const int rf = (A.len - 1) % RJ, cf = (A.len - 1) % RK;
+        uint32_t v = 0;
+#pragma unroll
+        for (int r = 0; r < RJ; ++r)
+#pragma unroll
+            for (int c = 0; c < RK; ++c)
+                if (r == rf && c == cf) v = n_all[r][c];
+        const int off = A.base + 2 * (3 * A.len);
+        const long long t0 = 2 * (pair_base + p);
+        if (t0 < A.n) A.scores[t0] = (int32_t)(v & 0xFFFFu) - off;
+        if (t0 + 1 < A.n) A.scores[t0 + 1] = (int32_t)(v >> 16) - off;
+    }
+
+#pragma unroll
+    for (int r = 0; r < RJ; ++r)
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            R.all[r][c] = n_all[r][c]; R.wX[r][c] = n_wX[r][c]; R.u1[r][c] = n_u1[r][c]; R.u3[r][c] = n_u3[r][c];
+        }
+}
+
+// Steps a CTA needs for P pairs, and the CTA-uniform actions of global step s.
+template <class C>
+TA_HD int batch_total_steps(int P) { return P * C::L + C::SKEW; }
+
+template <class C>
+TA_HD void batch_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, int s, int P, long long pair_base)
+{
+    const int q = (s >> 6) + 1;  // pair that starts entering the array at step 64*q
+    if (q < P) {
+        if ((s & 63) == 32) load_pair_sequences<C>(S, A, tid, pair_base + q, q & 1);
+        if ((s & 63) == 34) build_pair_tables<C>(S, tid, q & 1);
+    }
+}
+
+}  // namespace fast
+}  // namespace trialign

@@ -1,0 +1,113 @@
+// fast_core.cuh -- the factored max-plus cell update shared by the fast kernels (K1 batch, K2 long).
+//
+// Exactness domain: no candidate of the RTL recurrence wraps at score_bits (proved a priori from the envelope in
+// common.cuh, or established at run time by the range check).  Inside that domain the 49 wrapped candidates of
+// src/PE_1cyc.v:164-218 can be regrouped, because every transition cost has the form
+//     cost(q -> m) = GO*|G(m)| - (GO-GE)*|G(m) & G(q)|,   G(state) = set of sequences that state gaps
+//     G(M)={}  G(Ix)={B,C}  G(Iy)={A,C}  G(Iz)={A,B}  G(Ixy)={C}  G(Iyz)={A}  G(Ixz)={B}
+// (check against the cost table in SURVEY.md 8(a): e.g. Iy->Ix: C extends, B opens: GE+GO = 3).  With
+//     all = max7(V)   hC = max(Ix,Iy,Ixy)   hA = max(Iy,Iz,Iyz)   hB = max(Ix,Iz,Ixz)
+// a producer cell hands out seven reduced values instead of 7x7 candidates:
+//     to M   (i+1,j+1,k+1): all                       (+ S3(a,b,c) at the consumer)
+//     to Ixy (i+1,j+1,k)  : u1 = max(all-1, hC)   (= gXY+1)      to Ix: wX = max(max(u3,u1)-1, Ix)  (= gX+2)
+//     to Iyz (i,j+1,k+1)  : u2 = max(all-1, hA)                   to Iy: wY = max(max(u2,u1)-1, Iy)
+//     to Ixz (i+1,j,k+1)  : u3 = max(all-1, hB)                   to Iz: wZ = max(max(u2,u3)-1, Iz)
+// 14 max-type instructions (VIMNMX3 / VIMNMX / VIADDMNMX, .U16x2) per cell instead of 49 adds + 42 maxes.
+//
+// Potential trick: values are stored as  v~ = v + 2*(i+j+k) + base  (offset binary, unsigned 16-bit lanes).  A gap
+// move advances i+j+k by 1, so the "-2" of gX/gY/gZ is absorbed (Ix~ = wX directly); pair moves add (s+3) in {2,4}
+// and the M move adds (S3+6) in {3,6,9}: all remaining adds are additions of small positive constants, which are
+// carry-free on packed lanes and therefore plain 32-bit adds (IADD3 or IMAD, whichever pipe is free).
+//
+// Two independent problems ride in the two 16-bit halves of every 32-bit word.
+#pragma once
+
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define TA_HD __host__ __device__ __forceinline__
+#else
+#define TA_HD inline
+#endif
+
+namespace trialign {
+namespace fast {
+
+constexpr uint32_t kOnes = 0x00010001u;
+TA_HD uint32_t rep(uint32_t v) { return (v & 0xFFFFu) * kOnes; }  // same 16-bit value in both halves
+
+#if defined(__CUDA_ARCH__)
+TA_HD uint32_t vmax2(uint32_t a, uint32_t b) { return __vmaxu2(a, b); }
+TA_HD uint32_t vmin2(uint32_t a, uint32_t b) { return __vminu2(a, b); }
+TA_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2(a, b, c); }
+TA_HD uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
+// max(a - 1, c) per half
+TA_HD uint32_t vdecmax(uint32_t a, uint32_t c) { return __viaddmax_u16x2(a, 0xFFFFFFFFu, c); }
+#else
+TA_HD uint32_t vmax2(uint32_t a, uint32_t b)
+{
+    const uint32_t lo = (a & 0xFFFFu) > (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
+    const uint32_t hi = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+}
+TA_HD uint32_t vmin2(uint32_t a, uint32_t b)
+{
+    const uint32_t lo = (a & 0xFFFFu) < (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
+    const uint32_t hi = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+    return lo | (hi << 16);
+}
+TA_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return vmax2(vmax2(a, b), c); }
+TA_HD uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return vmin2(vmin2(a, b), c); }
+TA_HD uint32_t vdecmax(uint32_t a, uint32_t c)
+{
+    const uint32_t dec = (((a & 0xFFFFu) + 0xFFFFu) & 0xFFFFu) | ((((a >> 16) + 0xFFFFu) & 0xFFFFu) << 16);
+    return vmax2(dec, c);
+}
+#endif
+
+// Reduced outputs of one cell, all in the cell's own potential.
+struct CellOut {
+    uint32_t all, u1, u2, u3, wX, wY, wZ;
+};
+
+// One cell update.  Inputs (each already in the potential of THIS cell's predecessors, see header):
+//   p_all  = all(i-1,j-1,k-1)   p_wX = wX(i-1,j,k)   p_wY = wY(i,j-1,k)   p_wZ = wZ(i,j,k-1)
+//   p_u1   = u1(i-1,j-1,k)      p_u2 = u2(i,j-1,k-1) p_u3 = u3(i-1,j,k-1)
+//   cM in {3,6,9} = S3+6,  cAB/cBC/cAC in {2,4} = pair score + 3   (packed, per half)
+// Returns the 7 states through st[] (M,Ix,Iy,Iz,Ixy,Iyz,Ixz in potential form) when WANT_STATES.
+template <bool WANT_STATES>
+TA_HD CellOut cell_update(uint32_t p_all, uint32_t p_wX, uint32_t p_wY, uint32_t p_wZ, uint32_t p_u1, uint32_t p_u2,
+                          uint32_t p_u3, uint32_t cM, uint32_t cAB, uint32_t cBC, uint32_t cAC, uint32_t *st)
+{
+    const uint32_t M = p_all + cM;
+    const uint32_t X = p_wX, Y = p_wY, Z = p_wZ;
+    const uint32_t XY = p_u1 + cAB;
+    const uint32_t YZ = p_u2 + cBC;
+    const uint32_t XZ = p_u3 + cAC;
+    if (WANT_STATES) {
+        st[0] = M; st[1] = X; st[2] = Y; st[3] = Z; st[4] = XY; st[5] = YZ; st[6] = XZ;
+    }
+    CellOut o;
+    const uint32_t hC = vmax3(X, Y, XY);
+    const uint32_t hA = vmax3(Y, Z, YZ);
+    const uint32_t hB = vmax3(X, Z, XZ);
+    o.all = vmax2(vmax3(M, hC, hA), hB);
+    o.u1 = vdecmax(o.all, hC);
+    o.u2 = vdecmax(o.all, hA);
+    o.u3 = vdecmax(o.all, hB);
+    o.wX = vdecmax(vmax2(o.u3, o.u1), X);
+    o.wY = vdecmax(vmax2(o.u2, o.u1), Y);
+    o.wZ = vdecmax(vmax2(o.u2, o.u3), Z);
+    return o;
+}
+
+// pair-score constants from 2-bit symbols packed one per half (x, y in {0..3} per half)
+TA_HD uint32_t neq_flag(uint32_t x, uint32_t y) { return vmin2(x ^ y, kOnes); }       // 1 where x != y, per half
+TA_HD uint32_t pair_const(uint32_t neq) { return 0x00040004u - 2u * neq; }             // {4 (equal), 2 (differ)}
+TA_HD uint32_t triple_u(uint32_t neq_bc) { return 0x00060006u - 3u * neq_bc; }         // U = 3+3*[b==c]
+TA_HD uint32_t eq_mask(uint32_t neq) { return (kOnes - neq) * 0xFFFFu; }               // 0xFFFF where equal
+// cM = 3 + ([a==b] ? U : 0)   ->  {9 (a=b=c), 6 (a=b!=c), 3 (a!=b)} = S3 + 6   (src/PE_1cyc.v:162)
+TA_HD uint32_t triple_const(uint32_t mAB, uint32_t U) { return 0x00030003u + (mAB & U); }
+
+}  // namespace fast
+}  // namespace trialign

@@ -13,6 +13,12 @@ namespace trialign {
 int literal_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                 int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals);
 
+// K1: batched systolic kernel, two triples per 32-bit lane, len <= 64 (fast_batch.cu).  Exact only where no
+// candidate wraps at score_bits -- the dispatcher checks provably_wrap_free() first.
+bool fast_batch_supports(int len);
+int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                   int64_t n, int len, int32_t *d_scores);
+
 // synthetic generator on the device (synth_kernel.cu)
 int synth_run(cudaStream_t st, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a, uint8_t *d_b,
               uint8_t *d_c);
