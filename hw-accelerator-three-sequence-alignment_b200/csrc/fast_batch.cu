@@ -20,6 +20,9 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs 
     int tj, tk;
     fast::thread_pos<Cfg>(tid, tj, tk);
 
+    // threads that are still filling the pipeline (local step < 0) index buffer 1: give it in-range contents
+    for (int e = tid; e < 64; e += Cfg::NT) S.acode[1][e] = 0;
+    for (int e = tid; e < 3 * 2 * 64; e += Cfg::NT) (&S.seq[1][0][0][0])[e] = 0;
     fast::load_pair_sequences<Cfg>(S, A, tid, pair_base, 0);
     __syncthreads();
     fast::build_pair_tables<Cfg>(S, tid, 0);

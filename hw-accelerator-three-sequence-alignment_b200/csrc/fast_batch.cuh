@@ -137,6 +137,7 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, BatchSmem<C> &S, const BatchArgs &
 
     // per-step constants: a_i against the tile's rows / columns
     const int code = S.acode[buf][i - 1];
+    TA_CHECK(code >= 0 && code < 16);
     uint32_t cAB[RJ], mAB[RJ], cAC[RK];
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {

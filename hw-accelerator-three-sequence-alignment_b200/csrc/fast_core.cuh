@@ -30,6 +30,21 @@
 #define TA_HD inline
 #endif
 
+// Index checks that are active only in the host emulation (tests/emu); free on the device.
+#if !defined(__CUDACC__) && defined(TA_EMU_CHECKS)
+#include <cstdio>
+#include <cstdlib>
+#define TA_CHECK(cond)                                                              \
+    do {                                                                            \
+        if (!(cond)) {                                                              \
+            std::fprintf(stderr, "TA_CHECK failed: %s (%s:%d)\n", #cond, __FILE__, __LINE__); \
+            std::abort();                                                           \
+        }                                                                           \
+    } while (0)
+#else
+#define TA_CHECK(cond) ((void)0)
+#endif
+
 namespace trialign {
 namespace fast {
 

@@ -28,6 +28,8 @@ extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t 
         const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
         std::memset(S.get(), 0xA5, sizeof(BatchSmem<C>));  // poison: nothing may be read before it is written
         std::memset(R.data(), 0x5A, R.size() * sizeof(BatchRegs<C>));
+        std::memset(S->acode[1], 0, sizeof S->acode[1]);  // as the kernel prologue does
+        std::memset(S->seq[1], 0, sizeof S->seq[1]);
         for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
         for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
         const int steps = batch_total_steps<C>(P);
