@@ -1,4 +1,6 @@
 // fast_batch.cu -- K1 launcher: CTA-wide systolic kernel for batches of short triples (see fast_batch.cuh).
+#include <cstdlib>
+
 #include "fast_batch.cuh"
 #include "kernels.cuh"
 
@@ -8,7 +10,8 @@ namespace {
 
 using Cfg = fast::BatchCfg<4, 4, 16, 16>;
 
-__global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs A)
+template <int MINBLOCKS>
+__global__ void __launch_bounds__(Cfg::NT, MINBLOCKS) fast_batch_kernel(fast::BatchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
@@ -48,10 +51,19 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     if (n <= 0) return TRIALIGN_OK;
     static_assert(sizeof(fast::BatchSmem<Cfg>) <= 227 * 1024, "shared memory budget");
     const size_t smem = sizeof(fast::BatchSmem<Cfg>);
-    static bool attr_set[kMaxDevices] = {};
-    if (!attr_set[ctx->device]) {
-        TA_CUDA(cudaFuncSetAttribute(fast_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[ctx->device] = true;
+    // One 190-register CTA per SM is the measured optimum (1.10 TCUPS); the 128-register build that allows two
+    // CTAs per SM spills and measured 0.83 TCUPS.  TRIALIGN_K1_OCC=2 selects it for comparison.
+    static const int want_occ = []() {
+        const char *e = std::getenv("TRIALIGN_K1_OCC");
+        return (e && e[0] == '2') ? 2 : 1;
+    }();
+    auto kernel = want_occ == 1 ? fast_batch_kernel<1> : fast_batch_kernel<2>;
+    static bool attr_set[kMaxDevices][3] = {};
+    if (!attr_set[ctx->device][want_occ]) {
+        TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        attr_set[ctx->device][want_occ] = true;
     }
     fast::BatchArgs A;
     A.a = d_a; A.b = d_b; A.c = d_c;
@@ -59,7 +71,7 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     A.pairs_total = (n + 1) / 2;
     // one persistent CTA per SM slot; contiguous chunks so that the fill/drain is paid once per CTA
     int occ = 1;
-    TA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fast_batch_kernel, Cfg::NT, smem));
+    TA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, Cfg::NT, smem));
     if (occ < 1) occ = 1;
     const long long slots = (long long)ctx->sm_count * occ;
     long long ppc = (A.pairs_total + slots - 1) / slots;
@@ -68,7 +80,9 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     A.pairs_per_cta = (int)ppc;
     A.base = 2 * 64 + 32;  // >= 2*min(len)+8 plus the "-1" headroom of the reductions (common.cuh envelope)
     const long long grid = (A.pairs_total + ppc - 1) / ppc;
-    fast_batch_kernel<<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
+    if (std::getenv("TRIALIGN_DEBUG"))
+        std::fprintf(stderr, "[trialign] K1: occ=%d grid=%lld pairs/cta=%lld smem=%zu\n", occ, grid, ppc, smem);
+    kernel<<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TRIALIGN_OK;
