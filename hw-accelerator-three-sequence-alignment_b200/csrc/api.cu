@@ -119,10 +119,19 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     ThreadState &ts = tls();
     const bool want_fast = backend != TRIALIGN_BACKEND_GPU_LITERAL;
     // fast paths are used only where they are provably bit-exact: no candidate can wrap at score_bits
-    if (want_fast && !d_finals && la == lb && lb == lc && fast_batch_supports(la) &&
-        provably_wrap_free(la, lb, lc, score_bits)) {
-        ts.last_path = TRIALIGN_PATH_FAST_BATCH;
-        return fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
+    if (want_fast && provably_wrap_free(la, lb, lc, score_bits)) {
+        if (!d_finals && la == lb && lb == lc && fast_batch_supports(la)) {
+            ts.last_path = TRIALIGN_PATH_FAST_BATCH;
+            return fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
+        }
+        if (n == 1 && fast_sweep_supports(la, lb, lc)) {
+            ts.last_path = TRIALIGN_PATH_FAST_LONG;
+            return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals);
+        }
+        if (!d_finals && la == lb && lb == lc && fast_sweep_supports(la, lb, lc)) {
+            ts.last_path = TRIALIGN_PATH_FAST_LONG;
+            return fast_sweep_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
+        }
     }
     if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
     ts.last_path = TRIALIGN_PATH_LITERAL;

@@ -1,0 +1,258 @@
+// fast_sweep.cu -- K2 launchers: block-sweep kernels for long triples (see fast_sweep.cuh).
+//   sweep_long_kernel : one long triple; persistent CTAs claim (k-block-pair, j-block) tasks from a global counter
+//                       and stream block faces through global memory, gated by per-task progress counters.
+//   sweep_batch_kernel: many triples of equal length > 64; every CTA sweeps all blocks of its pairs one after the
+//                       other, faces stay private to the CTA, no inter-CTA synchronisation.
+#include <cstdio>
+#include <cstdlib>
+
+#include "fast_sweep.cuh"
+#include "kernels.cuh"
+
+namespace trialign {
+
+namespace {
+
+using LongCfg = fast::SweepCfg<true>;
+using BatchCfg = fast::SweepCfg<false>;
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <class C>
+__device__ __forceinline__ void setup_task(fast::SweepSmem<C> &S, fast::SweepRegs<C> &R, const fast::SweepArgs &A,
+                                           int tid, int tj, int tk)
+{
+    fast::sweep_load_bc<C>(S, A, tid);
+    __syncthreads();
+    fast::sweep_build_tables<C>(S, tid);
+    fast::sweep_init_thread<C>(R, S, tj, tk);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepArgs A)
+{
+    using C = LongCfg;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::SweepSmem<C> &S = *reinterpret_cast<fast::SweepSmem<C> *>(smem_raw);
+    const int tid = threadIdx.x;
+    int tj, tk;
+    fast::sweep_thread_pos<C>(tid, tj, tk);
+    fast::sweep_load_a<C>(S, A, tid, 0);
+    fast::SweepRegs<C> R;
+    const int steps = fast::sweep_task_steps<C>(A);
+
+    for (;;) {
+        __syncthreads();  // everybody is done with the previous task descriptor
+        if (tid == 0) {
+            const unsigned long long t = atomicAdd(A.counter, 1ull);
+            if (t < (unsigned long long)A.tasks_total) {
+                fast::sweep_describe_long<C>(A, (long long)t, S.task);
+                // ring re-use: the previous tenants of the face slots must have been consumed
+                if ((long long)t >= A.fj_ring) {  // previous tenant t-ring was read by task t-ring+1
+                    const long long consumer = (long long)t - A.fj_ring + 1;
+                    while (ld_acquire(A.progress + consumer) < fast::kProgressDone) __nanosleep(200);
+                }
+                if ((long long)t >= A.fk_ring) {  // previous tenant t-ring was read by task t-ring+nbj
+                    const long long consumer = (long long)t - A.fk_ring + A.nbj;
+                    if (consumer < A.tasks_total)
+                        while (ld_acquire(A.progress + consumer) < fast::kProgressDone) __nanosleep(200);
+                }
+            } else {
+                S.task.valid = 0;
+            }
+        }
+        __syncthreads();
+        if (!S.task.valid) break;
+        setup_task<C>(S, R, A, tid, tj, tk);
+        const fast::SweepTask &T = S.task;
+        const int *top_p = T.top_task >= 0 ? A.progress + T.top_task : nullptr;
+        const int *left_p = T.left_task >= 0 ? A.progress + T.left_task : nullptr;
+
+        // prologue: halos of step 0
+        if (tid == 0) {
+            while (!fast::sweep_deps_ready<C>(A, T, -1, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0))
+                __nanosleep(100);
+        }
+        __syncthreads();
+        fast::sweep_edge_fetch<C>(S, A, tj, tk, -1);
+        fast::ta_copy_wait();
+        __syncthreads();
+
+#pragma unroll 1
+        for (int s = 0; s <= steps; ++s) {
+            // the producers' progress is sampled at the top of the step, so the load latency hides under the tile
+            int tp = 0, lp = 0;
+            if (tid == 0) {
+                tp = top_p ? ld_acquire(top_p) : 0;
+                lp = left_p ? ld_acquire(left_p) : 0;
+            }
+            fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows gated by the check made before the previous barrier
+            fast::sweep_thread_step<C>(R, S, A, tj, tk, s);
+            fast::ta_copy_wait();
+            if (tid == 0) {
+                while (!fast::sweep_deps_ready<C>(A, T, s, tp, lp)) {
+                    __nanosleep(40);
+                    tp = top_p ? ld_acquire(top_p) : 0;
+                    lp = left_p ? ld_acquire(left_p) : 0;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // release: the edge threads' face stores of this step are ordered before the barrier above
+                const int done = fast::sweep_rows_done<C>(s);
+                if (done > 0) st_release(A.progress + T.self_task, done);
+            }
+        }
+        if (tid == 0) st_release(A.progress + T.self_task, fast::kProgressDone);
+    }
+}
+
+__global__ void __launch_bounds__(BatchCfg::NT, 1) sweep_batch_kernel(fast::SweepArgs A)
+{
+    using C = BatchCfg;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::SweepSmem<C> &S = *reinterpret_cast<fast::SweepSmem<C> *>(smem_raw);
+    const int tid = threadIdx.x;
+    int tj, tk;
+    fast::sweep_thread_pos<C>(tid, tj, tk);
+    fast::SweepRegs<C> R;
+    const int steps = fast::sweep_task_steps<C>(A);
+    const int tasks = A.nbj * A.nbkp;
+
+    for (long long pair = blockIdx.x; pair < A.pairs_total; pair += gridDim.x) {
+        __syncthreads();
+        fast::sweep_load_a<C>(S, A, tid, pair);
+        for (int q = 0; q < tasks; ++q) {
+            __syncthreads();
+            if (tid == 0) fast::sweep_describe_batch<C>(A, (int)blockIdx.x, pair, q, S.task);
+            __syncthreads();
+            setup_task<C>(S, R, A, tid, tj, tk);
+            fast::sweep_edge_fetch<C>(S, A, tj, tk, -1);
+            fast::ta_copy_wait();
+            __syncthreads();
+#pragma unroll 1
+            for (int s = 0; s <= steps; ++s) {
+                fast::sweep_edge_fetch<C>(S, A, tj, tk, s);
+                fast::sweep_thread_step<C>(R, S, A, tj, tk, s);
+                fast::ta_copy_wait();
+                __syncthreads();
+            }
+        }
+    }
+}
+
+template <class K>
+int prepare_kernel(K kernel, size_t smem, bool &done)
+{
+    if (!done) {
+        TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done = true;
+    }
+    return TRIALIGN_OK;
+}
+
+}  // namespace
+
+// 16-bit envelope of the fast kernels: stored value = v + 2*(i + jl + kl) + base, block-local jl,kl <= 64/128.
+bool fast_sweep_supports(int la, int lb, int lc)
+{
+    if (la < 1 || lb < 1 || lc < 1 || la > LongCfg::LA_MAX - 64) return false;
+    const long long m = la < lb ? (la < lc ? la : lc) : (lb < lc ? lb : lc);
+    const long long base = -envelope_lo(m) + 32;
+    const long long top = base + envelope_hi(m) + 9 + 2 * ((long long)la + LongCfg::LAG + LongCfg::DEPTH + 64 + 128) + 600;
+    return top < 65535;
+}
+
+static int sweep_base(int la, int lb, int lc)
+{
+    const long long m = la < lb ? (la < lc ? la : lc) : (lb < lc ? lb : lc);
+    return (int)(-envelope_lo(m) + 32);
+}
+
+int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
+                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states)
+{
+    using C = LongCfg;
+    const size_t smem = sizeof(fast::SweepSmem<C>);
+    static bool prepared[kMaxDevices] = {};
+    int rc = prepare_kernel(sweep_long_kernel, smem, prepared[ctx->device]);
+    if (rc) return rc;
+    fast::SweepArgs A{};
+    A.a = d_a; A.b = d_b; A.c = d_c;
+    A.n = 1; A.la = la; A.lb = lb; A.lc = lc;
+    A.nbj = (lb + C::BJ - 1) / C::BJ;
+    A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
+    A.tasks_total = (long long)A.nbj * A.nbkp;
+    int grid = ctx->sm_count;  // one persistent CTA per SM; all co-resident (spin-waits need that)
+    if (grid > A.tasks_total) grid = (int)A.tasks_total;
+    A.fj_slot_words = (long long)(la + C::LAG + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(la + C::LAG + 2) * C::FK_ROW_WORDS;
+    A.fj_ring = (int)std::min<long long>(A.tasks_total, 2 * grid + 2);
+    A.fk_ring = (int)std::min<long long>(A.tasks_total, (long long)A.nbj + 2 * grid + 2);
+    const size_t fj_bytes = (size_t)A.fj_ring * A.fj_slot_words * 4, fk_bytes = (size_t)A.fk_ring * A.fk_slot_words * 4;
+    const size_t ctl_bytes = (((size_t)A.tasks_total * sizeof(int) + 255) & ~(size_t)255) + 256;
+    if ((rc = ctx->faces.reserve(fj_bytes + fk_bytes + 512))) return rc;
+    if ((rc = ctx->misc.reserve(ctl_bytes))) return rc;
+    A.face_j = (uint32_t *)ctx->faces.ptr;
+    A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
+    A.counter = (unsigned long long *)ctx->misc.ptr;
+    A.progress = (int *)((char *)ctx->misc.ptr + 256);
+    A.out = d_score;
+    A.out_states = d_states;
+    A.base = sweep_base(la, lb, lc);
+    TA_CUDA(cudaMemsetAsync(ctx->misc.ptr, 0, ctl_bytes, st));
+    if (std::getenv("TRIALIGN_DEBUG"))
+        std::fprintf(stderr, "[trialign] K2 long: la=%d blocks %dx%d(pairs) tasks=%lld grid=%d faces=%.1f MB base=%d\n", la,
+                     A.nbj, A.nbkp, A.tasks_total, grid, (fj_bytes + fk_bytes) / 1e6, A.base);
+    sweep_long_kernel<<<grid, C::NT, smem, st>>>(A);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                         int64_t n, int len, int32_t *d_scores)
+{
+    using C = BatchCfg;
+    if (n <= 0) return TRIALIGN_OK;
+    const size_t smem = sizeof(fast::SweepSmem<C>);
+    static bool prepared[kMaxDevices] = {};
+    int rc = prepare_kernel(sweep_batch_kernel, smem, prepared[ctx->device]);
+    if (rc) return rc;
+    fast::SweepArgs A{};
+    A.a = d_a; A.b = d_b; A.c = d_c;
+    A.n = n; A.la = A.lb = A.lc = len;
+    A.nbj = (len + C::BJ - 1) / C::BJ;
+    A.nbkp = (len + C::KSPAN - 1) / C::KSPAN;
+    A.pairs_total = (n + 1) / 2;
+    int grid = (int)std::min<long long>(A.pairs_total, ctx->sm_count);
+    A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
+    A.fj_ring = 2;
+    A.fk_ring = A.nbj + 1;
+    const size_t fj_bytes = (size_t)grid * A.fj_ring * A.fj_slot_words * 4;
+    const size_t fk_bytes = (size_t)grid * A.fk_ring * A.fk_slot_words * 4;
+    if ((rc = ctx->faces.reserve(fj_bytes + fk_bytes + 512))) return rc;
+    A.face_j = (uint32_t *)ctx->faces.ptr;
+    A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
+    A.out = d_scores;
+    A.base = sweep_base(len, len, len);
+    if (std::getenv("TRIALIGN_DEBUG"))
+        std::fprintf(stderr, "[trialign] K2 batch: len=%d blocks %dx%d grid=%d faces=%.1f MB base=%d\n", len, A.nbj, A.nbkp,
+                     grid, (fj_bytes + fk_bytes) / 1e6, A.base);
+    sweep_batch_kernel<<<grid, C::NT, smem, st>>>(A);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+}  // namespace trialign

@@ -1,0 +1,553 @@
+// fast_sweep.cuh -- K2: block-sweep kernel for long triples (the GPU form of the RTL's slicing method,
+// src/TriAlign_1cyc.v:127-140,289-335: the (j,k) plane is cut into blocks, every block is swept over all of A, and the
+// faces between blocks are parked in memory -- face SRAMs there, HBM/L2 here).
+//
+//   * a task = one 64x64 (j,k) block per 16-bit half, swept over i = 1..la by the same 16x16-thread systolic array
+//     as K1 (thread (tj,tk) owns a 4x4 tile, state of plane i-1 in registers, wavefront skew tj+tk, edge exchange
+//     through shared memory, one __syncthreads per step);
+//   * LONG mode (one long triple): the two halves of a word are two k-ADJACENT blocks; the high half runs 16 planes
+//     behind the low half, which makes thread (tj,tk)'s high half the logical thread (tj,tk+16) of a 16x32 array:
+//     its left halo is the low half's right column of thread (tj,15), published one step earlier;
+//   * BATCH mode (many triples of equal length): the two halves are two triples, as in K1;
+//   * block faces live in global memory as PACKED words, exactly as the producing edge thread holds them, so the
+//     consuming edge thread of the next block copies them straight into the shared-memory halo slots with cp.async
+//     one step ahead of use (the RTL's z-face ping-pong and y-face ring, TriAlign_1cyc.v:157-181);
+//   * LONG mode: tasks are claimed in (k-block-pair, j-block) order from a global counter and synchronise through
+//     per-task progress counters (rows of face data completely written), release/acquire at GPU scope;
+//   * potentials are block-local in j,k and absolute in i (see fast_core.cuh); a face value is re-based when it is
+//     written (minus 2*block extent), so readers use it as is.
+#pragma once
+
+#include "fast_core.cuh"
+
+namespace trialign {
+namespace fast {
+
+template <bool LONG_>
+struct SweepCfg {
+    static constexpr bool LONG = LONG_;
+    static constexpr int RJ = 4, RK = 4, TJ = 16, TK = 16;
+    static constexpr int BJ = RJ * TJ, BK = RK * TK, NT = TJ * TK;
+    static constexpr int LAG = LONG ? TK : 0;          // planes the high half runs behind the low half
+    static constexpr int DEPTH = TJ + TK - 2;          // largest physical skew
+    static constexpr int KSPAN = LONG ? 2 * BK : BK;   // columns of C one task covers
+    static constexpr int ROW_W = BK;                   // words per face-J row and value
+    static constexpr int COL_W = BJ + 4;               // words per face-K row and value (index BJ = relay, padded)
+    static constexpr int TAB_STRIDE = 68;
+    static constexpr int LA_MAX = 8192 + 64;           // A symbols kept in shared memory
+    static constexpr uint32_t HI_OFF = LONG ? ((uint32_t)(2 * (BK - LAG)) << 16) : 0u;  // phi(high) - phi(low)
+    static constexpr int FJ_ROW_WORDS = 4 * ROW_W;     // one plane of a J face
+    static constexpr int FK_ROW_WORDS = 4 * COL_W;     // one plane of a K face
+};
+
+// Everything a CTA needs to know about one task (CTA-uniform, lives in shared memory).
+struct SweepTask {
+    int valid;
+    int bj, bkp;                  // block row, block column (LONG: column PAIR)
+    long long pair;               // BATCH: index of the pair of triples
+    uint32_t *fj_w, *fk_w;        // faces this task writes (nullptr: nobody needs them)
+    const uint32_t *fj_r, *fk_r;  // faces this task reads  (nullptr: zero border plane)
+    int top_task, left_task;      // LONG: tasks whose progress gates fj_r / fk_r (-1: none)
+    int self_task;                // LONG: index into progress[]
+    int final_here;               // this task holds cell (lb,lc)
+};
+
+struct SweepArgs {
+    const uint8_t *a, *b, *c;     // BATCH: [n][la],[n][lb],[n][lc]   LONG: one triple
+    long long n;
+    int la, lb, lc;
+    int nbj, nbkp;                // blocks per problem: rows, columns (LONG: column pairs)
+    long long tasks_total;        // LONG: nbj*nbkp
+    long long pairs_total;        // BATCH: ceil(n/2)
+    uint32_t *face_j, *face_k;    // ring storage
+    long long fj_slot_words, fk_slot_words;
+    int fj_ring, fk_ring;         // LONG: global ring sizes; BATCH: per-CTA ring sizes
+    int *progress;                // LONG: [tasks_total], zero-initialised
+    unsigned long long *counter;  // LONG: task counter, zero-initialised
+    int32_t *out;                 // BATCH: scores[n]; LONG: out[0] = score
+    int32_t *out_states;          // LONG: 7 final-cell states (or nullptr)
+    int base;                     // potential base
+};
+
+constexpr int kProgressDone = 1 << 30;
+
+template <class C>
+struct SweepSmem {
+    uint32_t row[2][4][C::TJ + 1][C::BK];     // [slot][wY,u2,u1(old),all(old)][tj+1 (0 = block halo)][k]
+    uint32_t col[2][4][C::TK + 1][C::COL_W];  // [slot][wZ,u2,u3(old),all(old)][tk+1 (0 = block halo)][j (+relay)]
+    uint32_t corner[2][2][C::TJ][C::TK];      // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
+    uint32_t cornerL[2][2][C::TJ];            // [slot][u2,all(old)][tj]  corner cell of the tiles on the block's left edge
+    uint32_t tabAB[16][C::TAB_STRIDE];        // [a code][j]  pair constant {4,2}
+    uint32_t tabMB[16][C::TAB_STRIDE];        // [a code][j]  0xFFFF where a == b
+    uint32_t tabAC[16][C::TAB_STRIDE];        // [a code][k]
+    uint8_t seqA[2][C::LA_MAX];               // [half][i]   (LONG: only [0] is used)
+    uint8_t seqB[2][64], seqC[2][64];         // [half][pos in block]
+    SweepTask task;
+};
+
+template <class C>
+struct SweepRegs {
+    uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
+    uint32_t cBC[C::RJ][C::RK], U[C::RJ][C::RK];                                       // per-cell constants
+};
+
+template <class C>
+TA_HD void sweep_thread_pos(int tid, int &tj, int &tk)
+{
+    const int lane = tid & 31, warp = tid >> 5;
+    tk = (lane & 7) + 8 * (warp & 1);
+    tj = (lane >> 3) + 4 * (warp >> 1);
+}
+
+// potential of a cell in block-local coordinates; the high half is the same expression for (i - LAG, kl + BK) in LONG
+// mode, which is a constant offset
+template <class C>
+TA_HD uint32_t sphi(const SweepArgs &A, int i0, int jl, int kl)
+{
+    return rep((uint32_t)(A.base + 2 * (i0 + jl + kl))) + C::HI_OFF;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Task geometry
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+TA_HD int sweep_task_steps(const SweepArgs &A) { return A.la + C::LAG + C::DEPTH; }  // steps 0 .. this value
+
+// LONG mode: task id -> descriptor.  Order: column pair outer, row inner, so that (bj-1,bkp) = t-1, (bj,bkp-1) = t-nbj.
+template <class C>
+TA_HD void sweep_describe_long(const SweepArgs &A, long long t, SweepTask &T)
+{
+    T.valid = 1;
+    T.pair = 0;
+    T.bkp = (int)(t / A.nbj);
+    T.bj = (int)(t % A.nbj);
+    T.self_task = (int)t;
+    T.top_task = T.bj > 0 ? (int)(t - 1) : -1;
+    T.left_task = T.bkp > 0 ? (int)(t - A.nbj) : -1;
+    T.fj_w = (T.bj + 1 < A.nbj) ? A.face_j + (t % A.fj_ring) * A.fj_slot_words : nullptr;
+    T.fk_w = (T.bkp + 1 < A.nbkp) ? A.face_k + (t % A.fk_ring) * A.fk_slot_words : nullptr;
+    T.fj_r = T.bj > 0 ? A.face_j + ((t - 1) % A.fj_ring) * A.fj_slot_words : nullptr;
+    T.fk_r = T.bkp > 0 ? A.face_k + ((t - A.nbj) % A.fk_ring) * A.fk_slot_words : nullptr;
+    T.final_here = (T.bj == (A.lb - 1) / C::BJ) && (T.bkp == (A.lc - 1) / C::KSPAN);
+}
+
+// BATCH mode: the q-th task of this CTA's current pair; faces are private to the CTA (region `cta`).
+template <class C>
+TA_HD void sweep_describe_batch(const SweepArgs &A, int cta, long long pair, int q, SweepTask &T)
+{
+    T.valid = 1;
+    T.pair = pair;
+    T.bkp = q / A.nbj;
+    T.bj = q % A.nbj;
+    T.self_task = T.top_task = T.left_task = -1;
+    uint32_t *fj = A.face_j + (long long)cta * A.fj_ring * A.fj_slot_words;
+    uint32_t *fk = A.face_k + (long long)cta * A.fk_ring * A.fk_slot_words;
+    T.fj_w = (T.bj + 1 < A.nbj) ? fj + (q % A.fj_ring) * A.fj_slot_words : nullptr;
+    T.fk_w = (T.bkp + 1 < A.nbkp) ? fk + (q % A.fk_ring) * A.fk_slot_words : nullptr;
+    T.fj_r = T.bj > 0 ? fj + ((q - 1) % A.fj_ring) * A.fj_slot_words : nullptr;
+    T.fk_r = T.bkp > 0 ? fk + ((q - A.nbj) % A.fk_ring) * A.fk_slot_words : nullptr;
+    T.final_here = (T.bj == (A.lb - 1) / C::BJ) && (T.bkp == (A.lc - 1) / C::KSPAN);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Task setup (CTA-uniform; barriers between the phases are the caller's)
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+TA_HD void sweep_load_a(SweepSmem<C> &S, const SweepArgs &A, int tid, long long pair)
+{
+    for (int h = 0; h < (C::LONG ? 1 : 2); ++h) {
+        const long long t = C::LONG ? 0 : 2 * pair + h;
+        for (int e = tid; e < A.la; e += C::NT) S.seqA[h][e] = (t < A.n) ? (A.a[t * A.la + e] & 3) : 0;
+    }
+}
+
+template <class C>
+TA_HD void sweep_load_bc(SweepSmem<C> &S, const SweepArgs &A, int tid)
+{
+    const SweepTask &T = S.task;
+    for (int e = tid; e < 2 * 2 * 64; e += C::NT) {
+        const int which = e >> 7, h = (e >> 6) & 1, pos = e & 63;
+        const long long t = C::LONG ? 0 : 2 * T.pair + h;
+        uint8_t v = 0;
+        if (which == 0) {  // B rows of this block (LONG: both halves share them)
+            const int j = T.bj * C::BJ + pos;
+            if (t < A.n && j < A.lb) v = A.b[t * A.lb + j] & 3;
+            S.seqB[h][pos] = v;
+        } else {           // C columns (LONG: high half is the next 64 columns)
+            const int k = T.bkp * C::KSPAN + (C::LONG ? h * C::BK : 0) + pos;
+            if (t < A.n && k < A.lc) v = A.c[t * A.lc + k] & 3;
+            S.seqC[h][pos] = v;
+        }
+    }
+}
+
+template <class C>
+TA_HD void sweep_build_tables(SweepSmem<C> &S, int tid)
+{
+    for (int e = tid; e < 16 * 64; e += C::NT) {
+        const int code = e >> 6, p = e & 63;
+        const uint32_t ap = (uint32_t)(code & 3) | ((uint32_t)(code >> 2) << 16);
+        const uint32_t bp = (uint32_t)S.seqB[0][p] | ((uint32_t)S.seqB[1][p] << 16);
+        const uint32_t cp = (uint32_t)S.seqC[0][p] | ((uint32_t)S.seqC[1][p] << 16);
+        const uint32_t nab = neq_flag(ap, bp), nac = neq_flag(ap, cp);
+        S.tabAB[code][p] = pair_const(nab);
+        S.tabMB[code][p] = eq_mask(nab);
+        S.tabAC[code][p] = pair_const(nac);
+    }
+}
+
+template <class C>
+TA_HD void sweep_init_thread(SweepRegs<C> &R, const SweepSmem<C> &S, int tj, int tk)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    const int j0 = tj * RJ, k0 = tk * RK;
+#pragma unroll
+    for (int r = 0; r < RJ; ++r)
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            const uint32_t bp = (uint32_t)S.seqB[0][j0 + r] | ((uint32_t)S.seqB[1][j0 + r] << 16);
+            const uint32_t cp = (uint32_t)S.seqC[0][k0 + c] | ((uint32_t)S.seqC[1][k0 + c] << 16);
+            const uint32_t nbc = neq_flag(bp, cp);
+            R.cBC[r][c] = pair_const(nbc);
+            R.U[r][c] = triple_u(nbc);
+            R.all[r][c] = R.wX[r][c] = R.u1[r][c] = R.u3[r][c] = 0;
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Block-edge halo traffic.  Called at step s (s = -1 in the task prologue) for the data thread (0,tk) / (tj,0) will
+// consume at step s+1; writes only the block-halo entries (index 0) of slot (s & 1).
+// Global faces are copied with TA_COPY16 / TA_COPY4 (cp.async on the device, plain copies in the host emulation).
+// ---------------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+TA_HD void ta_copy16(uint32_t *dst_smem, const uint32_t *src_gmem)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+TA_HD void ta_copy4(uint32_t *dst_smem, const uint32_t *src_gmem)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src_gmem) : "memory");
+}
+TA_HD void ta_copy_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+TA_HD uint32_t ta_prmt(uint32_t a, uint32_t b, uint32_t sel) { return __byte_perm(a, b, sel); }
+#else
+TA_HD void ta_copy16(uint32_t *d, const uint32_t *s) { d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3]; }
+TA_HD void ta_copy4(uint32_t *d, const uint32_t *s) { d[0] = s[0]; }
+TA_HD void ta_copy_wait() {}
+TA_HD uint32_t ta_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    const uint64_t v = ((uint64_t)b << 32) | a;
+    uint32_t r = 0;
+    for (int n = 0; n < 4; ++n) r |= (uint32_t)((v >> (8 * ((sel >> (4 * n)) & 7))) & 0xFF) << (8 * n);
+    return r;
+}
+#endif
+
+// low half <- high half of x ; high half <- low half of y
+TA_HD uint32_t hi_lo(uint32_t x, uint32_t y) { return ta_prmt(x, y, 0x5432); }
+
+template <class C>
+TA_HD void sweep_edge_fetch(SweepSmem<C> &S, const SweepArgs &A, int tj, int tk, int s)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    const SweepTask &T = S.task;
+    const int ws = s & 1;
+    const int rows = A.la + C::LAG;  // face rows 1..rows exist
+    if (tj == 0) {
+        const int i = s + 2 - tk;  // low-half plane of thread (0,tk) at step s+1
+        const int k0 = tk * RK;
+        if (T.fj_r) {
+            if (i >= 1 && i <= rows) {
+                const uint32_t *src = T.fj_r + (long long)i * C::FJ_ROW_WORDS + k0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) ta_copy16(&S.row[ws][v][0][k0], src + v * C::ROW_W);
+            }
+        } else {  // j = 0 border plane: all 7 states are 0 (src/TriAlign_1cyc.v:156-165), reduced values = phi
+#pragma unroll
+            for (int c = 0; c < RK; ++c) {
+                const uint32_t now = sphi<C>(A, i, 0, k0 + c + 1), old = sphi<C>(A, i - 1, 0, k0 + c + 1);
+                S.row[ws][0][0][k0 + c] = now;
+                S.row[ws][1][0][k0 + c] = now;
+                S.row[ws][2][0][k0 + c] = old;
+                S.row[ws][3][0][k0 + c] = old;
+            }
+        }
+    }
+    if (tk == 0) {
+        const int i = s + 2 - tj;  // low-half plane of thread (tj,0) at step s+1
+        const int j0 = tj * RJ;
+        if (T.fk_r) {
+            const int src_row = i + C::LAG;  // LONG: the producer's high half is LAG planes behind its row index
+            if (src_row >= 1 && src_row <= rows) {
+                const uint32_t *src = T.fk_r + (long long)src_row * C::FK_ROW_WORDS + j0;
+#pragma unroll
+                for (int v = 0; v < 4; ++v) ta_copy16(&S.col[ws][v][0][j0], src + v * C::COL_W);
+                // corner cell (row above the tile, column k0 of the block) for THIS thread's plane: face row entry j0-1,
+                // or the relay entry for the block's first tile row
+                const int cidx = tj > 0 ? j0 - 1 : C::BJ;
+                ta_copy4(&S.cornerL[ws][0][tj], T.fk_r + (long long)src_row * C::FK_ROW_WORDS + 1 * C::COL_W + cidx);
+                ta_copy4(&S.cornerL[ws][1][tj], T.fk_r + (long long)src_row * C::FK_ROW_WORDS + 3 * C::COL_W + cidx);
+            }
+        } else {  // k = 0 border plane (src/TriAlign_1cyc.v:166-174).  LONG: the consumer takes the HIGH half.
+            const int sh = C::LONG ? 16 : 0;
+#pragma unroll
+            for (int r = 0; r < RJ; ++r) {
+                const uint32_t now = (uint32_t)(A.base + 2 * (i + j0 + r + 1)), old = now - 2;
+                S.col[ws][0][0][j0 + r] = C::LONG ? (now << sh) : rep(now);
+                S.col[ws][1][0][j0 + r] = C::LONG ? (now << sh) : rep(now);
+                S.col[ws][2][0][j0 + r] = C::LONG ? (old << sh) : rep(old);
+                S.col[ws][3][0][j0 + r] = C::LONG ? (old << sh) : rep(old);
+            }
+            {  // corner cell (j0, 0) lies on the border plane too
+                const uint32_t now = (uint32_t)(A.base + 2 * (i + j0)), old = now - 2;
+                S.cornerL[ws][0][tj] = C::LONG ? (now << sh) : rep(now);
+                S.cornerL[ws][1][tj] = C::LONG ? (old << sh) : rep(old);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One wavefront step of one thread
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &A, int tj, int tk, int s)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    const SweepTask &T = S.task;
+    const int i0 = s - (tj + tk) + 1;  // low-half plane (valid 1..la)
+    const int i1 = i0 - C::LAG;        // high-half plane
+    const int j0 = tj * RJ, k0 = tk * RK;
+    const int ws = s & 1, rs = ws ^ 1;
+
+    // plane 0 is the all-zero border (PE override, src/PE_1cyc.v:164-178): reset the half whose plane 1 starts now
+    if (i0 == 1 || i1 == 1) {
+        const uint32_t keep = (i0 == 1 ? 0u : 0x0000FFFFu) | (i1 == 1 ? 0u : 0xFFFF0000u);
+#pragma unroll
+        for (int r = 0; r < RJ; ++r)
+#pragma unroll
+            for (int c = 0; c < RK; ++c) {
+                // sphi(i0-1,...) is phi(plane 0) in whichever half starts now: the low half starts at i0 = 1, the
+                // high half at i0 = 1 + LAG (its own plane index is i0 - LAG)
+                const uint32_t zz = sphi<C>(A, i0 - 1, j0 + r + 1, k0 + c + 1) & ~keep;
+                R.all[r][c] = (R.all[r][c] & keep) | zz;
+                R.wX[r][c] = (R.wX[r][c] & keep) | zz;
+                R.u1[r][c] = (R.u1[r][c] & keep) | zz;
+                R.u3[r][c] = (R.u3[r][c] & keep) | zz;
+            }
+    }
+
+    // per-step constants: the a symbols of both halves against the tile's rows / columns
+    int ia0 = i0 - 1, ia1 = i1 - 1;
+    ia0 = ia0 < 0 ? 0 : (ia0 >= A.la ? A.la - 1 : ia0);
+    ia1 = ia1 < 0 ? 0 : (ia1 >= A.la ? A.la - 1 : ia1);
+    const int code = S.seqA[0][ia0] | (S.seqA[C::LONG ? 0 : 1][ia1] << 2);
+    TA_CHECK(code >= 0 && code < 16);
+    uint32_t cAB[RJ], mAB[RJ], cAC[RK];
+#pragma unroll
+    for (int r = 0; r < RJ; ++r) {
+        cAB[r] = S.tabAB[code][j0 + r];
+        mAB[r] = S.tabMB[code][j0 + r];
+    }
+#pragma unroll
+    for (int c = 0; c < RK; ++c) cAC[c] = S.tabAC[code][k0 + c];
+
+    // halos (see fast_batch.cuh); index 0 of the first dimension of row/col is the block halo
+    uint32_t T_wY[RK], T_u1[RK], T_u2[RK + 1], T_all[RK + 1], L_wZ[RJ], L_u3[RJ], L_u2[RJ], L_all[RJ];
+#pragma unroll
+    for (int c = 0; c < RK; ++c) {
+        T_wY[c] = S.row[rs][0][tj][k0 + c];
+        T_u1[c] = S.row[rs][2][tj][k0 + c];
+        T_u2[c + 1] = S.row[rs][1][tj][k0 + c];
+        T_all[c + 1] = S.row[rs][3][tj][k0 + c];
+    }
+    if (tk > 0) {
+#pragma unroll
+        for (int r = 0; r < RJ; ++r) {
+            L_wZ[r] = S.col[rs][0][tk][j0 + r];
+            L_u3[r] = S.col[rs][2][tk][j0 + r];
+        }
+#pragma unroll
+        for (int r = 1; r < RJ; ++r) {
+            L_u2[r] = S.col[rs][1][tk][j0 + r - 1];
+            L_all[r] = S.col[rs][3][tk][j0 + r - 1];
+        }
+        T_u2[0] = S.corner[rs][0][tj][tk - 1];
+        T_all[0] = S.corner[rs][1][tj][tk - 1];
+    } else {
+        // left edge of the block.  BATCH: the block halo column as is.  LONG: low half <- high half of the block halo
+        // (the previous column pair's high block), high half <- low half of thread (tj,15)'s column (this pair's
+        // low block, one logical thread to the left).
+        uint32_t cu2 = S.cornerL[rs][0][tj], call = S.cornerL[rs][1][tj];
+        if (C::LONG) {
+            cu2 = hi_lo(cu2, S.corner[rs][0][tj][C::TK - 1]);
+            call = hi_lo(call, S.corner[rs][1][tj][C::TK - 1]);
+        }
+        T_u2[0] = cu2;
+        T_all[0] = call;
+#pragma unroll
+        for (int r = 0; r < RJ; ++r) {
+            uint32_t wz = S.col[rs][0][0][j0 + r], u3v = S.col[rs][2][0][j0 + r];
+            if (C::LONG) {
+                wz = hi_lo(wz, S.col[rs][0][C::TK][j0 + r]);
+                u3v = hi_lo(u3v, S.col[rs][2][C::TK][j0 + r]);
+            }
+            L_wZ[r] = wz;
+            L_u3[r] = u3v;
+        }
+#pragma unroll
+        for (int r = 1; r < RJ; ++r) {
+            uint32_t u2v = S.col[rs][1][0][j0 + r - 1], av = S.col[rs][3][0][j0 + r - 1];
+            if (C::LONG) {
+                u2v = hi_lo(u2v, S.col[rs][1][C::TK][j0 + r - 1]);
+                av = hi_lo(av, S.col[rs][3][C::TK][j0 + r - 1]);
+            }
+            L_u2[r] = u2v;
+            L_all[r] = av;
+        }
+    }
+    L_u2[0] = T_u2[0];
+    L_all[0] = T_all[0];
+    S.corner[ws][0][tj][tk] = T_u2[RK];
+    S.corner[ws][1][tj][tk] = T_all[RK];
+
+    // the tile
+    uint32_t n_all[RJ][RK], n_wX[RJ][RK], n_u1[RJ][RK], n_u3[RJ][RK], n_wY[RJ][RK], n_wZ[RJ][RK], n_u2[RJ][RK];
+#pragma unroll
+    for (int r = 0; r < RJ; ++r)
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            const uint32_t p_all = (r > 0 && c > 0) ? R.all[r - 1][c - 1] : (r == 0 ? T_all[c] : L_all[r]);
+            const uint32_t p_wY = r > 0 ? n_wY[r - 1][c] : T_wY[c];
+            const uint32_t p_wZ = c > 0 ? n_wZ[r][c - 1] : L_wZ[r];
+            const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
+            const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
+            const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
+            const uint32_t cM = triple_const(mAB[r], R.U[r][c]);
+            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, cAB[r],
+                                                 R.cBC[r][c], cAC[c], nullptr);
+            n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
+            n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
+        }
+
+    // publish the tile's bottom row and right column for the neighbours' next step
+#pragma unroll
+    for (int c = 0; c < RK; ++c) {
+        S.row[ws][0][tj + 1][k0 + c] = n_wY[RJ - 1][c];
+        S.row[ws][1][tj + 1][k0 + c] = n_u2[RJ - 1][c];
+        S.row[ws][2][tj + 1][k0 + c] = R.u1[RJ - 1][c];
+        S.row[ws][3][tj + 1][k0 + c] = R.all[RJ - 1][c];
+    }
+#pragma unroll
+    for (int r = 0; r < RJ; ++r) {
+        S.col[ws][0][tk + 1][j0 + r] = n_wZ[r][RK - 1];
+        S.col[ws][1][tk + 1][j0 + r] = n_u2[r][RK - 1];
+        S.col[ws][2][tk + 1][j0 + r] = R.u3[r][RK - 1];
+        S.col[ws][3][tk + 1][j0 + r] = R.all[r][RK - 1];
+    }
+
+    // block faces to global memory, re-based to the consumer's frame (its halo row / column has local index 0)
+    const int rows = A.la + C::LAG;
+    if (tj == C::TJ - 1 && T.fj_w && i0 >= 1 && i0 <= rows) {
+        const uint32_t adj = rep(2 * C::BJ);
+        uint32_t *dst = T.fj_w + (long long)i0 * C::FJ_ROW_WORDS + k0;
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            dst[0 * C::ROW_W + c] = n_wY[RJ - 1][c] - adj;
+            dst[1 * C::ROW_W + c] = n_u2[RJ - 1][c] - adj;
+            dst[2 * C::ROW_W + c] = R.u1[RJ - 1][c] - adj;
+            dst[3 * C::ROW_W + c] = R.all[RJ - 1][c] - adj;
+        }
+    }
+    if (tk == C::TK - 1 && T.fk_w && i0 >= 1 && i0 <= rows) {
+        // LONG: only the high half crosses to the next column pair (KSPAN columns to the right of this pair's origin)
+        const uint32_t adj = C::LONG ? ((uint32_t)(2 * C::KSPAN) << 16) : rep(2 * C::BK);
+        uint32_t *dst = T.fk_w + (long long)i0 * C::FK_ROW_WORDS + j0;
+#pragma unroll
+        for (int r = 0; r < RJ; ++r) {
+            dst[0 * C::COL_W + r] = n_wZ[r][RK - 1] - adj;
+            dst[1 * C::COL_W + r] = n_u2[r][RK - 1] - adj;
+            dst[2 * C::COL_W + r] = R.u3[r][RK - 1] - adj;
+            dst[3 * C::COL_W + r] = R.all[r][RK - 1] - adj;
+        }
+        if (tj == 0) {  // relay: the cell above-right of the block pair = corner of the next pair's first tile
+            uint32_t *rel = T.fk_w + (long long)i0 * C::FK_ROW_WORDS + C::BJ;
+            rel[1 * C::COL_W] = T_u2[RK] - adj;
+            rel[3 * C::COL_W] = T_all[RK] - adj;
+        }
+    }
+
+    // Score = max of the 7 states of cell (la,lb,lc) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
+    if (T.final_here) {
+        const int jl = A.lb - T.bj * C::BJ;                 // 1..64
+        const int kk = A.lc - T.bkp * C::KSPAN;             // 1..KSPAN
+        const int hf = C::LONG ? (kk - 1) / C::BK : 0;      // LONG: the half that holds column lc
+        const int kl = kk - hf * C::BK;                     // 1..64
+        const int iplane = hf ? i1 : i0;
+        if (iplane == A.la && tj == (jl - 1) / RJ && tk == (kl - 1) / RK) {
+            const int rf = (jl - 1) % RJ, cf = (kl - 1) % RK;
+            uint32_t v = 0, st[7] = {0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int r = 0; r < RJ; ++r)
+#pragma unroll
+                for (int c = 0; c < RK; ++c)
+                    if (r == rf && c == cf) {
+                        v = n_all[r][c];
+                        // the 7 states of the cell, recomputed from its inputs (rare path)
+                        const uint32_t p_all = (r > 0 && c > 0) ? R.all[r - 1][c - 1] : (r == 0 ? T_all[c] : L_all[r]);
+                        const uint32_t p_wY = r > 0 ? n_wY[r - 1][c] : T_wY[c];
+                        const uint32_t p_wZ = c > 0 ? n_wZ[r][c - 1] : L_wZ[r];
+                        const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
+                        const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
+                        const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
+                        cell_update<true>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3,
+                                          triple_const(mAB[r], R.U[r][c]), cAB[r], R.cBC[r][c], cAC[c], st);
+                    }
+            // potential of the cell in each half's own frame
+            const int off_lo = A.base + 2 * (A.la + jl + kl);
+            const int off_hi = off_lo + (C::LONG ? 2 * C::BK : 0);  // high half: kl + BK, plane la (iplane already = la)
+            if (C::LONG) {
+                const int off = hf ? off_hi : off_lo;
+                const int shv = hf ? 16 : 0;
+                A.out[0] = (int32_t)((v >> shv) & 0xFFFFu) - off;
+                if (A.out_states)
+                    for (int q = 0; q < 7; ++q) A.out_states[q] = (int32_t)((st[q] >> shv) & 0xFFFFu) - off;
+            } else {
+                const long long t0 = 2 * T.pair;
+                if (t0 < A.n) A.out[t0] = (int32_t)(v & 0xFFFFu) - off_lo;
+                if (t0 + 1 < A.n) A.out[t0 + 1] = (int32_t)(v >> 16) - off_lo;
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < RJ; ++r)
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            R.all[r][c] = n_all[r][c]; R.wX[r][c] = n_wX[r][c]; R.u1[r][c] = n_u1[r][c]; R.u3[r][c] = n_u3[r][c];
+        }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LONG mode dependency gating (evaluated by one thread).  progress[t] = face rows of task t completely written.
+// Before the barrier that ends step s (s = -2: before the prologue) the rows that sweep_edge_fetch(s+1) will copy
+// must be complete: top face row <= s+3, left face row <= s+3+LAG.
+// ---------------------------------------------------------------------------------------------------------------
+template <class C>
+TA_HD bool sweep_deps_ready(const SweepArgs &A, const SweepTask &T, int s, int top_prog, int left_prog)
+{
+    const int rows = A.la + C::LAG;
+    const int need_top = (s + 3 < rows) ? s + 3 : rows;
+    const int need_left = (s + 3 + C::LAG < rows) ? s + 3 + C::LAG : rows;
+    if (T.top_task >= 0 && top_prog < need_top) return false;
+    if (T.left_task >= 0 && left_prog < need_left) return false;
+    return true;
+}
+// rows complete after step s: the last writer of row i is thread (15,15) / (15,*) at step i - 1 + DEPTH
+template <class C>
+TA_HD int sweep_rows_done(int s) { return s - C::DEPTH + 1; }
+
+}  // namespace fast
+}  // namespace trialign

@@ -19,6 +19,14 @@ bool fast_batch_supports(int len);
 int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                    int64_t n, int len, int32_t *d_scores);
 
+// K2: block-sweep kernels for long triples (fast_sweep.cu); same exactness condition as K1 plus the 16-bit envelope
+// checked by fast_sweep_supports().
+bool fast_sweep_supports(int la, int lb, int lc);
+int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
+                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states);
+int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                         int64_t n, int len, int32_t *d_scores);
+
 // synthetic generator on the device (synth_kernel.cu)
 int synth_run(cudaStream_t st, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a, uint8_t *d_b,
               uint8_t *d_c);

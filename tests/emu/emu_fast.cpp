@@ -44,3 +44,149 @@ extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t 
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2 (fast_sweep.cuh): block sweep with faces in "global" memory.  LONG mode runs several emulated CTAs round-robin,
+// one wavefront step per turn; a CTA whose dependencies are not ready simply skips its turn (the kernel spins).
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_sweep.cuh"
+
+namespace {
+
+template <class C>
+struct EmuCta {
+    std::unique_ptr<SweepSmem<C>> S{new SweepSmem<C>};
+    std::vector<SweepRegs<C>> R = std::vector<SweepRegs<C>>(C::NT);
+    bool has_task = false, prologue_done = false;
+    int s = 0;
+    void setup(const SweepArgs &A)
+    {
+        for (int tid = 0; tid < C::NT; ++tid) sweep_load_bc<C>(*S, A, tid);
+        for (int tid = 0; tid < C::NT; ++tid) sweep_build_tables<C>(*S, tid);
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            sweep_thread_pos<C>(tid, tj, tk);
+            sweep_init_thread<C>(R[tid], *S, tj, tk);
+        }
+        prologue_done = false;
+        s = 0;
+    }
+    void fetch(const SweepArgs &A, int step)
+    {
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            sweep_thread_pos<C>(tid, tj, tk);
+            sweep_edge_fetch<C>(*S, A, tj, tk, step);
+        }
+    }
+    void step(const SweepArgs &A, int step)
+    {
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            sweep_thread_pos<C>(tid, tj, tk);
+            sweep_thread_step<C>(R[tid], *S, A, tj, tk, step);
+        }
+    }
+};
+
+}  // namespace
+
+extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
+                                   int base, int n_ctas, int want_states, int32_t *out8)
+{
+    using C = SweepCfg<true>;
+    if (la < 1 || lb < 1 || lc < 1 || la > C::LA_MAX || n_ctas < 1) return -1;
+    SweepArgs A{};
+    A.a = a; A.b = b; A.c = c; A.n = 1; A.la = la; A.lb = lb; A.lc = lc;
+    A.nbj = (lb + C::BJ - 1) / C::BJ;
+    A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
+    A.tasks_total = (long long)A.nbj * A.nbkp;
+    A.fj_slot_words = (long long)(la + C::LAG + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(la + C::LAG + 2) * C::FK_ROW_WORDS;
+    A.fj_ring = n_ctas + 2;
+    A.fk_ring = A.nbj + n_ctas + 2;
+    std::vector<uint32_t> fj((size_t)A.fj_ring * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
+    std::vector<int> prog((size_t)A.tasks_total, 0);
+    unsigned long long counter = 0;
+    A.face_j = fj.data(); A.face_k = fk.data(); A.progress = prog.data(); A.counter = &counter;
+    A.out = out8; A.out_states = want_states ? out8 + 1 : nullptr; A.base = base;
+    std::vector<EmuCta<C>> ctas(n_ctas);
+    for (auto &cta : ctas) {
+        std::memset(cta.S.get(), 0xA5, sizeof(SweepSmem<C>));
+        for (int tid = 0; tid < C::NT; ++tid) sweep_load_a<C>(*cta.S, A, tid, 0);
+    }
+    const int steps = sweep_task_steps<C>(A);
+    long long finished = 0, idle_rounds = 0;
+    while (finished < A.tasks_total) {
+        bool progressed = false;
+        for (auto &cta : ctas) {
+            if (!cta.has_task) {
+                if ((long long)counter >= A.tasks_total) continue;
+                sweep_describe_long<C>(A, (long long)counter++, cta.S->task);
+                cta.has_task = true;
+                cta.setup(A);
+                progressed = true;
+                continue;
+            }
+            const SweepTask &T = cta.S->task;
+            const int tp = T.top_task >= 0 ? prog[T.top_task] : 0, lp = T.left_task >= 0 ? prog[T.left_task] : 0;
+            if (!cta.prologue_done) {
+                if (!sweep_deps_ready<C>(A, T, -1, tp, lp)) continue;
+                cta.fetch(A, -1);
+                cta.prologue_done = true;
+                progressed = true;
+                continue;
+            }
+            if (!sweep_deps_ready<C>(A, T, cta.s - 1, tp, lp)) continue;  // gate of the fetch inside step s
+            cta.fetch(A, cta.s);
+            cta.step(A, cta.s);
+            const int done = sweep_rows_done<C>(cta.s);
+            if (done > prog[T.self_task]) prog[T.self_task] = done;
+            progressed = true;
+            if (++cta.s > steps) {
+                prog[T.self_task] = kProgressDone;
+                cta.has_task = false;
+                ++finished;
+            }
+        }
+        if (!progressed && ++idle_rounds > 4) return -2;  // deadlock
+    }
+    return 0;
+}
+
+extern "C" int emu_fast_sweep_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                                    int n_ctas, int32_t *scores)
+{
+    using C = SweepCfg<false>;
+    if (len < 1 || len > C::LA_MAX || n < 0 || n_ctas < 1) return -1;
+    SweepArgs A{};
+    A.a = a; A.b = b; A.c = c; A.n = n; A.la = A.lb = A.lc = len;
+    A.nbj = (len + C::BJ - 1) / C::BJ;
+    A.nbkp = (len + C::KSPAN - 1) / C::KSPAN;
+    A.pairs_total = (n + 1) / 2;
+    A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
+    A.fj_ring = 2;
+    A.fk_ring = A.nbj + 1;
+    std::vector<uint32_t> fj((size_t)n_ctas * A.fj_ring * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)n_ctas * A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
+    A.face_j = fj.data(); A.face_k = fk.data();
+    A.out = scores; A.base = base;
+    EmuCta<C> cta;
+    const int steps = sweep_task_steps<C>(A);
+    for (int cid = 0; cid < n_ctas; ++cid) {
+        std::memset(cta.S.get(), 0xA5, sizeof(SweepSmem<C>));
+        for (long long pair = cid; pair < A.pairs_total; pair += n_ctas) {
+            for (int tid = 0; tid < C::NT; ++tid) sweep_load_a<C>(*cta.S, A, tid, pair);
+            for (int q = 0; q < A.nbj * A.nbkp; ++q) {
+                sweep_describe_batch<C>(A, cid, pair, q, cta.S->task);
+                cta.setup(A);
+                cta.fetch(A, -1);
+                for (int s = 0; s <= steps; ++s) {
+                    cta.fetch(A, s);
+                    cta.step(A, s);
+                }
+            }
+        }
+    }
+    return 0;
+}

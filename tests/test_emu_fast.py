@@ -47,3 +47,53 @@ def test_batch_kernel_extremes(emu, ob):
     t = np.full((2, 64), 2, np.uint8)
     assert _run(emu, z, z, z, 1).tolist() == [192, 192]           # tb as shipped
     assert _run(emu, z, o, t, 1).tolist() == ob.score_batch(z, o, t, 16).tolist()  # all-mismatch: most negative
+
+
+# ---- K2: block sweep with faces in global memory (fast_sweep.cuh) ----
+@pytest.fixture(scope="module")
+def emu_sweep(emu):
+    emu.emu_fast_sweep_long.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    emu.emu_fast_sweep_batch.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, i32p]
+    return emu
+
+
+def _long(L, a, b, c, n_ctas):
+    a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (a, b, c))
+    out = np.zeros(8, np.int32)
+    base = 2 * min(len(a), len(b), len(c)) + 64
+    rc = L.emu_fast_sweep_long(a.ctypes.data_as(u8p), len(a), b.ctypes.data_as(u8p), len(b), c.ctypes.data_as(u8p),
+                               len(c), base, n_ctas, 1, out.ctypes.data_as(i32p))
+    assert rc == 0, "emulated CTAs deadlocked" if rc == -2 else rc
+    return int(out[0]), out[1:].tolist()
+
+
+@pytest.mark.parametrize("shape,n_ctas", [((5, 5, 5), 1), ((1, 5, 1), 1), ((20, 64, 64), 1), ((30, 64, 128), 1),
+                                          ((40, 70, 130), 2), ((33, 130, 200), 3), ((100, 200, 300), 4),
+                                          ((50, 129, 257), 5), ((10, 1, 1), 1), ((17, 260, 70), 2)])
+def test_sweep_long_choreography(emu_sweep, ob, shape, n_ctas):
+    la, lb, lc = shape
+    rng = np.random.default_rng(la * 7 + lb * 3 + lc)
+    for mutated in (True, False):
+        if mutated:
+            a, b, c = ob.mutated_triple(rng, max(shape))
+            a, b, c = a[:la], b[:lb], c[:lc]
+        else:
+            a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in shape)
+        s, fin = _long(emu_sweep, a, b, c, n_ctas)
+        es, efin = ob.score(a, b, c, 16)
+        assert s == es and fin == efin.tolist()
+
+
+@pytest.mark.parametrize("ln,n,n_ctas", [(10, 3, 1), (64, 2, 1), (65, 4, 2), (130, 3, 2), (200, 5, 3)])
+def test_sweep_batch_choreography(emu_sweep, ob, ln, n, n_ctas):
+    rng = np.random.default_rng(ln + n)
+    a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    for t in range(0, n, 2):
+        a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+    out = np.full(n, -99999, np.int32)
+    rc = emu_sweep.emu_fast_sweep_batch(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln,
+                                        2 * ln + 64, n_ctas, out.ctypes.data_as(i32p))
+    assert rc == 0
+    assert out.tolist() == ob.score_batch(a, b, c, 16).tolist()

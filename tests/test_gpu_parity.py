@@ -137,3 +137,43 @@ def test_launches_are_counted(gpu_ta):
     assert gpu_ta.launch_count() > before
     sec, cells = gpu_ta.last_timing()
     assert sec > 0 and cells == 64
+
+
+@pytest.mark.parametrize("shape", [(70, 65, 129), (100, 200, 300), (300, 64, 64), (64, 300, 64), (64, 64, 300),
+                                   (257, 513, 129), (1, 200, 200), (200, 1, 130), (512, 512, 512)])
+def test_fast_long_kernel_shapes(gpu_ta, ob, shape):
+    la, lb, lc = shape
+    rng = np.random.default_rng(sum(shape))
+    eng = gpu_ta.TriAlign(16)
+    for mutated in (True, False):
+        if mutated:
+            a, b, c = ob.mutated_triple(rng, max(shape))
+            a, b, c = a[:la], b[:lb], c[:lc]
+        else:
+            a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in shape)
+        s, fin = eng.align(a, b, c, return_states=True)
+        assert gpu_ta.last_path() == "fast_long"
+        es, efin = ob.score_mt(a, b, c, 16)
+        assert s == es and fin.tolist() == efin.tolist(), (shape, mutated)
+
+
+@pytest.mark.parametrize("ln,n", [(65, 7), (100, 12), (130, 5), (256, 6)])
+def test_fast_long_batch_kernel(gpu_ta, ob, ln, n):
+    rng = np.random.default_rng(ln * 31 + n)
+    a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    for t in range(0, n, 2):
+        a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+    for w in (12, 16):
+        got = gpu_ta.TriAlign(w).align_batch(a, b, c)
+        assert gpu_ta.last_path() == "fast_long"
+        assert got.tolist() == ob.score_batch(a, b, c, w).tolist(), (ln, n, w)
+
+
+def test_forced_fast_backend_refuses_unprovable_inputs(gpu_ta):
+    # W=12 at L=1024 is outside the a-priori wrap-free envelope: the forced-fast backend must refuse, AUTO falls back
+    a, b, c = (gpu_ta.synth(0x5EED0003, 0, s, 1024) for s in range(3))
+    with pytest.raises(gpu_ta.TriAlignError) as ei:
+        gpu_ta.TriAlign(12, backend=gpu_ta.BACKEND_GPU_FAST).align(a, b, c)
+    assert ei.value.rc == -9
