@@ -126,12 +126,32 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         }
         if (n == 1 && fast_sweep_supports(la, lb, lc)) {
             ts.last_path = TRIALIGN_PATH_FAST_LONG;
-            return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals);
+            return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, 0, nullptr);
         }
         if (!d_finals && la == lb && lb == lc && fast_sweep_supports(la, lb, lc)) {
             ts.last_path = TRIALIGN_PATH_FAST_LONG;
             return fast_sweep_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
         }
+    }
+    // One long triple whose wrap-freedom cannot be proved from the lengths: run the fast kernel with its run-time
+    // range check, and fall back to the literal kernel only if some value came near the score_bits limits.
+    if (want_fast && n == 1 && score_bits >= 10 && score_bits <= 16 && fast_sweep_supports(la, lb, lc)) {
+        int rc = ctx->misc.reserve(1024);
+        if (rc) return rc;
+        int *d_viol = (int *)((char *)ctx->misc.ptr + 128);  // the kernel's control block starts at offset 0 / 256
+        TA_CUDA(cudaMemsetAsync(d_viol, 0, sizeof(int), st));
+        rc = fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, score_bits, d_viol);
+        if (rc) return rc;
+        int viol = 0;
+        TA_CUDA(cudaMemcpyAsync(&viol, d_viol, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(cudaStreamSynchronize(st));
+        if (!viol) {
+            ts.last_path = TRIALIGN_PATH_FAST_LONG;
+            return TRIALIGN_OK;
+        }
+        if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
+        ts.last_path = TRIALIGN_PATH_FAST_THEN_LITERAL;
+        return literal_run(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals);
     }
     if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
     ts.last_path = TRIALIGN_PATH_LITERAL;

@@ -38,6 +38,7 @@ __device__ __forceinline__ void setup_task(fast::SweepSmem<C> &S, fast::SweepReg
     __syncthreads();
 }
 
+template <bool CHECK>
 __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepArgs A)
 {
     using C = LongCfg;
@@ -96,7 +97,7 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
                 lp = left_p ? ld_acquire(left_p) : 0;
             }
             fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows gated by the check made before the previous barrier
-            fast::sweep_thread_step<C>(R, S, A, tj, tk, s);
+            fast::sweep_thread_step<C, CHECK>(R, S, A, tj, tk, s);
             fast::ta_copy_wait();
             if (tid == 0) {
                 while (!fast::sweep_deps_ready<C>(A, T, s, tp, lp)) {
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
                 if (done > 0) st_release(A.progress + T.self_task, done);
             }
         }
+        if (CHECK && R.viol) atomicOr(A.viol_flag, 1);
         if (tid == 0) st_release(A.progress + T.self_task, fast::kProgressDone);
     }
 }
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(BatchCfg::NT, 1) sweep_batch_kernel(fast::Swee
 #pragma unroll 1
             for (int s = 0; s <= steps; ++s) {
                 fast::sweep_edge_fetch<C>(S, A, tj, tk, s);
-                fast::sweep_thread_step<C>(R, S, A, tj, tk, s);
+                fast::sweep_thread_step<C, false>(R, S, A, tj, tk, s);
                 fast::ta_copy_wait();
                 __syncthreads();
             }
@@ -179,16 +181,25 @@ static int sweep_base(int la, int lb, int lc)
 }
 
 int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
-                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states)
+                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol)
 {
     using C = LongCfg;
     const size_t smem = sizeof(fast::SweepSmem<C>);
-    static bool prepared[kMaxDevices] = {};
-    int rc = prepare_kernel(sweep_long_kernel, smem, prepared[ctx->device]);
+    static bool prepared[kMaxDevices][2] = {};
+    const bool check = check_bits > 0;
+    int rc = check ? prepare_kernel(sweep_long_kernel<true>, smem, prepared[ctx->device][1])
+                   : prepare_kernel(sweep_long_kernel<false>, smem, prepared[ctx->device][0]);
     if (rc) return rc;
     fast::SweepArgs A{};
     A.a = d_a; A.b = d_b; A.c = d_c;
     A.n = 1; A.la = la; A.lb = lb; A.lc = lc;
+    if (check) {
+        // candidates reach all+3 and (min all)-8; 45 / 60 cover the 15 unsampled planes between two samples
+        const int lim = 1 << (check_bits - 1);
+        A.check_hi = lim - 1 - 3 - 45;
+        A.check_lo = -lim + 8 + 60;
+        A.viol_flag = d_viol;
+    }
     A.nbj = (lb + C::BJ - 1) / C::BJ;
     A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
     A.tasks_total = (long long)A.nbj * A.nbkp;
@@ -213,7 +224,8 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
     if (std::getenv("TRIALIGN_DEBUG"))
         std::fprintf(stderr, "[trialign] K2 long: la=%d blocks %dx%d(pairs) tasks=%lld grid=%d faces=%.1f MB base=%d\n", la,
                      A.nbj, A.nbkp, A.tasks_total, grid, (fj_bytes + fk_bytes) / 1e6, A.base);
-    sweep_long_kernel<<<grid, C::NT, smem, st>>>(A);
+    if (check) sweep_long_kernel<true><<<grid, C::NT, smem, st>>>(A);
+    else sweep_long_kernel<false><<<grid, C::NT, smem, st>>>(A);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TRIALIGN_OK;

@@ -67,6 +67,8 @@ struct SweepArgs {
     int32_t *out;                 // BATCH: scores[n]; LONG: out[0] = score
     int32_t *out_states;          // LONG: 7 final-cell states (or nullptr)
     int base;                     // potential base
+    int check_lo, check_hi;       // range check (CHECK kernels): every sampled `all` must lie in [check_lo, check_hi]
+    int *viol_flag;               // set non-zero when the range check fails
 };
 
 constexpr int kProgressDone = 1 << 30;
@@ -89,6 +91,7 @@ template <class C>
 struct SweepRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
     uint32_t cBC[C::RJ][C::RK], U[C::RJ][C::RK];                                       // per-cell constants
+    uint32_t viol;                                                                     // range-check violations seen
 };
 
 template <class C>
@@ -168,13 +171,16 @@ TA_HD void sweep_load_bc(SweepSmem<C> &S, const SweepArgs &A, int tid)
     for (int e = tid; e < 2 * 2 * 64; e += C::NT) {
         const int which = e >> 7, h = (e >> 6) & 1, pos = e & 63;
         const long long t = C::LONG ? 0 : 2 * T.pair + h;
-        uint8_t v = 0;
+        // cells beyond lb / lc are padding: codes 4 and 5 match nothing (not even each other), so padded cells
+        // never create values above their real neighbours (keeps the run-time range check free of false alarms)
         if (which == 0) {  // B rows of this block (LONG: both halves share them)
             const int j = T.bj * C::BJ + pos;
+            uint8_t v = 4;
             if (t < A.n && j < A.lb) v = A.b[t * A.lb + j] & 3;
             S.seqB[h][pos] = v;
         } else {           // C columns (LONG: high half is the next 64 columns)
             const int k = T.bkp * C::KSPAN + (C::LONG ? h * C::BK : 0) + pos;
+            uint8_t v = 5;
             if (t < A.n && k < A.lc) v = A.c[t * A.lc + k] & 3;
             S.seqC[h][pos] = v;
         }
@@ -212,6 +218,7 @@ TA_HD void sweep_init_thread(SweepRegs<C> &R, const SweepSmem<C> &S, int tj, int
             R.U[r][c] = triple_u(nbc);
             R.all[r][c] = R.wX[r][c] = R.u1[r][c] = R.u3[r][c] = 0;
         }
+    R.viol = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -312,7 +319,7 @@ TA_HD void sweep_edge_fetch(SweepSmem<C> &S, const SweepArgs &A, int tj, int tk,
 // ---------------------------------------------------------------------------------------------------------------
 // One wavefront step of one thread
 // ---------------------------------------------------------------------------------------------------------------
-template <class C>
+template <class C, bool CHECK>
 TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &A, int tj, int tk, int s)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
@@ -477,6 +484,30 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
             rel[1 * C::COL_W] = T_u2[RK] - adj;
             rel[3 * C::COL_W] = T_all[RK] - adj;
         }
+    }
+
+    // Run-time wrap check (used when wrap-freedom at score_bits cannot be proved a priori).  `all` moves by at most
+    // +3 / -4 from one plane to the next (a cell's `all` is at most 3 above the best `all` of plane i-1 and at least
+    // all(i-1,j,k)-4), so sampling every 16th plane with a 45 / 60 margin in check_hi / check_lo bounds every plane.
+    if (CHECK && (i0 & 15) == 0) {
+        uint32_t mx = n_all[0][0], mn = n_all[0][0];
+#pragma unroll
+        for (int r = 0; r < RJ; ++r)
+#pragma unroll
+            for (int c = 0; c < RK; c += 2) {
+                mx = vmax3(mx, n_all[r][c], n_all[r][c + 1]);
+                mn = vmin3(mn, n_all[r][c], n_all[r][c + 1]);
+            }
+        // true value = stored - phi(cell); phi grows by 2 per row / column inside the tile (at most 12)
+        // (limits are formed per half in scalar arithmetic: check_lo is negative, a packed add would carry)
+        const uint32_t ph = sphi<C>(A, i0, j0 + 1, k0 + 1);
+        const int p0 = (int)(ph & 0xFFFFu), p1 = (int)(ph >> 16), slack = 2 * (RJ + RK - 2);
+        const int h0 = p0 + A.check_hi, h1 = p1 + A.check_hi, l0 = p0 + A.check_lo + slack, l1 = p1 + A.check_lo + slack;
+        const uint32_t hi_lim = (uint32_t)(h0 > 0xFFFF ? 0xFFFF : h0) | ((uint32_t)(h1 > 0xFFFF ? 0xFFFF : h1) << 16);
+        const uint32_t lo_lim = (uint32_t)(l0 < 0 ? 0 : l0) | ((uint32_t)(l1 < 0 ? 0 : l1) << 16);
+        const uint32_t bad = (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
+        const uint32_t live = ((i0 >= 1 && i0 <= A.la) ? 0x0000FFFFu : 0u) | ((i1 >= 1 && i1 <= A.la) ? 0xFFFF0000u : 0u);
+        R.viol |= bad & live;
     }
 
     // Score = max of the 7 states of cell (la,lb,lc) (src/TriAlign_1cyc.v:141-142) = `all` of that cell

@@ -23,7 +23,9 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
 // checked by fast_sweep_supports().
 bool fast_sweep_supports(int la, int lb, int lc);
 int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
-                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states);
+                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol);
+// check_bits > 0 selects the range-checked kernel: *d_viol (zeroed by the caller) becomes non-zero if some value came
+// close enough to the score_bits = check_bits limits that a wrap cannot be excluded.
 int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                          int64_t n, int len, int32_t *d_scores);
 

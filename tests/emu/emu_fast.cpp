@@ -79,12 +79,18 @@ struct EmuCta {
             sweep_edge_fetch<C>(*S, A, tj, tk, step);
         }
     }
+    uint32_t viol() const
+    {
+        uint32_t v = 0;
+        for (const auto &r : R) v |= r.viol;
+        return v;
+    }
     void step(const SweepArgs &A, int step)
     {
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             sweep_thread_pos<C>(tid, tj, tk);
-            sweep_thread_step<C>(R[tid], *S, A, tj, tk, step);
+            sweep_thread_step<C, true>(R[tid], *S, A, tj, tk, step);
         }
     }
 };
@@ -92,7 +98,7 @@ struct EmuCta {
 }  // namespace
 
 extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
-                                   int base, int n_ctas, int want_states, int32_t *out8)
+                                   int base, int n_ctas, int want_states, int32_t *out8, int check_bits, int *viol_out)
 {
     using C = SweepCfg<true>;
     if (la < 1 || lb < 1 || lc < 1 || la > C::LA_MAX || n_ctas < 1) return -1;
@@ -110,6 +116,11 @@ extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, i
     unsigned long long counter = 0;
     A.face_j = fj.data(); A.face_k = fk.data(); A.progress = prog.data(); A.counter = &counter;
     A.out = out8; A.out_states = want_states ? out8 + 1 : nullptr; A.base = base;
+    int viol = 0;
+    A.viol_flag = &viol;
+    const int lim = 1 << ((check_bits > 0 ? check_bits : 16) - 1);
+    A.check_hi = lim - 1 - 3 - 45;
+    A.check_lo = -lim + 8 + 60;
     std::vector<EmuCta<C>> ctas(n_ctas);
     for (auto &cta : ctas) {
         std::memset(cta.S.get(), 0xA5, sizeof(SweepSmem<C>));
@@ -144,6 +155,7 @@ extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, i
             if (done > prog[T.self_task]) prog[T.self_task] = done;
             progressed = true;
             if (++cta.s > steps) {
+                if (cta.viol()) viol = 1;
                 prog[T.self_task] = kProgressDone;
                 cta.has_task = false;
                 ++finished;
@@ -151,6 +163,7 @@ extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, i
         }
         if (!progressed && ++idle_rounds > 4) return -2;  // deadlock
     }
+    if (viol_out) *viol_out = viol;
     return 0;
 }
 

@@ -52,19 +52,41 @@ def test_batch_kernel_extremes(emu, ob):
 # ---- K2: block sweep with faces in global memory (fast_sweep.cuh) ----
 @pytest.fixture(scope="module")
 def emu_sweep(emu):
-    emu.emu_fast_sweep_long.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    emu.emu_fast_sweep_long.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int,
+                                        C.POINTER(C.c_int)]
     emu.emu_fast_sweep_batch.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, i32p]
     return emu
 
 
-def _long(L, a, b, c, n_ctas):
+def _long(L, a, b, c, n_ctas, check_bits=0):
     a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (a, b, c))
     out = np.zeros(8, np.int32)
+    viol = C.c_int(0)
     base = 2 * min(len(a), len(b), len(c)) + 64
     rc = L.emu_fast_sweep_long(a.ctypes.data_as(u8p), len(a), b.ctypes.data_as(u8p), len(b), c.ctypes.data_as(u8p),
-                               len(c), base, n_ctas, 1, out.ctypes.data_as(i32p))
+                               len(c), base, n_ctas, 1, out.ctypes.data_as(i32p), check_bits, C.byref(viol))
     assert rc == 0, "emulated CTAs deadlocked" if rc == -2 else rc
+    if check_bits:
+        return int(out[0]), out[1:].tolist(), int(viol.value)
     return int(out[0]), out[1:].tolist()
+
+
+def test_sweep_range_check_is_sound_and_not_trigger_happy(emu_sweep, ob):
+    """The run-time wrap check must fire whenever the oracle's value range leaves the safe band of score_bits, and
+    must stay quiet for ordinary inputs."""
+    rng = np.random.default_rng(77)
+    a, b, c = ob.mutated_triple(rng, 150, rate=0.02)        # nearly identical: all grows to ~3*150 = 450
+    _, _, (lo, hi) = ob.score(a, b, c, 32, want_range=True)
+    for w in (9, 10, 11, 12):
+        lim = 1 << (w - 1)
+        _, _, viol = _long(emu_sweep, a, b, c, 2, check_bits=w)
+        wraps_possible = hi + 3 > lim - 1 or lo - 4 < -lim
+        if wraps_possible:
+            assert viol, (w, lo, hi)                       # soundness: never miss a possible wrap
+        if hi + 3 + 45 + 12 <= lim - 1 and lo - 8 - 60 - 12 >= -lim:
+            assert not viol, (w, lo, hi)                   # and no false alarm when far from the limits
+    x, y, z = (rng.integers(0, 4, 150, dtype=np.uint8) for _ in range(3))
+    assert _long(emu_sweep, x, y, z, 2, check_bits=10)[2] == 0
 
 
 @pytest.mark.parametrize("shape,n_ctas", [((5, 5, 5), 1), ((1, 5, 1), 1), ((20, 64, 64), 1), ((30, 64, 128), 1),

@@ -171,9 +171,25 @@ def test_fast_long_batch_kernel(gpu_ta, ob, ln, n):
         assert got.tolist() == ob.score_batch(a, b, c, w).tolist(), (ln, n, w)
 
 
-def test_forced_fast_backend_refuses_unprovable_inputs(gpu_ta):
-    # W=12 at L=1024 is outside the a-priori wrap-free envelope: the forced-fast backend must refuse, AUTO falls back
-    a, b, c = (gpu_ta.synth(0x5EED0003, 0, s, 1024) for s in range(3))
+def test_range_checked_fast_path_and_literal_fallback(gpu_ta, ob, golden):
+    # W=12 at L=1024 is outside the a-priori wrap-free envelope (3*1024 > 2047): the fast kernel runs with its
+    # run-time range check; random ACGT stays far from the limits, so no fallback is needed ...
+    ent = next(e for e in golden["synth"] if e.get("single") and e["len"] == 1024 and e["score_bits"] == 12)
+    a, b, c = (gpu_ta.synth(ent["seed"], 0, s, 1024) for s in range(3))
+    s, fin = gpu_ta.TriAlign(12).align(a, b, c, return_states=True)
+    assert gpu_ta.last_path() == "fast_long"
+    assert s == ent["score"] and fin.tolist() == ent["final_states"]
+    # ... while near-identical sequences really wrap at W=12 (3*700 > 2047): the check fires and the literal kernel
+    # reproduces the RTL's wrapped result; forcing the fast backend is refused instead of returning a wrong score
+    rng = np.random.default_rng(12)
+    x, y, z = ob.mutated_triple(rng, 700, rate=0.01)
+    es, efin = ob.score_mt(x, y, z, 12)
+    s, fin = gpu_ta.TriAlign(12).align(x, y, z, return_states=True)
+    assert gpu_ta.last_path() == "fast_then_literal"
+    assert s == es and fin.tolist() == efin.tolist()
     with pytest.raises(gpu_ta.TriAlignError) as ei:
-        gpu_ta.TriAlign(12, backend=gpu_ta.BACKEND_GPU_FAST).align(a, b, c)
+        gpu_ta.TriAlign(12, backend=gpu_ta.BACKEND_GPU_FAST).align(x, y, z)
     assert ei.value.rc == -9
+    # at W=16 the same triple is provably wrap-free and scores ~3*700
+    s16 = gpu_ta.TriAlign(16).align(x, y, z)
+    assert gpu_ta.last_path() == "fast_long" and s16 == ob.score_mt(x, y, z, 16)[0] and s16 > 1800
