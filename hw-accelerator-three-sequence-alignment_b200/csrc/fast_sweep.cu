@@ -90,16 +90,17 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
 
 #pragma unroll 1
         for (int s = 0; s <= steps; ++s) {
-            // the producers' progress is sampled at the top of the step, so the load latency hides under the tile
+            const bool gate = fast::sweep_is_gate<C>(s);
+            // the producers' progress is sampled at the top of a gate step, so the load latency hides under the tile
             int tp = 0, lp = 0;
-            if (tid == 0) {
+            if (gate && tid == 0) {
                 tp = top_p ? ld_acquire(top_p) : 0;
                 lp = left_p ? ld_acquire(left_p) : 0;
             }
-            fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows gated by the check made before the previous barrier
+            fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows certified by the last gate
             fast::sweep_thread_step<C, CHECK>(R, S, A, tj, tk, s);
             fast::ta_copy_wait();
-            if (tid == 0) {
+            if (gate && tid == 0) {
                 while (!fast::sweep_deps_ready<C>(A, T, s, tp, lp)) {
                     __nanosleep(40);
                     tp = top_p ? ld_acquire(top_p) : 0;
@@ -107,11 +108,8 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
                 }
             }
             __syncthreads();
-            if (tid == 0) {
-                // release: the edge threads' face stores of this step are ordered before the barrier above
-                const int done = fast::sweep_rows_done<C>(s);
-                if (done > 0) st_release(A.progress + T.self_task, done);
-            }
+            // release: the edge threads' face stores of the steps so far are ordered before the barrier above
+            if (gate && tid == 0) st_release(A.progress + T.self_task, s + 1);
         }
         if (CHECK && R.viol) atomicOr(A.viol_flag, 1);
         if (tid == 0) st_release(A.progress + T.self_task, fast::kProgressDone);

@@ -562,23 +562,28 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// LONG mode dependency gating (evaluated by one thread).  progress[t] = face rows of task t completely written.
-// Before the barrier that ends step s (s = -2: before the prologue) the rows that sweep_edge_fetch(s+1) will copy
-// must be complete: top face row <= s+3, left face row <= s+3+LAG.
+// LONG mode dependency gating (evaluated by one thread).  progress[t] = number of wavefront steps task t has completed
+// (kProgressDone once it is finished).  Writers and readers of a face are skewed alike: thread (0,tk) fetches at its
+// step f the row that producer thread (15,tk) wrote at producer step f+16, and thread (tj,0) fetches the row that
+// producer thread (tj,15) wrote at step f+16+LAG.  Gates are evaluated every kSweepGate steps, before the barrier
+// that ends step g, and certify the fetches of steps g+1 .. g+kSweepGate.
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kSweepGate = 4;
+
 template <class C>
-TA_HD bool sweep_deps_ready(const SweepArgs &A, const SweepTask &T, int s, int top_prog, int left_prog)
+TA_HD bool sweep_is_gate(int g) { return ((g + 1) % kSweepGate) == 0; }
+
+template <class C>
+TA_HD bool sweep_deps_ready(const SweepArgs &A, const SweepTask &T, int g, int top_prog, int left_prog)
 {
-    const int rows = A.la + C::LAG;
-    const int need_top = (s + 3 < rows) ? s + 3 : rows;
-    const int need_left = (s + 3 + C::LAG < rows) ? s + 3 + C::LAG : rows;
+    const int total = sweep_task_steps<C>(A) + 1;  // steps 0..steps
+    const int f = g + kSweepGate;                  // last fetch this gate certifies
+    const int need_top = (f + C::TJ + 1 < total) ? f + C::TJ + 1 : total;
+    const int need_left = (f + C::TK + C::LAG + 1 < total) ? f + C::TK + C::LAG + 1 : total;
     if (T.top_task >= 0 && top_prog < need_top) return false;
     if (T.left_task >= 0 && left_prog < need_left) return false;
     return true;
 }
-// rows complete after step s: the last writer of row i is thread (15,15) / (15,*) at step i - 1 + DEPTH
-template <class C>
-TA_HD int sweep_rows_done(int s) { return s - C::DEPTH + 1; }
 
 }  // namespace fast
 }  // namespace trialign

@@ -148,11 +148,11 @@ extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, i
                 progressed = true;
                 continue;
             }
-            if (!sweep_deps_ready<C>(A, T, cta.s - 1, tp, lp)) continue;  // gate of the fetch inside step s
+            // the gate before the barrier of step s-1 certifies the fetches of the following steps
+            if (sweep_is_gate<C>(cta.s - 1) && !sweep_deps_ready<C>(A, T, cta.s - 1, tp, lp)) continue;
             cta.fetch(A, cta.s);
             cta.step(A, cta.s);
-            const int done = sweep_rows_done<C>(cta.s);
-            if (done > prog[T.self_task]) prog[T.self_task] = done;
+            if (sweep_is_gate<C>(cta.s)) prog[T.self_task] = cta.s + 1;
             progressed = true;
             if (++cta.s > steps) {
                 if (cta.viol()) viol = 1;
