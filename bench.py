@@ -197,16 +197,32 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     eng = ta.TriAlign(score_bits=w, devices=[local_rank])
     seed = 0x5EED0000 + cfg
-    first = rank * n  # each rank owns a contiguous shard of independent triples
-    if length <= 256:
-        da, db, dc = ta.synth_batch_cuda(seed, first, n, length, device=local_rank)
-    else:
-        da, db, dc = ta.synth_batch_cuda(seed, first, n, length, device=local_rank)
-    out = torch.empty(n, dtype=torch.int32, device=dev)
+    single = length > 256  # one long triple (configs 3 and 5) instead of a batch
+    slab = single and world > 1
+    scaling = "strong" if slab else "weak"
+    first = 0 if single else rank * n  # batch: each rank owns a contiguous shard of independent triples
+    da, db, dc = ta.synth_batch_cuda(seed, first, n, length, device=local_rank)
     cells_step = float(n) * float(length) ** 3
+    if single:
+        out = torch.zeros(8, dtype=torch.int32, device=dev)
+        a1, b1, c1 = da[0], db[0], dc[0]
+        if slab:
+            # config 5: i-slab pipeline, rank g computes planes (la*g/N, la*(g+1)/N] and hands block states to rank g+1
+            pipe = ta.SlabPipeline(length, length, score_bits=w, device=local_rank)
+            sync_t = torch.zeros(1, device=dev)
 
-    def step():
-        eng.align_batch_cuda(da, db, dc, out=out)
+            def step():
+                pipe.run(a1, b1, c1, out=out)
+                dist.all_reduce(sync_t)  # stream-ordered: nobody starts run k+1 before every rank finished run k
+            cells_step /= world  # per rank; the job total is restored below
+        else:
+            def step():
+                eng.align_cuda(a1, b1, c1, out=out)
+    else:
+        out = torch.empty(n, dtype=torch.int32, device=dev)
+
+        def step():
+            eng.align_batch_cuda(da, db, dc, out=out)
 
     def barrier():
         if dist is not None:
@@ -235,20 +251,49 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
-    checksum = int(out.sum().item())
+    if slab:  # the score lives on the last rank
+        res = out[:1].clone().to(torch.int64)
+        if rank != world - 1:
+            res.zero_()
+        dist.all_reduce(res)
+        checksum = int(res.item())
+    else:
+        checksum = int(out[0].item()) if single else int(out.sum().item())
 
     # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ----
-    ha, hb, hc = (x.cpu().pin_memory() for x in (da, db, dc))
-    hout = torch.empty(n, dtype=torch.int32).pin_memory()
-    L = ta.library()
     import ctypes as C
 
-    def e2e_step():
-        rc = L.trialign_score_batch(C.cast(ha.data_ptr(), C.POINTER(C.c_uint8)), C.cast(hb.data_ptr(), C.POINTER(C.c_uint8)),
-                                    C.cast(hc.data_ptr(), C.POINTER(C.c_uint8)), n, length, w, 0, 1 << local_rank,
-                                    C.cast(hout.data_ptr(), C.POINTER(C.c_int32)))
-        if rc:
-            raise RuntimeError(f"trialign_score_batch rc={rc}")
+    L = ta.library()
+    u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    ha, hb, hc = (x.cpu().pin_memory() for x in (da, db, dc))
+    if slab:
+        # the pipeline has no host-pointer form; e2e = device run + staging of the three sequences and the result
+        hres = torch.empty(8, dtype=torch.int32).pin_memory()
+
+        def e2e_step():
+            da.copy_(ha, non_blocking=True); db.copy_(hb, non_blocking=True); dc.copy_(hc, non_blocking=True)
+            step()
+            hres.copy_(out, non_blocking=True)
+            torch.cuda.synchronize()
+        h2d, d2h = 3 * length, 32
+    elif single:
+        hs = C.c_int32(0)
+
+        def e2e_step():
+            rc = L.trialign_score(C.cast(ha.data_ptr(), u8p), length, C.cast(hb.data_ptr(), u8p), length,
+                                  C.cast(hc.data_ptr(), u8p), length, w, 0, 1 << local_rank, C.byref(hs), None)
+            if rc:
+                raise RuntimeError(f"trialign_score rc={rc}")
+        h2d, d2h = 3 * length, 4
+    else:
+        hout = torch.empty(n, dtype=torch.int32).pin_memory()
+
+        def e2e_step():
+            rc = L.trialign_score_batch(C.cast(ha.data_ptr(), u8p), C.cast(hb.data_ptr(), u8p), C.cast(hc.data_ptr(), u8p),
+                                        n, length, w, 0, 1 << local_rank, C.cast(hout.data_ptr(), i32p))
+            if rc:
+                raise RuntimeError(f"trialign_score_batch rc={rc}")
+        h2d, d2h = 3 * n * length, 4 * n
 
     e2e_step()
     barrier()
@@ -262,7 +307,9 @@ def run_ours(args, rank, world, local_rank):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = float(te.item())
-    if int(hout.sum().item()) != checksum:
+    if single and not slab and int(hs.value) != checksum:
+        raise RuntimeError("e2e score differs from the device-resident score")
+    if not single and int(hout.sum().item()) != checksum:
         raise RuntimeError("e2e scores differ from the device-resident scores")
 
     if rank == 0:
@@ -272,15 +319,16 @@ def run_ours(args, rank, world, local_rank):
         achieved = cells_step / per_step_s * OPS_PER_CELL  # per GPU, the dominant (only) kernel of the step
         line = {
             "metric": "3D-GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": per_step_s * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": max(args.warmup, 3), "ms_per_step": per_step_s * 1e3, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "u16x2 (packed 16-bit integer lanes)" if path.startswith("fast") else "int16/int32",
             "data": "synthetic",
             "config": {"workload": args.workload, "baseline_config": cfg, "triples_per_gpu": n, "length": length,
+                       "parallelism": ("i-slab pipeline over %d GPUs, NVLink peer stores" % world) if slab else ("batch shard per GPU, no exchange" if world > 1 else "single GPU"),
                        "score_bits": w, "kernel_path": path, "l2": "inputs (3 x n x len bytes) larger than L2" if 3 * n * length > 126e6 else "inputs smaller than L2; compute-bound kernel, no reuse across steps assumed",
                        "reduced": reduced, "scores_checksum": checksum},
             "gpu_launches": launches,
-            "e2e": {"value": cells_step * world / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": 3 * n * length,
-                    "d2h_bytes_per_step": 4 * n},
+            "e2e": {"value": cells_step * world / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h},
             "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_how,
                          "algorithmic_ops_per_cell": OPS_PER_CELL,

@@ -29,3 +29,4 @@ from .trialign import (  # noqa: F401
     write_scores,
     write_seq_dat,
 )
+from .parallel import SlabPipeline, shard_range, slab_range  # noqa: E402,F401

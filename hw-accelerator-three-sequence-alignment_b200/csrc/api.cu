@@ -378,6 +378,95 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
     return TRIALIGN_OK;
 }
 
+int trialign_slab_buffer_bytes(int lb, int lc, int64_t *state_bytes, int64_t *flag_bytes)
+{
+    if (lb < 1 || lc < 1 || !state_bytes || !flag_bytes) return TRIALIGN_EINVAL;
+    *state_bytes = (int64_t)fast_sweep_slab_state_bytes(lb, lc);
+    *flag_bytes = (int64_t)fast_sweep_slab_flag_bytes(lb, lc);
+    return TRIALIGN_OK;
+}
+
+int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
+                            int lc, int i_begin, int i_end, const void *in_state, const void *in_flags,
+                            void *out_state, void *out_flags, int epoch, int score_bits, int32_t *d_out, void *stream)
+{
+    if (la < 1 || lb < 1 || lc < 1 || score_bits < 2 || score_bits > 32 || !d_a || !d_b || !d_c) return TRIALIGN_EINVAL;
+    if (i_begin < 0 || i_end <= i_begin || i_end > la) return TRIALIGN_EINVAL;
+    if ((i_begin > 0) != (in_state != nullptr) || (in_state != nullptr) != (in_flags != nullptr)) return TRIALIGN_EINVAL;
+    if ((i_end < la) != (out_state != nullptr) || (out_state != nullptr) != (out_flags != nullptr)) return TRIALIGN_EINVAL;
+    if (i_end == la && !d_out) return TRIALIGN_EINVAL;
+    ThreadState &ts = tls();
+    ts.last_seconds = -1.0;
+    ts.last_cells = (double)(i_end - i_begin) * lb * lc;
+    ts.last_path = TRIALIGN_PATH_NONE;
+    if (!provably_wrap_free(la, lb, lc, score_bits) || !fast_sweep_supports(la, lb, lc)) return TRIALIGN_EINEXACT;
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    SlabLink link;
+    link.la_total = la;
+    link.last = (i_end == la);
+    link.epoch = epoch;
+    link.in_state = in_state;
+    link.in_flags = in_flags;
+    link.out_state = out_state;
+    link.out_flags = out_flags;
+    ts.last_path = TRIALIGN_PATH_FAST_LONG;
+    return fast_sweep_long_run(ctx, (cudaStream_t)stream, d_a + i_begin, i_end - i_begin, d_b, lb, d_c, lc, d_out,
+                               d_out ? d_out + 1 : nullptr, 0, nullptr, &link);
+}
+
+int trialign_device_alloc(int device, int64_t bytes, void **dptr)
+{
+    if (bytes <= 0 || !dptr) return TRIALIGN_EINVAL;
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    TA_CUDA(cudaMalloc(dptr, (size_t)bytes));
+    TA_CUDA(cudaMemset(*dptr, 0, (size_t)bytes));
+    return TRIALIGN_OK;
+}
+
+int trialign_device_free(int device, void *dptr)
+{
+    if (!dptr) return TRIALIGN_EINVAL;
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    TA_CUDA(cudaFree(dptr));
+    return TRIALIGN_OK;
+}
+
+int trialign_ipc_export(const void *dptr, unsigned char handle[64])
+{
+    if (!dptr || !handle) return TRIALIGN_EINVAL;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    cudaIpcMemHandle_t h;
+    TA_CUDA(cudaIpcGetMemHandle(&h, const_cast<void *>(dptr)));
+    std::memcpy(handle, &h, 64);
+    return TRIALIGN_OK;
+}
+
+int trialign_ipc_open(int device, const unsigned char handle[64], void **dptr)
+{
+    if (!handle || !dptr) return TRIALIGN_EINVAL;
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    TA_CUDA(cudaIpcOpenMemHandle(dptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TRIALIGN_OK;
+}
+
+int trialign_ipc_close(void *dptr)
+{
+    if (!dptr) return TRIALIGN_EINVAL;
+    TA_CUDA(cudaIpcCloseMemHandle(dptr));
+    return TRIALIGN_OK;
+}
+
 int trialign_synth_batch_dev(int device, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a,
                              uint8_t *d_b, uint8_t *d_c, void *stream)
 {

@@ -26,6 +26,17 @@ __device__ __forceinline__ void st_release(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// system scope: the flag / data may live in a peer GPU's memory (i-slab pipeline over NVLink)
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 template <class C>
 __device__ __forceinline__ void setup_task(fast::SweepSmem<C> &S, fast::SweepRegs<C> &R, const fast::SweepArgs &A,
@@ -67,6 +78,9 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
                     if (consumer < A.tasks_total)
                         while (ld_acquire(A.progress + consumer) < fast::kProgressDone) __nanosleep(200);
                 }
+                // i-slab pipeline: the previous slab (another GPU) must have delivered this task's plane-0 state
+                if (A.iface_in_flag)
+                    while (ld_acquire_sys(A.iface_in_flag + t) != A.epoch) __nanosleep(500);
             } else {
                 S.task.valid = 0;
             }
@@ -98,7 +112,7 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
                 lp = left_p ? ld_acquire(left_p) : 0;
             }
             fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows certified by the last gate
-            fast::sweep_thread_step<C, CHECK>(R, S, A, tj, tk, s);
+            fast::sweep_thread_step<C, CHECK>(R, S, A, tj, tk, s, tid);
             fast::ta_copy_wait();
             if (gate && tid == 0) {
                 while (!fast::sweep_deps_ready<C>(A, T, s, tp, lp)) {
@@ -112,7 +126,13 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
             if (gate && tid == 0) st_release(A.progress + T.self_task, s + 1);
         }
         if (CHECK && R.viol) atomicOr(A.viol_flag, 1);
-        if (tid == 0) st_release(A.progress + T.self_task, fast::kProgressDone);
+        if (tid == 0) {
+            st_release(A.progress + T.self_task, fast::kProgressDone);
+            if (A.iface_out_flag) {  // every thread's hand-over stores precede the last barrier of the step loop
+                __threadfence_system();
+                st_release_sys(A.iface_out_flag + T.self_task, A.epoch);
+            }
+        }
     }
 }
 
@@ -142,7 +162,7 @@ __global__ void __launch_bounds__(BatchCfg::NT, 1) sweep_batch_kernel(fast::Swee
 #pragma unroll 1
             for (int s = 0; s <= steps; ++s) {
                 fast::sweep_edge_fetch<C>(S, A, tj, tk, s);
-                fast::sweep_thread_step<C, false>(R, S, A, tj, tk, s);
+                fast::sweep_thread_step<C, false>(R, S, A, tj, tk, s, tid);
                 fast::ta_copy_wait();
                 __syncthreads();
             }
@@ -163,6 +183,17 @@ int prepare_kernel(K kernel, size_t smem, bool &done)
 }  // namespace
 
 // 16-bit envelope of the fast kernels: stored value = v + 2*(i + jl + kl) + base, block-local jl,kl <= 64/128.
+size_t fast_sweep_slab_state_bytes(int lb, int lc)
+{
+    const long long tasks = (long long)((lb + LongCfg::BJ - 1) / LongCfg::BJ) * ((lc + LongCfg::KSPAN - 1) / LongCfg::KSPAN);
+    return (size_t)tasks * 4 * 16 * LongCfg::NT * sizeof(uint32_t);
+}
+size_t fast_sweep_slab_flag_bytes(int lb, int lc)
+{
+    const long long tasks = (long long)((lb + LongCfg::BJ - 1) / LongCfg::BJ) * ((lc + LongCfg::KSPAN - 1) / LongCfg::KSPAN);
+    return (size_t)tasks * sizeof(int);
+}
+
 bool fast_sweep_supports(int la, int lb, int lc)
 {
     if (la < 1 || lb < 1 || lc < 1 || la > LongCfg::LA_MAX - 64) return false;
@@ -179,7 +210,8 @@ static int sweep_base(int la, int lb, int lc)
 }
 
 int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
-                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol)
+                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
+                        const SlabLink *slab)
 {
     using C = LongCfg;
     const size_t smem = sizeof(fast::SweepSmem<C>);
@@ -218,6 +250,16 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
     A.out = d_score;
     A.out_states = d_states;
     A.base = sweep_base(la, lb, lc);
+    A.last_slab = 1;
+    if (slab) {  // planes i_begin+1 .. i_end of a triple of slab->la_total planes
+        A.base = sweep_base(slab->la_total, lb, lc);
+        A.iface_in = (const uint32_t *)slab->in_state;
+        A.iface_in_flag = (const int *)slab->in_flags;
+        A.iface_out = (uint32_t *)slab->out_state;
+        A.iface_out_flag = (int *)slab->out_flags;
+        A.last_slab = slab->last ? 1 : 0;
+        A.epoch = slab->epoch;
+    }
     TA_CUDA(cudaMemsetAsync(ctx->misc.ptr, 0, ctl_bytes, st));
     if (std::getenv("TRIALIGN_DEBUG"))
         std::fprintf(stderr, "[trialign] K2 long: la=%d blocks %dx%d(pairs) tasks=%lld grid=%d faces=%.1f MB base=%d\n", la,

@@ -64,6 +64,17 @@ struct SweepArgs {
     int fj_ring, fk_ring;         // LONG: global ring sizes; BATCH: per-CTA ring sizes
     int *progress;                // LONG: [tasks_total], zero-initialised
     unsigned long long *counter;  // LONG: task counter, zero-initialised
+    // i-slab pipeline (LONG, several GPUs): this launch computes planes i_begin+1 .. i_begin+la of the triple (a already
+    // points at symbol i_begin).  The plane-i_begin state of every task comes from the previous slab (iface_in, on
+    // this GPU) and the plane-(i_begin+la) state goes to the next slab's GPU (iface_out, possibly a peer pointer).
+    // Layout: [task][all,wX,u1,u3][cell 0..15][thread 0..255] packed words, re-based so that the reader sees them as
+    // its plane 0.  Flags: one int per task, 1 = state complete (release/acquire at system scope).
+    const uint32_t *iface_in;
+    uint32_t *iface_out;
+    const int *iface_in_flag;
+    int *iface_out_flag;
+    int last_slab;                // emit the score (the slab ends at plane la of the whole triple)
+    int epoch;                    // value the hand-over flags take in this run (lets runs repeat without clearing)
     int32_t *out;                 // BATCH: scores[n]; LONG: out[0] = score
     int32_t *out_states;          // LONG: 7 final-cell states (or nullptr)
     int base;                     // potential base
@@ -320,7 +331,7 @@ TA_HD void sweep_edge_fetch(SweepSmem<C> &S, const SweepArgs &A, int tj, int tk,
 // One wavefront step of one thread
 // ---------------------------------------------------------------------------------------------------------------
 template <class C, bool CHECK>
-TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &A, int tj, int tk, int s)
+TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &A, int tj, int tk, int s, int tid)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const SweepTask &T = S.task;
@@ -339,10 +350,18 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
                 // sphi(i0-1,...) is phi(plane 0) in whichever half starts now: the low half starts at i0 = 1, the
                 // high half at i0 = 1 + LAG (its own plane index is i0 - LAG)
                 const uint32_t zz = sphi<C>(A, i0 - 1, j0 + r + 1, k0 + c + 1) & ~keep;
-                R.all[r][c] = (R.all[r][c] & keep) | zz;
-                R.wX[r][c] = (R.wX[r][c] & keep) | zz;
-                R.u1[r][c] = (R.u1[r][c] & keep) | zz;
-                R.u3[r][c] = (R.u3[r][c] & keep) | zz;
+                if (C::LONG && A.iface_in) {  // continue from the previous slab instead of the zero border
+                    const uint32_t *src = A.iface_in + (((long long)T.self_task * 4) * 16 + (r * RK + c)) * C::NT + tid;
+                    R.all[r][c] = (R.all[r][c] & keep) | (src[0 * 16 * C::NT] & ~keep);
+                    R.wX[r][c] = (R.wX[r][c] & keep) | (src[1 * 16 * C::NT] & ~keep);
+                    R.u1[r][c] = (R.u1[r][c] & keep) | (src[2 * 16 * C::NT] & ~keep);
+                    R.u3[r][c] = (R.u3[r][c] & keep) | (src[3 * 16 * C::NT] & ~keep);
+                } else {
+                    R.all[r][c] = (R.all[r][c] & keep) | zz;
+                    R.wX[r][c] = (R.wX[r][c] & keep) | zz;
+                    R.u1[r][c] = (R.u1[r][c] & keep) | zz;
+                    R.u3[r][c] = (R.u3[r][c] & keep) | zz;
+                }
             }
     }
 
@@ -511,7 +530,7 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
     }
 
     // Score = max of the 7 states of cell (la,lb,lc) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
-    if (T.final_here) {
+    if (T.final_here && (!C::LONG || A.last_slab)) {
         const int jl = A.lb - T.bj * C::BJ;                 // 1..64
         const int kk = A.lc - T.bkp * C::KSPAN;             // 1..KSPAN
         const int hf = C::LONG ? (kk - 1) / C::BK : 0;      // LONG: the half that holds column lc
@@ -559,6 +578,26 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
         for (int c = 0; c < RK; ++c) {
             R.all[r][c] = n_all[r][c]; R.wX[r][c] = n_wX[r][c]; R.u1[r][c] = n_u1[r][c]; R.u3[r][c] = n_u3[r][c];
         }
+
+    // i-slab hand-over: the half that has just finished the slab's last plane stores its state for the next slab,
+    // re-based by the slab's 2*la so that the reader's plane index restarts at 0 (16-bit stores: the halves finish
+    // LAG steps apart)
+    if (C::LONG && A.iface_out && (i0 == A.la || i1 == A.la)) {
+        const uint32_t adj = rep((uint32_t)(2 * A.la));
+        uint16_t *dst16 = reinterpret_cast<uint16_t *>(A.iface_out + (((long long)T.self_task * 4) * 16) * C::NT + tid);
+        const int hsel = (i0 == A.la) ? 0 : 1;
+#pragma unroll
+        for (int r = 0; r < RJ; ++r)
+#pragma unroll
+            for (int c = 0; c < RK; ++c) {
+                const long long w = (long long)(r * RK + c) * C::NT;  // word offset of this cell within a value plane
+                const uint32_t v0 = R.all[r][c] - adj, v1 = R.wX[r][c] - adj, v2 = R.u1[r][c] - adj, v3 = R.u3[r][c] - adj;
+                dst16[2 * (w + 0LL * 16 * C::NT) + hsel] = (uint16_t)(hsel ? v0 >> 16 : v0);
+                dst16[2 * (w + 1LL * 16 * C::NT) + hsel] = (uint16_t)(hsel ? v1 >> 16 : v1);
+                dst16[2 * (w + 2LL * 16 * C::NT) + hsel] = (uint16_t)(hsel ? v2 >> 16 : v2);
+                dst16[2 * (w + 3LL * 16 * C::NT) + hsel] = (uint16_t)(hsel ? v3 >> 16 : v3);
+            }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -22,8 +22,22 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
 // K2: block-sweep kernels for long triples (fast_sweep.cu); same exactness condition as K1 plus the 16-bit envelope
 // checked by fast_sweep_supports().
 bool fast_sweep_supports(int la, int lb, int lc);
+// i-slab pipeline of one long triple over several GPUs: a launch computes planes (i_begin, i_begin+la] and hands the
+// plane state of every block task to the next slab.  in_* live on this GPU, out_* may be peer memory.
+struct SlabLink {
+    int la_total;          // planes of the whole triple
+    int last;              // this slab ends at plane la_total: emit the score
+    int epoch;             // flag value of this run
+    const void *in_state;  // nullptr for the first slab
+    const void *in_flags;
+    void *out_state;       // nullptr for the last slab
+    void *out_flags;
+};
+size_t fast_sweep_slab_state_bytes(int lb, int lc);
+size_t fast_sweep_slab_flag_bytes(int lb, int lc);
 int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
-                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol);
+                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
+                        const SlabLink *slab = nullptr);
 // check_bits > 0 selects the range-checked kernel: *d_viol (zeroed by the caller) becomes non-zero if some value came
 // close enough to the score_bits = check_bits limits that a wrap cannot be excluded.
 int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,

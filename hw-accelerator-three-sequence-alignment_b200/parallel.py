@@ -1,0 +1,109 @@
+"""Multi-GPU plumbing, one process per GPU (torch.distributed): the two shardings of SURVEY.md 8(e).
+
+1. Independent triples: `shard_range` gives every rank a contiguous slice of the batch; no data-path collective, the
+   scores are gathered (or simply checksummed) at the end.
+2. One long triple: `SlabPipeline` splits the planes i = 1..la into consecutive slabs, one per rank.  Rank g's kernel
+   writes the plane state of every (j,k) block task straight into rank g+1's memory over NVLink (CUDA IPC mapping)
+   and raises a per-task flag there; rank g+1's kernel starts each block as soon as its flag is up.  The traffic is a
+   point-to-point chain g -> g+1; torch.distributed only carries the 64-byte IPC handles at set-up time.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+from . import trialign as _ta
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous split of n independent triples: rank r owns [n*r/world, n*(r+1)/world)."""
+    if world < 1 or not (0 <= rank < world) or n < 0:
+        raise ValueError("bad shard request")
+    return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def slab_range(la: int, rank: int, world: int) -> Tuple[int, int]:
+    """Planes (i_begin, i_end] of rank `rank`: i_begin = la*rank/world, i_end = la*(rank+1)/world."""
+    if world < 1 or not (0 <= rank < world) or la < world:
+        raise ValueError("need at least one plane per rank")
+    return (la * rank) // world, (la * (rank + 1)) // world
+
+
+def exchange_objects(obj, group=None) -> List:
+    """all_gather of a small picklable object (IPC handles, shapes) over the given process group."""
+    import torch.distributed as dist
+
+    out = [None] * dist.get_world_size(group)
+    dist.all_gather_object(out, obj, group=group)
+    return out
+
+
+class SlabPipeline:
+    """i-slab pipeline for one long triple; build once per (lb, lc), call run() as often as needed."""
+
+    def __init__(self, lb: int, lc: int, score_bits: int = 16, device: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.cuda.current_device() if device is None else device
+        self.lb, self.lc, self.score_bits = lb, lc, score_bits
+        self.epoch = 0
+        L = _ta.library()
+        sb, fb = C.c_int64(0), C.c_int64(0)
+        _ta._check(L.trialign_slab_buffer_bytes(lb, lc, C.byref(sb), C.byref(fb)), "trialign_slab_buffer_bytes")
+        # hand-over buffers of THIS rank (written by rank-1 through its peer mapping); rank 0 owns none.  They are whole
+        # cudaMalloc allocations made by the library, because an IPC handle names an allocation, not a sub-range.
+        self.state = self.flags = None
+        handles = None
+        if self.rank > 0:
+            ps, pf = C.c_void_p(), C.c_void_p()
+            _ta._check(L.trialign_device_alloc(self.device, sb.value, C.byref(ps)), "trialign_device_alloc")
+            _ta._check(L.trialign_device_alloc(self.device, fb.value, C.byref(pf)), "trialign_device_alloc")
+            self.state, self.flags = ps.value, pf.value
+            hs, hf = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+            _ta._check(L.trialign_ipc_export(C.c_void_p(self.state), hs), "trialign_ipc_export")
+            _ta._check(L.trialign_ipc_export(C.c_void_p(self.flags), hf), "trialign_ipc_export")
+            handles = (bytes(hs), bytes(hf))
+        everyone = exchange_objects(handles, group)
+        self.next_state = self.next_flags = None
+        if self.rank + 1 < self.world:
+            hs, hf = everyone[self.rank + 1]
+            ps, pf = C.c_void_p(), C.c_void_p()
+            _ta._check(L.trialign_ipc_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hs), C.byref(ps)), "trialign_ipc_open")
+            _ta._check(L.trialign_ipc_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hf), C.byref(pf)), "trialign_ipc_open")
+            self.next_state, self.next_flags = ps.value, pf.value
+
+    def run(self, A, B, C_, out=None, stream=None):
+        """A, B, C_: uint8 CUDA tensors holding the WHOLE sequences on every rank.  Returns the int32[8] result tensor
+        (score + 7 final states), meaningful on the last rank only."""
+        import torch
+
+        la = A.numel()
+        i0, i1 = slab_range(la, self.rank, self.world)
+        if out is None:
+            out = torch.zeros(8, dtype=torch.int32, device=A.device)
+        st = stream if stream is not None else torch.cuda.current_stream(A.device)
+        self.epoch += 1
+        rc = _ta.library().trialign_slab_score_dev(
+            self.device, C.c_void_p(A.data_ptr()), la, C.c_void_p(B.data_ptr()), B.numel(), C.c_void_p(C_.data_ptr()),
+            C_.numel(), i0, i1,
+            C.c_void_p(self.state) if self.rank > 0 else None,
+            C.c_void_p(self.flags) if self.rank > 0 else None,
+            C.c_void_p(self.next_state) if self.next_state else None,
+            C.c_void_p(self.next_flags) if self.next_flags else None,
+            self.epoch, self.score_bits, C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+        _ta._check(rc, "trialign_slab_score_dev")
+        return out
+
+    def close(self):
+        L = _ta.library()
+        for p in (self.next_state, self.next_flags):
+            if p:
+                L.trialign_ipc_close(C.c_void_p(p))
+        for p in (self.state, self.flags):
+            if p:
+                L.trialign_device_free(self.device, C.c_void_p(p))
+        self.next_state = self.next_flags = self.state = self.flags = None

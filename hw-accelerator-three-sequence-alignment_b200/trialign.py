@@ -97,6 +97,22 @@ def library() -> C.CDLL:
     L.trialign_synth_batch_dev.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
     L.trialign_synth_batch_dev.restype = C.c_int
+    L.trialign_slab_buffer_bytes.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.trialign_slab_buffer_bytes.restype = C.c_int
+    L.trialign_slab_score_dev.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]
+    L.trialign_slab_score_dev.restype = C.c_int
+    L.trialign_device_alloc.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+    L.trialign_device_alloc.restype = C.c_int
+    L.trialign_device_free.argtypes = [C.c_int, C.c_void_p]
+    L.trialign_device_free.restype = C.c_int
+    L.trialign_ipc_export.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte)]
+    L.trialign_ipc_export.restype = C.c_int
+    L.trialign_ipc_open.argtypes = [C.c_int, C.POINTER(C.c_ubyte), C.POINTER(C.c_void_p)]
+    L.trialign_ipc_open.restype = C.c_int
+    L.trialign_ipc_close.argtypes = [C.c_void_p]
+    L.trialign_ipc_close.restype = C.c_int
     L.trialign_last_timing.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.trialign_last_timing.restype = C.c_int
     L.trialign_last_path.restype = C.c_int

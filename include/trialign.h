@@ -97,6 +97,28 @@ int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b,
 int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
                        int lc, int score_bits, int backend, int32_t *d_out, void *stream);
 
+/* ---- i-slab pipeline: ONE long triple over several GPUs, one process per GPU ----
+ * Rank g computes planes (i_begin, i_end] of the cube for every (j,k) block and hands the plane-i_end state of each
+ * block task to rank g+1, whose kernel picks it up task by task while rank g is already working on later blocks.  The
+ * hand-over buffers (state + one int flag per block task) live on the RECEIVING GPU; the sender writes them through a
+ * peer mapping (NVLink), so there is no host round trip and no collective.  Sizes come from
+ * trialign_slab_buffer_bytes(); in_* = this rank's own buffers (NULL on the first rank), out_* = the next rank's
+ * buffers as mapped with trialign_ipc_open() (NULL on the last rank).  `epoch` must differ between consecutive runs
+ * that reuse the buffers (flags are compared for equality, never cleared).  Only the last rank writes d_out
+ * (int32[8]: score + 7 final states).  Requires an input that is provably wrap-free at score_bits (else EINEXACT). */
+int trialign_slab_buffer_bytes(int lb, int lc, int64_t *state_bytes, int64_t *flag_bytes);
+int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
+                            int lc, int i_begin, int i_end, const void *in_state, const void *in_flags,
+                            void *out_state, void *out_flags, int epoch, int score_bits, int32_t *d_out,
+                            void *stream);
+/* Hand-over buffers must be whole cudaMalloc allocations (IPC handles name allocations, not sub-ranges). */
+int trialign_device_alloc(int device, int64_t bytes, void **dptr); /* zero-filled */
+int trialign_device_free(int device, void *dptr);
+/* CUDA IPC plumbing for the above (one process per GPU): export a device allocation, map a peer's, unmap it. */
+int trialign_ipc_export(const void *dptr, unsigned char handle[64]);
+int trialign_ipc_open(int device, const unsigned char handle[64], void **dptr);
+int trialign_ipc_close(void *dptr);
+
 /* dat/{A,B,C}_seq.dat reader: one decimal digit 0-3 per line, CRLF or LF, optional trailing newline.
  * Writes at most cap symbols into buf, *n = symbols in the file (ECAPACITY if *n > cap). */
 int trialign_read_seq_dat(const char *path, uint8_t *buf, int cap, int *n);

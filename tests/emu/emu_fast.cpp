@@ -90,15 +90,18 @@ struct EmuCta {
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             sweep_thread_pos<C>(tid, tj, tk);
-            sweep_thread_step<C, true>(R[tid], *S, A, tj, tk, step);
+            sweep_thread_step<C, true>(R[tid], *S, A, tj, tk, step, tid);
         }
     }
 };
 
 }  // namespace
 
-extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
-                                   int base, int n_ctas, int want_states, int32_t *out8, int check_bits, int *viol_out)
+namespace {
+// one (slab of a) long triple on n_ctas emulated CTAs; iface_* may be null
+int run_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int base, int n_ctas,
+             int want_states, int32_t *out8, int check_bits, int *viol_out, const uint32_t *iface_in, uint32_t *iface_out,
+             int last_slab)
 {
     using C = SweepCfg<true>;
     if (la < 1 || lb < 1 || lc < 1 || la > C::LA_MAX || n_ctas < 1) return -1;
@@ -116,6 +119,7 @@ extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, i
     unsigned long long counter = 0;
     A.face_j = fj.data(); A.face_k = fk.data(); A.progress = prog.data(); A.counter = &counter;
     A.out = out8; A.out_states = want_states ? out8 + 1 : nullptr; A.base = base;
+    A.iface_in = iface_in; A.iface_out = iface_out; A.last_slab = last_slab;
     int viol = 0;
     A.viol_flag = &viol;
     const int lim = 1 << ((check_bits > 0 ? check_bits : 16) - 1);
@@ -164,6 +168,33 @@ extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, i
         if (!progressed && ++idle_rounds > 4) return -2;  // deadlock
     }
     if (viol_out) *viol_out = viol;
+    return 0;
+}
+}  // namespace
+
+extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
+                                   int base, int n_ctas, int want_states, int32_t *out8, int check_bits, int *viol_out)
+{
+    return run_long(a, la, b, lb, c, lc, base, n_ctas, want_states, out8, check_bits, viol_out, nullptr, nullptr, 1);
+}
+
+// the i-slab pipeline, slabs run one after the other (what n_slabs GPUs do concurrently, task by task)
+extern "C" int emu_fast_sweep_slabs(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
+                                    int base, int n_ctas, int n_slabs, int32_t *out8)
+{
+    using C = SweepCfg<true>;
+    const long long tasks = (long long)((lb + C::BJ - 1) / C::BJ) * ((lc + C::KSPAN - 1) / C::KSPAN);
+    std::vector<uint32_t> st[2];
+    st[0].assign((size_t)tasks * 4 * 16 * C::NT, 0xDEADBEEFu);
+    st[1] = st[0];
+    for (int g = 0; g < n_slabs; ++g) {
+        const int i0 = (int)((long long)la * g / n_slabs), i1 = (int)((long long)la * (g + 1) / n_slabs);
+        if (i1 <= i0) return -3;
+        const int rc = run_long(a + i0, i1 - i0, b, lb, c, lc, base, n_ctas, 1, out8, 0, nullptr,
+                                g > 0 ? st[(g - 1) & 1].data() : nullptr, g + 1 < n_slabs ? st[g & 1].data() : nullptr,
+                                g + 1 == n_slabs);
+        if (rc) return rc;
+    }
     return 0;
 }
 

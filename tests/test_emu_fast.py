@@ -119,3 +119,21 @@ def test_sweep_batch_choreography(emu_sweep, ob, ln, n, n_ctas):
                                         2 * ln + 64, n_ctas, out.ctypes.data_as(i32p))
     assert rc == 0
     assert out.tolist() == ob.score_batch(a, b, c, 16).tolist()
+
+
+@pytest.mark.parametrize("shape,n_slabs,n_ctas", [((40, 70, 130), 2, 2), ((64, 64, 64), 4, 1), ((100, 129, 257), 3, 3),
+                                                  ((37, 200, 140), 8, 2)])
+def test_sweep_i_slab_pipeline(emu_sweep, ob, shape, n_slabs, n_ctas):
+    """Planes split into slabs, each slab continuing from the hand-over state of the previous one (the multi-GPU
+    path of SURVEY.md 8(e)(2)), must give the single-pass result."""
+    emu_sweep.emu_fast_sweep_slabs.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    la, lb, lc = shape
+    rng = np.random.default_rng(sum(shape) + n_slabs)
+    a, b, c = ob.mutated_triple(rng, max(shape))
+    a, b, c = (np.ascontiguousarray(x) for x in (a[:la], b[:lb], c[:lc]))
+    out = np.zeros(8, np.int32)
+    rc = emu_sweep.emu_fast_sweep_slabs(a.ctypes.data_as(u8p), la, b.ctypes.data_as(u8p), lb, c.ctypes.data_as(u8p), lc,
+                                        2 * min(shape) + 64, n_ctas, n_slabs, out.ctypes.data_as(i32p))
+    assert rc == 0
+    es, efin = ob.score(a, b, c, 16)
+    assert int(out[0]) == es and out[1:].tolist() == efin.tolist()

@@ -193,3 +193,58 @@ def test_range_checked_fast_path_and_literal_fallback(gpu_ta, ob, golden):
     # at W=16 the same triple is provably wrap-free and scores ~3*700
     s16 = gpu_ta.TriAlign(16).align(x, y, z)
     assert gpu_ta.last_path() == "fast_long" and s16 == ob.score_mt(x, y, z, 16)[0] and s16 > 1800
+
+
+@pytest.mark.parametrize("shape,n_slabs", [((300, 200, 260), 2), ((512, 512, 512), 4), ((1000, 130, 129), 8)])
+def test_i_slab_pipeline_back_to_back_on_one_gpu(gpu_ta, ob, shape, n_slabs):
+    """The multi-GPU i-slab path with the slabs run one after the other on a single GPU: each
+    slab continues from the hand-over state the previous one wrote; result must equal the single-pass score."""
+    import ctypes as C
+
+    import torch
+
+    la, lb, lc = shape
+    rng = np.random.default_rng(sum(shape))
+    a, b, c = ob.mutated_triple(rng, max(shape))
+    a, b, c = a[:la], b[:lb], c[:lc]
+    L = gpu_ta.library()
+    sb, fb = C.c_int64(0), C.c_int64(0)
+    assert L.trialign_slab_buffer_bytes(lb, lc, C.byref(sb), C.byref(fb)) == 0
+    bufs = []
+    for _ in range(2):
+        ps, pf = C.c_void_p(), C.c_void_p()
+        assert L.trialign_device_alloc(0, sb.value, C.byref(ps)) == 0
+        assert L.trialign_device_alloc(0, fb.value, C.byref(pf)) == 0
+        bufs.append((ps, pf))
+    da, db, dc = (torch.from_numpy(x.copy()).cuda() for x in (a, b, c))
+    out = torch.zeros(8, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    try:
+        for epoch in (1, 2):  # the buffers are reused without clearing: flags compare against the epoch
+            for g in range(n_slabs):
+                i0, i1 = gpu_ta.slab_range(la, g, n_slabs)
+                src = bufs[(g - 1) & 1] if g > 0 else (None, None)
+                dst = bufs[g & 1] if g + 1 < n_slabs else (None, None)
+                rc = L.trialign_slab_score_dev(0, da.data_ptr(), la, db.data_ptr(), lb, dc.data_ptr(), lc, i0, i1,
+                                               src[0], src[1], dst[0], dst[1], epoch, 16, out.data_ptr(), st)
+                assert rc == 0, rc
+            torch.cuda.synchronize()
+            es, efin = ob.score_mt(a, b, c, 16)
+            assert out.cpu().numpy().tolist() == [es] + efin.tolist()
+    finally:
+        for ps, pf in bufs:
+            L.trialign_device_free(0, ps)
+            L.trialign_device_free(0, pf)
+
+
+def test_fast_kernels_agree_with_literal_kernel_beyond_oracle_sizes(gpu_ta):
+    """At sizes the CPU oracle cannot reach in seconds, the factored block-sweep kernel and the literal plane-sweep
+    kernel (two independent implementations) must agree; identical sequences must score 3L."""
+    a, b, c = (gpu_ta.synth(0x5EED0005, 0, s, n) for s, n in ((0, 1500), (1, 1100), (2, 900)))
+    fast = gpu_ta.TriAlign(16).align(a, b, c, return_states=True)
+    assert gpu_ta.last_path() == "fast_long"
+    lit = gpu_ta.TriAlign(16, backend=gpu_ta.BACKEND_GPU_LITERAL).align(a, b, c, return_states=True)
+    assert gpu_ta.last_path() == "literal"
+    assert fast[0] == lit[0] and fast[1].tolist() == lit[1].tolist()
+    x = gpu_ta.synth(0x5EED0005, 0, 0, 4096)
+    assert gpu_ta.TriAlign(16).align(x, x, x) == 3 * 4096
