@@ -136,9 +136,9 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     // One long triple whose wrap-freedom cannot be proved from the lengths: run the fast kernel with its run-time
     // range check, and fall back to the literal kernel only if some value came near the score_bits limits.
     if (want_fast && n == 1 && score_bits >= 10 && score_bits <= 16 && fast_sweep_supports(la, lb, lc)) {
-        int rc = ctx->misc.reserve(1024);
+        int rc = ctx->viol.reserve(256);
         if (rc) return rc;
-        int *d_viol = (int *)((char *)ctx->misc.ptr + 128);  // the kernel's control block starts at offset 0 / 256
+        int *d_viol = (int *)ctx->viol.ptr;
         TA_CUDA(cudaMemsetAsync(d_viol, 0, sizeof(int), st));
         rc = fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, score_bits, d_viol);
         if (rc) return rc;

@@ -50,7 +50,7 @@ struct DeviceCtx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     Scratch seq, out, planes, faces, misc;
-    Scratch pinned_out;  // unused slot kept for symmetry (pinned memory is handled separately)
+    Scratch viol;        // range-check flag of the checked fast path (never reallocated by the kernels)
 };
 
 constexpr int kMaxDevices = 32;

@@ -3,8 +3,10 @@
 //                       and stream block faces through global memory, gated by per-task progress counters.
 //   sweep_batch_kernel: many triples of equal length > 64; every CTA sweeps all blocks of its pairs one after the
 //                       other, faces stay private to the CTA, no inter-CTA synchronisation.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "fast_sweep.cuh"
 #include "kernels.cuh"
@@ -69,18 +71,21 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
             if (t < (unsigned long long)A.tasks_total) {
                 fast::sweep_describe_long<C>(A, (long long)t, S.task);
                 // ring re-use: the previous tenants of the face slots must have been consumed
-                if ((long long)t >= A.fj_ring) {  // previous tenant t-ring was read by task t-ring+1
-                    const long long consumer = (long long)t - A.fj_ring + 1;
-                    while (ld_acquire(A.progress + consumer) < fast::kProgressDone) __nanosleep(200);
+                // (t is the claim position; the ring sizes exceed the largest producer->consumer distance in claim
+                // order by more than the grid size, so every consumer waited for here was claimed long ago)
+                if ((long long)t >= A.fj_ring) {
+                    const int prev = A.order[t - A.fj_ring];
+                    if (prev % A.nbj + 1 < A.nbj)
+                        while (ld_acquire(A.progress + prev + 1) < fast::kProgressDone) __nanosleep(200);
                 }
-                if ((long long)t >= A.fk_ring) {  // previous tenant t-ring was read by task t-ring+nbj
-                    const long long consumer = (long long)t - A.fk_ring + A.nbj;
-                    if (consumer < A.tasks_total)
-                        while (ld_acquire(A.progress + consumer) < fast::kProgressDone) __nanosleep(200);
+                if ((long long)t >= A.fk_ring) {
+                    const int prev = A.order[t - A.fk_ring];
+                    if (prev / A.nbj + 1 < A.nbkp)
+                        while (ld_acquire(A.progress + prev + A.nbj) < fast::kProgressDone) __nanosleep(200);
                 }
                 // i-slab pipeline: the previous slab (another GPU) must have delivered this task's plane-0 state
                 if (A.iface_in_flag)
-                    while (ld_acquire_sys(A.iface_in_flag + t) != A.epoch) __nanosleep(500);
+                    while (ld_acquire_sys(A.iface_in_flag + S.task.self_task) != A.epoch) __nanosleep(500);
             } else {
                 S.task.valid = 0;
             }
@@ -237,16 +242,37 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
     if (grid > A.tasks_total) grid = (int)A.tasks_total;
     A.fj_slot_words = (long long)(la + C::LAG + 2) * C::FJ_ROW_WORDS;
     A.fk_slot_words = (long long)(la + C::LAG + 2) * C::FK_ROW_WORDS;
-    A.fj_ring = (int)std::min<long long>(A.tasks_total, 2 * grid + 2);
-    A.fk_ring = (int)std::min<long long>(A.tasks_total, (long long)A.nbj + 2 * grid + 2);
+    // claim order (earliest possible start first) and the face-ring sizes it needs
+    std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
+    for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
+    const int nbj = A.nbj;
+    std::stable_sort(order.begin(), order.end(), [nbj](int x, int y) {
+        return fast::sweep_order_key(x % nbj, x / nbj) < fast::sweep_order_key(y % nbj, y / nbj);
+    });
+    for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;
+    int dist_j = 0, dist_k = 0;  // largest producer -> consumer distance in claim order
+    for (int t = 0; t < (int)A.tasks_total; ++t) {
+        if (t % nbj + 1 < nbj) dist_j = std::max(dist_j, pos_of[t + 1] - pos_of[t]);
+        if (t / nbj + 1 < A.nbkp) dist_k = std::max(dist_k, pos_of[t + nbj] - pos_of[t]);
+    }
+    A.fj_ring = (int)std::min<long long>(A.tasks_total, (long long)dist_j + 2 * grid + 2);
+    A.fk_ring = (int)std::min<long long>(A.tasks_total, (long long)dist_k + 2 * grid + 2);
     const size_t fj_bytes = (size_t)A.fj_ring * A.fj_slot_words * 4, fk_bytes = (size_t)A.fk_ring * A.fk_slot_words * 4;
-    const size_t ctl_bytes = (((size_t)A.tasks_total * sizeof(int) + 255) & ~(size_t)255) + 256;
+    const size_t prog_bytes = (((size_t)A.tasks_total * sizeof(int) + 255) & ~(size_t)255);
+    const size_t ctl_bytes = 256 + prog_bytes;           // task counter, progress[]
+    const size_t ord_bytes = 2 * prog_bytes;             // order[], pos_of[]
     if ((rc = ctx->faces.reserve(fj_bytes + fk_bytes + 512))) return rc;
-    if ((rc = ctx->misc.reserve(ctl_bytes))) return rc;
+    if ((rc = ctx->misc.reserve(ctl_bytes + ord_bytes))) return rc;
     A.face_j = (uint32_t *)ctx->faces.ptr;
     A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
     A.counter = (unsigned long long *)ctx->misc.ptr;
     A.progress = (int *)((char *)ctx->misc.ptr + 256);
+    int *d_order = (int *)((char *)ctx->misc.ptr + ctl_bytes);
+    int *d_pos = (int *)((char *)ctx->misc.ptr + ctl_bytes + prog_bytes);
+    A.order = d_order;
+    A.pos_of = d_pos;
+    TA_CUDA(cudaMemcpyAsync(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMemcpyAsync(d_pos, pos_of.data(), pos_of.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     A.out = d_score;
     A.out_states = d_states;
     A.base = sweep_base(la, lb, lc);

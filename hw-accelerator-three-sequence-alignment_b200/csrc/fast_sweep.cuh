@@ -62,7 +62,9 @@ struct SweepArgs {
     uint32_t *face_j, *face_k;    // ring storage
     long long fj_slot_words, fk_slot_words;
     int fj_ring, fk_ring;         // LONG: global ring sizes; BATCH: per-CTA ring sizes
-    int *progress;                // LONG: [tasks_total], zero-initialised
+    int *progress;                // LONG: [tasks_total] indexed by task id bj + nbj*bkp, zero-initialised
+    const int *order;             // LONG: claim position -> task id (sorted by earliest possible start, sweep_order_key)
+    const int *pos_of;            // LONG: task id -> claim position
     unsigned long long *counter;  // LONG: task counter, zero-initialised
     // i-slab pipeline (LONG, several GPUs): this launch computes planes i_begin+1 .. i_begin+la of the triple (a already
     // points at symbol i_begin).  The plane-i_begin state of every task comes from the previous slab (iface_in, on
@@ -127,21 +129,27 @@ TA_HD uint32_t sphi(const SweepArgs &A, int i0, int jl, int kl)
 template <class C>
 TA_HD int sweep_task_steps(const SweepArgs &A) { return A.la + C::LAG + C::DEPTH; }  // steps 0 .. this value
 
-// LONG mode: task id -> descriptor.  Order: column pair outer, row inner, so that (bj-1,bkp) = t-1, (bj,bkp-1) = t-nbj.
+// LONG mode: tasks are claimed in the order of their earliest possible start: block (bj,bkp) can start about
+// (TJ+gate) steps after (bj-1,bkp) and (TK+LAG+gate) steps after (bj,bkp-1), so with short tasks (i-slabs, L~1024) a
+// column-major order would leave most CTAs waiting on a chain.  Both predecessors have a smaller key.
+TA_HD int sweep_order_key(int bj, int bkp) { return 3 * bj + 5 * bkp; }
+
+// claim position -> descriptor.  Face ring slots are indexed by the claim position.
 template <class C>
-TA_HD void sweep_describe_long(const SweepArgs &A, long long t, SweepTask &T)
+TA_HD void sweep_describe_long(const SweepArgs &A, long long pos, SweepTask &T)
 {
+    const int t = A.order[pos];
     T.valid = 1;
     T.pair = 0;
-    T.bkp = (int)(t / A.nbj);
-    T.bj = (int)(t % A.nbj);
-    T.self_task = (int)t;
-    T.top_task = T.bj > 0 ? (int)(t - 1) : -1;
-    T.left_task = T.bkp > 0 ? (int)(t - A.nbj) : -1;
-    T.fj_w = (T.bj + 1 < A.nbj) ? A.face_j + (t % A.fj_ring) * A.fj_slot_words : nullptr;
-    T.fk_w = (T.bkp + 1 < A.nbkp) ? A.face_k + (t % A.fk_ring) * A.fk_slot_words : nullptr;
-    T.fj_r = T.bj > 0 ? A.face_j + ((t - 1) % A.fj_ring) * A.fj_slot_words : nullptr;
-    T.fk_r = T.bkp > 0 ? A.face_k + ((t - A.nbj) % A.fk_ring) * A.fk_slot_words : nullptr;
+    T.bkp = t / A.nbj;
+    T.bj = t % A.nbj;
+    T.self_task = t;
+    T.top_task = T.bj > 0 ? t - 1 : -1;
+    T.left_task = T.bkp > 0 ? t - A.nbj : -1;
+    T.fj_w = (T.bj + 1 < A.nbj) ? A.face_j + (pos % A.fj_ring) * A.fj_slot_words : nullptr;
+    T.fk_w = (T.bkp + 1 < A.nbkp) ? A.face_k + (pos % A.fk_ring) * A.fk_slot_words : nullptr;
+    T.fj_r = T.bj > 0 ? A.face_j + (A.pos_of[t - 1] % A.fj_ring) * A.fj_slot_words : nullptr;
+    T.fk_r = T.bkp > 0 ? A.face_k + (A.pos_of[t - A.nbj] % A.fk_ring) * A.fk_slot_words : nullptr;
     T.final_here = (T.bj == (A.lb - 1) / C::BJ) && (T.bkp == (A.lc - 1) / C::KSPAN);
 }
 

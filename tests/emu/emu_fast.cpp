@@ -3,6 +3,7 @@
 // sequentially inside each barrier-delimited step, which is exactly the kernel's schedule (threads only read what
 // was published before the previous barrier).  Lets the CPU test-suite check the skewing, halo exchange, pair
 // hand-over and score extraction against the oracle without a GPU.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <memory>
@@ -112,11 +113,20 @@ int run_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *
     A.tasks_total = (long long)A.nbj * A.nbkp;
     A.fj_slot_words = (long long)(la + C::LAG + 2) * C::FJ_ROW_WORDS;
     A.fk_slot_words = (long long)(la + C::LAG + 2) * C::FK_ROW_WORDS;
-    A.fj_ring = n_ctas + 2;
-    A.fk_ring = A.nbj + n_ctas + 2;
+    A.fj_ring = (int)A.tasks_total;  // the emulation keeps every face (ring re-use is a launcher concern)
+    A.fk_ring = (int)A.tasks_total;
     std::vector<uint32_t> fj((size_t)A.fj_ring * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
     std::vector<int> prog((size_t)A.tasks_total, 0);
     unsigned long long counter = 0;
+    // claim order exactly as the launcher builds it
+    std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
+    for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
+    const int nbj = A.nbj;
+    std::stable_sort(order.begin(), order.end(), [nbj](int x, int y) {
+        return sweep_order_key(x % nbj, x / nbj) < sweep_order_key(y % nbj, y / nbj);
+    });
+    for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;
+    A.order = order.data(); A.pos_of = pos_of.data();
     A.face_j = fj.data(); A.face_k = fk.data(); A.progress = prog.data(); A.counter = &counter;
     A.out = out8; A.out_states = want_states ? out8 + 1 : nullptr; A.base = base;
     A.iface_in = iface_in; A.iface_out = iface_out; A.last_slab = last_slab;
