@@ -545,6 +545,273 @@ struct Trialign1 : ArrayBase {
     }
 };
 
+/* ---------------------------------------------------------------- TRIALIGN, 2cyc ---------------------- */
+struct Trialign2 : ArrayBase {
+    int A_TOTAL, ADDR_BITS;
+    uint32_t A_idx, B_idx, C_idx;
+    uint32_t amask_z, amask_y;
+    /* registers */
+    int state;
+    uint32_t input_counter, compute_counter, slice_y, slice_z, pp_counter;
+    uint8_t EN_start;
+    Sym A_start;
+    uint32_t y_read_idx, y_write_idx;
+    Val score_reg;
+    uint8_t finish;
+    uint32_t A_addr, B_addr, C_addr;
+    std::vector<uint8_t> y_WEN, y_CEN, ny_WEN, ny_CEN; /* [3][2][P+1] */
+    std::vector<uint32_t> y_A, ny_A;
+    std::vector<uint8_t> z_WEN, z_CEN, nz_WEN, nz_CEN; /* [2][P+1] */
+    std::vector<uint32_t> z_A, nz_A;
+    std::vector<Sram> ysram, zsram;
+
+    inline int zi(int b, int j) const { return b * (P + 1) + j; }
+    inline int yi(int i, int j, int k) const { return (i * 2 + j) * (P + 1) + k; }
+
+    void init(const rtl_cfg &c, int la, int lb, int lc)
+    {
+        base_init(c.pe_len, c.score_bits, 2);
+        A_TOTAL = c.a_total_len;
+        ADDR_BITS = c.sram_addr_bits;
+        amask_z = (1u << ADDR_BITS) - 1u;
+        amask_y = (1u << (ADDR_BITS + 4)) - 1u;
+        A_idx = (uint32_t)la; B_idx = (uint32_t)lb; C_idx = (uint32_t)lc;
+        state = IDLE;
+        input_counter = compute_counter = slice_y = slice_z = pp_counter = 0;
+        EN_start = 0;
+        A_start = Sym{0, 1}; /* A_start <= 1'bz (TriAlign_2cyc.v:648) */
+        y_read_idx = 16;     /* :650 */
+        y_write_idx = 0;
+        score_reg = K(0);
+        finish = 0;
+        A_addr = B_addr = C_addr = 0;
+        const int ny = 3 * 2 * (P + 1);
+        y_WEN.assign(ny, 1); y_CEN.assign(ny, 1); y_A.assign(ny, 0);
+        z_WEN.assign(2 * (P + 1), 1); z_CEN.assign(2 * (P + 1), 1); z_A.assign(2 * (P + 1), 0);
+        ysram.resize(ny);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 2; ++j)
+                for (int k = 0; k <= P; ++k) ysram[yi(i, j, k)].init(i < 2 ? ADDR_BITS + 4 : ADDR_BITS); /* :141-157 */
+        zsram.resize(2 * (P + 1));
+        for (auto &s : zsram) s.init(ADDR_BITS);
+    }
+
+    inline uint32_t border_00() const
+    {
+        return ((y_read_idx == 0) ? (A_idx + 2 * P - 1) : (y_read_idx - 1)) & wmask;
+    }
+    /* :178-180: "group 2 discrimination" uses fixed bit positions 6..9 of the index against B_idx */
+    inline bool bank2(uint32_t idx) const
+    {
+        for (int b = 6; b <= 9; ++b)
+            if (((idx >> b) & 1u) && ((B_idx >> b) & 1u)) return true;
+        return false;
+    }
+    static inline int bit(uint32_t v, int b) { return (int)((v >> b) & 1u); }
+
+    int step(TbPort &tb, Word7 *final_cell)
+    {
+        const uint32_t b00 = border_00();
+        const bool b00_b = bank2(b00), yr_b = bank2(y_read_idx), yw_b = bank2(y_write_idx);
+        const int yr4 = bit(y_read_idx, 4), yr3 = bit(y_read_idx, 3);
+        const int yw4 = bit(y_write_idx, 4), yw3 = bit(y_write_idx, 3);
+        const int b4 = bit(b00, 4), b3 = bit(b00, 3);
+        const int r_bank = yr_b ? 2 : yr4, w_bank = yw_b ? 2 : yw4, c_bank = b00_b ? 2 : b4;
+        const uint32_t yr_hi = ((y_read_idx >> 5) & 31u) << 9, yw_hi = ((y_write_idx >> 5) & 31u) << 9,
+                       b00_hi = ((b00 >> 5) & 31u) << 9;
+
+        /* ---- borders (:186-221) ---- */
+        for (int gi = 1; gi <= P; ++gi)
+            out[g(0, gi)] = (slice_y == 0) ? word_zero() : ((slice_y % 2 == 1) ? zsram[zi(0, gi)].Q : zsram[zi(1, gi)].Q);
+        for (int ge = 1; ge <= P; ++ge)
+            out[g(ge, 0)] = (slice_z == 0) ? word_zero() : ysram[yi(r_bank, yr3, ge)].Q;
+        out[g(0, 0)] = (slice_y == 0 || slice_z == 0) ? word_zero() : ysram[yi(c_bank, b3, P)].Q;
+        gather_outputs(A_start, EN_start);
+        eval_pes((int)pp_counter);
+
+        /* ---- control FSM, combinational (:232-484) ---- */
+        int nstate = state;
+        uint32_t n_ic = input_counter, n_cc = compute_counter, n_sy = slice_y, n_sz = slice_z, n_pp = pp_counter;
+        uint8_t n_EN_start = EN_start;
+        Sym n_A_start = A_start;
+        uint32_t n_yr = y_read_idx, n_yw = y_write_idx;
+        Val n_score = score_reg;
+        uint8_t n_finish = finish;
+        uint32_t n_Aa = A_addr, n_Ba = B_addr, n_Ca = C_addr;
+        nB_i = B_i; nC_i = C_i;
+        ny_WEN = y_WEN; ny_CEN = y_CEN; ny_A = y_A;
+        nz_WEN = z_WEN; nz_CEN = z_CEN; nz_A = z_A;
+        const uint32_t TOTAL_PE = (uint32_t)P * P;
+        const uint32_t slice_y_max = ((B_idx / P) - 1) & 0xFF, slice_z_max = ((C_idx / P) - 1) & 0xFF;
+
+        switch (state) {
+        case IDLE:
+            if (tb.start_r) {
+                nstate = INITIAL;
+                n_ic = 0;
+                nz_A[zi(0, 0)] = 0;
+                nz_A[zi(1, 0)] = 0;
+                n_Aa = n_Ba = n_Ca = 0;
+            }
+            break;
+        case INITIAL: {
+            if (input_counter >= 1) {
+                const uint32_t r = (input_counter - 1) % P + 1, cidx = (input_counter - 1) / P + 1;
+                if (r <= (uint32_t)P && cidx <= (uint32_t)P) {
+                    nB_i[g(r, cidx)] = tb.sym[1];
+                    nC_i[g(r, cidx)] = tb.sym[2];
+                }
+            }
+            for (int j = 1; j <= P; ++j) {
+                nz_WEN[zi(0, j)] = (slice_y % 2 == 1) ? 1 : 0;
+                nz_WEN[zi(1, j)] = (slice_y % 2 == 1) ? 0 : 1;
+                nz_CEN[zi(0, j)] = 0;
+                nz_CEN[zi(1, j)] = 0;
+                nz_A[zi(0, j)] = 0;
+                nz_A[zi(1, j)] = 0;
+            }
+            for (int k = 1; k <= P; ++k) { /* :305-322, read first then write (write wins on a clash) */
+                ny_WEN[yi(r_bank, yr3, k)] = 1;
+                ny_CEN[yi(r_bank, yr3, k)] = 0;
+                ny_WEN[yi(w_bank, yw3, k)] = 0;
+                ny_CEN[yi(w_bank, yw3, k)] = 0;
+            }
+            ny_WEN[yi(c_bank, b3, P)] = 1; /* :325-331 */
+            ny_CEN[yi(c_bank, b3, P)] = 0;
+            if (input_counter < TOTAL_PE - 1) { /* :334-352 */
+                for (int k = 0; k <= P; ++k) ny_A[yi(r_bank, yr3, k)] = yr_hi & amask_y;
+            } else {
+                ny_A[yi(c_bank, b3, P)] = b00_hi & amask_y;
+            }
+            nstate = (input_counter == TOTAL_PE) ? COMPUTE : INITIAL;
+            n_ic = (input_counter == TOTAL_PE) ? 0 : ((input_counter + 1) & wmask);
+            const bool b_last = (B_addr == (slice_y + 1) * P - 1);
+            n_Ca = b_last ? ((C_addr == (slice_z + 1) * P - 1) ? slice_z * P : C_addr + 1) : C_addr;
+            n_Ba = b_last ? slice_y * P : B_addr + 1;
+            n_Aa = (input_counter >= TOTAL_PE - 1) ? 1 : 0;
+            n_cc = 0;
+            n_A_start = tb.sym[0];
+            n_pp = (pp_counter == 1) ? 0 : ((pp_counter + 1) & 7);
+            break;
+        }
+        case COMPUTE: {
+            const uint32_t cc = compute_counter;
+            if (cc < A_idx - 1) { /* READ addresses :368-390 */
+                ny_A[yi(r_bank, yr3, 1)] = (cc + yr_hi) & amask_y;
+                ny_A[yi(c_bank, b3, P)] = (cc + 1 + b00_hi) & amask_y;
+                if (slice_y % 2 == 1) nz_A[zi(0, 1)] = cc & amask_z;
+                else nz_A[zi(1, 1)] = cc & amask_z;
+            } else if (cc >= A_idx - 1 && cc < A_idx + P) {
+                ny_A[yi(r_bank, yr3, 1)] = (A_idx - 1 + yr_hi) & amask_y;
+                nz_A[zi(0, 1)] = (A_idx - 1) & amask_z;
+                nz_A[zi(1, 1)] = (A_idx - 1) & amask_z;
+            }
+            if (cc >= (uint32_t)P && cc < P + A_idx) { /* WRITE addresses :406-431 */
+                if (slice_y % 2 == 1) nz_A[zi(1, 1)] = (cc - P) & amask_z;
+                else nz_A[zi(0, 1)] = (cc - P) & amask_z;
+                ny_A[yi(w_bank, yw3, 1)] = (cc - P + yw_hi) & amask_y;
+            } else if (cc >= P + A_idx && cc < 2 * P + A_idx - 1) {
+                nz_CEN[zi(0, 1)] = 1;
+                nz_CEN[zi(1, 1)] = 1;
+                ny_CEN[yi(w_bank, yw3, 1)] = 1;
+            }
+            nstate = WAIT;
+            n_pp = 1;
+            break;
+        }
+        case OUT: nstate = OUT; break;
+        case WAIT: {
+            const uint32_t cc = compute_counter;
+            n_cc = (cc == 2 * P + A_idx - 1) ? 0 : ((cc + 1) & wmask);
+            n_pp = 0;
+            if (cc == 2 * P + A_idx - 1) {
+                n_sy = (slice_y == slice_y_max) ? 0 : ((slice_y + 1) & 0x1FF);
+                n_sz = (slice_y == slice_y_max) ? ((slice_z == slice_z_max) ? 0 : ((slice_z + 1) & 0x1FF)) : slice_z;
+                n_yw = (y_write_idx == A_idx + P) ? 0 : ((y_write_idx + P) & 0x3FF);
+                n_yr = (y_read_idx >= A_idx + P) ? 0 : ((y_read_idx + P) & 0x3FF);
+                nstate = (slice_y == slice_y_max && slice_z == slice_z_max) ? OUT : INITIAL;
+                n_Aa = 0;
+                n_Ba = (slice_y == slice_y_max) ? 0 : (slice_y + 1) * P;
+                n_Ca = (slice_y == slice_y_max) ? ((slice_z == slice_z_max) ? 0 : (slice_z + 1) * P) : C_addr;
+                if (slice_z == slice_z_max && slice_y == slice_y_max) {
+                    n_score = final_max();
+                    n_finish = 1;
+                    if (final_cell) *final_cell = out[g(P, P)];
+                }
+            } else {
+                if (cc < A_idx - 1) {
+                    n_A_start = tb.sym[0];
+                    n_Aa = A_addr + 1;
+                }
+                nstate = COMPUTE;
+                if (cc == 0) n_EN_start = 1;
+                if (cc == A_idx) n_EN_start = 0;
+            }
+            break;
+        }
+        default: break;
+        }
+
+        /* ---- SRAMs see pre-edge control and data ---- */
+        for (int b = 0; b <= 1; ++b)
+            for (int gsz = 1; gsz <= P; ++gsz)
+                zsram[zi(b, gsz)].clock(z_CEN[zi(b, gsz)], z_WEN[zi(b, gsz)], z_A[zi(b, gsz)], out[g(P, gsz)]);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 2; ++j)
+                for (int k = 1; k <= P; ++k) {
+                    const int id = yi(i, j, k);
+                    if (y_CEN[id]) continue;
+                    const uint32_t addr = (i == 2) ? (y_A[id] & 0x1FFu) : y_A[id]; /* :155: y_A_i[2][..][8:0] */
+                    ysram[id].clock(0, y_WEN[id], addr, out[g(k, P)]);              /* :162: row gsy, last column */
+                }
+
+        /* ---- SRAM control registers (:496-631) ---- */
+        if (state == COMPUTE) {
+            for (int i = 0; i <= 1; ++i)
+                for (int j = 0; j <= 1; ++j)
+                    for (int k = 0; k <= P; ++k) y_WEN[yi(i, j, k)] = ny_WEN[yi(i, j, k)]; /* bank 2 holds (:524-529) */
+            z_WEN = nz_WEN;
+            for (int i = 0; i <= 2; ++i)
+                for (int j = 0; j <= 1; ++j)
+                    for (int k = P; k >= 0; --k) { /* downwards: [k-1] is still the pre-edge value */
+                        const int id = yi(i, j, k);
+                        const bool wsel = yw_b ? (i == 2 && yw3 == j) : (yw4 == i && yw3 == j);
+                        const bool rsel = yr_b ? (i == 2 && yr3 == j) : (yr4 == i && yr3 == j);
+                        if (k > 1 && wsel) y_CEN[id] = y_CEN[id - 1];
+                        else y_CEN[id] = ny_CEN[id];
+                        if (k > 1 && (wsel || rsel)) y_A[id] = y_A[id - 1];
+                        else y_A[id] = ny_A[id];
+                    }
+            for (int b = 0; b <= 1; ++b) {
+                for (int j = P; j >= 2; --j) {
+                    z_A[zi(b, j)] = z_A[zi(b, j - 1)];
+                    z_CEN[zi(b, j)] = z_CEN[zi(b, j - 1)];
+                }
+                z_A[zi(b, 1)] = nz_A[zi(b, 1)];
+                z_CEN[zi(b, 1)] = nz_CEN[zi(b, 1)];
+            }
+        } else {
+            z_WEN = nz_WEN; z_CEN = nz_CEN; z_A = nz_A;
+            y_WEN = ny_WEN; y_CEN = ny_CEN; y_A = ny_A;
+        }
+
+        const uint32_t addr[3] = {A_addr, B_addr, C_addr};
+        tb.clock(addr);
+
+        for (auto &p : pe) p.commit(2);
+        state = nstate;
+        input_counter = n_ic; compute_counter = n_cc; slice_y = n_sy; slice_z = n_sz; pp_counter = n_pp;
+        B_i.swap(nB_i); C_i.swap(nC_i);
+        EN_start = n_EN_start;
+        A_start = n_A_start;
+        y_read_idx = n_yr; y_write_idx = n_yw;
+        score_reg = n_score;
+        finish = n_finish;
+        A_addr = n_Aa & 0x7FFF; B_addr = n_Ba & 0x7FFF; C_addr = n_Ca & 0x7FFF;
+        return finish;
+    }
+};
+
 int ceil_log2(int v)
 {
     int b = 0;
@@ -567,6 +834,12 @@ int in_domain(const rtl_cfg &c, int la, int lb, int lc)
     if (lb / P - 1 > 255 || lc / P - 1 > 255) return 0; /* slice_*_max_idx are 8 bits */
     if (c.variant == 1) {
         if (lc > P && la < lb) return 0;               /* y ring has A_idx/P+2 groups */
+    } else {
+        /* TriAlign_2cyc selects its y-SRAM bank from fixed bit positions of the ring indices
+         * (TriAlign_2cyc.v:178-180,205-219, y_read_idx resets to 16 at :650): built for A=B=C in {64,128,256,512};
+         * e.g. 24 and 32 put the read and the write group into the same single-port SRAM and yield X. */
+        if (la != lb || lb != lc) return 0;
+        if (la % 64) return 0;
     }
     return 1;
 }
@@ -624,7 +897,13 @@ int rtl_model_run(const rtl_cfg *cfg_in, const uint8_t *a, int la, const uint8_t
         }
         sc = dut->score_reg;
     } else {
-        return RTL_EARG; /* filled in by rtl_model_2cyc (see below) */
+        auto dut = std::make_unique<Trialign2>();
+        dut->init(cfg, la, lb, lc);
+        while (n < limit) {
+            ++n;
+            if (dut->step(tb, &fin)) { done = true; break; }
+        }
+        sc = dut->score_reg;
     }
     if (cycles) *cycles = n;
     if (!done) return RTL_ETIMEOUT;

@@ -120,3 +120,37 @@ def test_batch_oracle_matches_golden(golden, ob):
     n = len(ent["scores"])
     a, b, c = ob.synth_batch(ent["seed"], 0, n, ent["len"])
     assert ob.score_batch(a, b, c, ent["score_bits"]).tolist() == ent["scores"]
+
+
+def test_rtl_2cyc_model_equals_oracle_and_published_cycle_counts(ob, golden):
+    """PE_2cyc + TriAlign_2cyc compute the same function with 2 clocks per wavefront step; the cycle counts are the
+    ones that reproduce the paper's FPGA/ASIC runtimes (14,402 @ L=64, 90,370 @ L=128)."""
+    d = golden["dat"]
+    rc, s, fin, cyc = ob.rtl_run(d["A"], d["B"], d["C"], 2)
+    assert (rc, s, fin.tolist(), cyc) == (0, 1, [-1, 1, -4, -5, 1, -7, -2], 14402)
+    z = np.zeros(64, np.uint8)
+    rc, s, fin, cyc = ob.rtl_run(z, z, z, 2)
+    assert (rc, s, fin.tolist(), cyc) == (0, 192, [192, 185, 185, 185, 188, 188, 188], 14402)
+    rng = np.random.default_rng(21)
+    for L in (64, 128):
+        for mutated in (False, True):
+            a, b, c = ob.mutated_triple(rng, L) if mutated else tuple(rng.integers(0, 4, L, dtype=np.uint8) for _ in range(3))
+            es, efin = ob.score(a, b, c, 12)
+            rc, s, fin, cyc = ob.rtl_run(a, b, c, 2)
+            assert rc == ob.RTL_OK and s == es and fin.tolist() == efin.tolist()
+            assert cyc == ob.rtl_cycle_formula(2, 8, L, L, L) == {64: 14402, 128: 90370}[L]
+
+
+def test_rtl_2cyc_bank_select_quirk(ob):
+    """Outside its design points the 2cyc control reads and writes one single-port SRAM at once: the model's X
+    poisoning reaches the score at L=24 and L=32, while 8, 16, 40, 48 still come out right."""
+    rng = np.random.default_rng(0)
+    for L, ok in ((8, True), (16, True), (24, False), (32, False), (40, True), (48, True)):
+        a, b, c = (rng.integers(0, 4, L, dtype=np.uint8) for _ in range(3))
+        assert ob.rtl_run(a, b, c, 2)[0] == ob.RTL_EDOMAIN           # strict mode refuses all of them
+        rc, s, fin, cyc = ob.rtl_run(a, b, c, 2, strict=False)
+        assert cyc == ob.rtl_cycle_formula(2, 8, L, L, L)
+        if ok:
+            assert rc == ob.RTL_OK and s == ob.score(a, b, c, 12)[0]
+        else:
+            assert rc == ob.RTL_EX
