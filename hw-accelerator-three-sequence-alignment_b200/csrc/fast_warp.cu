@@ -13,13 +13,29 @@ using C = fast::WarpCfg;
 
 __device__ __forceinline__ int ld_vol(const int *p) { return *(const volatile int *)p; }
 
-__device__ __forceinline__ void shfl_out(fast::LaneOut &dst, const fast::LaneOut &src, int delta)
+// Only the bottom row travels to lane+LK and only the right column (+ relay) to lane+1: 16 + 18 shuffles per step.
+__device__ __forceinline__ void shfl_up_part(fast::LaneOut &dst, const fast::LaneOut &src, bool right_part)
 {
-    // the struct is 34 words; shuffle it word by word
-    const uint32_t *s = reinterpret_cast<const uint32_t *>(&src);
-    uint32_t *d = reinterpret_cast<uint32_t *>(&dst);
+    const unsigned m = 0xFFFFFFFFu;
+    if (!right_part) {
 #pragma unroll
-    for (int q = 0; q < (int)(sizeof(fast::LaneOut) / 4); ++q) d[q] = __shfl_up_sync(0xFFFFFFFFu, s[q], delta);
+        for (int q = 0; q < 4; ++q) {
+            dst.b_wY[q] = __shfl_up_sync(m, src.b_wY[q], C::LK);
+            dst.b_u2[q] = __shfl_up_sync(m, src.b_u2[q], C::LK);
+            dst.b_u1[q] = __shfl_up_sync(m, src.b_u1[q], C::LK);
+            dst.b_all[q] = __shfl_up_sync(m, src.b_all[q], C::LK);
+        }
+    } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            dst.r_wZ[q] = __shfl_up_sync(m, src.r_wZ[q], 1);
+            dst.r_u2[q] = __shfl_up_sync(m, src.r_u2[q], 1);
+            dst.r_u3[q] = __shfl_up_sync(m, src.r_u3[q], 1);
+            dst.r_all[q] = __shfl_up_sync(m, src.r_all[q], 1);
+        }
+        dst.relay_u2 = __shfl_up_sync(m, src.relay_u2, 1);
+        dst.relay_all = __shfl_up_sync(m, src.relay_all, 1);
+    }
 }
 
 __global__ void __launch_bounds__(C::NT, 1) fast_warp_kernel(fast::WarpArgs A)
@@ -58,12 +74,12 @@ __global__ void __launch_bounds__(C::NT, 1) fast_warp_kernel(fast::WarpArgs A)
 
 #pragma unroll 1
     for (int w = 0; w <= last; ++w) {
-        if (lane == 0) {
-            while (!fast::warp_can_step(S, a, b, w, last, prod_top ? ld_vol(prod_top) : 0, prod_left ? ld_vol(prod_left) : 0,
-                                        cons_below ? ld_vol(cons_below) : 0, cons_right ? ld_vol(cons_right) : 0)) {
-            }
-            __threadfence_block();  // acquire: ring data written before the producer's counter update
+        // every lane polls the same four counters (broadcast reads): the loop stays warp-uniform, so the warp does not
+        // split into "lane 0" and "the rest" (a split warp pushes every shuffle below onto a slow per-lane path)
+        while (!fast::warp_can_step(S, a, b, w, last, prod_top ? ld_vol(prod_top) : 0, prod_left ? ld_vol(prod_left) : 0,
+                                    cons_below ? ld_vol(cons_below) : 0, cons_right ? ld_vol(cons_right) : 0)) {
         }
+        __threadfence_block();  // acquire: ring data written before the producer's counter update
         __syncwarp();
         if (fast::warp_rebuild_step(w)) {
             const int q = (w >> 6) + 1;
@@ -75,16 +91,17 @@ __global__ void __launch_bounds__(C::NT, 1) fast_warp_kernel(fast::WarpArgs A)
             }
         }
         fast::warp_lane_step(R, S, A, a, b, lj, lk, w, P, pair_base, last, O);
-        __syncwarp();  // every lane has read its ring entries and written its own
-        if (lane == 0) {
-            __threadfence_block();  // release: the lanes' ring stores above
-            if (a > 0) *(volatile int *)&S.consumed_top[a][b] = w + C::TOP_LEAD + 1;
-            if (b > 0) *(volatile int *)&S.consumed_left[a][b] = w + C::LEFT_LEAD + 1;
-            *(volatile int *)&S.produced[a][b] = w + 1;
-        }
-        shfl_out(up, O, C::LK);  // from lane - LK: the tile above
-        shfl_out(lf, O, 1);      // from lane - 1: the tile to the left
+        __syncwarp();  // every lane has read its ring entries and written its own; the warp is converged here, which
+                       // keeps the shuffles below on the hardware path (a diverged warp falls back to a per-lane loop)
+        shfl_up_part(up, O, false);  // from lane - LK: the tile above (bottom row)
+        shfl_up_part(lf, O, true);   // from lane - 1: the tile to the left (right column + relay)
         fast::warp_take_halo(R.H, up, lf);
+        __threadfence_block();  // release: the lanes' ring stores above (every lane fences its own stores)
+        __syncwarp();
+        // all lanes store the same values (benign): no divergent region around the counter update
+        if (a > 0) *(volatile int *)&S.consumed_top[a][b] = w + C::TOP_LEAD + 1;
+        if (b > 0) *(volatile int *)&S.consumed_left[a][b] = w + C::LEFT_LEAD + 1;
+        *(volatile int *)&S.produced[a][b] = w + 1;
     }
 }
 
