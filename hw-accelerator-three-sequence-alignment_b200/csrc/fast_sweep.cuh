@@ -271,6 +271,19 @@ TA_HD uint32_t ta_prmt(uint32_t a, uint32_t b, uint32_t sel)
 }
 #endif
 
+// 16-byte store of four packed words (dst is 16-byte aligned: face rows are 64 / 68 words, tiles start at multiples of 4)
+#if defined(__CUDA_ARCH__)
+TA_HD void ta_store4(uint32_t *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    *reinterpret_cast<uint4 *>(dst) = make_uint4(a, b, c, d);
+}
+#else
+TA_HD void ta_store4(uint32_t *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    dst[0] = a; dst[1] = b; dst[2] = c; dst[3] = d;
+}
+#endif
+
 // low half <- high half of x ; high half <- low half of y
 TA_HD uint32_t hi_lo(uint32_t x, uint32_t y) { return ta_prmt(x, y, 0x5432); }
 
@@ -487,25 +500,19 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
     if (tj == C::TJ - 1 && T.fj_w && i0 >= 1 && i0 <= rows) {
         const uint32_t adj = rep(2 * C::BJ);
         uint32_t *dst = T.fj_w + (long long)i0 * C::FJ_ROW_WORDS + k0;
-#pragma unroll
-        for (int c = 0; c < RK; ++c) {
-            dst[0 * C::ROW_W + c] = n_wY[RJ - 1][c] - adj;
-            dst[1 * C::ROW_W + c] = n_u2[RJ - 1][c] - adj;
-            dst[2 * C::ROW_W + c] = R.u1[RJ - 1][c] - adj;
-            dst[3 * C::ROW_W + c] = R.all[RJ - 1][c] - adj;
-        }
+        ta_store4(dst + 0 * C::ROW_W, n_wY[RJ - 1][0] - adj, n_wY[RJ - 1][1] - adj, n_wY[RJ - 1][2] - adj, n_wY[RJ - 1][3] - adj);
+        ta_store4(dst + 1 * C::ROW_W, n_u2[RJ - 1][0] - adj, n_u2[RJ - 1][1] - adj, n_u2[RJ - 1][2] - adj, n_u2[RJ - 1][3] - adj);
+        ta_store4(dst + 2 * C::ROW_W, R.u1[RJ - 1][0] - adj, R.u1[RJ - 1][1] - adj, R.u1[RJ - 1][2] - adj, R.u1[RJ - 1][3] - adj);
+        ta_store4(dst + 3 * C::ROW_W, R.all[RJ - 1][0] - adj, R.all[RJ - 1][1] - adj, R.all[RJ - 1][2] - adj, R.all[RJ - 1][3] - adj);
     }
     if (tk == C::TK - 1 && T.fk_w && i0 >= 1 && i0 <= rows) {
         // LONG: only the high half crosses to the next column pair (KSPAN columns to the right of this pair's origin)
         const uint32_t adj = C::LONG ? ((uint32_t)(2 * C::KSPAN) << 16) : rep(2 * C::BK);
         uint32_t *dst = T.fk_w + (long long)i0 * C::FK_ROW_WORDS + j0;
-#pragma unroll
-        for (int r = 0; r < RJ; ++r) {
-            dst[0 * C::COL_W + r] = n_wZ[r][RK - 1] - adj;
-            dst[1 * C::COL_W + r] = n_u2[r][RK - 1] - adj;
-            dst[2 * C::COL_W + r] = R.u3[r][RK - 1] - adj;
-            dst[3 * C::COL_W + r] = R.all[r][RK - 1] - adj;
-        }
+        ta_store4(dst + 0 * C::COL_W, n_wZ[0][RK - 1] - adj, n_wZ[1][RK - 1] - adj, n_wZ[2][RK - 1] - adj, n_wZ[3][RK - 1] - adj);
+        ta_store4(dst + 1 * C::COL_W, n_u2[0][RK - 1] - adj, n_u2[1][RK - 1] - adj, n_u2[2][RK - 1] - adj, n_u2[3][RK - 1] - adj);
+        ta_store4(dst + 2 * C::COL_W, R.u3[0][RK - 1] - adj, R.u3[1][RK - 1] - adj, R.u3[2][RK - 1] - adj, R.u3[3][RK - 1] - adj);
+        ta_store4(dst + 3 * C::COL_W, R.all[0][RK - 1] - adj, R.all[1][RK - 1] - adj, R.all[2][RK - 1] - adj, R.all[3][RK - 1] - adj);
         if (tj == 0) {  // relay: the cell above-right of the block pair = corner of the next pair's first tile
             uint32_t *rel = T.fk_w + (long long)i0 * C::FK_ROW_WORDS + C::BJ;
             rel[1 * C::COL_W] = T_u2[RK] - adj;
