@@ -123,11 +123,6 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     if (want_fast && provably_wrap_free(la, lb, lc, score_bits)) {
         if (!d_finals && la == lb && lb == lc && fast_batch_supports(la)) {
             ts.last_path = TRIALIGN_PATH_FAST_BATCH;
-            static const bool use_warp = []() {
-                const char *e = std::getenv("TRIALIGN_K1");
-                return e && e[0] == 'w';
-            }();
-            if (use_warp) return fast_warp_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
             return fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
         }
         if (n == 1 && fast_sweep_supports(la, lb, lc)) {

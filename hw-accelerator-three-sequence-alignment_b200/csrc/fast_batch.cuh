@@ -47,8 +47,10 @@ struct BatchSmem {
     uint32_t col[2][4][C::TK][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk][j]   right columns
     uint32_t corner[2][2][C::TJ][C::TK];       // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
     uint32_t tabAB[2][16][C::TAB_STRIDE];      // [buf][a code][j]  pair constant {4,2}
-    uint32_t tabMB[2][16][C::TAB_STRIDE];      // [buf][a code][j]  0xFFFF where a == b
-    uint32_t tabAC[2][16][C::TAB_STRIDE];      // [buf][a code][k]
+    uint32_t tabMB[2][16][C::TAB_STRIDE];      // [buf][a code][j]  triple row constant {9,3}
+    uint32_t tabAC[2][16][C::TAB_STRIDE];      // [buf][a code][k]  pair constant {4,2}
+    uint32_t tabMC[2][16][C::TAB_STRIDE];      // [buf][a code][k]  triple column constant {9,6}
+    uint32_t bpk[2][64], cpk[2][64];           // [buf][pos]  b / c symbols of the two triples, one per 16-bit half
     uint8_t seq[2][3][2][64];                  // [buf][A,B,C][half][pos]
     uint8_t acode[2][64];                      // a_lo | a_hi << 2
 };
@@ -56,7 +58,14 @@ struct BatchSmem {
 template <class C>
 struct BatchRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
-    uint32_t cBC[C::RJ][C::RK], U[C::RJ][C::RK];                                       // per-cell constants
+    uint32_t cBC[C::RJ][C::RK];                                                        // per-cell constant
+};
+
+// Constants of the step a thread is about to run (a_i against the tile's rows / columns), fetched one step ahead in
+// the shadow of the barrier (batch_thread_prepare).
+template <class C>
+struct BatchConsts {
+    uint32_t cAB[C::RJ], tB[C::RJ], cAC[C::RK], tC[C::RK];
 };
 
 // thread id -> position in the TJ x TK thread grid.  A quarter-warp holds 8 consecutive tk of one tj
@@ -95,16 +104,21 @@ TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf)
         const uint32_t cp = (uint32_t)S.seq[buf][2][0][p] | ((uint32_t)S.seq[buf][2][1][p] << 16);
         const uint32_t nab = neq_flag(ap, bp), nac = neq_flag(ap, cp);
         S.tabAB[buf][code][p] = pair_const(nab);
-        S.tabMB[buf][code][p] = eq_mask(nab);
+        S.tabMB[buf][code][p] = triple_row_const(nab);
         S.tabAC[buf][code][p] = pair_const(nac);
+        S.tabMC[buf][code][p] = triple_col_const(nac);
+        if (code == 0) {
+            S.bpk[buf][p] = bp;
+            S.cpk[buf][p] = cp;
+        }
     }
     for (int p = tid; p < 64; p += C::NT) S.acode[buf][p] = (uint8_t)(S.seq[buf][0][0][p] | (S.seq[buf][0][1][p] << 2));
 }
 
-// ---- one wavefront step of one thread ----
+// ---- the part of step s that does not depend on the neighbours' step s-1 (runs between arrive and wait) ----
 template <class C>
-TA_HD void batch_thread_step(BatchRegs<C> &R, BatchSmem<C> &S, const BatchArgs &A, int tj, int tk, int s, int P,
-                             long long pair_base)
+TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
+                                int tk, int s)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int u = s - (tj + tk);
@@ -116,36 +130,42 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, BatchSmem<C> &S, const BatchArgs &
     if (i == 1) {
         // new pair enters this thread: plane 0 is the all-zero border (src/PE_1cyc.v:164-178 override), and the
         // tile's (b,c) constants change
-        uint32_t bp[RJ], cp[RK];
-#pragma unroll
-        for (int r = 0; r < RJ; ++r)
-            bp[r] = (uint32_t)S.seq[buf][1][0][j0 + r] | ((uint32_t)S.seq[buf][1][1][j0 + r] << 16);
-#pragma unroll
-        for (int c = 0; c < RK; ++c)
-            cp[c] = (uint32_t)S.seq[buf][2][0][k0 + c] | ((uint32_t)S.seq[buf][2][1][k0 + c] << 16);
+        const uint32_t zb = phi(A, 0, j0 + 1, k0 + 1);
 #pragma unroll
         for (int r = 0; r < RJ; ++r)
 #pragma unroll
             for (int c = 0; c < RK; ++c) {
-                const uint32_t z = phi(A, 0, j0 + r + 1, k0 + c + 1);
+                const uint32_t z = zb + (uint32_t)(r + c) * 0x00020002u;
                 R.all[r][c] = z; R.wX[r][c] = z; R.u1[r][c] = z; R.u3[r][c] = z;
-                const uint32_t nbc = neq_flag(bp[r], cp[c]);
+                const uint32_t nbc = neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]);
                 R.cBC[r][c] = pair_const(nbc);
-                R.U[r][c] = triple_u(nbc);
             }
     }
 
-    // per-step constants: a_i against the tile's rows / columns
     const int code = S.acode[buf][i - 1];
     TA_CHECK(code >= 0 && code < 16);
-    uint32_t cAB[RJ], mAB[RJ], cAC[RK];
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
-        cAB[r] = S.tabAB[buf][code][j0 + r];
-        mAB[r] = S.tabMB[buf][code][j0 + r];
+        K.cAB[r] = S.tabAB[buf][code][j0 + r];
+        K.tB[r] = S.tabMB[buf][code][j0 + r];
     }
 #pragma unroll
-    for (int c = 0; c < RK; ++c) cAC[c] = S.tabAC[buf][code][k0 + c];
+    for (int c = 0; c < RK; ++c) {
+        K.cAC[c] = S.tabAC[buf][code][k0 + c];
+        K.tC[c] = S.tabMC[buf][code][k0 + c];
+    }
+}
+
+// ---- one wavefront step of one thread: halos published at step s-1 -> tile -> publish for step s+1 ----
+template <class C>
+TA_HD void batch_thread_step(BatchRegs<C> &R, const BatchConsts<C> &K, BatchSmem<C> &S, const BatchArgs &A, int tj,
+                             int tk, int s, int P, long long pair_base)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    const int u = s - (tj + tk);
+    const int p = u >> 6;
+    const int i = (u & 63) + 1;
+    const int j0 = tj * RJ, k0 = tk * RK;
 
     // halos: top = bottom row of thread (tj-1,tk), left = right column of (tj,tk-1), both published at step s-1.
     // T_u2/T_all[c] belong to column k0+c (c = 0 is the corner cell, c = RK the cell above-right of the tile);
@@ -217,9 +237,9 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, BatchSmem<C> &S, const BatchArgs &
             const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
             const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
             const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
-            const uint32_t cM = triple_const(mAB[r], R.U[r][c]);
-            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, cAB[r],
-                                                 R.cBC[r][c], cAC[c], nullptr);
+            const uint32_t cM = triple_const(K.tB[r], K.tC[c]);
+            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
+                                                 R.cBC[r][c], K.cAC[c], nullptr);
             n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
             n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
         }

@@ -12,7 +12,8 @@
 //     to Ixy (i+1,j+1,k)  : u1 = max(all-1, hC)   (= gXY+1)      to Ix: wX = max(max(u3,u1)-1, Ix)  (= gX+2)
 //     to Iyz (i,j+1,k+1)  : u2 = max(all-1, hA)                   to Iy: wY = max(max(u2,u1)-1, Iy)
 //     to Ixz (i+1,j,k+1)  : u3 = max(all-1, hB)                   to Iz: wZ = max(max(u2,u3)-1, Iz)
-// 14 max-type instructions (VIMNMX3 / VIMNMX / VIADDMNMX, .U16x2) per cell instead of 49 adds + 42 maxes.
+// 11 max-type instructions (VIMNMX3 / VIADDMNMX, .U16x2) per cell instead of 49 adds + 42 maxes: wX is evaluated as
+// max3(u3-1, u1-1, Ix) with the decrements as plain 32-bit subtractions (see cell_update).
 //
 // Potential trick: values are stored as  v~ = v + 2*(i+j+k) + base  (offset binary, unsigned 16-bit lanes).  A gap
 // move advances i+j+k by 1, so the "-2" of gX/gY/gZ is absorbed (Ix~ = wX directly); pair moves add (s+3) in {2,4}
@@ -45,6 +46,10 @@
 #define TA_CHECK(cond) ((void)0)
 #endif
 
+#if defined(__CUDACC__)
+static __constant__ uint32_t trialign_fma_one = 1;  // opaque multiplier of fast::fadd
+#endif
+
 namespace trialign {
 namespace fast {
 
@@ -58,7 +63,13 @@ TA_HD uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c) { return __vimax3_u16x2
 TA_HD uint32_t vmin3(uint32_t a, uint32_t b, uint32_t c) { return __vimin3_u16x2(a, b, c); }
 // max(a - 1, c) per half
 TA_HD uint32_t vdecmax(uint32_t a, uint32_t c) { return __viaddmax_u16x2(a, 0xFFFFFFFFu, c); }
+// max(a + b, c) per half (the add wraps per half)
+TA_HD uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c) { return __viaddmax_u16x2(a, b, c); }
+// a + b issued as IMAD on the FMA pipe: the multiplier is a __constant__ the compiler cannot fold, so ptxas cannot
+// turn it back into an ALU-pipe IADD3 / VIADD (the ALU pipe is the bound, the FMA pipe idles otherwise)
+TA_HD uint32_t fadd(uint32_t a, uint32_t b) { return a * ::trialign_fma_one + b; }
 #else
+TA_HD uint32_t fadd(uint32_t a, uint32_t b) { return a + b; }
 TA_HD uint32_t vmax2(uint32_t a, uint32_t b)
 {
     const uint32_t lo = (a & 0xFFFFu) > (b & 0xFFFFu) ? (a & 0xFFFFu) : (b & 0xFFFFu);
@@ -78,6 +89,11 @@ TA_HD uint32_t vdecmax(uint32_t a, uint32_t c)
     const uint32_t dec = (((a & 0xFFFFu) + 0xFFFFu) & 0xFFFFu) | ((((a >> 16) + 0xFFFFu) & 0xFFFFu) << 16);
     return vmax2(dec, c);
 }
+TA_HD uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c)
+{
+    const uint32_t sum = (((a & 0xFFFFu) + (b & 0xFFFFu)) & 0xFFFFu) | ((((a >> 16) + (b >> 16)) & 0xFFFFu) << 16);
+    return vmax2(sum, c);
+}
 #endif
 
 // Reduced outputs of one cell, all in the cell's own potential.
@@ -90,39 +106,48 @@ struct CellOut {
 //   p_u1   = u1(i-1,j-1,k)      p_u2 = u2(i,j-1,k-1) p_u3 = u3(i-1,j,k-1)
 //   cM in {3,6,9} = S3+6,  cAB/cBC/cAC in {2,4} = pair score + 3   (packed, per half)
 // Returns the 7 states through st[] (M,Ix,Iy,Iz,Ixy,Iyz,Ixz in potential form) when WANT_STATES.
+//
+// Pipe balance (profiles/alu_peak.json: the integer-ALU pipe issues 2 warp-instr/clk/SM and is the bound; plain
+// 32-bit adds can also issue as IMAD on the FMA pipe): 11 max-type instructions on the ALU pipe -- the M add is fused
+// into the `all` reduction (VIADDMNMX) and the three "-1" of wX/wY/wZ are plain 32-bit subtractions of 0x00010001.
+// Those are lane-exact as long as the LOW lane is >= 1, which holds for every live value (potentials are >= base -
+// envelope > 0, common.cuh); a dead low lane can only disturb a dead high lane (the halves of a word start and stop
+// together in BATCH mode, and in LONG mode the low half stays live -- clamped a index -- until the high half ends).
 template <bool WANT_STATES>
 TA_HD CellOut cell_update(uint32_t p_all, uint32_t p_wX, uint32_t p_wY, uint32_t p_wZ, uint32_t p_u1, uint32_t p_u2,
                           uint32_t p_u3, uint32_t cM, uint32_t cAB, uint32_t cBC, uint32_t cAC, uint32_t *st)
 {
-    const uint32_t M = p_all + cM;
     const uint32_t X = p_wX, Y = p_wY, Z = p_wZ;
-    const uint32_t XY = p_u1 + cAB;
-    const uint32_t YZ = p_u2 + cBC;
-    const uint32_t XZ = p_u3 + cAC;
+    const uint32_t XY = fadd(p_u1, cAB);
+    const uint32_t YZ = fadd(p_u2, cBC);
+    const uint32_t XZ = fadd(p_u3, cAC);
     if (WANT_STATES) {
-        st[0] = M; st[1] = X; st[2] = Y; st[3] = Z; st[4] = XY; st[5] = YZ; st[6] = XZ;
+        st[0] = p_all + cM; st[1] = X; st[2] = Y; st[3] = Z; st[4] = XY; st[5] = YZ; st[6] = XZ;
     }
     CellOut o;
     const uint32_t hC = vmax3(X, Y, XY);
     const uint32_t hA = vmax3(Y, Z, YZ);
     const uint32_t hB = vmax3(X, Z, XZ);
-    o.all = vmax2(vmax3(M, hC, hA), hB);
+    o.all = vaddmax(p_all, cM, vmax3(hC, hA, hB));
     o.u1 = vdecmax(o.all, hC);
     o.u2 = vdecmax(o.all, hA);
     o.u3 = vdecmax(o.all, hB);
-    o.wX = vdecmax(vmax2(o.u3, o.u1), X);
-    o.wY = vdecmax(vmax2(o.u2, o.u1), Y);
-    o.wZ = vdecmax(vmax2(o.u2, o.u3), Z);
+    const uint32_t d1 = fadd(o.u1, 0u - kOnes), d2 = fadd(o.u2, 0u - kOnes), d3 = fadd(o.u3, 0u - kOnes);
+    o.wX = vmax3(d3, d1, X);
+    o.wY = vmax3(d2, d1, Y);
+    o.wZ = vmax3(d2, d3, Z);
     return o;
 }
 
 // pair-score constants from 2-bit symbols packed one per half (x, y in {0..3} per half)
 TA_HD uint32_t neq_flag(uint32_t x, uint32_t y) { return vmin2(x ^ y, kOnes); }       // 1 where x != y, per half
 TA_HD uint32_t pair_const(uint32_t neq) { return 0x00040004u - 2u * neq; }             // {4 (equal), 2 (differ)}
-TA_HD uint32_t triple_u(uint32_t neq_bc) { return 0x00060006u - 3u * neq_bc; }         // U = 3+3*[b==c]
-TA_HD uint32_t eq_mask(uint32_t neq) { return (kOnes - neq) * 0xFFFFu; }               // 0xFFFF where equal
-// cM = 3 + ([a==b] ? U : 0)   ->  {9 (a=b=c), 6 (a=b!=c), 3 (a!=b)} = S3 + 6   (src/PE_1cyc.v:162)
-TA_HD uint32_t triple_const(uint32_t mAB, uint32_t U) { return 0x00030003u + (mAB & U); }
+// S3 + 6 = {9 (a=b=c), 6 (a=b!=c), 3 (a!=b)} (src/PE_1cyc.v:162) factorises into a row and a column constant:
+//   cM = min(tB, tC),  tB = 9 - 6*[a!=b] in {9,3},  tC = 9 - 3*[a!=c] in {9,6}
+// (a!=b -> 3 whatever c is; a=b -> b=c iff a=c, so tC decides between 9 and 6).  No per-cell (b,c) constant needed.
+TA_HD uint32_t triple_row_const(uint32_t neq_ab) { return 0x00090009u - 6u * neq_ab; }
+TA_HD uint32_t triple_col_const(uint32_t neq_ac) { return 0x00090009u - 3u * neq_ac; }
+TA_HD uint32_t triple_const(uint32_t tB, uint32_t tC) { return vmin2(tB, tC); }
 
 }  // namespace fast
 }  // namespace trialign

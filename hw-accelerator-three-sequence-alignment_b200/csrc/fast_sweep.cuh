@@ -93,8 +93,9 @@ struct SweepSmem {
     uint32_t corner[2][2][C::TJ][C::TK];      // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
     uint32_t cornerL[2][2][C::TJ];            // [slot][u2,all(old)][tj]  corner cell of the tiles on the block's left edge
     uint32_t tabAB[16][C::TAB_STRIDE];        // [a code][j]  pair constant {4,2}
-    uint32_t tabMB[16][C::TAB_STRIDE];        // [a code][j]  0xFFFF where a == b
-    uint32_t tabAC[16][C::TAB_STRIDE];        // [a code][k]
+    uint32_t tabMB[16][C::TAB_STRIDE];        // [a code][j]  triple row constant {9,3}
+    uint32_t tabAC[16][C::TAB_STRIDE];        // [a code][k]  pair constant {4,2}
+    uint32_t tabMC[16][C::TAB_STRIDE];        // [a code][k]  triple column constant {9,6}
     uint8_t seqA[2][C::LA_MAX];               // [half][i]   (LONG: only [0] is used)
     uint8_t seqB[2][64], seqC[2][64];         // [half][pos in block]
     SweepTask task;
@@ -103,7 +104,7 @@ struct SweepSmem {
 template <class C>
 struct SweepRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
-    uint32_t cBC[C::RJ][C::RK], U[C::RJ][C::RK];                                       // per-cell constants
+    uint32_t cBC[C::RJ][C::RK];                                                        // per-cell constant
     uint32_t viol;                                                                     // range-check violations seen
 };
 
@@ -216,8 +217,9 @@ TA_HD void sweep_build_tables(SweepSmem<C> &S, int tid)
         const uint32_t cp = (uint32_t)S.seqC[0][p] | ((uint32_t)S.seqC[1][p] << 16);
         const uint32_t nab = neq_flag(ap, bp), nac = neq_flag(ap, cp);
         S.tabAB[code][p] = pair_const(nab);
-        S.tabMB[code][p] = eq_mask(nab);
+        S.tabMB[code][p] = triple_row_const(nab);
         S.tabAC[code][p] = pair_const(nac);
+        S.tabMC[code][p] = triple_col_const(nac);
     }
 }
 
@@ -234,7 +236,6 @@ TA_HD void sweep_init_thread(SweepRegs<C> &R, const SweepSmem<C> &S, int tj, int
             const uint32_t cp = (uint32_t)S.seqC[0][k0 + c] | ((uint32_t)S.seqC[1][k0 + c] << 16);
             const uint32_t nbc = neq_flag(bp, cp);
             R.cBC[r][c] = pair_const(nbc);
-            R.U[r][c] = triple_u(nbc);
             R.all[r][c] = R.wX[r][c] = R.u1[r][c] = R.u3[r][c] = 0;
         }
     R.viol = 0;
@@ -392,14 +393,17 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
     ia1 = ia1 < 0 ? 0 : (ia1 >= A.la ? A.la - 1 : ia1);
     const int code = S.seqA[0][ia0] | (S.seqA[C::LONG ? 0 : 1][ia1] << 2);
     TA_CHECK(code >= 0 && code < 16);
-    uint32_t cAB[RJ], mAB[RJ], cAC[RK];
+    uint32_t cAB[RJ], tB[RJ], cAC[RK], tC[RK];
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
         cAB[r] = S.tabAB[code][j0 + r];
-        mAB[r] = S.tabMB[code][j0 + r];
+        tB[r] = S.tabMB[code][j0 + r];
     }
 #pragma unroll
-    for (int c = 0; c < RK; ++c) cAC[c] = S.tabAC[code][k0 + c];
+    for (int c = 0; c < RK; ++c) {
+        cAC[c] = S.tabAC[code][k0 + c];
+        tC[c] = S.tabMC[code][k0 + c];
+    }
 
     // halos (see fast_batch.cuh); index 0 of the first dimension of row/col is the block halo
     uint32_t T_wY[RK], T_u1[RK], T_u2[RK + 1], T_all[RK + 1], L_wZ[RJ], L_u3[RJ], L_u2[RJ], L_all[RJ];
@@ -472,7 +476,7 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
             const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
             const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
             const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
-            const uint32_t cM = triple_const(mAB[r], R.U[r][c]);
+            const uint32_t cM = triple_const(tB[r], tC[c]);
             const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, cAB[r],
                                                  R.cBC[r][c], cAC[c], nullptr);
             n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
@@ -568,7 +572,7 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
                         const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
                         const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
                         cell_update<true>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3,
-                                          triple_const(mAB[r], R.U[r][c]), cAB[r], R.cBC[r][c], cAC[c], st);
+                                          triple_const(tB[r], tC[c]), cAB[r], R.cBC[r][c], cAC[c], st);
                     }
             // potential of the cell in each half's own frame
             const int off_lo = A.base + 2 * (A.la + jl + kl);

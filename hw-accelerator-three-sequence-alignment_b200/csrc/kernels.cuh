@@ -19,10 +19,6 @@ bool fast_batch_supports(int len);
 int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                    int64_t n, int len, int32_t *d_scores);
 
-// K1w: same job as K1 with eight asynchronous warp-wide systolic arrays per CTA (fast_warp.cu)
-int fast_warp_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c, int64_t n,
-                  int len, int32_t *d_scores);
-
 // K2: block-sweep kernels for long triples (fast_sweep.cu); same exactness condition as K1 plus the 16-bit envelope
 // checked by fast_sweep_supports().
 bool fast_sweep_supports(int la, int lb, int lc);

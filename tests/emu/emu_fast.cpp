@@ -34,12 +34,27 @@ extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t 
         for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
         for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
         const int steps = batch_total_steps<C>(P);
+        std::vector<BatchConsts<C>> K(C::NT);
+        std::memset(S->bpk[1], 0, sizeof S->bpk[1]);
+        std::memset(S->cpk[1], 0, sizeof S->cpk[1]);
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            thread_pos<C>(tid, tj, tk);
+            batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, 0);
+        }
+        // the kernel's schedule: step s | arrive | uniform actions, prepare s+1 | wait.  Two passes per step: nothing
+        // written after the arrive (pair staging, registers) may be needed by another thread's step s.
         for (int s = 0; s <= steps; ++s) {
             for (int tid = 0; tid < C::NT; ++tid) {
                 int tj, tk;
                 thread_pos<C>(tid, tj, tk);
+                batch_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+            }
+            for (int tid = C::NT - 1; tid >= 0; --tid) {
+                int tj, tk;
+                thread_pos<C>(tid, tj, tk);
                 batch_uniform_actions<C>(*S, A, tid, s, P, pair_base);
-                batch_thread_step<C>(R[tid], *S, A, tj, tk, s, P, pair_base);
+                batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, s + 1);
             }
         }
     }
@@ -240,84 +255,6 @@ extern "C" int emu_fast_sweep_batch(const uint8_t *a, const uint8_t *b, const ui
                     cta.step(A, s);
                 }
             }
-        }
-    }
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// K1w (fast_warp.cuh): eight asynchronous warps per CTA.  Warps take turns; a warp whose ring conditions are not met
-// skips its turn (the kernel spins).  Shuffles are emulated after all 32 lanes of a warp have finished their step.
-// ---------------------------------------------------------------------------------------------------------------
-#include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_warp.cuh"
-
-extern "C" int emu_fast_warp(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
-                             int pairs_per_cta, int schedule_seed, int32_t *scores)
-{
-    using C = WarpCfg;
-    if (len < 1 || len > 64 || n < 0) return -1;
-    WarpArgs A;
-    A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
-    A.pairs_total = (n + 1) / 2;
-    A.pairs_per_cta = pairs_per_cta;
-    A.base = base;
-    auto S = std::make_unique<WarpSmem>();
-    std::vector<LaneRegs> R((size_t)C::NW * 32);
-    std::vector<LaneOut> O(32);
-    unsigned rng = 12345u + (unsigned)schedule_seed;
-    for (long long pair_base = 0; pair_base < A.pairs_total; pair_base += pairs_per_cta) {
-        const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
-        const int last = warp_total_steps(P);
-        std::memset(S.get(), 0xA5, sizeof(WarpSmem));
-        std::memset(R.data(), 0x5A, R.size() * sizeof(LaneRegs));
-        int wstep[C::NW];
-        for (int wid = 0; wid < C::NW; ++wid) {
-            const int wa = wid / C::WB, wb = wid % C::WB;
-            S->produced[wa][wb] = S->consumed_top[wa][wb] = S->consumed_left[wa][wb] = 0;
-            std::memset(S->w[wid].acode[1], 0, 64);
-            std::memset(S->w[wid].seqB[1], 0, sizeof S->w[wid].seqB[1]);
-            std::memset(S->w[wid].seqC[1], 0, sizeof S->w[wid].seqC[1]);
-            for (int lane = 0; lane < 32; ++lane) warp_load_pair(S->w[wid], A, lane, wa, wb, pair_base, 0);
-            for (int lane = 0; lane < 32; ++lane) warp_build_tables(S->w[wid], lane, 0);
-            wstep[wid] = 0;
-        }
-        int finished = 0, idle = 0;
-        while (finished < C::NW) {
-            bool progressed = false;
-            for (int turn = 0; turn < C::NW; ++turn) {
-                // pseudo-random warp order and burst length: exercises run-ahead up to the ring depth
-                rng = rng * 1664525u + 1013904223u;
-                const int wid = schedule_seed ? (int)((rng >> 16) % C::NW) : turn;
-                const int burst = schedule_seed ? 1 + (int)((rng >> 8) % 5) : 1;
-                for (int rep_ = 0; rep_ < burst; ++rep_) {
-                    const int wa = wid / C::WB, wb = wid % C::WB, w = wstep[wid];
-                    if (w > last) break;
-                    if (!warp_can_step(*S, wa, wb, w, last, wa > 0 ? S->produced[wa - 1][wb] : 0,
-                                       wb > 0 ? S->produced[wa][wb - 1] : 0, wa + 1 < C::WA ? S->consumed_top[wa + 1][wb] : 0,
-                                       wb + 1 < C::WB ? S->consumed_left[wa][wb + 1] : 0))
-                        break;
-                    if (warp_rebuild_step(w)) {
-                        const int q = (w >> 6) + 1;
-                        if (q < P) {
-                            for (int lane = 0; lane < 32; ++lane) warp_load_pair(S->w[wid], A, lane, wa, wb, pair_base + q, q & 1);
-                            for (int lane = 0; lane < 32; ++lane) warp_build_tables(S->w[wid], lane, q & 1);
-                        }
-                    }
-                    for (int lane = 0; lane < 32; ++lane)
-                        warp_lane_step(R[(size_t)wid * 32 + lane], *S, A, wa, wb, lane / C::LK, lane % C::LK, w, P, pair_base,
-                                       last, O[lane]);
-                    if (wa > 0) S->consumed_top[wa][wb] = w + C::TOP_LEAD + 1;
-                    if (wb > 0) S->consumed_left[wa][wb] = w + C::LEFT_LEAD + 1;
-                    S->produced[wa][wb] = w + 1;
-                    for (int lane = 0; lane < 32; ++lane)  // __shfl_up_sync: lanes below delta keep their own value
-                        warp_take_halo(R[(size_t)wid * 32 + lane].H, O[lane >= C::LK ? lane - C::LK : lane],
-                                       O[lane >= 1 ? lane - 1 : lane]);
-                    progressed = true;
-                    if (++wstep[wid] > last) ++finished;
-                }
-            }
-            if (!progressed && ++idle > 64) return -2;  // deadlock
-            if (progressed) idle = 0;
         }
     }
     return 0;

@@ -137,22 +137,3 @@ def test_sweep_i_slab_pipeline(emu_sweep, ob, shape, n_slabs, n_ctas):
     assert rc == 0
     es, efin = ob.score(a, b, c, 16)
     assert int(out[0]) == es and out[1:].tolist() == efin.tolist()
-
-
-@pytest.mark.parametrize("ln,n,ppc,seed", [(1, 2, 1, 0), (5, 2, 1, 0), (17, 2, 1, 0), (33, 2, 1, 0), (64, 7, 3, 0),
-                                           (64, 8, 2, 5), (40, 5, 1, 7), (63, 3, 5, 9), (17, 9, 4, 11), (64, 12, 6, 3)])
-def test_warp_systolic_batch_kernel_choreography(emu, ob, ln, n, ppc, seed):
-    """K1w: eight asynchronous warps with shuffles inside a warp and rings between warps; seed != 0 runs the warps in
-    a pseudo-random order with bursts, so that producers run ahead by up to the ring depth."""
-    emu.emu_fast_warp.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
-    rng = np.random.default_rng(ln * 100 + n)
-    a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
-    b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
-    c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
-    for t in range(0, n, 2):
-        a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
-    out = np.full(n, -99999, np.int32)
-    rc = emu.emu_fast_warp(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, 160, ppc, seed,
-                           out.ctypes.data_as(i32p))
-    assert rc == 0, "emulated warps deadlocked" if rc == -2 else rc
-    assert out.tolist() == ob.score_batch(a, b, c, 16).tolist()

@@ -25,7 +25,7 @@ def batch(n, ln, w=16):
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
 if which in ("all", "k1"):
-    batch(9, 64)       # K1 (or K1w with TRIALIGN_K1=w)
+    batch(9, 64)       # K1
 if which in ("all", "k2b"):
     batch(3, 130)      # K2 batch: 3x3 blocks per pair
 if which in ("all", "k2l"):
