@@ -8,7 +8,9 @@ namespace trialign {
 
 namespace {
 
-using Cfg = fast::BatchCfg<4, 4, 16, 16>;
+using Cfg256 = fast::BatchCfg<4, 4, 16, 16>;  // 256 threads, 4x4 cells each, <= 255 registers
+using Cfg512 = fast::BatchCfg<4, 2, 16, 32>;  // 512 threads, 4x2 cells each, <= 128 registers: 4 warps per scheduler
+using Cfg256L = fast::BatchCfg<4, 4, 16, 16, 2>;  // edges consumed two steps after publication (lagged barrier)
 
 // Split-phase CTA barrier (mbarrier, one arrival per warp): a thread ARRIVES as soon as its tile edges of step s are
 // published and WAITS only when it needs its neighbours' edges for step s+1; the work in between (per-pair reset,
@@ -36,12 +38,12 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-template <bool SPLIT>
+template <class Cfg, bool SPLIT>
 __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
-    __shared__ __align__(8) uint64_t step_bar;
+    __shared__ __align__(8) uint64_t step_bar[2];
     const int tid = threadIdx.x;
     const long long pair_base = (long long)blockIdx.x * A.pairs_per_cta;
     long long left = A.pairs_total - pair_base;
@@ -50,14 +52,20 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs 
     int tj, tk;
     fast::thread_pos<Cfg>(tid, tj, tk);
 
-    if (tid == 0) bar_init(&step_bar, Cfg::NT / 32);
-    // threads that are still filling the pipeline (local step < 0) index buffer 1: give it in-range contents
-    for (int e = tid; e < 64; e += Cfg::NT) {
-        S.acode[1][e] = 0;
-        S.bpk[1][e] = 0;
-        S.cpk[1][e] = 0;
+    if (tid == 0) {
+        bar_init(&step_bar[0], Cfg::NT / 32);
+        bar_init(&step_bar[1], Cfg::NT / 32);
     }
-    for (int e = tid; e < 3 * 2 * 64; e += Cfg::NT) (&S.seq[1][0][0][0])[e] = 0;
+    // threads that are filling / draining the pipeline index buffers no pair was staged into: give them in-range
+    // contents
+    for (int fill = 1; fill < Cfg::NBUF; ++fill) {
+        for (int e = tid; e < 64; e += Cfg::NT) {
+            S.acode[fill][e] = 0;
+            S.bpk[fill][e] = 0;
+            S.cpk[fill][e] = 0;
+        }
+        for (int e = tid; e < 3 * 2 * 64; e += Cfg::NT) (&S.seq[fill][0][0][0])[e] = 0;
+    }
     fast::load_pair_sequences<Cfg>(S, A, tid, pair_base, 0);
     __syncthreads();
     fast::build_pair_tables<Cfg>(S, tid, 0);
@@ -69,12 +77,22 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs 
     const int steps = fast::batch_total_steps<Cfg>(P);
 #pragma unroll 1
     for (int s = 0; s <= steps; ++s) {
-        fast::batch_thread_step<Cfg>(R, K, S, A, tj, tk, s, P, pair_base);
-        if (SPLIT) bar_arrive_warp(&step_bar);
-        fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
-        fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, s + 1);
-        if (SPLIT) bar_wait(&step_bar, s & 1);
-        else __syncthreads();
+        if (Cfg::LAG == 2) {
+            // everybody has finished step s-2 (even and odd steps use separate barriers, so the one waited on is at
+            // most one phase ahead of this thread's own arrivals)
+            if (s >= 2) bar_wait(&step_bar[s & 1], ((s - 2) >> 1) & 1);
+            fast::batch_thread_step<Cfg>(R, K, S, A, tj, tk, s, P, pair_base);
+            bar_arrive_warp(&step_bar[s & 1]);
+            fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
+            fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, s + 1);
+        } else {
+            fast::batch_thread_step<Cfg>(R, K, S, A, tj, tk, s, P, pair_base);
+            if (SPLIT) bar_arrive_warp(&step_bar[0]);
+            fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
+            fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, s + 1);
+            if (SPLIT) bar_wait(&step_bar[0], s & 1);
+            else __syncthreads();
+        }
     }
 }
 
@@ -82,47 +100,66 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs 
 
 bool fast_batch_supports(int len) { return len >= 1 && len <= 64; }
 
-int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                   int64_t n, int len, int32_t *d_scores)
+namespace {
+
+template <class Cfg, bool SPLIT>
+int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant)
 {
-    if (n <= 0) return TRIALIGN_OK;
     static_assert(sizeof(fast::BatchSmem<Cfg>) <= 227 * 1024, "shared memory budget");
     const size_t smem = sizeof(fast::BatchSmem<Cfg>);
-    // One CTA per SM (the 128-register build that would allow two spills).  TRIALIGN_K1_BAR=sync selects the
-    // variant with a plain __syncthreads per step for comparison.
-    static const int variant = []() {
-        const char *e = std::getenv("TRIALIGN_K1_BAR");
-        return (e && e[0] == 's') ? 0 : 1;
-    }();
-    auto kernel = variant == 1 ? fast_batch_kernel<true> : fast_batch_kernel<false>;
-    static bool attr_set[kMaxDevices][2] = {};
-    if (!attr_set[ctx->device][variant]) {
+    auto kernel = fast_batch_kernel<Cfg, SPLIT>;
+    static bool attr_set[kMaxDevices] = {};
+    if (!attr_set[ctx->device]) {
         TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
-        attr_set[ctx->device][variant] = true;
+        attr_set[ctx->device] = true;
     }
-    fast::BatchArgs A;
-    A.a = d_a; A.b = d_b; A.c = d_c;
-    A.n = n; A.len = len; A.scores = d_scores;
-    A.pairs_total = (n + 1) / 2;
-    // one persistent CTA per SM slot; contiguous chunks so that the fill/drain is paid once per CTA
-    int occ = 1;
-    TA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, Cfg::NT, smem));
-    if (occ < 1) occ = 1;
-    const long long slots = (long long)ctx->sm_count * occ;
+    // one persistent CTA per SM; contiguous chunks so that the fill/drain is paid once per CTA
+    const long long slots = ctx->sm_count;
     long long ppc = (A.pairs_total + slots - 1) / slots;
     if (ppc < 1) ppc = 1;
     if (ppc > (1 << 20)) ppc = 1 << 20;  // keep the step counter far from int overflow
     A.pairs_per_cta = (int)ppc;
-    A.base = 2 * 64 + 32;  // >= 2*min(len)+8 plus the "-1" headroom of the reductions (common.cuh envelope)
     const long long grid = (A.pairs_total + ppc - 1) / ppc;
     if (std::getenv("TRIALIGN_DEBUG"))
-        std::fprintf(stderr, "[trialign] K1: occ=%d grid=%lld pairs/cta=%lld smem=%zu\n", occ, grid, ppc, smem);
+        std::fprintf(stderr, "[trialign] K1: variant=%d threads=%d grid=%lld pairs/cta=%lld smem=%zu\n", variant, Cfg::NT,
+                     grid, ppc, smem);
     kernel<<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TRIALIGN_OK;
+}
+
+}  // namespace
+
+int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                   int64_t n, int len, int32_t *d_scores)
+{
+    if (n <= 0) return TRIALIGN_OK;
+    // TRIALIGN_K1 selects a variant for comparison: "256" / "512" threads per CTA; suffix "m" = split-phase mbarrier
+    // instead of __syncthreads, suffix "l" = lagged barrier (LAG 2), e.g. TRIALIGN_K1=512m.
+    static const int variant = []() {
+        const char *e = std::getenv("TRIALIGN_K1");
+        int v = 0;  // default
+        if (e && e[0] == '5') v = 2;
+        if (e && e[0] && e[1] && e[2] && e[3] == 'm') v |= 1;
+        if (e && e[0] && e[1] && e[2] && e[3] == 'l') v |= 4;
+        return v;
+    }();
+    fast::BatchArgs A;
+    A.a = d_a; A.b = d_b; A.c = d_c;
+    A.n = n; A.len = len; A.scores = d_scores;
+    A.pairs_total = (n + 1) / 2;
+    A.pairs_per_cta = 1;
+    A.base = 2 * 64 + 32;  // >= 2*min(len)+8 plus the "-1" headroom of the reductions (common.cuh envelope)
+    switch (variant) {
+    case 1: return launch_batch<Cfg256, true>(ctx, st, A, variant);
+    case 2: return launch_batch<Cfg512, false>(ctx, st, A, variant);
+    case 3: return launch_batch<Cfg512, true>(ctx, st, A, variant);
+    case 4: return launch_batch<Cfg256L, true>(ctx, st, A, variant);
+    default: return launch_batch<Cfg256, false>(ctx, st, A, variant);
+    }
 }
 
 }  // namespace trialign

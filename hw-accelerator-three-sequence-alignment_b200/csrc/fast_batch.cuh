@@ -4,10 +4,12 @@
 // cells per side and the whole 64x64 (j,k) plane resident, so no slicing / face SRAM is needed at this length):
 //   * one CTA = TJ x TK threads; thread (tj,tk) owns the RJ x RK cells j in (tj*RJ, tj*RJ+RJ], k likewise, for ALL i;
 //   * the plane-(i-1) state of those cells (all, wX, u1, u3 -- see fast_core.cuh) lives in registers;
-//   * thread (tj,tk) works on plane i at global step s = i + tj + tk (wavefront skew, like PE(j,k) at step i+j+k);
-//   * neighbours exchange tile edges through shared memory, double buffered, one __syncthreads per step
+//   * thread (tj,tk) works on plane i at global step s = i + LAG*(tj + tk) (wavefront skew, like PE(j,k) at step
+//     i+j+k; LAG: see BatchCfg);
+//   * neighbours exchange tile edges through shared memory, double buffered, one CTA barrier per step
 //     (the counterpart of the PE-to-PE wires; the RTL's _d1/_d2 delay registers are the "old" values published
-//     one step late);
+//     one step late -- measured: keeping them in the consumer's registers instead, so that half of the halo loads
+//     leave the critical path, is slower, because it moves all stores to the end of the step);
 //   * two triples ride in the two 16-bit halves of every word; consecutive pairs of triples stream through the array
 //     back to back, so the (TJ+TK-2)-step fill/drain is paid once per CTA, not once per triple.
 // Per-pair score tables (a vs b, a vs c for all 16 combinations of the two a symbols) are rebuilt in shared memory
@@ -19,17 +21,42 @@
 namespace trialign {
 namespace fast {
 
-template <int RJ_, int RK_, int TJ_, int TK_>
+// LAG = steps between a thread and its top / left neighbour.  LAG 1: edges published at step s-1 are consumed at
+// step s, so every step ends with a CTA barrier that everybody waits for.  LAG 2: edges are consumed TWO steps after
+// they were published, so a thread only has to know that everybody finished step s-2 before it starts step s; the
+// barrier of step s-1 is never waited for directly and warps drift up to one step apart, which spreads the
+// shared-memory bursts at the start / end of a step over the other warps' tiles.
+template <int RJ_, int RK_, int TJ_, int TK_, int LAG_ = 1>
 struct BatchCfg {
-    static constexpr int RJ = RJ_, RK = RK_, TJ = TJ_, TK = TK_;
+    static constexpr int RJ = RJ_, RK = RK_, TJ = TJ_, TK = TK_, LAG = LAG_;
+    static constexpr int NSLOT = 2 * LAG;        // edge buffers: written at step s, read at step s+LAG
+    static constexpr int NBUF = LAG + 1;         // per-pair sequence / table buffers
     static constexpr int BJ = RJ * TJ, BK = RK * TK, NT = TJ * TK;
     static constexpr int L = 64;                 // planes per pair (sequences are padded to 64)
-    static constexpr int COL_STRIDE = BJ + 4;    // +16 B: conflict-free 128-bit column reads
-    static constexpr int TAB_STRIDE = 68;
-    static constexpr int SKEW = TJ + TK - 2;
+    // shared-memory strides (32-bit words), chosen so that the 8 / 16 lanes of one access wavefront (8 consecutive tk
+    // of one tj per quarter-warp, see thread_pos) fall into distinct banks
+    static constexpr int ROW_STRIDE = RK == 4 ? BK : BK + 16;   // 64-bit row accesses: two tj per wavefront
+    static constexpr int COL_STRIDE = BJ + 4;                   // 128-bit column accesses: lanes differ in tk
+    static constexpr int CORNER_STRIDE = TK + 8;                // 32-bit accesses: a warp spans 4 tj x 8 tk
+    static constexpr int TABJ_STRIDE = 68;                      // j-indexed tables: lanes of a wavefront differ in code only
+    static constexpr int TABK_STRIDE = 128;                     // k-indexed tables: {cAC, tC} per code, see tabk_index
+    static constexpr int SKEW = LAG * (TJ + TK - 2);
+    // pair q is staged into buffer q % NBUF while earlier pairs drain: LAG 1 (2 buffers): after pair q-2 has left the
+    // last thread, SKEW steps after pair q-1 entered; LAG 2 (3 buffers): pair q-3 left long ago
+    static constexpr int LOAD_AT = LAG == 1 ? SKEW + 2 : 8, BUILD_AT = LOAD_AT + 4;
+    static_assert(LAG == 1 || LAG == 2, "NSLOT must be a power of two");
     static_assert(BJ == 64 && BK == 64, "K1 keeps the whole 64x64 (j,k) plane in one CTA");
-    static_assert(RJ == 4 && RK == 4, "edge exchange is written for 4-word (128-bit) groups");
+    static_assert(RJ == 4 && (RK == 4 || RK == 2), "edge exchange is laid out for 128-bit / 64-bit groups");
+    static_assert(TK % 8 == 0 && TJ % 4 == 0 && BUILD_AT < L - 1, "thread_pos / staging schedule");
 };
+
+// position of the k-indexed constants (which = 0: cAC, 1: tC) inside a code's TABK_STRIDE words: a thread's RK values
+// of both kinds are fetched with 128-bit loads whose bank group depends on tk only (the codes differ between lanes)
+template <class C>
+TA_HD int tabk_index(int which, int k)
+{
+    return C::RK == 4 ? which * 64 + k : (k / C::RK) * (2 * C::RK) + which * C::RK + (k % C::RK);
+}
 
 struct BatchArgs {
     const uint8_t *a, *b, *c;  // [n][len] device
@@ -43,16 +70,15 @@ struct BatchArgs {
 
 template <class C>
 struct BatchSmem {
-    uint32_t row[2][4][C::TJ][C::BK];          // [slot][wY,u2,u1(old),all(old)][tj][k]   bottom rows
-    uint32_t col[2][4][C::TK][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk][j]   right columns
-    uint32_t corner[2][2][C::TJ][C::TK];       // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
-    uint32_t tabAB[2][16][C::TAB_STRIDE];      // [buf][a code][j]  pair constant {4,2}
-    uint32_t tabMB[2][16][C::TAB_STRIDE];      // [buf][a code][j]  triple row constant {9,3}
-    uint32_t tabAC[2][16][C::TAB_STRIDE];      // [buf][a code][k]  pair constant {4,2}
-    uint32_t tabMC[2][16][C::TAB_STRIDE];      // [buf][a code][k]  triple column constant {9,6}
-    uint32_t bpk[2][64], cpk[2][64];           // [buf][pos]  b / c symbols of the two triples, one per 16-bit half
-    uint8_t seq[2][3][2][64];                  // [buf][A,B,C][half][pos]
-    uint8_t acode[2][64];                      // a_lo | a_hi << 2
+    uint32_t row[C::NSLOT][4][C::TJ][C::ROW_STRIDE];  // [slot][wY,u2,u1(old),all(old)][tj][k]   bottom rows
+    uint32_t col[C::NSLOT][4][C::TK][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk][j]   right columns
+    uint32_t corner[C::NSLOT][2][C::TJ][C::CORNER_STRIDE];  // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
+    uint32_t tabAB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  pair constant {4,2}
+    uint32_t tabMB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  triple row constant {9,3}
+    uint32_t tabK[C::NBUF][16][C::TABK_STRIDE];      // [buf][a code][tabk_index]  pair constant {4,2} and triple column constant {9,6}
+    uint32_t bpk[C::NBUF][64], cpk[C::NBUF][64];           // [buf][pos]  b / c symbols of the two triples, one per 16-bit half
+    uint8_t seq[C::NBUF][3][2][64];                  // [buf][A,B,C][half][pos]
+    uint8_t acode[C::NBUF][64];                      // a_lo | a_hi << 2
 };
 
 template <class C>
@@ -69,13 +95,13 @@ struct BatchConsts {
 };
 
 // thread id -> position in the TJ x TK thread grid.  A quarter-warp holds 8 consecutive tk of one tj
-// (conflict-free 128-bit shared-memory accesses); a warp spans 4 tj x 8 tk (11 distinct skews).
+// (conflict-free shared-memory accesses, see BatchCfg); a warp spans 4 tj x 8 tk (11 distinct skews).
 template <class C>
 TA_HD void thread_pos(int tid, int &tj, int &tk)
 {
     const int lane = tid & 31, warp = tid >> 5;
-    tk = (lane & 7) + 8 * (warp & 1);
-    tj = (lane >> 3) + 4 * (warp >> 1);
+    tk = (lane & 7) + 8 * (warp % (C::TK / 8));
+    tj = (lane >> 3) + 4 * (warp / (C::TK / 8));
 }
 
 TA_HD uint32_t phi(const BatchArgs &A, int i, int jl, int kl) { return rep((uint32_t)(A.base + 2 * (i + jl + kl))); }
@@ -105,8 +131,8 @@ TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf)
         const uint32_t nab = neq_flag(ap, bp), nac = neq_flag(ap, cp);
         S.tabAB[buf][code][p] = pair_const(nab);
         S.tabMB[buf][code][p] = triple_row_const(nab);
-        S.tabAC[buf][code][p] = pair_const(nac);
-        S.tabMC[buf][code][p] = triple_col_const(nac);
+        S.tabK[buf][code][tabk_index<C>(0, p)] = pair_const(nac);
+        S.tabK[buf][code][tabk_index<C>(1, p)] = triple_col_const(nac);
         if (code == 0) {
             S.bpk[buf][p] = bp;
             S.cpk[buf][p] = cp;
@@ -121,10 +147,10 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
                                 int tk, int s)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
-    const int u = s - (tj + tk);
-    const int p = u >> 6;          // pair index within this CTA's chunk (negative while the pipeline fills)
+    const int u = s - C::LAG * (tj + tk);
+    const int p = u >> 6;          // pair index within this CTA's chunk (-1 while the pipeline fills)
     const int i = (u & 63) + 1;    // plane 1..64
-    const int buf = p & 1;
+    const int buf = (p + C::NBUF) % C::NBUF;
     const int j0 = tj * RJ, k0 = tk * RK;  // block-local index of the cell left/above the tile
 
     if (i == 1) {
@@ -151,8 +177,8 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
     }
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
-        K.cAC[c] = S.tabAC[buf][code][k0 + c];
-        K.tC[c] = S.tabMC[buf][code][k0 + c];
+        K.cAC[c] = S.tabK[buf][code][tabk_index<C>(0, k0 + c)];
+        K.tC[c] = S.tabK[buf][code][tabk_index<C>(1, k0 + c)];
     }
 }
 
@@ -162,7 +188,7 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, const BatchConsts<C> &K, BatchSmem
                              int tk, int s, int P, long long pair_base)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
-    const int u = s - (tj + tk);
+    const int u = s - C::LAG * (tj + tk);
     const int p = u >> 6;
     const int i = (u & 63) + 1;
     const int j0 = tj * RJ, k0 = tk * RK;
@@ -171,7 +197,9 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, const BatchConsts<C> &K, BatchSmem
     // T_u2/T_all[c] belong to column k0+c (c = 0 is the corner cell, c = RK the cell above-right of the tile);
     // L_u2/L_all[r] belong to row j0+r.  The corner cell belongs to thread (tj-1,tk-1), which is TWO steps ahead,
     // so its value is relayed by the left neighbour (which read it one step ago as its own T_*[RK]).
-    const int rs = (s - 1) & 1, ws = s & 1;
+    // "old" = plane i-1 values, which the neighbours publish one step late (the RTL's _d1/_d2 delay registers,
+    // src/PE_1cyc.v:80-109): they are known at the START of the publishing step, so those stores leave early.
+    const int rs = (s - C::LAG) & (C::NSLOT - 1), ws = s & (C::NSLOT - 1);
     uint32_t T_wY[RK], T_u1[RK], T_u2[RK + 1], T_all[RK + 1], L_wZ[RJ], L_u3[RJ], L_u2[RJ], L_all[RJ];
     if (tj > 0) {
 #pragma unroll
@@ -224,6 +252,17 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, const BatchConsts<C> &K, BatchSmem
     L_all[0] = T_all[0];
     S.corner[ws][0][tj][tk] = T_u2[RK];
     S.corner[ws][1][tj][tk] = T_all[RK];
+    // the plane i-1 half of this thread's own edges is already known
+#pragma unroll
+    for (int c = 0; c < RK; ++c) {
+        S.row[ws][2][tj][k0 + c] = R.u1[RJ - 1][c];
+        S.row[ws][3][tj][k0 + c] = R.all[RJ - 1][c];
+    }
+#pragma unroll
+    for (int r = 0; r < RJ; ++r) {
+        S.col[ws][2][tk][j0 + r] = R.u3[r][RK - 1];
+        S.col[ws][3][tk][j0 + r] = R.all[r][RK - 1];
+    }
 
     // the tile, row-major (within a plane a cell needs its j-1, k-1 and (j-1,k-1) neighbours)
     uint32_t n_all[RJ][RK], n_wX[RJ][RK], n_u1[RJ][RK], n_u3[RJ][RK], n_wY[RJ][RK], n_wZ[RJ][RK], n_u2[RJ][RK];
@@ -244,20 +283,16 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, const BatchConsts<C> &K, BatchSmem
             n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
         }
 
-    // publish the tile's bottom row and right column for step s+1 (old = plane i-1 values, see header)
+    // publish the plane-i half of the tile's bottom row and right column for the neighbours' step s+1
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
         S.row[ws][0][tj][k0 + c] = n_wY[RJ - 1][c];
         S.row[ws][1][tj][k0 + c] = n_u2[RJ - 1][c];
-        S.row[ws][2][tj][k0 + c] = R.u1[RJ - 1][c];
-        S.row[ws][3][tj][k0 + c] = R.all[RJ - 1][c];
     }
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
         S.col[ws][0][tk][j0 + r] = n_wZ[r][RK - 1];
         S.col[ws][1][tk][j0 + r] = n_u2[r][RK - 1];
-        S.col[ws][2][tk][j0 + r] = R.u3[r][RK - 1];
-        S.col[ws][3][tk][j0 + r] = R.all[r][RK - 1];
     }
 
     // Score = max of the 7 states of cell (len,len,len) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
@@ -292,8 +327,8 @@ TA_HD void batch_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, i
 {
     const int q = (s >> 6) + 1;  // pair that starts entering the array at step 64*q
     if (q < P) {
-        if ((s & 63) == 32) load_pair_sequences<C>(S, A, tid, pair_base + q, q & 1);
-        if ((s & 63) == 34) build_pair_tables<C>(S, tid, q & 1);
+        if ((s & 63) == C::LOAD_AT) load_pair_sequences<C>(S, A, tid, pair_base + q, q % C::NBUF);
+        if ((s & 63) == C::BUILD_AT) build_pair_tables<C>(S, tid, q % C::NBUF);
     }
 }
 

@@ -13,10 +13,10 @@
 
 using namespace trialign::fast;
 
-extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
-                              int pairs_per_cta, int32_t *scores)
+template <class C>
+static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                              int pairs_per_cta, int schedule_seed, int32_t *scores)
 {
-    using C = BatchCfg<4, 4, 16, 16>;
     if (len < 1 || len > 64 || n < 0) return -1;
     BatchArgs A;
     A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
@@ -29,36 +29,87 @@ extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t 
         const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
         std::memset(S.get(), 0xA5, sizeof(BatchSmem<C>));  // poison: nothing may be read before it is written
         std::memset(R.data(), 0x5A, R.size() * sizeof(BatchRegs<C>));
-        std::memset(S->acode[1], 0, sizeof S->acode[1]);  // as the kernel prologue does
-        std::memset(S->seq[1], 0, sizeof S->seq[1]);
+        for (int fill = 1; fill < C::NBUF; ++fill) {  // as the kernel prologue does
+            std::memset(S->acode[fill], 0, sizeof S->acode[fill]);
+            std::memset(S->seq[fill], 0, sizeof S->seq[fill]);
+            std::memset(S->bpk[fill], 0, sizeof S->bpk[fill]);
+            std::memset(S->cpk[fill], 0, sizeof S->cpk[fill]);
+        }
         for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
         for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
         const int steps = batch_total_steps<C>(P);
         std::vector<BatchConsts<C>> K(C::NT);
-        std::memset(S->bpk[1], 0, sizeof S->bpk[1]);
-        std::memset(S->cpk[1], 0, sizeof S->cpk[1]);
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             thread_pos<C>(tid, tj, tk);
             batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, 0);
         }
-        // the kernel's schedule: step s | arrive | uniform actions, prepare s+1 | wait.  Two passes per step: nothing
-        // written after the arrive (pair staging, registers) may be needed by another thread's step s.
-        for (int s = 0; s <= steps; ++s) {
-            for (int tid = 0; tid < C::NT; ++tid) {
-                int tj, tk;
-                thread_pos<C>(tid, tj, tk);
-                batch_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+        if (C::LAG == 1) {
+            // the kernel's schedule: step s | arrive | uniform actions, prepare s+1 | wait.  Two passes per step: nothing
+            // written after the arrive (pair staging, registers) may be needed by another thread's step s.
+            for (int s = 0; s <= steps; ++s) {
+                for (int tid = 0; tid < C::NT; ++tid) {
+                    int tj, tk;
+                    thread_pos<C>(tid, tj, tk);
+                    batch_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+                }
+                for (int tid = C::NT - 1; tid >= 0; --tid) {
+                    int tj, tk;
+                    thread_pos<C>(tid, tj, tk);
+                    batch_uniform_actions<C>(*S, A, tid, s, P, pair_base);
+                    batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, s + 1);
+                }
             }
-            for (int tid = C::NT - 1; tid >= 0; --tid) {
-                int tj, tk;
-                thread_pos<C>(tid, tj, tk);
-                batch_uniform_actions<C>(*S, A, tid, s, P, pair_base);
-                batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, s + 1);
+        } else {
+            // lagged barrier: a WARP may run step s as soon as every warp has finished step s-2, so warps drift up to
+            // one step apart.  Warps are advanced in a pseudo-random order (schedule_seed), one whole step per turn
+            // (step | arrive | uniform actions, prepare s+1), lanes in order -- lanes of a warp never read each other's
+            // edges of the same step.
+            constexpr int NW = C::NT / 32;
+            std::vector<int> done(NW, -1);  // last finished step per warp
+            uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)schedule_seed;
+            int finished = 0;
+            while (finished < NW) {
+                rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+                int w = (int)((rng >> 33) % NW);
+                const int burst = schedule_seed ? 1 + (int)((rng >> 20) % 3) : 1;
+                for (int b = 0; b < burst; ++b) {
+                    const int s = done[w] + 1;
+                    if (s > steps) break;
+                    const int mn = *std::min_element(done.begin(), done.end());
+                    if (mn < s - 2) break;  // bar_wait(step s-2) would block
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int tid = w * 32 + lane;
+                        int tj, tk;
+                        thread_pos<C>(tid, tj, tk);
+                        batch_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+                    }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int tid = w * 32 + lane;
+                        int tj, tk;
+                        thread_pos<C>(tid, tj, tk);
+                        batch_uniform_actions<C>(*S, A, tid, s, P, pair_base);
+                        batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, s + 1);
+                    }
+                    done[w] = s;
+                    if (s == steps) ++finished;
+                }
             }
         }
     }
     return 0;
+}
+
+// threads = 256: 16x16 threads x 4x4 cells; threads = 512: 16x32 threads x 4x2 cells; lag = 1 / 2 (see BatchCfg);
+// schedule_seed != 0 (lag 2 only): warps advance in a pseudo-random order with bursts
+extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                              int pairs_per_cta, int threads, int lag, int schedule_seed, int32_t *scores)
+{
+    (void)schedule_seed;
+    if (threads == 256 && lag == 1) return emu_fast_batch_cfg<BatchCfg<4, 4, 16, 16>>(a, b, c, n, len, base, pairs_per_cta, 0, scores);
+    if (threads == 512 && lag == 1) return emu_fast_batch_cfg<BatchCfg<4, 2, 16, 32>>(a, b, c, n, len, base, pairs_per_cta, 0, scores);
+    if (threads == 256 && lag == 2) return emu_fast_batch_cfg<BatchCfg<4, 4, 16, 16, 2>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores);
+    return -1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -17,17 +17,23 @@ def emu():
     d = os.path.join(ROOT, "tests", "emu")
     subprocess.run(["make", "-C", d], check=True, capture_output=True)
     L = C.CDLL(os.path.join(d, "build", "libemu.so"))
-    L.emu_fast_batch.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, i32p]
+    L.emu_fast_batch.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
     return L
 
 
 def _run(L, a, b, c, pairs_per_cta):
+    """All CTA configurations of K1 must agree: 256 threads x 4x4 cells / 512 threads x 4x2 cells, barrier lag 1 / 2
+    (lag 2 also with warps drifting in a pseudo-random order)."""
     n, ln = a.shape
-    out = np.full(n, -99999, np.int32)
-    rc = L.emu_fast_batch(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, 2 * 64 + 32,
-                          pairs_per_cta, out.ctypes.data_as(i32p))
-    assert rc == 0
-    return out
+    outs = []
+    for th, lag, seed in [(256, 1, 0), (512, 1, 0), (256, 2, 0), (256, 2, 7), (256, 2, 11)]:
+        out = np.full(n, -99999, np.int32)
+        rc = L.emu_fast_batch(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, 2 * 64 + 32,
+                              pairs_per_cta, th, lag, seed, out.ctypes.data_as(i32p))
+        assert rc == 0
+        outs.append(out)
+    assert all(o.tolist() == outs[0].tolist() for o in outs)
+    return outs[0]
 
 
 @pytest.mark.parametrize("ln,n,ppc", [(64, 7, 3), (64, 4, 4), (40, 5, 1), (1, 4, 2), (63, 3, 5), (17, 9, 4), (9, 2, 1)])
