@@ -141,10 +141,11 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     // instead of __syncthreads, suffix "l" = lagged barrier (LAG 2), e.g. TRIALIGN_K1=512m.
     static const int variant = []() {
         const char *e = std::getenv("TRIALIGN_K1");
-        int v = 0;  // default
-        if (e && e[0] == '5') v = 2;
-        if (e && e[0] && e[1] && e[2] && e[3] == 'm') v |= 1;
-        if (e && e[0] && e[1] && e[2] && e[3] == 'l') v |= 4;
+        if (!e || !e[0]) return 4;  // default: 256 threads, lagged barrier (measured fastest)
+        int v = 0;
+        if (e[0] == '5') v = 2;
+        if (e[1] && e[2] && e[3] == 'm') v |= 1;
+        if (e[1] && e[2] && e[3] == 'l') v |= 4;
         return v;
     }();
     fast::BatchArgs A;

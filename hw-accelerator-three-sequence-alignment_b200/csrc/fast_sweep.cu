@@ -55,6 +55,10 @@ template <bool CHECK>
 __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepArgs A)
 {
     using C = LongCfg;
+    // The thread that polls / releases the progress counters sits in warp 3 (tiles tj 4..7, tk 8..15): that warp has no
+    // block-edge duty (no halo fetch, no left-edge merge, few face stores), so the MEMBAR of a release eats its slack
+    // instead of delaying the warp every barrier already waits for.
+    constexpr int kGateTid = 96;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::SweepSmem<C> &S = *reinterpret_cast<fast::SweepSmem<C> *>(smem_raw);
     const int tid = threadIdx.x;
@@ -62,11 +66,12 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
     fast::sweep_thread_pos<C>(tid, tj, tk);
     fast::sweep_load_a<C>(S, A, tid, 0);
     fast::SweepRegs<C> R;
+    fast::SweepConsts<C> K;
     const int steps = fast::sweep_task_steps<C>(A);
 
     for (;;) {
         __syncthreads();  // everybody is done with the previous task descriptor
-        if (tid == 0) {
+        if (tid == kGateTid) {
             const unsigned long long t = atomicAdd(A.counter, 1ull);
             if (t < (unsigned long long)A.tasks_total) {
                 fast::sweep_describe_long<C>(A, (long long)t, S.task);
@@ -98,28 +103,30 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
         const int *left_p = T.left_task >= 0 ? A.progress + T.left_task : nullptr;
 
         // prologue: halos of step 0
-        if (tid == 0) {
+        if (tid == kGateTid) {
             while (!fast::sweep_deps_ready<C>(A, T, -1, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0))
                 __nanosleep(100);
         }
         __syncthreads();
         fast::sweep_edge_fetch<C>(S, A, tj, tk, -1);
+        fast::sweep_thread_prepare<C>(R, K, S, A, tj, tk, 0, tid);
         fast::ta_copy_wait();
         __syncthreads();
 
 #pragma unroll 1
         for (int s = 0; s <= steps; ++s) {
-            const bool gate = fast::sweep_is_gate<C>(s);
+            const bool gate = fast::sweep_is_gate<C>(A, s);
             // the producers' progress is sampled at the top of a gate step, so the load latency hides under the tile
             int tp = 0, lp = 0;
-            if (gate && tid == 0) {
+            if (gate && tid == kGateTid) {
                 tp = top_p ? ld_acquire(top_p) : 0;
                 lp = left_p ? ld_acquire(left_p) : 0;
             }
             fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows certified by the last gate
-            fast::sweep_thread_step<C, CHECK>(R, S, A, tj, tk, s, tid);
+            fast::sweep_thread_step<C, CHECK>(R, K, S, A, tj, tk, s, tid);
+            fast::sweep_thread_prepare<C>(R, K, S, A, tj, tk, s + 1, tid);
             fast::ta_copy_wait();
-            if (gate && tid == 0) {
+            if (gate && tid == kGateTid) {
                 while (!fast::sweep_deps_ready<C>(A, T, s, tp, lp)) {
                     __nanosleep(40);
                     tp = top_p ? ld_acquire(top_p) : 0;
@@ -128,10 +135,10 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
             }
             __syncthreads();
             // release: the edge threads' face stores of the steps so far are ordered before the barrier above
-            if (gate && tid == 0) st_release(A.progress + T.self_task, s + 1);
+            if (gate && tid == kGateTid) st_release(A.progress + T.self_task, s + 1);
         }
         if (CHECK && R.viol) atomicOr(A.viol_flag, 1);
-        if (tid == 0) {
+        if (tid == kGateTid) {
             st_release(A.progress + T.self_task, fast::kProgressDone);
             if (A.iface_out_flag) {  // every thread's hand-over stores precede the last barrier of the step loop
                 __threadfence_system();
@@ -150,6 +157,7 @@ __global__ void __launch_bounds__(BatchCfg::NT, 1) sweep_batch_kernel(fast::Swee
     int tj, tk;
     fast::sweep_thread_pos<C>(tid, tj, tk);
     fast::SweepRegs<C> R;
+    fast::SweepConsts<C> K;
     const int steps = fast::sweep_task_steps<C>(A);
     const int tasks = A.nbj * A.nbkp;
 
@@ -162,12 +170,14 @@ __global__ void __launch_bounds__(BatchCfg::NT, 1) sweep_batch_kernel(fast::Swee
             __syncthreads();
             setup_task<C>(S, R, A, tid, tj, tk);
             fast::sweep_edge_fetch<C>(S, A, tj, tk, -1);
+            fast::sweep_thread_prepare<C>(R, K, S, A, tj, tk, 0, tid);
             fast::ta_copy_wait();
             __syncthreads();
 #pragma unroll 1
             for (int s = 0; s <= steps; ++s) {
                 fast::sweep_edge_fetch<C>(S, A, tj, tk, s);
-                fast::sweep_thread_step<C, false>(R, S, A, tj, tk, s, tid);
+                fast::sweep_thread_step<C, false>(R, K, S, A, tj, tk, s, tid);
+                fast::sweep_thread_prepare<C>(R, K, S, A, tj, tk, s + 1, tid);
                 fast::ta_copy_wait();
                 __syncthreads();
             }
@@ -238,6 +248,12 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
     A.nbj = (lb + C::BJ - 1) / C::BJ;
     A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
     A.tasks_total = (long long)A.nbj * A.nbkp;
+    // long sweeps release their progress less often (see fast_sweep.cuh); TRIALIGN_K2_GATE overrides for experiments
+    A.gate = la >= 4096 ? 16 : 8;
+    if (const char *e = std::getenv("TRIALIGN_K2_GATE")) {
+        const int g = std::atoi(e);
+        if (g >= 1 && g <= 64 && (g & (g - 1)) == 0) A.gate = g;
+    }
     int grid = ctx->sm_count;  // one persistent CTA per SM; all co-resident (spin-waits need that)
     if (grid > A.tasks_total) grid = (int)A.tasks_total;
     A.fj_slot_words = (long long)(la + C::LAG + 2) * C::FJ_ROW_WORDS;

@@ -33,7 +33,9 @@ struct SweepCfg {
     static constexpr int KSPAN = LONG ? 2 * BK : BK;   // columns of C one task covers
     static constexpr int ROW_W = BK;                   // words per face-J row and value
     static constexpr int COL_W = BJ + 4;               // words per face-K row and value (index BJ = relay, padded)
-    static constexpr int TAB_STRIDE = 68;
+    static constexpr int TAB_STRIDE = 68;              // j-indexed tables: lanes of a wavefront differ in the code only
+    static constexpr int TABK_STRIDE = 128;            // k-indexed tables {cAC[64], tC[64]}: bank group depends on tk only
+    static constexpr int CORNER_STRIDE = TK + 8;       // a warp spans 4 tj x 8 tk: distinct banks
     static constexpr int LA_MAX = 8192 + 64;           // A symbols kept in shared memory
     static constexpr uint32_t HI_OFF = LONG ? ((uint32_t)(2 * (BK - LAG)) << 16) : 0u;  // phi(high) - phi(low)
     static constexpr int FJ_ROW_WORDS = 4 * ROW_W;     // one plane of a J face
@@ -62,6 +64,7 @@ struct SweepArgs {
     uint32_t *face_j, *face_k;    // ring storage
     long long fj_slot_words, fk_slot_words;
     int fj_ring, fk_ring;         // LONG: global ring sizes; BATCH: per-CTA ring sizes
+    int gate;                     // LONG: steps between two dependency gates / progress releases (power of two)
     int *progress;                // LONG: [tasks_total] indexed by task id bj + nbj*bkp, zero-initialised
     const int *order;             // LONG: claim position -> task id (sorted by earliest possible start, sweep_order_key)
     const int *pos_of;            // LONG: task id -> claim position
@@ -90,12 +93,11 @@ template <class C>
 struct SweepSmem {
     uint32_t row[2][4][C::TJ + 1][C::BK];     // [slot][wY,u2,u1(old),all(old)][tj+1 (0 = block halo)][k]
     uint32_t col[2][4][C::TK + 1][C::COL_W];  // [slot][wZ,u2,u3(old),all(old)][tk+1 (0 = block halo)][j (+relay)]
-    uint32_t corner[2][2][C::TJ][C::TK];      // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
+    uint32_t corner[2][2][C::TJ][C::CORNER_STRIDE];  // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
     uint32_t cornerL[2][2][C::TJ];            // [slot][u2,all(old)][tj]  corner cell of the tiles on the block's left edge
     uint32_t tabAB[16][C::TAB_STRIDE];        // [a code][j]  pair constant {4,2}
     uint32_t tabMB[16][C::TAB_STRIDE];        // [a code][j]  triple row constant {9,3}
-    uint32_t tabAC[16][C::TAB_STRIDE];        // [a code][k]  pair constant {4,2}
-    uint32_t tabMC[16][C::TAB_STRIDE];        // [a code][k]  triple column constant {9,6}
+    uint32_t tabK[16][C::TABK_STRIDE];        // [a code][k] pair constant {4,2}, [a code][64 + k] triple column constant {9,6}
     uint8_t seqA[2][C::LA_MAX];               // [half][i]   (LONG: only [0] is used)
     uint8_t seqB[2][64], seqC[2][64];         // [half][pos in block]
     SweepTask task;
@@ -106,6 +108,13 @@ struct SweepRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
     uint32_t cBC[C::RJ][C::RK];                                                        // per-cell constant
     uint32_t viol;                                                                     // range-check violations seen
+};
+
+// Constants of the step a thread is about to run (the a symbols of both halves against the tile's rows / columns),
+// fetched one step ahead, before the barrier (sweep_thread_prepare).
+template <class C>
+struct SweepConsts {
+    uint32_t cAB[C::RJ], tB[C::RJ], cAC[C::RK], tC[C::RK];
 };
 
 template <class C>
@@ -218,8 +227,8 @@ TA_HD void sweep_build_tables(SweepSmem<C> &S, int tid)
         const uint32_t nab = neq_flag(ap, bp), nac = neq_flag(ap, cp);
         S.tabAB[code][p] = pair_const(nab);
         S.tabMB[code][p] = triple_row_const(nab);
-        S.tabAC[code][p] = pair_const(nac);
-        S.tabMC[code][p] = triple_col_const(nac);
+        S.tabK[code][p] = pair_const(nac);
+        S.tabK[code][64 + p] = triple_col_const(nac);
     }
 }
 
@@ -350,17 +359,18 @@ TA_HD void sweep_edge_fetch(SweepSmem<C> &S, const SweepArgs &A, int tj, int tk,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// One wavefront step of one thread
+// The part of step s that does not depend on the neighbours' step s-1: plane-0 reset and the step's constants.
+// Runs at the end of step s-1, before its barrier, so that the table look-ups are off the critical path.
 // ---------------------------------------------------------------------------------------------------------------
-template <class C, bool CHECK>
-TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &A, int tj, int tk, int s, int tid)
+template <class C>
+TA_HD void sweep_thread_prepare(SweepRegs<C> &R, SweepConsts<C> &K, const SweepSmem<C> &S, const SweepArgs &A, int tj,
+                                int tk, int s, int tid)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const SweepTask &T = S.task;
     const int i0 = s - (tj + tk) + 1;  // low-half plane (valid 1..la)
     const int i1 = i0 - C::LAG;        // high-half plane
     const int j0 = tj * RJ, k0 = tk * RK;
-    const int ws = s & 1, rs = ws ^ 1;
 
     // plane 0 is the all-zero border (PE override, src/PE_1cyc.v:164-178): reset the half whose plane 1 starts now
     if (i0 == 1 || i1 == 1) {
@@ -393,17 +403,31 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
     ia1 = ia1 < 0 ? 0 : (ia1 >= A.la ? A.la - 1 : ia1);
     const int code = S.seqA[0][ia0] | (S.seqA[C::LONG ? 0 : 1][ia1] << 2);
     TA_CHECK(code >= 0 && code < 16);
-    uint32_t cAB[RJ], tB[RJ], cAC[RK], tC[RK];
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
-        cAB[r] = S.tabAB[code][j0 + r];
-        tB[r] = S.tabMB[code][j0 + r];
+        K.cAB[r] = S.tabAB[code][j0 + r];
+        K.tB[r] = S.tabMB[code][j0 + r];
     }
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
-        cAC[c] = S.tabAC[code][k0 + c];
-        tC[c] = S.tabMC[code][k0 + c];
+        K.cAC[c] = S.tabK[code][k0 + c];
+        K.tC[c] = S.tabK[code][64 + k0 + c];
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// One wavefront step of one thread
+// ---------------------------------------------------------------------------------------------------------------
+template <class C, bool CHECK>
+TA_HD void sweep_thread_step(SweepRegs<C> &R, const SweepConsts<C> &K, SweepSmem<C> &S, const SweepArgs &A, int tj,
+                             int tk, int s, int tid)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    const SweepTask &T = S.task;
+    const int i0 = s - (tj + tk) + 1;  // low-half plane (valid 1..la)
+    const int i1 = i0 - C::LAG;        // high-half plane
+    const int j0 = tj * RJ, k0 = tk * RK;
+    const int ws = s & 1, rs = ws ^ 1;
 
     // halos (see fast_batch.cuh); index 0 of the first dimension of row/col is the block halo
     uint32_t T_wY[RK], T_u1[RK], T_u2[RK + 1], T_all[RK + 1], L_wZ[RJ], L_u3[RJ], L_u2[RJ], L_all[RJ];
@@ -463,6 +487,17 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
     L_all[0] = T_all[0];
     S.corner[ws][0][tj][tk] = T_u2[RK];
     S.corner[ws][1][tj][tk] = T_all[RK];
+    // the plane i-1 half of this thread's own edges is known already: these stores leave before the tile
+#pragma unroll
+    for (int c = 0; c < RK; ++c) {
+        S.row[ws][2][tj + 1][k0 + c] = R.u1[RJ - 1][c];
+        S.row[ws][3][tj + 1][k0 + c] = R.all[RJ - 1][c];
+    }
+#pragma unroll
+    for (int r = 0; r < RJ; ++r) {
+        S.col[ws][2][tk + 1][j0 + r] = R.u3[r][RK - 1];
+        S.col[ws][3][tk + 1][j0 + r] = R.all[r][RK - 1];
+    }
 
     // the tile
     uint32_t n_all[RJ][RK], n_wX[RJ][RK], n_u1[RJ][RK], n_u3[RJ][RK], n_wY[RJ][RK], n_wZ[RJ][RK], n_u2[RJ][RK];
@@ -476,9 +511,9 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
             const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
             const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
             const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
-            const uint32_t cM = triple_const(tB[r], tC[c]);
-            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, cAB[r],
-                                                 R.cBC[r][c], cAC[c], nullptr);
+            const uint32_t cM = triple_const(K.tB[r], K.tC[c]);
+            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
+                                                 R.cBC[r][c], K.cAC[c], nullptr);
             n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
             n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
         }
@@ -488,15 +523,11 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
     for (int c = 0; c < RK; ++c) {
         S.row[ws][0][tj + 1][k0 + c] = n_wY[RJ - 1][c];
         S.row[ws][1][tj + 1][k0 + c] = n_u2[RJ - 1][c];
-        S.row[ws][2][tj + 1][k0 + c] = R.u1[RJ - 1][c];
-        S.row[ws][3][tj + 1][k0 + c] = R.all[RJ - 1][c];
     }
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
         S.col[ws][0][tk + 1][j0 + r] = n_wZ[r][RK - 1];
         S.col[ws][1][tk + 1][j0 + r] = n_u2[r][RK - 1];
-        S.col[ws][2][tk + 1][j0 + r] = R.u3[r][RK - 1];
-        S.col[ws][3][tk + 1][j0 + r] = R.all[r][RK - 1];
     }
 
     // block faces to global memory, re-based to the consumer's frame (its halo row / column has local index 0)
@@ -572,7 +603,7 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
                         const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
                         const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
                         cell_update<true>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3,
-                                          triple_const(tB[r], tC[c]), cAB[r], R.cBC[r][c], cAC[c], st);
+                                          triple_const(K.tB[r], K.tC[c]), K.cAB[r], R.cBC[r][c], K.cAC[c], st);
                     }
             // potential of the cell in each half's own frame
             const int off_lo = A.base + 2 * (A.la + jl + kl);
@@ -624,18 +655,18 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, SweepSmem<C> &S, const SweepArgs &
 // (kProgressDone once it is finished).  Writers and readers of a face are skewed alike: thread (0,tk) fetches at its
 // step f the row that producer thread (15,tk) wrote at producer step f+16, and thread (tj,0) fetches the row that
 // producer thread (tj,15) wrote at step f+16+LAG.  Gates are evaluated every kSweepGate steps, before the barrier
-// that ends step g, and certify the fetches of steps g+1 .. g+kSweepGate.
+// that ends step g, and certify the fetches of steps g+1 .. g+gate.  The gate interval A.gate (a power of two) trades
+// pipeline fill (a consumer trails its producer by 16 + gate steps) against the cost of a release: the st.release.gpu
+// is a MEMBAR that holds one warp, and hence the next CTA barrier, for hundreds of cycles.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kSweepGate = 4;
-
 template <class C>
-TA_HD bool sweep_is_gate(int g) { return ((g + 1) % kSweepGate) == 0; }
+TA_HD bool sweep_is_gate(const SweepArgs &A, int g) { return ((g + 1) & (A.gate - 1)) == 0; }
 
 template <class C>
 TA_HD bool sweep_deps_ready(const SweepArgs &A, const SweepTask &T, int g, int top_prog, int left_prog)
 {
     const int total = sweep_task_steps<C>(A) + 1;  // steps 0..steps
-    const int f = g + kSweepGate;                  // last fetch this gate certifies
+    const int f = g + A.gate;                      // last fetch this gate certifies
     const int need_top = (f + C::TJ + 1 < total) ? f + C::TJ + 1 : total;
     const int need_left = (f + C::TK + C::LAG + 1 < total) ? f + C::TK + C::LAG + 1 : total;
     if (T.top_task >= 0 && top_prog < need_top) return false;

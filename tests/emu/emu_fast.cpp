@@ -124,6 +124,7 @@ template <class C>
 struct EmuCta {
     std::unique_ptr<SweepSmem<C>> S{new SweepSmem<C>};
     std::vector<SweepRegs<C>> R = std::vector<SweepRegs<C>>(C::NT);
+    std::vector<SweepConsts<C>> K = std::vector<SweepConsts<C>>(C::NT);
     bool has_task = false, prologue_done = false;
     int s = 0;
     void setup(const SweepArgs &A)
@@ -157,12 +158,24 @@ struct EmuCta {
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             sweep_thread_pos<C>(tid, tj, tk);
-            sweep_thread_step<C, true>(R[tid], *S, A, tj, tk, step, tid);
+            sweep_thread_step<C, true>(R[tid], K[tid], *S, A, tj, tk, step, tid);
+            sweep_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, step + 1, tid);
+        }
+    }
+    void prepare0(const SweepArgs &A)
+    {
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            sweep_thread_pos<C>(tid, tj, tk);
+            sweep_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, 0, tid);
         }
     }
 };
 
 }  // namespace
+
+static int g_emu_gate = 4;
+extern "C" void emu_set_gate(int gate) { g_emu_gate = gate; }  // gate interval of the emulated LONG-mode runs
 
 namespace {
 // one (slab of a) long triple on n_ctas emulated CTAs; iface_* may be null
@@ -177,6 +190,7 @@ int run_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *
     A.nbj = (lb + C::BJ - 1) / C::BJ;
     A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
     A.tasks_total = (long long)A.nbj * A.nbkp;
+    A.gate = g_emu_gate;
     A.fj_slot_words = (long long)(la + C::LAG + 2) * C::FJ_ROW_WORDS;
     A.fk_slot_words = (long long)(la + C::LAG + 2) * C::FK_ROW_WORDS;
     A.fj_ring = (int)A.tasks_total;  // the emulation keeps every face (ring re-use is a launcher concern)
@@ -224,15 +238,16 @@ int run_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *
             if (!cta.prologue_done) {
                 if (!sweep_deps_ready<C>(A, T, -1, tp, lp)) continue;
                 cta.fetch(A, -1);
+                cta.prepare0(A);
                 cta.prologue_done = true;
                 progressed = true;
                 continue;
             }
             // the gate before the barrier of step s-1 certifies the fetches of the following steps
-            if (sweep_is_gate<C>(cta.s - 1) && !sweep_deps_ready<C>(A, T, cta.s - 1, tp, lp)) continue;
+            if (sweep_is_gate<C>(A, cta.s - 1) && !sweep_deps_ready<C>(A, T, cta.s - 1, tp, lp)) continue;
             cta.fetch(A, cta.s);
             cta.step(A, cta.s);
-            if (sweep_is_gate<C>(cta.s)) prog[T.self_task] = cta.s + 1;
+            if (sweep_is_gate<C>(A, cta.s)) prog[T.self_task] = cta.s + 1;
             progressed = true;
             if (++cta.s > steps) {
                 if (cta.viol()) viol = 1;
@@ -301,6 +316,7 @@ extern "C" int emu_fast_sweep_batch(const uint8_t *a, const uint8_t *b, const ui
                 sweep_describe_batch<C>(A, cid, pair, q, cta.S->task);
                 cta.setup(A);
                 cta.fetch(A, -1);
+                cta.prepare0(A);
                 for (int s = 0; s <= steps; ++s) {
                     cta.fetch(A, s);
                     cta.step(A, s);

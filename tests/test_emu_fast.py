@@ -64,7 +64,14 @@ def emu_sweep(emu):
     return emu
 
 
-def _long(L, a, b, c, n_ctas, check_bits=0):
+def _long(L, a, b, c, n_ctas, check_bits=0, gate=None):
+    """One long triple on n_ctas emulated CTAs.  Without an explicit gate interval both of the launcher's settings
+    (4 and 16 steps between progress releases) are run and must agree."""
+    if gate is None:
+        r4, r16 = _long(L, a, b, c, n_ctas, check_bits, 4), _long(L, a, b, c, n_ctas, check_bits, 16)
+        assert r4 == r16
+        return r4
+    L.emu_set_gate(gate)
     a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (a, b, c))
     out = np.zeros(8, np.int32)
     viol = C.c_int(0)
