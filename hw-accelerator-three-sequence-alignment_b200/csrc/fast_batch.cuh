@@ -96,10 +96,15 @@ struct BatchConsts {
 
 // thread id -> position in the TJ x TK thread grid.  A quarter-warp holds 8 consecutive tk of one tj
 // (conflict-free shared-memory accesses, see BatchCfg); a warp spans 4 tj x 8 tk (11 distinct skews).
+// Warps whose tiles touch the j = 0 / k = 0 border planes execute the border code on top of the common path; hardware
+// warp w issues from scheduler w % 4, so the 4x8-tile patches are dealt to the warps such that every scheduler gets
+// about the same amount of border work (256 threads: patches {both borders, none}, {top, left}, {left, none} x 2).
 template <class C>
 TA_HD void thread_pos(int tid, int &tj, int &tk)
 {
-    const int lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31;
+    int warp = tid >> 5;
+    if (C::NT == 256) warp = (0x75632410u >> (4 * warp)) & 7;  // warps 0..7 -> patches 0,1,4,2,3,6,5,7
     tk = (lane & 7) + 8 * (warp % (C::TK / 8));
     tj = (lane >> 3) + 4 * (warp / (C::TK / 8));
 }

@@ -22,7 +22,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "lib", "libtrialign.so")
+_LIB = os.environ.get("TRIALIGN_LIB") or os.path.join(_HERE, "lib", "libtrialign.so")  # override: development A/B builds
 
 BACKEND_AUTO, BACKEND_GPU, BACKEND_GPU_LITERAL, BACKEND_GPU_FAST = 0, 4, 5, 6
 PATH_NAMES = {0: "none", 1: "literal", 2: "fast_batch", 3: "fast_long", 4: "fast_then_literal"}
