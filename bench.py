@@ -33,6 +33,16 @@ WORKLOADS = {
 }
 
 
+def kernel_stats(workload):
+    """Per-launch DRAM traffic and issued-instruction utilisation of the dominant kernel, taken from the committed
+    `ncu --set full` captures (profiles/ncu_kernel_stats.json); never measured under this process."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_kernel_stats.json")) as f:
+            return json.load(f).get(workload)
+    except Exception:
+        return None
+
+
 def alu_peak():
     """Measured integer-ALU peak (tools/alu_microbench.cu on this pool's B200), else the nominal figure."""
     path = os.path.join(ROOT, "profiles", "alu_peak.json")
@@ -106,13 +116,14 @@ def cpu_baseline(length, score_bits, target_s=12.0):
     threads = ob.lib().oracle_hw_threads()
     L = min(length, 256) if length > 256 else length
     per = float(L) ** 3
-    probe_n = max(threads, 8) if L <= 64 else max(1, threads // 4)
+    probe_n = max(4 * threads, 64) if L <= 64 else max(2, threads // 2)
     a, b, c = ob.synth_batch(0x5EED0002, 0, probe_n, L)
-    t0 = time.perf_counter()
-    ob.score_batch(a, b, c, score_bits)
-    dt = time.perf_counter() - t0
-    rate = probe_n * per / dt
-    n = int(max(probe_n, min(1 << 16, target_s * rate / per)))
+    rate = 0.0
+    for _ in range(2):  # the first pass also pays for the OpenMP thread start-up
+        t0 = time.perf_counter()
+        ob.score_batch(a, b, c, score_bits)
+        rate = max(rate, probe_n * per / (time.perf_counter() - t0))
+    n = int(max(probe_n, min(1 << 18, target_s * rate / per)))
     a, b, c = ob.synth_batch(0x5EED0002, 0, n, L)
     t0 = time.perf_counter()
     ob.score_batch(a, b, c, score_bits)
@@ -123,7 +134,7 @@ def cpu_baseline(length, score_bits, target_s=12.0):
     try:
         import ctypes as C
 
-        m = max(threads, 8) * 2
+        m = max(threads, 8) * 48  # about 5 s: one triple of length 64 is 9,282 simulated clocks
         ra, rb, rc = ob.synth_batch(0x5EED0002, 0, m, 64)
         cfg = ob.RtlCfg()
         ob.lib().rtl_default_cfg(C.byref(cfg), 1)
@@ -335,6 +346,14 @@ def run_ours(args, rank, world, local_rank):
                          "note": "achieved counts the RTL's 91 lane-ops per cell; the factored kernel issues fewer (see DESIGN.md), so frac can exceed 1"},
             "clocks": clocks,
         }
+        ks = kernel_stats(args.workload)
+        if ks:
+            # DRAM bytes of one launch from the ncu capture, scaled by the number of triples when the captured launch
+            # was a reduced batch (traffic is the input arrays + scores, linear in n)
+            scale = float(n) / ks["triples_in_capture"] if ks.get("triples_in_capture") else 1.0
+            line["roofline"]["traffic"] = (ks["dram_bytes_read"] + ks["dram_bytes_write"]) * scale
+            line["roofline"]["issued"] = {k: ks[k] for k in ("alu_pipe_pct", "issue_slot_pct", "warp_instr_per_cell_pair",
+                                                              "alu_instr_per_cell_pair", "capture") if k in ks}
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline(length, w)
         print(json.dumps(line), flush=True)

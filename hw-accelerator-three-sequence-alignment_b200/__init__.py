@@ -20,13 +20,16 @@ from .trialign import (  # noqa: F401
     launch_count,
     library,
     library_path,
+    pack_seq_ram128,
     read_scores,
     read_seq_dat,
     synth,
+    unpack_seq_ram128,
     synth_batch,
     synth_batch_cuda,
     version,
     write_scores,
     write_seq_dat,
+    write_tb_init,
 )
 from .parallel import SlabPipeline, shard_range, slab_range  # noqa: E402,F401

@@ -3,6 +3,7 @@
 // Formats follow the reference's fixtures:
 //   dat/A_seq.dat, B_seq.dat, C_seq.dat : one decimal digit 0-3 per line, CRLF line ends, 64 lines
 //   dat/Pattern1.dat                    : signed decimals, one per line, LF separated, no trailing newline
+//   src/TriAlign_tb.sv seq?_ram         : 128-bit words of 32 four-bit symbols, and the initial block that fills them
 #include <cerrno>
 #include <cstdint>
 #include <cstdio>
@@ -123,6 +124,47 @@ int trialign_read_scores(const char *path, int32_t *v, int64_t cap, int64_t *n)
     }
     *n = count;
     return count > cap ? TRIALIGN_ECAPACITY : TRIALIGN_OK;
+}
+
+int trialign_pack_seq_ram128(const uint8_t *sym, int n, uint8_t *ram, int cap_words)
+{
+    if (n < 0 || cap_words < 0 || (n > 0 && !sym) || (cap_words > 0 && !ram)) return TRIALIGN_EINVAL;
+    const int words = (n + 31) / 32;
+    if (words > cap_words) return TRIALIGN_ECAPACITY;
+    std::memset(ram, 0, (size_t)words * 16);
+    for (int p = 0; p < n; ++p) ram[p >> 1] |= (uint8_t)((sym[p] & 15) << (4 * (p & 1)));
+    return TRIALIGN_OK;
+}
+
+int trialign_unpack_seq_ram128(const uint8_t *ram, int n, uint8_t *sym, int cap)
+{
+    if (n < 0 || cap < 0 || (n > 0 && !ram) || (cap > 0 && !sym)) return TRIALIGN_EINVAL;
+    if (n > cap) return TRIALIGN_ECAPACITY;
+    for (int p = 0; p < n; ++p) sym[p] = (uint8_t)((ram[p >> 1] >> (4 * (p & 1))) & 15);
+    return TRIALIGN_OK;
+}
+
+int trialign_write_tb_init(const char *path, const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c,
+                           int lc, int total_len)
+{
+    if (!path || la < 0 || lb < 0 || lc < 0 || total_len < 0 || (la > 0 && !a) || (lb > 0 && !b) || (lc > 0 && !c))
+        return TRIALIGN_EINVAL;
+    if (la > total_len || lb > total_len || lc > total_len) return TRIALIGN_ECAPACITY;
+    static const char *const kName[5] = {"A", "T", "C", "G", "N"};  // localparams of src/TriAlign_tb.sv:42-46
+    const uint8_t *seq[3] = {a, b, c};
+    const int len[3] = {la, lb, lc};
+    std::string s;
+    s.reserve((size_t)total_len * 3 * 30);
+    char line[64];
+    for (int which = 0; which < 3; ++which)
+        for (int p = 0; p < total_len; ++p) {
+            const int code = p < len[which] ? (seq[which][p] & 15) : 0;
+            if (code > 4) return TRIALIGN_EINVAL;
+            const int lo = 4 * (p & 31);
+            std::snprintf(line, sizeof line, "seq%c_ram[%d][%d:%d] <= %s;\n", "ABC"[which], p >> 5, lo + 3, lo, kName[code]);
+            s += line;
+        }
+    return spill(path, s);
 }
 
 void trialign_synth(uint64_t seed, int64_t triple, int which, int len, uint8_t *out)

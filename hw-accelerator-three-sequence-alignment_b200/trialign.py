@@ -92,6 +92,12 @@ def library() -> C.CDLL:
     L.trialign_write_scores.restype = C.c_int
     L.trialign_read_scores.argtypes = [C.c_char_p, _i32p, C.c_int64, C.POINTER(C.c_int64)]
     L.trialign_read_scores.restype = C.c_int
+    L.trialign_pack_seq_ram128.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+    L.trialign_pack_seq_ram128.restype = C.c_int
+    L.trialign_unpack_seq_ram128.argtypes = [_u8p, C.c_int, _u8p, C.c_int]
+    L.trialign_unpack_seq_ram128.restype = C.c_int
+    L.trialign_write_tb_init.argtypes = [C.c_char_p, _u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int]
+    L.trialign_write_tb_init.restype = C.c_int
     L.trialign_synth.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, _u8p]
     L.trialign_synth.restype = None
     L.trialign_synth_batch_dev.argtypes = [C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p,
@@ -252,6 +258,33 @@ def read_scores(path: str, cap: int = 1 << 22) -> np.ndarray:
     n = C.c_int64(0)
     _check(library().trialign_read_scores(os.fsencode(path), _p(buf, _i32p), cap, C.byref(n)), "trialign_read_scores")
     return buf[: n.value].copy()
+
+
+# ---- the testbench's packed sequence RAMs and stimulus block (src/TriAlign_tb.sv:94-96, :423-1959) ----
+def pack_seq_ram128(seq) -> np.ndarray:
+    """Symbols -> the testbench RAM image: uint8 [ceil(n/32)][16], one row per 128-bit word, LSB first."""
+    s = _u8(seq)
+    words = (s.size + 31) // 32
+    ram = np.zeros((words, 16), np.uint8)
+    _check(library().trialign_pack_seq_ram128(_p(s, _u8p), s.size, _p(ram, _u8p), words), "trialign_pack_seq_ram128")
+    return ram
+
+
+def unpack_seq_ram128(ram, n: int) -> np.ndarray:
+    """The first n 4-bit symbol codes of a RAM image produced by pack_seq_ram128 (or dumped from the testbench)."""
+    r = np.ascontiguousarray(np.asarray(ram, dtype=np.uint8)).reshape(-1)
+    if n > 2 * r.size:
+        raise ValueError("RAM image holds fewer than n symbols")
+    out = np.zeros(max(n, 0), np.uint8)
+    _check(library().trialign_unpack_seq_ram128(_p(r, _u8p), n, _p(out, _u8p), out.size), "trialign_unpack_seq_ram128")
+    return out
+
+
+def write_tb_init(path: str, a, b, c, total_len: int = 512) -> None:
+    """Writes the `seq?_ram[w][hi:lo] <= SYM;` lines that replace the testbench's initial block for this triple."""
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    _check(library().trialign_write_tb_init(os.fsencode(path), _p(a, _u8p), a.size, _p(b, _u8p), b.size, _p(c, _u8p),
+                                            c.size, total_len), "trialign_write_tb_init")
 
 
 # ---- synthetic inputs (SURVEY.md 8(d)) ----

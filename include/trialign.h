@@ -128,6 +128,21 @@ int trialign_write_seq_dat(const char *path, const uint8_t *buf, int n, int crlf
 int trialign_write_scores(const char *path, const int32_t *s, int64_t n);
 int trialign_read_scores(const char *path, int32_t *s, int64_t cap, int64_t *n);
 
+/* The testbench's sequence RAMs (src/TriAlign_tb.sv:94-96,150-169): 128-bit words of 32 four-bit symbols, symbol n in
+ * word n>>5 at bits [4*(n&31)+3 : 4*(n&31)]; codes A=0 T=1 C=2 G=3 N=4 (:42-46).  A word is 16 bytes here, least
+ * significant byte first, so symbol n is nibble (n&1) of byte (n>>1).  pack: n symbols -> ceil(n/32) words (the rest of
+ * the last word is 0 = 'A', the value the shipped testbench fills unused positions with); only bits [3:0] of a symbol
+ * byte are stored.  unpack: the 4-bit codes as stored (the PE uses bits [1:0], src/PE_1cyc.v:63-66; the compute entry
+ * points apply that truncation themselves).  cap_words / cap count 128-bit words / symbols; ECAPACITY if too small. */
+int trialign_pack_seq_ram128(const uint8_t *sym, int n, uint8_t *ram, int cap_words);
+int trialign_unpack_seq_ram128(const uint8_t *ram, int n, uint8_t *sym, int cap);
+/* Stimulus for the reference testbench: the `seqA_ram[w][hi:lo] <= SYM;` lines of its initial block
+ * (src/TriAlign_tb.sv:423-1959), one per symbol position for A, then B, then C, each padded with `A` up to total_len
+ * positions (the testbench ships total_len = 512).  A maintainer pastes / `include`s the file in place of that block
+ * and sets A/B/C_LENGTH (:48-50) to replay any triple on the RTL; tools/make_tb.py does both. */
+int trialign_write_tb_init(const char *path, const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c,
+                           int lc, int total_len);
+
 /* Synthetic symbols: sym = mix(seed ^ ((3*triple+which) << 32) ^ p) >> 62, splitmix64 finaliser. */
 void trialign_synth(uint64_t seed, int64_t triple, int which, int len, uint8_t *out);
 /* Same generator on the GPU: fills d_a/d_b/d_c [n][len] for triples first..first+n-1. */

@@ -135,3 +135,69 @@ def test_product_does_not_link_the_oracle(ta):
                 text = open(os.path.join(dirpath, fn)).read()
                 for needle in ("liboracle", "trialign_oracle.h", "rtl_model.h", "oracle_bindings", "oracle_score"):
                     assert needle not in text, f"{fn} references the test oracle ({needle})"
+
+
+# ---- the testbench's packed sequence RAMs and stimulus block ----
+def _tb_ram_symbol(ram_rows, n):
+    """src/TriAlign_tb.sv:150-169 restated: word n>>5 of the 128-bit RAM, nibble n&31 counted from the LSB."""
+    word = int.from_bytes(bytes(ram_rows[n >> 5].tolist()), "little")
+    return (word >> (4 * (n & 31))) & 15
+
+
+def test_seq_ram128_layout_and_roundtrip(ta):
+    rng = np.random.default_rng(5)
+    for n in (0, 1, 31, 32, 33, 64, 100, 512):
+        s = rng.integers(0, 5, n, dtype=np.uint8)           # codes A,T,C,G,N
+        ram = ta.pack_seq_ram128(s)
+        assert ram.shape == ((n + 31) // 32, 16)
+        assert [_tb_ram_symbol(ram, p) for p in range(n)] == s.tolist()
+        assert all(_tb_ram_symbol(ram, p) == 0 for p in range(n, 32 * ram.shape[0]))  # padding = 'A' like the tb
+        assert ta.unpack_seq_ram128(ram, n).tolist() == s.tolist()
+    L = ta.library()
+    buf = np.zeros(16, np.uint8)
+    s = np.zeros(33, np.uint8)
+    u8p = C.POINTER(C.c_uint8)
+    assert L.trialign_pack_seq_ram128(s.ctypes.data_as(u8p), 33, buf.ctypes.data_as(u8p), 1) == -8   # ECAPACITY
+    assert L.trialign_pack_seq_ram128(None, 3, buf.ctypes.data_as(u8p), 1) == -1                      # EINVAL
+    assert L.trialign_unpack_seq_ram128(buf.ctypes.data_as(u8p), 5, s.ctypes.data_as(u8p), 4) == -8
+
+
+def test_tb_init_block_lines(ta, golden, tmp_path):
+    A, B, Cs = (np.array(golden["dat"][k], np.uint8) for k in "ABC")
+    p = str(tmp_path / "init.sv")
+    ta.write_tb_init(p, A, B, Cs, 512)
+    lines = open(p).read().split("\n")
+    assert lines[-1] == "" and len(lines) == 3 * 512 + 1
+    names = "ATCG"
+    assert lines[0] == f"seqA_ram[0][3:0] <= {names[A[0]]};"
+    assert lines[63] == f"seqA_ram[1][127:124] <= {names[A[63]]};"
+    assert lines[64] == "seqA_ram[2][3:0] <= A;"                      # beyond the length: 'A', as the tb ships
+    assert lines[512 + 33] == f"seqB_ram[1][7:4] <= {names[B[33]]};"
+    assert lines[1024 + 5] == f"seqC_ram[0][23:20] <= {names[Cs[5]]};"
+    with pytest.raises(ta.TriAlignError):
+        ta.write_tb_init(p, np.zeros(600, np.uint8), B, Cs, 512)       # longer than the RAM
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/TriAlign_tb.sv"), reason="reference only in the build container")
+def test_tb_generator_reproduces_the_shipped_testbench(ta, tmp_path):
+    """tools/make_tb.py's rewrite, fed the triple the reference testbench ships (all-'A', lengths 64), must give the
+    reference's own file back except for the commented-out FSDB calls -- i.e. the generated stimulus is in exactly
+    the form the RTL's environment expects; with the dat/ triple only lengths and symbol names change."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_tb", os.path.join(ROOT, "tools", "make_tb.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    tb = open("/root/reference/src/TriAlign_tb.sv").read()
+    z = np.zeros(64, np.uint8)
+    p = str(tmp_path / "init.sv")
+    ta.write_tb_init(p, z, z, z, 512)
+    out = mk.rewrite_testbench(tb, open(p).read(), 64, 64, 64, 12)
+    diff = [(a, b) for a, b in zip(tb.split("\n"), out.split("\n")) if a != b]
+    assert len(tb.split("\n")) == len(out.split("\n"))
+    assert len(diff) == 2 and all("$fsdbDump" in a and b.strip().startswith("// $fsdbDump") for a, b in diff)
+    A = ta.read_seq_dat("/root/reference/dat/A_seq.dat")
+    ta.write_tb_init(p, A[:40], A[:24], A[:16], 512)
+    out2 = mk.rewrite_testbench(tb, open(p).read(), 40, 24, 16, 10)
+    assert "localparam A_LENGTH = 40;" in out2 and "localparam B_LENGTH = 24;" in out2 and "localparam C_LENGTH = 16;" in out2
+    assert "localparam SCORE_BITS = 10;" in out2 and "seqA_ram[1][31:28] <= " in out2
