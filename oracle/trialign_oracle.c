@@ -168,6 +168,93 @@ int oracle_cube(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Traceback.  The RTL ships score-only, but carries the hook: MAX7's commented-out `act` output
+ * (PE_1cyc.v:12,30) would report WHICH of its seven inputs won.  The tie rule follows from the compare-select tree
+ * (:22-28, `a > b ? a : b`: the second operand wins a tie), i.e. on equal values the ports win in the order
+ * G4, G3_B, G3_A, G2_B, G2_A, G1_B, G1_A.  Which source state sits on which port differs per MAX7 instance (:139-145).
+ * Tables below: ports in max7()'s argument order (G4, G1_A, G1_B, G3_A, G2_A, G2_B, G3_B).
+ * ------------------------------------------------------------------------------------------------------------------ */
+static const int kPortSrc[7][7] = {
+    /* M   :139 */ {TA_M, TA_IX, TA_IY, TA_IZ, TA_IXY, TA_IYZ, TA_IXZ},
+    /* Ix  :140 */ {TA_IX, TA_M, TA_IYZ, TA_IY, TA_IXY, TA_IXZ, TA_IZ},
+    /* Iy  :141 */ {TA_IY, TA_M, TA_IXZ, TA_IX, TA_IXY, TA_IYZ, TA_IZ},
+    /* Iz  :142 */ {TA_IZ, TA_M, TA_IXY, TA_IX, TA_IXZ, TA_IYZ, TA_IY},
+    /* Ixy :143 */ {TA_IY, TA_M, TA_IXZ, TA_IYZ, TA_IXY, TA_IX, TA_IZ},
+    /* Iyz :144 */ {TA_IZ, TA_M, TA_IXY, TA_IYZ, TA_IXZ, TA_IX, TA_IY},
+    /* Ixz :145 */ {TA_IZ, TA_M, TA_IXY, TA_IYZ, TA_IXZ, TA_IX, TA_IY},
+};
+/* FINAL_MAX, TriAlign_1cyc.v:141-142 */
+static const int kFinalPortSrc[7] = {TA_IXZ, TA_M, TA_IX, TA_IXY, TA_IY, TA_IZ, TA_IYZ};
+/* cost subtracted by destination (row) and source (column), PE_1cyc.v:164-218 */
+static const int kCost[7][7] = {
+    {0, 0, 0, 0, 0, 0, 0},                         /* M   */
+    {GO2, GE2, GOGE, GOGE, GOGE, GO2, GOGE},       /* Ix  */
+    {GO2, GOGE, GE2, GOGE, GOGE, GOGE, GO2},       /* Iy  */
+    {GO2, GOGE, GOGE, GE2, GO2, GOGE, GOGE},       /* Iz  */
+    {GO, GE, GE, GO, GE, GO, GO},                  /* Ixy */
+    {GO, GO, GE, GE, GO, GE, GO},                  /* Iyz */
+    {GO, GE, GO, GE, GO, GO, GE},                  /* Ixz */
+};
+/* predecessor offset of a destination state, and the alignment column it emits (bit0 = A advances, bit1 = B, bit2 = C) */
+static const int kDelta[7][3] = {{1, 1, 1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {1, 1, 0}, {0, 1, 1}, {1, 0, 1}};
+
+/* index (in port order) of the input MAX7 selects */
+static inline int max7_port(const int32_t g[7])
+{
+    const int i1 = g[1] > g[2] ? 1 : 2, i2 = g[4] > g[5] ? 4 : 5, i3 = g[3] > g[6] ? 3 : 6;
+    const int i12 = g[i1] > g[i2] ? i1 : i2;
+    const int i34 = g[i3] > g[0] ? i3 : 0;
+    return g[i12] > g[i34] ? i12 : i34;
+}
+
+int oracle_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                 int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves)
+{
+    if (bad_args(a, la, b, lb, c, lc, score_bits) || !score || !start || !n_moves || cap < 0 || (cap && !moves))
+        return -1;
+    const int sh = 32 - score_bits;
+    *n_moves = 0;
+    start[0] = la; start[1] = lb; start[2] = lc;
+    if (la == 0 || lb == 0 || lc == 0) { *score = 0; return 0; }
+    const size_t sk = 7, sj = (size_t)(lc + 1) * sk, si = (size_t)(lb + 1) * sj;
+    int32_t *cube = (int32_t *)malloc((size_t)(la + 1) * si * sizeof(int32_t));
+    if (!cube) return -2;
+    int rc = oracle_cube(a, la, b, lb, c, lc, score_bits, cube);
+    if (rc) { free(cube); return rc; }
+#define AT(I, J, K) (cube + (size_t)(I) * si + (size_t)(J) * sj + (size_t)(K) * sk)
+    int32_t g[7];
+    const int32_t *fin = AT(la, lb, lc);
+    for (int p = 0; p < 7; ++p) g[p] = fin[kFinalPortSrc[p]];
+    int port = max7_port(g);
+    *score = g[port];
+    int state = kFinalPortSrc[port];
+    int i = la, j = lb, k = lc, n = 0;
+    while (i > 0 && j > 0 && k > 0) {
+        if (n >= cap) { free(cube); return -4; }
+        moves[n++] = (uint8_t)(kDelta[state][0] | (kDelta[state][1] << 1) | (kDelta[state][2] << 2));
+        int sAB, sBC, sAC, sABC;
+        pe_scores(a[i - 1] & 3u, b[j - 1] & 3u, c[k - 1] & 3u, &sAB, &sBC, &sAC, &sABC);
+        const int add = state == TA_M ? sABC : state == TA_IXY ? sAB : state == TA_IYZ ? sBC : state == TA_IXZ ? sAC : 0;
+        const int32_t own = AT(i, j, k)[state];
+        i -= kDelta[state][0]; j -= kDelta[state][1]; k -= kDelta[state][2];
+        const int32_t *pred = AT(i, j, k);  /* all-zero on the three border planes (TriAlign_1cyc.v:156-181) */
+        for (int p = 0; p < 7; ++p) {
+            const int q = kPortSrc[state][p];
+            g[p] = wrapw((uint32_t)(pred[q] - kCost[state][q] + add), sh);
+        }
+        port = max7_port(g);
+        if (g[port] != own) { free(cube); return -3; }  /* the tables above disagree with pe_cell(): a bug */
+        state = kPortSrc[state][port];
+    }
+#undef AT
+    free(cube);
+    for (int x = 0; x < n / 2; ++x) { const uint8_t t = moves[x]; moves[x] = moves[n - 1 - x]; moves[n - 1 - x] = t; }
+    start[0] = i; start[1] = j; start[2] = k;
+    *n_moves = n;
+    return 0;
+}
+
 int oracle_score_mt(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
                     int score_bits, int threads, int32_t *score, int32_t final_states[7])
 {

@@ -46,6 +46,15 @@ int oracle_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, int
 int oracle_cube(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
                 int score_bits, int32_t *out);
 
+/* Traceback of the recurrence (small cases: keeps the whole cube).  The path starts in the state
+ * FINAL_MAX selects at cell (la,lb,lc) and follows, at every cell, the input the state's MAX7 instance selects (tie rule
+ * of the compare-select tree, PE_1cyc.v:22-28, port wiring :139-145) until it reaches a zero border plane (i, j or k = 0).
+ * moves[0..*n_moves): one byte per alignment column in forward order, bit0/1/2 = A/B/C advances (7 = M, 1 = Ix, 2 = Iy,
+ * 4 = Iz, 3 = Ixy, 6 = Iyz, 5 = Ixz); start[] = the border cell the path begins at.  Returns 0, -1 bad arguments,
+ * -2 out of memory, -3 internal table mismatch, -4 moves[] too small. */
+int oracle_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                 int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves);
+
 /* Synthetic symbol generator of SURVEY.md 8(d): splitmix64 finaliser, top 2 bits. */
 void oracle_synth(uint64_t seed, int64_t triple, int which, int len, uint8_t *out);
 

@@ -58,6 +58,9 @@ def lib() -> C.CDLL:
         L.oracle_cube.restype = C.c_int
         L.oracle_synth.argtypes = [C.c_uint64, C.c_int64, C.c_int, C.c_int, u8p]
         L.oracle_synth.restype = None
+        L.oracle_align.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, i32p, i32p, u8p, C.c_int,
+                                   C.POINTER(C.c_int)]
+        L.oracle_align.restype = C.c_int
         L.oracle_hw_threads.restype = C.c_int
         L.rtl_default_cfg.argtypes = [C.POINTER(RtlCfg), C.c_int]
         L.rtl_model_run.argtypes = [C.POINTER(RtlCfg), u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, i32p, i32p, i64p]
@@ -124,6 +127,55 @@ def cube(a, b, c, score_bits: int = 12) -> np.ndarray:
     if rc:
         raise ValueError(f"oracle_cube rc={rc}")
     return out
+
+
+def align(a, b, c, score_bits: int = 12):
+    """Traceback -> (score, start cell (i,j,k), moves uint8[n] in forward order; bit0/1/2 = A/B/C advances)."""
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    s = C.c_int32()
+    start = np.zeros(3, np.int32)
+    cap = len(a) + len(b) + len(c) + 1
+    moves = np.zeros(cap, np.uint8)
+    n = C.c_int(0)
+    rc = lib().oracle_align(_ptr(a, u8p), len(a), _ptr(b, u8p), len(b), _ptr(c, u8p), len(c), score_bits, C.byref(s),
+                            _ptr(start, i32p), _ptr(moves, u8p), cap, C.byref(n))
+    if rc:
+        raise ValueError(f"oracle_align rc={rc}")
+    return int(s.value), tuple(int(x) for x in start), moves[: n.value].copy()
+
+
+# cost subtracted by destination state (row) and source state (column), order M,Ix,Iy,Iz,Ixy,Iyz,Ixz (SURVEY.md 8(a))
+COST = [[0, 0, 0, 0, 0, 0, 0], [4, 2, 3, 3, 3, 4, 3], [4, 3, 2, 3, 3, 3, 4], [4, 3, 3, 2, 4, 3, 3],
+        [2, 1, 1, 2, 1, 2, 2], [2, 2, 1, 1, 2, 1, 2], [2, 1, 2, 1, 2, 2, 1]]
+STATE_OF_MOVE = {7: 0, 1: 1, 2: 2, 4: 3, 3: 4, 6: 5, 5: 6}
+
+
+def rescore_path(a, b, c, start, moves) -> int:
+    """Independent (pure Python, no wrap) score of an alignment path: the sum of the column scores of SURVEY.md 8(a)
+    minus the transition costs between consecutive columns.  The first column leaves a zero border cell, where all
+    seven states are 0, so it pays the cheapest cost into its state."""
+    i, j, k = start
+    total, prev = 0, None
+    for mv in (int(m) for m in moves):
+        st = STATE_OF_MOVE[mv]
+        i += mv & 1
+        j += (mv >> 1) & 1
+        k += (mv >> 2) & 1
+        A, B, Cc = int(a[i - 1]) & 3, int(b[j - 1]) & 3, int(c[k - 1]) & 3
+        if st == 0:
+            add = 3 if (A == B == Cc) else (0 if A == B else -3)   # src/PE_1cyc.v:162 with Verilog precedence
+        elif st == 4:
+            add = 1 if A == B else -1
+        elif st == 5:
+            add = 1 if B == Cc else -1
+        elif st == 6:
+            add = 1 if A == Cc else -1
+        else:
+            add = 0
+        total += add - (min(COST[st]) if prev is None else COST[st][prev])
+        prev = st
+    assert (i, j, k) == (len(a), len(b), len(c)), "path does not end at (la,lb,lc)"
+    return total
 
 
 def synth(seed: int, triple: int, which: int, length: int) -> np.ndarray:

@@ -154,3 +154,41 @@ def test_rtl_2cyc_bank_select_quirk(ob):
             assert rc == ob.RTL_OK and s == ob.score(a, b, c, 12)[0]
         else:
             assert rc == ob.RTL_EX
+
+
+# ---- traceback ----
+def test_traceback_of_identical_sequences_is_the_main_diagonal(ob):
+    rng = np.random.default_rng(2)
+    a = rng.integers(0, 4, 40, dtype=np.uint8)
+    s, start, moves = ob.align(a, a, a, 12)
+    assert s == 3 * 40 and start == (0, 0, 0) and moves.tolist() == [7] * 40
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 1), (5, 7, 3), (24, 24, 24), (40, 17, 33), (48, 48, 48)])
+def test_traceback_path_rescored_independently_gives_the_score(ob, shape):
+    """Without wrap the path the traceback returns must be worth exactly the score, it must end at (la,lb,lc) and
+    begin on a zero border plane."""
+    rng = np.random.default_rng(sum(shape))
+    for mutated in (True, False):
+        if mutated:
+            a, b, c = ob.mutated_triple(rng, max(shape))
+            a, b, c = a[: shape[0]], b[: shape[1]], c[: shape[2]]
+        else:
+            a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in shape)
+        s, start, moves = ob.align(a, b, c, 16)
+        assert s == ob.score(a, b, c, 16)[0]
+        assert min(start) == 0 and all(m in (1, 2, 3, 4, 5, 6, 7) for m in moves)
+        assert ob.rescore_path(a, b, c, start, moves) == s
+
+
+def test_traceback_follows_wrapped_values_too(ob):
+    """At a score_bits where candidates wrap the traceback still follows what the RTL's MAX7 instances would select
+    (internal check of oracle_align: every step's selected candidate equals the cell's stored state)."""
+    z = np.zeros(24, np.uint8)
+    s, start, moves = ob.align(z, z, z, 7)   # all-'A' L=24 at W=7: score 62, not wrap(72) (SURVEY.md 8(c))
+    assert s == 62 and len(moves) >= 24
+    rng = np.random.default_rng(9)
+    for w in (5, 6, 7, 8):
+        a, b, c = ob.mutated_triple(rng, 30, rate=0.05)
+        s, start, moves = ob.align(a, b, c, w)
+        assert s == ob.score(a, b, c, w)[0]
