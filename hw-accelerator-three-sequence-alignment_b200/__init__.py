@@ -15,6 +15,7 @@ from .trialign import (  # noqa: F401
     TriAlignError,
     build_library,
     device_count,
+    format_alignment,
     last_path,
     last_timing,
     launch_count,

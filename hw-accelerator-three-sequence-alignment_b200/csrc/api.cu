@@ -316,6 +316,60 @@ int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     return TRIALIGN_OK;
 }
 
+int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                   unsigned devices, int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves)
+{
+    if (la < 0 || lb < 0 || lc < 0 || score_bits < 2 || score_bits > 32 || !score || !start || !n_moves) return TRIALIGN_EINVAL;
+    if ((la && !a) || (lb && !b) || (lc && !c) || cap < 0 || (cap && !moves)) return TRIALIGN_EINVAL;
+    ThreadState &ts = tls();
+    ts.last_seconds = -1.0;
+    ts.last_cells = (double)la * lb * lc;
+    ts.last_path = TRIALIGN_PATH_NONE;
+    if (trialign_device_count() == 0) return TRIALIGN_ENODEVICE;
+    *n_moves = 0;
+    start[0] = la; start[1] = lb; start[2] = lc;
+    if (la == 0 || lb == 0 || lc == 0) {  // already on a border plane: empty path, score 0
+        *score = 0;
+        ts.last_seconds = 0.0;
+        return TRIALIGN_OK;
+    }
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(first_device(devices), &ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t total = (size_t)la + lb + lc;
+    if ((rc = ctx->seq.reserve(up(la) + up(lb) + up(lc) + 256))) return rc;
+    if ((rc = ctx->out.reserve(256 + up(total)))) return rc;
+    uint8_t *d_a = (uint8_t *)ctx->seq.ptr, *d_b = d_a + up(la), *d_c = d_b + up(lb);
+    int32_t *d_out = (int32_t *)ctx->out.ptr;
+    uint8_t *d_moves = (uint8_t *)ctx->out.ptr + 256;
+    TA_CUDA(cudaMemcpyAsync(d_a, a, la, cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMemcpyAsync(d_b, b, lb, cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMemcpyAsync(d_c, c, lc, cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaEventRecord(ctx->ev0, st));
+    ts.last_path = TRIALIGN_PATH_TRACEBACK;
+    rc = traceback_run(ctx, st, d_a, la, d_b, lb, d_c, lc, score_bits, d_out, d_moves);
+    if (rc) {
+        cudaStreamSynchronize(st);
+        return rc;
+    }
+    TA_CUDA(cudaEventRecord(ctx->ev1, st));
+    int32_t head[5];
+    TA_CUDA(cudaMemcpyAsync(head, d_out, sizeof head, cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    TA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ts.last_seconds = (double)ms * 1e-3;
+    *score = head[0];
+    start[0] = head[1]; start[1] = head[2]; start[2] = head[3];
+    *n_moves = head[4];
+    if (head[4] > cap) return TRIALIGN_ECAPACITY;
+    if (head[4] > 0) TA_CUDA(cudaMemcpy(moves, d_moves, (size_t)head[4], cudaMemcpyDeviceToHost));
+    return TRIALIGN_OK;
+}
+
 int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len, int score_bits,
                          int backend, unsigned devices, int32_t *scores)
 {

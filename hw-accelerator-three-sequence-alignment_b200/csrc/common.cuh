@@ -50,6 +50,7 @@ struct DeviceCtx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     Scratch seq, out, planes, faces, misc;
+    Scratch dirs;        // direction cube of the traceback path
     Scratch viol;        // range-check flag of the checked fast path (never reallocated by the kernels)
 };
 

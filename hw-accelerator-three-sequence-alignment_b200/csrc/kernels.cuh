@@ -43,6 +43,12 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
 int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                          int64_t n, int len, int32_t *d_scores);
 
+// KT: traceback of one triple (traceback.cu).  d_out: 5 int32 (score, start cell i/j/k, number of columns); d_moves:
+// la+lb+lc bytes, forward order, bit0/1/2 = A/B/C advances.
+size_t traceback_dir_bytes(int la, int lb, int lc);
+int traceback_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
+                  const uint8_t *d_c, int lc, int score_bits, int32_t *d_out, uint8_t *d_moves);
+
 // synthetic generator on the device (synth_kernel.cu)
 int synth_run(cudaStream_t st, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a, uint8_t *d_b,
               uint8_t *d_c);

@@ -1,0 +1,180 @@
+// traceback.cu -- KT: optimal alignment (traceback) of one triple.  SURVEY.md 8(f).2: the RTL ships score-only but
+// carries the hook, MAX7's commented-out `act` output (src/PE_1cyc.v:12,30), which would report WHICH of its seven
+// inputs won.  This path defines the alignment as exactly what those `act` signals would select:
+//   * forward: the literal plane sweep (one launch per anti-diagonal plane d = i+j+k, 49 wrapped candidates per cell)
+//     with every MAX7 evaluated as the RTL's compare-select tree (src/PE_1cyc.v:22-28: `a > b ? a : b`, the second
+//     operand wins a tie) over the instance's own port wiring (:139-145); the winning SOURCE STATE of each of the 7
+//     destination states is packed into one 21-bit direction word per cell, kept for the whole cube in HBM
+//     ([la][lb][lc] uint32, k fastest: coalesced 4-byte stores, 4 B of the ~200 B a cell moves anyway);
+//   * backward: one thread walks from FINAL_MAX's choice at (la,lb,lc) (src/TriAlign_1cyc.v:141-142) along the
+//     direction words until it reaches a zero border plane (i, j or k = 0; src/TriAlign_1cyc.v:156-181), <= la+lb+lc
+//     dependent 4-byte loads.
+// Works for any score_bits in [2,32] (it follows the wrapped values, like the RTL would).  The direction cube limits
+// the size: la*lb*lc*4 bytes must fit the device (4.3 GB at 1024^3); longer triples need checkpointed recomputation,
+// which is not built.
+#include <climits>
+
+#include "kernels.cuh"
+
+namespace trialign {
+
+namespace {
+
+constexpr int kGO = 2, kGE = 1, kGO2 = 4, kGE2 = 2, kGOGE = 3;  // src/PE_1cyc.v:55-61
+
+// state order M,Ix,Iy,Iz,Ixy,Iyz,Ixz; ports in the order G4, G1_A, G1_B, G3_A, G2_A, G2_B, G3_B
+__constant__ int c_port_src[8][7] = {
+    {0, 1, 2, 3, 4, 5, 6},  // M   src/PE_1cyc.v:139
+    {1, 0, 5, 2, 4, 6, 3},  // Ix  :140
+    {2, 0, 6, 1, 4, 5, 3},  // Iy  :141
+    {3, 0, 4, 1, 6, 5, 2},  // Iz  :142
+    {2, 0, 6, 5, 4, 1, 3},  // Ixy :143
+    {3, 0, 4, 5, 6, 1, 2},  // Iyz :144
+    {3, 0, 4, 5, 6, 1, 2},  // Ixz :145
+    {6, 0, 1, 4, 2, 3, 5},  // FINAL_MAX src/TriAlign_1cyc.v:141-142
+};
+// cost subtracted by destination (row) and source (column); src/PE_1cyc.v:164-218, SURVEY.md 8(a)
+__constant__ int c_cost[7][7] = {
+    {0, 0, 0, 0, 0, 0, 0},
+    {kGO2, kGE2, kGOGE, kGOGE, kGOGE, kGO2, kGOGE},
+    {kGO2, kGOGE, kGE2, kGOGE, kGOGE, kGOGE, kGO2},
+    {kGO2, kGOGE, kGOGE, kGE2, kGO2, kGOGE, kGOGE},
+    {kGO, kGE, kGE, kGO, kGE, kGO, kGO},
+    {kGO, kGO, kGE, kGE, kGO, kGE, kGO},
+    {kGO, kGE, kGO, kGE, kGO, kGO, kGE},
+};
+
+__device__ __forceinline__ int wrapw(int x, int sh) { return (int)((unsigned)x << sh) >> sh; }
+
+// index (in port order) of the input the MAX7 tree selects
+__device__ __forceinline__ int max7_port(const int g[7])
+{
+    const int i1 = g[1] > g[2] ? 1 : 2, i2 = g[4] > g[5] ? 4 : 5, i3 = g[3] > g[6] ? 3 : 6;
+    const int v1 = g[1] > g[2] ? g[1] : g[2], v2 = g[4] > g[5] ? g[4] : g[5], v3 = g[3] > g[6] ? g[3] : g[6];
+    const int i12 = v1 > v2 ? i1 : i2, v12 = v1 > v2 ? v1 : v2;
+    const int i34 = v3 > g[0] ? i3 : 0, v34 = v3 > g[0] ? v3 : g[0];
+    return v12 > v34 ? i12 : i34;
+}
+
+// one destination state: value and winning source state
+__device__ __forceinline__ void dest_state(int dest, const int *__restrict__ plane, size_t qstride, size_t idx, bool zero,
+                                           int add, int sh, int &value, unsigned &src)
+{
+    int p[7], g[7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) p[q] = zero ? 0 : plane[q * qstride + idx];
+#pragma unroll
+    for (int port = 0; port < 7; ++port) {
+        int q = c_port_src[dest][port], pv = 0;
+#pragma unroll
+        for (int x = 0; x < 7; ++x) pv = (x == q) ? p[x] : pv;  // keeps p[] in registers
+        g[port] = wrapw((int)((unsigned)pv - (unsigned)c_cost[dest][q] + (unsigned)add), sh);
+    }
+    const int port = max7_port(g);
+    int v = g[0];
+#pragma unroll
+    for (int x = 1; x < 7; ++x) v = (x == port) ? g[x] : v;
+    value = v;
+    src = (unsigned)c_port_src[dest][port];
+}
+
+__global__ void __launch_bounds__(256)
+trace_plane_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, const uint8_t *__restrict__ c, int la,
+                   int lb, int lc, int d, int sh, int *__restrict__ P0, const int *__restrict__ P1,
+                   const int *__restrict__ P2, const int *__restrict__ P3, uint32_t *__restrict__ dir)
+{
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)lb * lc) return;
+    const int k = (int)(e % lc) + 1;
+    const int j = (int)(e / lc) + 1;
+    const int i = d - j - k;
+    if (i < 1 || i > la) return;
+    const size_t row = (size_t)(lc + 1);
+    const size_t qstride = (size_t)(lb + 1) * row;
+    const size_t at = (size_t)j * row + k;
+    const unsigned A = a[i - 1] & 3u, B = b[j - 1] & 3u, C = c[k - 1] & 3u;
+    // src/PE_1cyc.v:159-162 (Verilog precedence: `+` binds tighter than `<<`)
+    const int sAB = (A == B) ? 1 : -1, sBC = (B == C) ? 1 : -1, sAC = (A == C) ? 1 : -1;
+    const int sABC = (A == B) ? ((B == C) ? 3 : 0) : -3;
+    const bool first = (i == 1);  // the i = 0 plane is all-zero (PE override, src/PE_1cyc.v:164-178)
+    int v[7];
+    unsigned s[7];
+    dest_state(0, P3, qstride, at - row - 1, first, sABC, sh, v[0], s[0]);  // M   <- (i-1,j-1,k-1)
+    dest_state(1, P1, qstride, at, first, 0, sh, v[1], s[1]);               // Ix  <- (i-1,j,k)
+    dest_state(2, P1, qstride, at - row, false, 0, sh, v[2], s[2]);         // Iy  <- (i,j-1,k)
+    dest_state(3, P1, qstride, at - 1, false, 0, sh, v[3], s[3]);           // Iz  <- (i,j,k-1)
+    dest_state(4, P2, qstride, at - row, first, sAB, sh, v[4], s[4]);       // Ixy <- (i-1,j-1,k)
+    dest_state(5, P2, qstride, at - row - 1, false, sBC, sh, v[5], s[5]);   // Iyz <- (i,j-1,k-1)
+    dest_state(6, P2, qstride, at - 1, first, sAC, sh, v[6], s[6]);         // Ixz <- (i-1,j,k-1)
+    unsigned word = 0;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        P0[q * qstride + at] = v[q];
+        word |= s[q] << (3 * q);
+    }
+    dir[((size_t)(i - 1) * lb + (j - 1)) * lc + (k - 1)] = word;
+}
+
+// out[0] = score, out[1..3] = start cell, out[4] = number of columns; moves[] in forward order
+__global__ void trace_walk_kernel(const uint32_t *__restrict__ dir, const int *__restrict__ Pfin, int la, int lb, int lc,
+                                  int32_t *__restrict__ out, uint8_t *__restrict__ moves)
+{
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const size_t row = (size_t)(lc + 1), qstride = (size_t)(lb + 1) * row, at = (size_t)lb * row + lc;
+    int g[7];
+    for (int port = 0; port < 7; ++port) g[port] = Pfin[c_port_src[7][port] * qstride + at];
+    int port = max7_port(g);
+    out[0] = g[port];
+    int state = c_port_src[7][port];
+    int i = la, j = lb, k = lc, n = 0;
+    while (i > 0 && j > 0 && k > 0) {
+        // M=7 (all advance), Ix=1 (A), Iy=2 (B), Iz=4 (C), Ixy=3, Iyz=6, Ixz=5
+        const int mv = state == 0 ? 7 : state == 1 ? 1 : state == 2 ? 2 : state == 3 ? 4 : state == 4 ? 3 : state == 5 ? 6 : 5;
+        moves[n++] = (uint8_t)mv;
+        const uint32_t w = dir[((size_t)(i - 1) * lb + (j - 1)) * lc + (k - 1)];
+        i -= mv & 1;
+        j -= (mv >> 1) & 1;
+        k -= (mv >> 2) & 1;
+        state = (int)((w >> (3 * state)) & 7u);
+    }
+    for (int x = 0; x < n / 2; ++x) {
+        const uint8_t t = moves[x];
+        moves[x] = moves[n - 1 - x];
+        moves[n - 1 - x] = t;
+    }
+    out[1] = i; out[2] = j; out[3] = k; out[4] = n;
+}
+
+}  // namespace
+
+size_t traceback_dir_bytes(int la, int lb, int lc) { return (size_t)la * lb * lc * sizeof(uint32_t); }
+
+// d_out: 5 int32 (score, start i/j/k, columns); d_moves: la+lb+lc bytes
+int traceback_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
+                  const uint8_t *d_c, int lc, int score_bits, int32_t *d_out, uint8_t *d_moves)
+{
+    const int sh = 32 - score_bits;
+    const size_t plane_elems = 7 * (size_t)(lb + 1) * (lc + 1);
+    int rc = ctx->planes.reserve(4 * plane_elems * sizeof(int));
+    if (rc) return rc;
+    if ((rc = ctx->dirs.reserve(traceback_dir_bytes(la, lb, lc)))) return rc;
+    int *base = (int *)ctx->planes.ptr;
+    uint32_t *dir = (uint32_t *)ctx->dirs.ptr;
+    TA_CUDA(cudaMemsetAsync(base, 0, 4 * plane_elems * sizeof(int), st));
+    const long long cells = (long long)lb * lc;
+    const unsigned blocks = (unsigned)((cells + 255) / 256);
+    for (int d = 3; d <= la + lb + lc; ++d) {
+        trace_plane_kernel<<<blocks, 256, 0, st>>>(d_a, d_b, d_c, la, lb, lc, d, sh, base + (size_t)(d & 3) * plane_elems,
+                                                   base + (size_t)((d - 1) & 3) * plane_elems,
+                                                   base + (size_t)((d - 2) & 3) * plane_elems,
+                                                   base + (size_t)((d - 3) & 3) * plane_elems, dir);
+        count_launch();
+    }
+    TA_CUDA(cudaGetLastError());
+    trace_walk_kernel<<<1, 32, 0, st>>>(dir, base + (size_t)((la + lb + lc) & 3) * plane_elems, la, lb, lc, d_out, d_moves);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+}  // namespace trialign

@@ -25,7 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.environ.get("TRIALIGN_LIB") or os.path.join(_HERE, "lib", "libtrialign.so")  # override: development A/B builds
 
 BACKEND_AUTO, BACKEND_GPU, BACKEND_GPU_LITERAL, BACKEND_GPU_FAST = 0, 4, 5, 6
-PATH_NAMES = {0: "none", 1: "literal", 2: "fast_batch", 3: "fast_long", 4: "fast_then_literal"}
+PATH_NAMES = {0: "none", 1: "literal", 2: "fast_batch", 3: "fast_long", 4: "fast_then_literal", 5: "traceback"}
 
 _u8p = C.POINTER(C.c_uint8)
 _i32p = C.POINTER(C.c_int32)
@@ -76,6 +76,9 @@ def library() -> C.CDLL:
     L.trialign_device_count.restype = C.c_int
     L.trialign_score.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p, _i32p]
     L.trialign_score.restype = C.c_int
+    L.trialign_align.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_uint, _i32p, _i32p, _u8p,
+                                 C.c_int, C.POINTER(C.c_int)]
+    L.trialign_align.restype = C.c_int
     L.trialign_score_batch.argtypes = [_u8p, _u8p, _u8p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p]
     L.trialign_score_batch.restype = C.c_int
     L.trialign_score_batch_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
@@ -191,6 +194,21 @@ class TriAlign:
         _check(rc, "trialign_score")
         return (int(s.value), fin) if return_states else int(s.value)
 
+    def traceback(self, A, B, C_):
+        """Optimal alignment of one triple -> (score, start cell (i0,j0,k0), moves uint8[columns]).  moves are in
+        forward order, bit0/1/2 = A/B/C advances (7 = all three aligned); see format_alignment()."""
+        a, b, c = _u8(A), _u8(B), _u8(C_)
+        s = C.c_int32(0)
+        start = np.zeros(3, np.int32)
+        cap = a.size + b.size + c.size + 1
+        moves = np.zeros(cap, np.uint8)
+        n = C.c_int(0)
+        rc = library().trialign_align(_p(a, _u8p), a.size, _p(b, _u8p), b.size, _p(c, _u8p), c.size, self.score_bits,
+                                      _devmask(self.devices), C.byref(s), _p(start, _i32p), _p(moves, _u8p), cap,
+                                      C.byref(n))
+        _check(rc, "trialign_align")
+        return int(s.value), tuple(int(x) for x in start), moves[: n.value].copy()
+
     def align_batch(self, A, B, C_) -> np.ndarray:
         a, b, c = _u8(A), _u8(B), _u8(C_)
         if a.ndim != 2 or a.shape != b.shape or a.shape != c.shape:
@@ -233,6 +251,21 @@ class TriAlign:
                                           st.cuda_stream)
         _check(rc, "trialign_score_dev")
         return out
+
+
+def format_alignment(A, B, C_, start, moves, alphabet: str = "ATCGN") -> Tuple[str, str, str]:
+    """Three gapped rows for the path TriAlign.traceback() returns (testbench symbol names: A=0 T=1 C=2 G=3 N=4)."""
+    seqs = (_u8(A), _u8(B), _u8(C_))
+    pos = [int(x) for x in start]
+    rows = ["", "", ""]
+    for mv in (int(m) for m in moves):
+        for w in range(3):
+            if (mv >> w) & 1:
+                rows[w] += alphabet[int(seqs[w][pos[w]]) & 7] if int(seqs[w][pos[w]]) < len(alphabet) else "?"
+                pos[w] += 1
+            else:
+                rows[w] += "-"
+    return rows[0], rows[1], rows[2]
 
 
 # ---- file formats of the reference's dat/ directory ----

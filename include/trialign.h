@@ -69,7 +69,8 @@ enum trialign_path {
     TRIALIGN_PATH_LITERAL = 1,        /* plane-sweep literal kernel */
     TRIALIGN_PATH_FAST_BATCH = 2,     /* K1: batched systolic kernel, two triples per 32-bit lane */
     TRIALIGN_PATH_FAST_LONG = 3,      /* K2: block-dataflow kernel for one long triple */
-    TRIALIGN_PATH_FAST_THEN_LITERAL = 4 /* fast kernel ran, its range check failed, literal kernel re-ran */
+    TRIALIGN_PATH_FAST_THEN_LITERAL = 4, /* fast kernel ran, its range check failed, literal kernel re-ran */
+    TRIALIGN_PATH_TRACEBACK = 5       /* KT: literal plane sweep with a direction cube + backward walk */
 };
 
 int trialign_version(void);
@@ -96,6 +97,17 @@ int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b,
 /* d_out: int32[8] = score followed by the 7 final states. */
 int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
                        int lc, int score_bits, int backend, int32_t *d_out, void *stream);
+
+/* Optimal alignment of one triple (host pointers): the traceback of the recurrence, defined as what the MAX7
+ * instances' commented-out `act` outputs would select (src/PE_1cyc.v:12,22-30,139-145; SURVEY.md 8(f).2 -- the RTL
+ * itself ships score-only).  The path runs from the border cell start[] = (i0,j0,k0) (one of them 0: all three border
+ * planes are zero, src/TriAlign_1cyc.v:156-181, so the symbols before it are unaligned and free) to (la,lb,lc).
+ * moves[0..*n_moves): one byte per alignment column, first column first: bit0 = A advances, bit1 = B, bit2 = C
+ * (7 = three symbols aligned / state M, 1 = Ix, 2 = Iy, 4 = Iz, 3 = Ixy, 6 = Iyz, 5 = Ixz).  *score equals
+ * trialign_score()'s.  cap < *n_moves gives ECAPACITY (cap = la+lb+lc always suffices); the direction cube needs
+ * la*lb*lc*4 bytes of device memory (ENOMEM beyond that).  Any score_bits in [2,32]. */
+int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                   unsigned devices, int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves);
 
 /* ---- i-slab pipeline: ONE long triple over several GPUs, one process per GPU ----
  * Rank g computes planes (i_begin, i_end] of the cube for every (j,k) block and hands the plane-i_end state of each

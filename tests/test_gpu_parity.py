@@ -248,3 +248,61 @@ def test_fast_kernels_agree_with_literal_kernel_beyond_oracle_sizes(gpu_ta):
     assert fast[0] == lit[0] and fast[1].tolist() == lit[1].tolist()
     x = gpu_ta.synth(0x5EED0005, 0, 0, 4096)
     assert gpu_ta.TriAlign(16).align(x, x, x) == 3 * 4096
+
+
+# ---- traceback (trialign_align) ----
+@pytest.mark.parametrize("shape,w", [((1, 1, 1), 12), ((5, 7, 3), 12), ((24, 24, 24), 7), ((40, 17, 33), 12),
+                                     ((64, 64, 64), 12), ((30, 30, 30), 6), ((96, 80, 100), 16), ((128, 128, 128), 12)])
+def test_traceback_matches_the_oracle_move_for_move(gpu_ta, ob, shape, w):
+    """Same MAX7 tie rule on both sides, so the whole path -- not only its score -- must be identical, also where
+    candidates wrap at score_bits."""
+    rng = np.random.default_rng(sum(shape) * 31 + w)
+    eng = gpu_ta.TriAlign(score_bits=w)
+    for mutated in (True, False):
+        if mutated:
+            a, b, c = ob.mutated_triple(rng, max(shape), rate=0.1)
+            a, b, c = a[: shape[0]], b[: shape[1]], c[: shape[2]]
+        else:
+            a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in shape)
+        s, start, moves = eng.traceback(a, b, c)
+        es, estart, emoves = ob.align(a, b, c, w)
+        assert gpu_ta.last_path() == "traceback"
+        assert (s, start) == (es, estart), (shape, w, mutated)
+        assert moves.tolist() == emoves.tolist(), (shape, w, mutated)
+
+
+def test_traceback_golden_dat_triple_and_edges(gpu_ta, ob, golden):
+    d = golden["dat"]
+    eng = gpu_ta.TriAlign(score_bits=12)
+    s, start, moves = eng.traceback(d["A"], d["B"], d["C"])
+    assert s == 1 and ob.rescore_path(d["A"], d["B"], d["C"], start, moves) == 1
+    assert (s, start, moves.tolist()) == (lambda r: (r[0], r[1], r[2].tolist()))(ob.align(d["A"], d["B"], d["C"], 12))
+    z = np.zeros(64, np.uint8)
+    s, start, moves = eng.traceback(z, z, z)                      # the testbench as shipped
+    assert s == 192 and start == (0, 0, 0) and moves.tolist() == [7] * 64
+    rows = gpu_ta.format_alignment(z, z, z, start, moves)
+    assert rows == ("A" * 64,) * 3
+    e = np.zeros(0, np.uint8)
+    assert eng.traceback(e, z, z)[0] == 0 and eng.traceback(e, z, z)[2].size == 0
+    # capacity error instead of a truncated path
+    import ctypes as C
+    L = gpu_ta.library()
+    u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
+    sc, n = C.c_int32(0), C.c_int(0)
+    st = np.zeros(3, np.int32)
+    mv = np.zeros(8, np.uint8)
+    rc = L.trialign_align(z.ctypes.data_as(u8p), 64, z.ctypes.data_as(u8p), 64, z.ctypes.data_as(u8p), 64, 12, 0,
+                          C.byref(sc), st.ctypes.data_as(i32p), mv.ctypes.data_as(u8p), 8, C.byref(n))
+    assert rc == -8 and n.value == 64 and sc.value == 192
+
+
+@pytest.mark.parametrize("length", [256, 384])
+def test_traceback_long_triple_path_is_worth_the_fast_kernels_score(gpu_ta, ob, length):
+    """Beyond the sizes the CPU oracle's cube handles quickly: the path must be a valid alignment whose independent
+    re-scoring equals the score the (separately verified) fast kernels report."""
+    rng = np.random.default_rng(length)
+    a, b, c = ob.mutated_triple(rng, length, rate=0.2)
+    eng = gpu_ta.TriAlign(score_bits=16)
+    s, start, moves = eng.traceback(a, b, c)
+    assert s == eng.align(a, b, c) and min(start) == 0
+    assert ob.rescore_path(a, b, c, start, moves) == s

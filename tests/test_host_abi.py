@@ -118,6 +118,9 @@ def test_no_cpu_fallback_without_a_gpu(ta):
     with pytest.raises(ta.TriAlignError) as ei:
         ta.TriAlign().align([0, 1, 2], [0, 1, 2], [0, 1, 2])
     assert ei.value.rc == -7  # ENODEVICE, not a silently computed score
+    with pytest.raises(ta.TriAlignError) as ei:
+        ta.TriAlign(12).traceback([0, 1, 2], [0, 1, 2], [0, 1, 2])
+    assert ei.value.rc == -7
     with pytest.raises(ta.TriAlignError):
         ta.TriAlign().align_batch(np.zeros((2, 4), np.uint8), np.zeros((2, 4), np.uint8), np.zeros((2, 4), np.uint8))
     assert ta.launch_count() == 0
