@@ -98,6 +98,8 @@ struct SweepSmem {
     uint32_t tabAB[16][C::TAB_STRIDE];        // [a code][j]  pair constant {4,2}
     uint32_t tabMB[16][C::TAB_STRIDE];        // [a code][j]  triple row constant {9,3}
     uint32_t tabK[16][C::TABK_STRIDE];        // [a code][k] pair constant {4,2}, [a code][64 + k] triple column constant {9,6}
+    uint32_t tabBC[C::BJ][C::BK];             // [j][k]  (b,c) pair constant {4,2} of every cell of the block: read every step
+                                              // instead of living in 16 registers (the LONG kernel is register-bound)
     uint8_t seqA[2][C::LA_MAX];               // [half][i]   (LONG: only [0] is used)
     uint8_t seqB[2][64], seqC[2][64];         // [half][pos in block]
     SweepTask task;
@@ -106,7 +108,6 @@ struct SweepSmem {
 template <class C>
 struct SweepRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
-    uint32_t cBC[C::RJ][C::RK];                                                        // per-cell constant
     uint32_t viol;                                                                     // range-check violations seen
 };
 
@@ -233,7 +234,7 @@ TA_HD void sweep_build_tables(SweepSmem<C> &S, int tid)
 }
 
 template <class C>
-TA_HD void sweep_init_thread(SweepRegs<C> &R, const SweepSmem<C> &S, int tj, int tk)
+TA_HD void sweep_init_thread(SweepRegs<C> &R, SweepSmem<C> &S, int tj, int tk)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int j0 = tj * RJ, k0 = tk * RK;
@@ -244,7 +245,7 @@ TA_HD void sweep_init_thread(SweepRegs<C> &R, const SweepSmem<C> &S, int tj, int
             const uint32_t bp = (uint32_t)S.seqB[0][j0 + r] | ((uint32_t)S.seqB[1][j0 + r] << 16);
             const uint32_t cp = (uint32_t)S.seqC[0][k0 + c] | ((uint32_t)S.seqC[1][k0 + c] << 16);
             const uint32_t nbc = neq_flag(bp, cp);
-            R.cBC[r][c] = pair_const(nbc);
+            S.tabBC[j0 + r][k0 + c] = pair_const(nbc);
             R.all[r][c] = R.wX[r][c] = R.u1[r][c] = R.u3[r][c] = 0;
         }
     R.viol = 0;
@@ -513,7 +514,7 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, const SweepConsts<C> &K, SweepSmem
             const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
             const uint32_t cM = triple_const(K.tB[r], K.tC[c]);
             const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
-                                                 R.cBC[r][c], K.cAC[c], nullptr);
+                                                 S.tabBC[j0 + r][k0 + c], K.cAC[c], nullptr);
             n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
             n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
         }
@@ -603,7 +604,7 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, const SweepConsts<C> &K, SweepSmem
                         const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
                         const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
                         cell_update<true>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3,
-                                          triple_const(K.tB[r], K.tC[c]), K.cAB[r], R.cBC[r][c], K.cAC[c], st);
+                                          triple_const(K.tB[r], K.tC[c]), K.cAB[r], S.tabBC[j0 + r][k0 + c], K.cAC[c], st);
                     }
             // potential of the cell in each half's own frame
             const int off_lo = A.base + 2 * (A.la + jl + kl);
