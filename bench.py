@@ -107,13 +107,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline(length, score_bits, target_s=12.0):
+def host_threads():
+    """Cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU baseline)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline(length, score_bits, target_s=22.0):
     """Times the CPU oracle (kind 'port': O1, all host threads) and the RTL cycle model on a bounded sample."""
     import numpy as np
 
     import oracle_bindings as ob
 
-    threads = ob.lib().oracle_hw_threads()
+    threads = host_threads()
     L = min(length, 256) if length > 256 else length
     per = float(L) ** 3
     probe_n = max(4 * threads, 64) if L <= 64 else max(2, threads // 2)
@@ -121,12 +129,12 @@ def cpu_baseline(length, score_bits, target_s=12.0):
     rate = 0.0
     for _ in range(2):  # the first pass also pays for the OpenMP thread start-up
         t0 = time.perf_counter()
-        ob.score_batch(a, b, c, score_bits)
+        ob.score_batch(a, b, c, score_bits, threads)
         rate = max(rate, probe_n * per / (time.perf_counter() - t0))
     n = int(max(probe_n, min(1 << 18, target_s * rate / per)))
     a, b, c = ob.synth_batch(0x5EED0002, 0, n, L)
     t0 = time.perf_counter()
-    ob.score_batch(a, b, c, score_bits)
+    ob.score_batch(a, b, c, score_bits, threads)
     dt = time.perf_counter() - t0
     out = {"value": n * per / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
            "sample": f"{n} synthetic triples of length {L}, W={score_bits}, functional oracle O1 (OpenMP over triples), {dt:.1f} s"}
@@ -142,7 +150,7 @@ def cpu_baseline(length, score_bits, target_s=12.0):
         tot = C.c_int64(0)
         t0 = time.perf_counter()
         rcode = ob.lib().rtl_model_run_batch(C.byref(cfg), ra.ctypes.data_as(ob.u8p), rb.ctypes.data_as(ob.u8p),
-                                             rc.ctypes.data_as(ob.u8p), m, 64, 0, sc.ctypes.data_as(ob.i32p), C.byref(tot))
+                                             rc.ctypes.data_as(ob.u8p), m, 64, threads, sc.ctypes.data_as(ob.i32p), C.byref(tot))
         dt = time.perf_counter() - t0
         if rcode == 0:
             out["rtl_sim"] = {"kind": "hand-written cycle-accurate C++ model of TriAlign_1cyc/PE_1cyc (no Verilog simulator in the image)",
@@ -161,22 +169,22 @@ def run_reference(args, rank, world):
     import oracle_bindings as ob
 
     cfg, n_full, length, w = WORKLOADS[args.workload]
-    threads = ob.lib().oracle_hw_threads()
+    threads = host_threads()
     L = min(length, 256)
     per = float(L) ** 3
     n = max(threads * 2, 16) if L <= 64 else max(2, threads // 2)
     a, b, c = ob.synth_batch(0x5EED0000 + cfg, 0, n, L)
     t0 = time.perf_counter()
-    ob.score_batch(a, b, c, w)
+    ob.score_batch(a, b, c, w, threads)
     probe = time.perf_counter() - t0
     n = int(max(n, min(1 << 15, 6.0 / max(probe / n, 1e-9))))  # ~6 s per step
     a, b, c = ob.synth_batch(0x5EED0000 + cfg, 0, n, L)
     for _ in range(max(args.warmup, 0) and 1):
-        ob.score_batch(a, b, c, w)
+        ob.score_batch(a, b, c, w, threads)
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        ob.score_batch(a, b, c, w)
+        ob.score_batch(a, b, c, w, threads)
         times.append(time.perf_counter() - t0)
     dt = sum(times) / len(times)
     val = n * per / dt / 1e9
@@ -184,7 +192,8 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "3D-GCUPS", "value": val, "unit": "GCUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int32 (wrap at W)", "data": "synthetic",
-            "config": {"workload": args.workload, "triples_per_step": n, "length": L, "score_bits": w},
+            "config": {"workload": args.workload, "baseline_config": cfg, "triples_per_gpu": n_full, "length": length,
+                       "score_bits": w, "sample_triples_per_step": n, "sample_length": L},
             "cpu_baseline": {"value": val, "unit": "GCUPS", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
