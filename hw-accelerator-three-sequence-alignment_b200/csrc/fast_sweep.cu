@@ -102,10 +102,14 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
         const int *top_p = T.top_task >= 0 ? A.progress + T.top_task : nullptr;
         const int *left_p = T.left_task >= 0 ? A.progress + T.left_task : nullptr;
 
-        // prologue: halos of step 0
+        // prologue: halos of step 0.  cert = last fetch step whose face rows are known to be complete.
+        int cert = -2;
         if (tid == kGateTid) {
-            while (!fast::sweep_deps_ready<C>(A, T, -1, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0))
+            for (;;) {
+                cert = fast::sweep_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);
+                if (cert >= -1) break;
                 __nanosleep(100);
+            }
         }
         __syncthreads();
         fast::sweep_edge_fetch<C>(S, A, tj, tk, -1);
@@ -115,27 +119,28 @@ __global__ void __launch_bounds__(LongCfg::NT, 1) sweep_long_kernel(fast::SweepA
 
 #pragma unroll 1
         for (int s = 0; s <= steps; ++s) {
-            const bool gate = fast::sweep_is_gate<C>(A, s);
-            // the producers' progress is sampled at the top of a gate step, so the load latency hides under the tile
+            // the fetch of step s+1 must be certified before the barrier that ends step s; the producers' progress is
+            // sampled at the top of the step, so the load latency hides under the tile
+            const bool need = tid == kGateTid && cert < s + 1;
             int tp = 0, lp = 0;
-            if (gate && tid == kGateTid) {
+            if (need) {
                 tp = top_p ? ld_acquire(top_p) : 0;
                 lp = left_p ? ld_acquire(left_p) : 0;
             }
-            fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows certified by the last gate
+            fast::sweep_edge_fetch<C>(S, A, tj, tk, s);  // rows certified during the previous steps
             fast::sweep_thread_step<C, CHECK>(R, K, S, A, tj, tk, s, tid);
             fast::sweep_thread_prepare<C>(R, K, S, A, tj, tk, s + 1, tid);
             fast::ta_copy_wait();
-            if (gate && tid == kGateTid) {
-                while (!fast::sweep_deps_ready<C>(A, T, s, tp, lp)) {
+            if (need) {
+                cert = fast::sweep_certified<C>(A, T, tp, lp);
+                while (cert < s + 1) {
                     __nanosleep(40);
-                    tp = top_p ? ld_acquire(top_p) : 0;
-                    lp = left_p ? ld_acquire(left_p) : 0;
+                    cert = fast::sweep_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);
                 }
             }
             __syncthreads();
             // release: the edge threads' face stores of the steps so far are ordered before the barrier above
-            if (gate && tid == kGateTid) st_release(A.progress + T.self_task, s + 1);
+            if (tid == kGateTid && fast::sweep_publish_now<C>(A, s)) st_release(A.progress + T.self_task, s + 1);
         }
         if (CHECK && R.viol) atomicOr(A.viol_flag, 1);
         if (tid == kGateTid) {

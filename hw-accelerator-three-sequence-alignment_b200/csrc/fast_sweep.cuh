@@ -64,7 +64,7 @@ struct SweepArgs {
     uint32_t *face_j, *face_k;    // ring storage
     long long fj_slot_words, fk_slot_words;
     int fj_ring, fk_ring;         // LONG: global ring sizes; BATCH: per-CTA ring sizes
-    int gate;                     // LONG: steps between two dependency gates / progress releases (power of two)
+    int gate;                     // LONG: steps between two progress releases in steady state (power of two)
     int *progress;                // LONG: [tasks_total] indexed by task id bj + nbj*bkp, zero-initialised
     const int *order;             // LONG: claim position -> task id (sorted by earliest possible start, sweep_order_key)
     const int *pos_of;            // LONG: task id -> claim position
@@ -652,27 +652,39 @@ TA_HD void sweep_thread_step(SweepRegs<C> &R, const SweepConsts<C> &K, SweepSmem
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// LONG mode dependency gating (evaluated by one thread).  progress[t] = number of wavefront steps task t has completed
-// (kProgressDone once it is finished).  Writers and readers of a face are skewed alike: thread (0,tk) fetches at its
-// step f the row that producer thread (15,tk) wrote at producer step f+16, and thread (tj,0) fetches the row that
-// producer thread (tj,15) wrote at step f+16+LAG.  Gates are evaluated every kSweepGate steps, before the barrier
-// that ends step g, and certify the fetches of steps g+1 .. g+gate.  The gate interval A.gate (a power of two) trades
-// pipeline fill (a consumer trails its producer by 16 + gate steps) against the cost of a release: the st.release.gpu
-// is a MEMBAR that holds one warp, and hence the next CTA barrier, for hundreds of cycles.
+// LONG mode dependency tracking (evaluated by one thread).  progress[t] = number of wavefront steps task t has completed
+// AND published (kProgressDone once it is finished).  Writers and readers of a face are skewed alike: thread (0,tk)
+// fetches at its step f the row that producer thread (15,tk) wrote at producer step f+16, and thread (tj,0) fetches the
+// row that producer thread (tj,15) wrote at step f+16+LAG.
+//   consumer: sweep_certified() turns the producers' progress into the last fetch step that is safe; the kernel samples
+//     the counters only when its next fetch is not certified yet, whatever the producers' publication rhythm;
+//   producer: sweep_publish_now() -- every 2 steps during the first kEarlySteps steps of a task (tasks waiting to start
+//     need only 16 / 32 rows: the pipeline fill per block hop is 18 / 34 steps), every A.gate steps afterwards (a
+//     release is a MEMBAR.GPU that holds one warp, and hence the next CTA barrier, for hundreds of cycles).
 // ---------------------------------------------------------------------------------------------------------------
-template <class C>
-TA_HD bool sweep_is_gate(const SweepArgs &A, int g) { return ((g + 1) & (A.gate - 1)) == 0; }
+constexpr int kEarlySteps = 64, kEarlyGate = 2;
+constexpr int kCertifiedAll = 1 << 30;
 
 template <class C>
-TA_HD bool sweep_deps_ready(const SweepArgs &A, const SweepTask &T, int g, int top_prog, int left_prog)
+TA_HD bool sweep_publish_now(const SweepArgs &A, int s)
+{
+    const int gate = (s < kEarlySteps && A.gate > kEarlyGate) ? kEarlyGate : A.gate;
+    return ((s + 1) & (gate - 1)) == 0;
+}
+
+// last fetch step (the fetch at step f brings the halos of step f+1; the prologue fetch is f = -1) whose face rows are
+// complete, given the progress of the task above (top) and of the task to the left
+template <class C>
+TA_HD int sweep_certified(const SweepArgs &A, const SweepTask &T, int top_prog, int left_prog)
 {
     const int total = sweep_task_steps<C>(A) + 1;  // steps 0..steps
-    const int f = g + A.gate;                      // last fetch this gate certifies
-    const int need_top = (f + C::TJ + 1 < total) ? f + C::TJ + 1 : total;
-    const int need_left = (f + C::TK + C::LAG + 1 < total) ? f + C::TK + C::LAG + 1 : total;
-    if (T.top_task >= 0 && top_prog < need_top) return false;
-    if (T.left_task >= 0 && left_prog < need_left) return false;
-    return true;
+    int cert = kCertifiedAll;
+    if (T.top_task >= 0 && top_prog < total) cert = top_prog - (C::TJ + 1);
+    if (T.left_task >= 0 && left_prog < total) {
+        const int c2 = left_prog - (C::TK + C::LAG + 1);
+        cert = c2 < cert ? c2 : cert;
+    }
+    return cert;
 }
 
 }  // namespace fast

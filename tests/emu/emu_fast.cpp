@@ -126,7 +126,7 @@ struct EmuCta {
     std::vector<SweepRegs<C>> R = std::vector<SweepRegs<C>>(C::NT);
     std::vector<SweepConsts<C>> K = std::vector<SweepConsts<C>>(C::NT);
     bool has_task = false, prologue_done = false;
-    int s = 0;
+    int s = 0, cert = -2;
     void setup(const SweepArgs &A)
     {
         for (int tid = 0; tid < C::NT; ++tid) sweep_load_bc<C>(*S, A, tid);
@@ -138,6 +138,7 @@ struct EmuCta {
         }
         prologue_done = false;
         s = 0;
+        cert = -2;
     }
     void fetch(const SweepArgs &A, int step)
     {
@@ -236,18 +237,23 @@ int run_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *
             const SweepTask &T = cta.S->task;
             const int tp = T.top_task >= 0 ? prog[T.top_task] : 0, lp = T.left_task >= 0 ? prog[T.left_task] : 0;
             if (!cta.prologue_done) {
-                if (!sweep_deps_ready<C>(A, T, -1, tp, lp)) continue;
+                cta.cert = sweep_certified<C>(A, T, tp, lp);
+                if (cta.cert < -1) continue;
                 cta.fetch(A, -1);
                 cta.prepare0(A);
                 cta.prologue_done = true;
                 progressed = true;
                 continue;
             }
-            // the gate before the barrier of step s-1 certifies the fetches of the following steps
-            if (sweep_is_gate<C>(A, cta.s - 1) && !sweep_deps_ready<C>(A, T, cta.s - 1, tp, lp)) continue;
+            // the fetch of step s must have been certified before the barrier that ended step s-1 (the kernel samples
+            // the counters only when it has to)
+            if (cta.cert < cta.s) {
+                cta.cert = sweep_certified<C>(A, T, tp, lp);
+                if (cta.cert < cta.s) continue;
+            }
             cta.fetch(A, cta.s);
             cta.step(A, cta.s);
-            if (sweep_is_gate<C>(A, cta.s)) prog[T.self_task] = cta.s + 1;
+            if (sweep_publish_now<C>(A, cta.s)) prog[T.self_task] = cta.s + 1;
             progressed = true;
             if (++cta.s > steps) {
                 if (cta.viol()) viol = 1;

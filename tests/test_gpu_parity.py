@@ -306,3 +306,14 @@ def test_traceback_long_triple_path_is_worth_the_fast_kernels_score(gpu_ta, ob, 
     s, start, moves = eng.traceback(a, b, c)
     assert s == eng.align(a, b, c) and min(start) == 0
     assert ob.rescore_path(a, b, c, start, moves) == s
+
+
+def test_traceback_golden_paths(gpu_ta, golden):
+    """Every golden case (dat/ triple, prefixes, role permutations, wrap cases, ragged lengths): the GPU traceback
+    must reproduce the frozen path, start cell and score."""
+    for case in golden["cases"]:
+        a, b, c = _abc(case)
+        s, start, moves = gpu_ta.TriAlign(score_bits=case["score_bits"]).traceback(a, b, c)
+        assert s == case["score"], case["name"]
+        assert list(start) == case["traceback"]["start"], case["name"]
+        assert "".join(str(int(m)) for m in moves) == case["traceback"]["moves"], case["name"]

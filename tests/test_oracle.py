@@ -192,3 +192,14 @@ def test_traceback_follows_wrapped_values_too(ob):
         a, b, c = ob.mutated_triple(rng, 30, rate=0.05)
         s, start, moves = ob.align(a, b, c, w)
         assert s == ob.score(a, b, c, w)[0]
+
+
+def test_traceback_golden_paths(ob, golden):
+    """tests/golden/golden.json freezes oracle_align's path for every golden case (make_golden.py also re-scores each
+    wrap-free one); the oracle must keep reproducing them."""
+    for case in golden["cases"]:
+        a, b, c = (np.array(case[k], np.uint8) for k in "abc")
+        s, start, moves = ob.align(a, b, c, case["score_bits"])
+        assert s == case["score"], case["name"]
+        assert list(start) == case["traceback"]["start"], case["name"]
+        assert "".join(str(int(m)) for m in moves) == case["traceback"]["moves"], case["name"]

@@ -1,4 +1,5 @@
-"""Small driver for compute-sanitizer runs: exercises every kernel family once on tiny inputs and checks the oracle."""
+"""Exercises every kernel family once on tiny inputs and checks the oracle (seconds on a GPU box; used before timing
+runs in tools/perf_quick.sh).  usage: python tools/tiny_cases.py [all|k1|k2b|k2l|lit]"""
 import os
 import sys
 
