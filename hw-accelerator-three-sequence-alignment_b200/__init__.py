@@ -25,6 +25,7 @@ from .trialign import (  # noqa: F401
     read_scores,
     read_seq_dat,
     synth,
+    triple_indices,
     unpack_seq_ram128,
     synth_batch,
     synth_batch_cuda,

@@ -316,6 +316,58 @@ int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     return TRIALIGN_OK;
 }
 
+int64_t trialign_triple_count(int nseq) { return nseq < 3 ? 0 : (int64_t)all_triples_count(nseq); }
+
+int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score_bits, int backend, unsigned devices,
+                               int32_t *scores)
+{
+    if (nseq < 0 || len < 0 || score_bits < 2 || score_bits > 32) return TRIALIGN_EINVAL;
+    const int64_t total = trialign_triple_count(nseq);
+    if (total > 0 && (!scores || (len > 0 && !seqs))) return TRIALIGN_EINVAL;
+    int rc = check_backend(backend);
+    if (rc) return rc;
+    ThreadState &ts = tls();
+    ts.last_seconds = -1.0;
+    ts.last_cells = (double)total * len * len * len;
+    ts.last_path = TRIALIGN_PATH_NONE;
+    if (trialign_device_count() == 0) return TRIALIGN_ENODEVICE;
+    if (total == 0) return TRIALIGN_OK;
+    if (len == 0) {
+        std::memset(scores, 0, (size_t)total * sizeof(int32_t));
+        ts.last_seconds = 0.0;
+        return TRIALIGN_OK;
+    }
+    DeviceCtx *ctx = nullptr;
+    if ((rc = get_ctx(first_device(devices), &ctx))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    // chunks of at most 2^20 triples bound the staging arrays (3 x chunk x len bytes) whatever nseq is
+    const int64_t chunk = total < (1 << 20) ? total : (1 << 20);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t set_bytes = up((size_t)nseq * len), arr = up((size_t)chunk * len);
+    if ((rc = ctx->seq.reserve(set_bytes + 3 * arr + 256))) return rc;
+    if ((rc = ctx->out.reserve((size_t)chunk * sizeof(int32_t)))) return rc;
+    uint8_t *d_set = (uint8_t *)ctx->seq.ptr, *d_a = d_set + set_bytes, *d_b = d_a + arr, *d_c = d_b + arr;
+    int32_t *d_scores = (int32_t *)ctx->out.ptr;
+    TA_CUDA(cudaMemcpyAsync(d_set, seqs, (size_t)nseq * len, cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaEventRecord(ctx->ev0, st));
+    for (int64_t t0 = 0; t0 < total; t0 += chunk) {
+        const int64_t cnt = total - t0 < chunk ? total - t0 : chunk;
+        if ((rc = all_triples_gather(st, d_set, nseq, len, t0, cnt, d_a, d_b, d_c)) ||
+            (rc = dispatch_batch(ctx, st, d_a, d_b, d_c, cnt, len, len, len, score_bits, backend, d_scores, nullptr))) {
+            cudaStreamSynchronize(st);
+            return rc;
+        }
+        TA_CUDA(cudaMemcpyAsync(scores + t0, d_scores, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    TA_CUDA(cudaEventRecord(ctx->ev1, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    TA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ts.last_seconds = (double)ms * 1e-3;
+    return TRIALIGN_OK;
+}
+
 int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                    unsigned devices, int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves)
 {

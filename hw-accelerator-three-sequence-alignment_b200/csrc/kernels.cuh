@@ -49,6 +49,12 @@ size_t traceback_dir_bytes(int la, int lb, int lc);
 int traceback_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
                   const uint8_t *d_c, int lc, int score_bits, int32_t *d_out, uint8_t *d_moves);
 
+// all triples of a sequence set (all_triples.cu): lays triples first..first+count-1 (lexicographic x<y<z, roles
+// A=x, B=y, C=z) out as [count][len] batch arrays on the device
+long long all_triples_count(int nseq);
+int all_triples_gather(cudaStream_t st, const uint8_t *d_seqs, int nseq, int len, long long first, long long count,
+                       uint8_t *d_a, uint8_t *d_b, uint8_t *d_c);
+
 // synthetic generator on the device (synth_kernel.cu)
 int synth_run(cudaStream_t st, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a, uint8_t *d_b,
               uint8_t *d_c);

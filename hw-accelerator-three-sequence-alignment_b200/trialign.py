@@ -76,6 +76,10 @@ def library() -> C.CDLL:
     L.trialign_device_count.restype = C.c_int
     L.trialign_score.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p, _i32p]
     L.trialign_score.restype = C.c_int
+    L.trialign_triple_count.argtypes = [C.c_int]
+    L.trialign_triple_count.restype = C.c_int64
+    L.trialign_score_all_triples.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p]
+    L.trialign_score_all_triples.restype = C.c_int
     L.trialign_align.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_uint, _i32p, _i32p, _u8p,
                                  C.c_int, C.POINTER(C.c_int)]
     L.trialign_align.restype = C.c_int
@@ -209,6 +213,19 @@ class TriAlign:
         _check(rc, "trialign_align")
         return int(s.value), tuple(int(x) for x in start), moves[: n.value].copy()
 
+    def align_all_triples(self, seqs) -> np.ndarray:
+        """Scores of every triple (x < y < z, roles A=x, B=y, C=z) of a sequence set [nseq][len], in the order of
+        triple_indices(nseq).  The set is uploaded once; the triples are laid out on the device."""
+        s = _u8(seqs)
+        if s.ndim != 2:
+            raise ValueError("align_all_triples wants one [nseq][len] array")
+        nseq, ln = s.shape
+        out = np.zeros(int(library().trialign_triple_count(nseq)), np.int32)
+        rc = library().trialign_score_all_triples(_p(s, _u8p), nseq, ln, self.score_bits, self.backend,
+                                                  _devmask(self.devices), _p(out, _i32p))
+        _check(rc, "trialign_score_all_triples")
+        return out
+
     def align_batch(self, A, B, C_) -> np.ndarray:
         a, b, c = _u8(A), _u8(B), _u8(C_)
         if a.ndim != 2 or a.shape != b.shape or a.shape != c.shape:
@@ -251,6 +268,13 @@ class TriAlign:
                                           st.cuda_stream)
         _check(rc, "trialign_score_dev")
         return out
+
+
+def triple_indices(nseq: int) -> np.ndarray:
+    """[C(nseq,3)][3] indices (x < y < z) in the order trialign_score_all_triples scores them (lexicographic)."""
+    from itertools import combinations
+
+    return np.array(list(combinations(range(nseq), 3)), dtype=np.int32).reshape(-1, 3)
 
 
 def format_alignment(A, B, C_, start, moves, alphabet: str = "ATCGN") -> Tuple[str, str, str]:

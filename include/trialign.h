@@ -109,6 +109,15 @@ int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_
 int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                    unsigned devices, int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves);
 
+/* Every triple of a sequence set (the progressive three-way alignment of pic/Motivation.png scores
+ * all triples of its input -- the workload behind "a million short triples": 186 sequences give 1,055,240).
+ * seqs: [nseq][len] symbols, uploaded once; the C(nseq,3) triples are laid out on the device and scored by the batch
+ * kernels.  scores[t] belongs to the t-th triple (x < y < z) in lexicographic order with roles A = x, B = y, C = z
+ * (the RTL's score is not symmetric in the roles, src/PE_1cyc.v:162); trialign_triple_count(nseq) = C(nseq,3) entries. */
+int64_t trialign_triple_count(int nseq);
+int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score_bits, int backend, unsigned devices,
+                               int32_t *scores);
+
 /* ---- i-slab pipeline: ONE long triple over several GPUs, one process per GPU ----
  * Rank g computes planes (i_begin, i_end] of the cube for every (j,k) block and hands the plane-i_end state of each
  * block task to rank g+1, whose kernel picks it up task by task while rank g is already working on later blocks.  The

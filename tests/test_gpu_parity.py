@@ -317,3 +317,35 @@ def test_traceback_golden_paths(gpu_ta, golden):
         assert s == case["score"], case["name"]
         assert list(start) == case["traceback"]["start"], case["name"]
         assert "".join(str(int(m)) for m in moves) == case["traceback"]["moves"], case["name"]
+
+
+# ---- all triples of a sequence set (trialign_score_all_triples) ----
+@pytest.mark.parametrize("nseq,ln,w", [(3, 64, 12), (7, 40, 12), (12, 64, 12), (9, 100, 12), (6, 33, 7), (2, 10, 12)])
+def test_all_triples_of_a_set_match_the_oracle(gpu_ta, ob, nseq, ln, w):
+    rng = np.random.default_rng(nseq * 100 + ln)
+    base = rng.integers(0, 4, ln, dtype=np.uint8)
+    seqs = np.stack([base.copy() for _ in range(nseq)])
+    for r in range(nseq):                                   # a family of related sequences, like an MSA input
+        m = rng.random(ln) < 0.05 * (r + 1)
+        seqs[r, m] = rng.integers(0, 4, int(m.sum()), dtype=np.uint8)
+    idx = gpu_ta.triple_indices(nseq)
+    assert len(idx) == gpu_ta.library().trialign_triple_count(nseq) == nseq * (nseq - 1) * (nseq - 2) // 6
+    got = gpu_ta.TriAlign(score_bits=w).align_all_triples(seqs)
+    if len(idx) == 0:
+        assert got.size == 0
+        return
+    want = ob.score_batch(seqs[idx[:, 0]], seqs[idx[:, 1]], seqs[idx[:, 2]], w)
+    assert got.tolist() == want.tolist()
+
+
+def test_all_triples_of_186_sequences_is_the_million_triple_batch(gpu_ta):
+    """186 sequences -> 1,055,240 triples (two gather chunks): identical to scoring the materialised batch."""
+    rng = np.random.default_rng(186)
+    seqs = rng.integers(0, 4, (186, 64), dtype=np.uint8)
+    eng = gpu_ta.TriAlign(score_bits=12)
+    got = eng.align_all_triples(seqs)
+    assert got.size == 1055240 and gpu_ta.last_path() == "fast_batch"
+    idx = gpu_ta.triple_indices(186)
+    pick = np.concatenate([np.arange(0, 4096), np.arange(1 << 20, (1 << 20) + 2048), np.arange(got.size - 4096, got.size)])
+    want = eng.align_batch(seqs[idx[pick, 0]], seqs[idx[pick, 1]], seqs[idx[pick, 2]])
+    assert got[pick].tolist() == want.tolist()

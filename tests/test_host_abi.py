@@ -121,6 +121,11 @@ def test_no_cpu_fallback_without_a_gpu(ta):
     with pytest.raises(ta.TriAlignError) as ei:
         ta.TriAlign(12).traceback([0, 1, 2], [0, 1, 2], [0, 1, 2])
     assert ei.value.rc == -7
+    with pytest.raises(ta.TriAlignError) as ei:
+        ta.TriAlign(12).align_all_triples(np.zeros((4, 8), np.uint8))
+    assert ei.value.rc == -7
+    assert ta.library().trialign_triple_count(186) == 1055240 and ta.library().trialign_triple_count(2) == 0
+    assert ta.triple_indices(5).tolist()[:4] == [[0, 1, 2], [0, 1, 3], [0, 1, 4], [0, 2, 3]]
     with pytest.raises(ta.TriAlignError):
         ta.TriAlign().align_batch(np.zeros((2, 4), np.uint8), np.zeros((2, 4), np.uint8), np.zeros((2, 4), np.uint8))
     assert ta.launch_count() == 0
