@@ -315,9 +315,10 @@ TA_HD void sweep_edge_fetch(SweepSmem<C> &S, const SweepArgs &A, int tj, int tk,
                 for (int v = 0; v < 4; ++v) ta_copy16(&S.row[ws][v][0][k0], src + v * C::ROW_W);
             }
         } else {  // j = 0 border plane: all 7 states are 0 (src/TriAlign_1cyc.v:156-165), reduced values = phi
+            const uint32_t e = sphi<C>(A, i, 0, k0 + 1);  // phi is linear: one evaluation, carry-free offsets
 #pragma unroll
             for (int c = 0; c < RK; ++c) {
-                const uint32_t now = sphi<C>(A, i, 0, k0 + c + 1), old = sphi<C>(A, i - 1, 0, k0 + c + 1);
+                const uint32_t now = e + (uint32_t)c * 0x00020002u, old = now - 0x00020002u;
                 S.row[ws][0][0][k0 + c] = now;
                 S.row[ws][1][0][k0 + c] = now;
                 S.row[ws][2][0][k0 + c] = old;

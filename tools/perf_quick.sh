@@ -1,9 +1,10 @@
-# quick development measurements (one gpurun call): parity on tiny cases, then workloads, device-resident value only
-one() { python bench.py --no-cpu "$@" 2>> gpurun_out/p_err.log | python -c "import sys,json,os; d=json.loads(sys.stdin.read()); print('%-8s %-44s %8.1f GCUPS %9.3f ms  %s' % (os.environ.get('TRIALIGN_K2_GATE',''), ' '.join(sys.argv[1:]), d['value'], d['ms_per_step'], d['config']['kernel_path']))" "$@"; }
+# quick development measurements (one gpurun call)
+one() { python bench.py --no-cpu "$@" 2>> gpurun_out/p_err.log | python -c "import sys,json,os; d=json.loads(sys.stdin.read()); print('%-18s %-44s %8.1f GCUPS %9.3f ms  %s' % (os.environ.get('TAG',''), ' '.join(sys.argv[1:]), d['value'], d['ms_per_step'], d['config']['kernel_path']))" "$@"; }
 : > gpurun_out/p_err.log
-python tools/tiny_cases.py all 2>&1 | tail -4
-for g in 2 4; do
-TRIALIGN_K2_GATE=$g one --steps 5 --warmup 3 --workload long1024
+D=$PWD/hw-accelerator-three-sequence-alignment_b200/lib_alt
+for v in hint_oldborder hint_newborder; do
+TRIALIGN_LIB=$D/libtrialign_$v.so python tools/tiny_cases.py k1 | tail -1
+TAG=$v TRIALIGN_LIB=$D/libtrialign_$v.so one --steps 3 --warmup 3 --triples 131072
+TAG=$v-256m TRIALIGN_K1=256m TRIALIGN_LIB=$D/libtrialign_$v.so one --steps 3 --warmup 3 --triples 131072
 done
-python tools/time_traceback.py 64 256 512 1024 | tee gpurun_out/traceback_r01.jsonl
 tail -5 gpurun_out/p_err.log
