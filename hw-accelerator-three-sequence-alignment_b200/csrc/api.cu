@@ -96,6 +96,12 @@ int get_ctx(int device, DeviceCtx **out)
 
 namespace {
 
+bool env_is(const char *name, const char *value)
+{
+    const char *e = std::getenv(name);
+    return e && std::strcmp(e, value) == 0;
+}
+
 bool backend_is_gpu(int backend)
 {
     return backend == TRIALIGN_BACKEND_AUTO || backend == TRIALIGN_BACKEND_GPU ||
@@ -128,6 +134,11 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         if (n == 1 && fast_sweep_supports(la, lb, lc)) {
             ts.last_path = TRIALIGN_PATH_FAST_LONG;
             return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, 0, nullptr);
+        }
+        if (!d_finals && la == lb && lb == lc && fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count) &&
+            !env_is("TRIALIGN_K2", "sweep")) {  // TRIALIGN_K2=sweep: the per-block kernel below, for A/B runs
+            ts.last_path = TRIALIGN_PATH_FAST_STREAM;
+            return fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
         }
         if (!d_finals && la == lb && lb == lc && fast_sweep_supports(la, lb, lc)) {
             ts.last_path = TRIALIGN_PATH_FAST_LONG;

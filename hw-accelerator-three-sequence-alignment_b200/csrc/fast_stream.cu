@@ -1,0 +1,167 @@
+// fast_stream.cu -- K2S launcher: streaming block-sweep kernel for batches of triples longer than 64
+// (see fast_stream.cuh).  One persistent CTA per SM sweeps all blocks of its contiguous chunk of pairs back to back.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+
+#include "fast_stream.cuh"
+#include "kernels.cuh"
+
+namespace trialign {
+
+namespace {
+
+using Cfg = fast::StreamCfg;
+
+// Split-phase CTA barrier, one arrival per warp (as in fast_batch.cu): a warp ARRIVES once its tile edges of step s are
+// published and WAITS, two steps later, for everybody's step s.
+__device__ __forceinline__ void bar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_warp(uint64_t *bar)
+{
+    __syncwarp();  // orders the other lanes' shared-memory / global stores before lane 0's release
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArgs A)
+{
+    using C = Cfg;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::StreamSmem<C> &S = *reinterpret_cast<fast::StreamSmem<C> *>(smem_raw);
+    __shared__ __align__(8) uint64_t step_bar[2];
+    const int tid = threadIdx.x, cta = blockIdx.x;
+    const long long pair_base = (long long)cta * A.pairs_per_cta;
+    const long long left = A.pairs_total - pair_base;
+    if (left <= 0) return;
+    const int P = left < A.pairs_per_cta ? (int)left : A.pairs_per_cta;
+    const int tasks = P * A.nbj * A.nbk;
+    int tj, tk;
+    fast::stream_thread_pos<C>(tid, tj, tk);
+
+    if (tid == 0) {
+        bar_init(&step_bar[0], C::NT / 32);
+        bar_init(&step_bar[1], C::NT / 32);
+    }
+    fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, -1);  // filler the pipeline fill runs on
+    fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, 0);
+    __syncthreads();
+    fast::stream_stage_build<C>(S, tid, -1);
+    fast::stream_stage_build<C>(S, tid, 0);
+    __syncthreads();
+
+    fast::StreamRegs<C> R;
+    fast::StreamConsts<C> K;
+    fast::StreamPos pos = fast::stream_start_pos<C>(A, tj, tk);
+    if (tj == 0 || tk == 0) fast::stream_edge_fetch<C>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1));
+    fast::ta_copy_commit();
+    fast::stream_thread_prepare<C>(R, K, S, A, tj, tk, pos, 0, false);
+    const int steps = (int)fast::stream_total_steps<C>(A, P);
+    int g_t = 0, g_off = 0;
+#pragma unroll 1
+    for (int s = 0; s <= steps; ++s) {
+        // everybody has finished step s-2 (even and odd steps use separate barriers)
+        if (s >= 2) bar_wait(&step_bar[s & 1], ((s - 2) >> 1) & 1);
+        fast::ta_copy_wait_prev();  // this thread's block-halo fetch for step s has landed
+        fast::stream_thread_step<C>(R, K, S, A, tj, tk, s, pos);
+        bar_arrive_warp(&step_bar[s & 1]);
+        if (g_t < tasks) fast::stream_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off);
+        fast::stream_thread_prepare<C>(R, K, S, A, tj, tk, pos, s + 1, true);
+        if (++g_off == A.len) {
+            g_off = 0;
+            ++g_t;
+        }
+    }
+}
+
+// contiguous chunks of pairs, one persistent CTA per SM (fill/drain once per CTA); the step counter stays below 2^30
+void stream_plan(int len, int64_t n, int sm_count, long long &ppc, long long &grid)
+{
+    const long long nb = (len + Cfg::BJ - 1) / Cfg::BJ, pairs = (n + 1) / 2;
+    const long long steps_per_pair = nb * nb * len;
+    ppc = (pairs + sm_count - 1) / sm_count;
+    ppc = std::max<long long>(1, std::min<long long>(ppc, (1ll << 30) / steps_per_pair));
+    grid = (pairs + ppc - 1) / ppc;
+}
+
+long long stream_face_bytes(int len, long long grid)
+{
+    const int nbj = (len + Cfg::BJ - 1) / Cfg::BJ;
+    const long long fj = (long long)(len + 2) * Cfg::FJ_ROW_WORDS, fk = (long long)(len + 2) * Cfg::FK_ROW_WORDS;
+    return grid * (2 * fj + (nbj + 1) * fk) * 4 + 1024;
+}
+
+}  // namespace
+
+bool fast_stream_supports(int len)
+{
+    return len >= Cfg::LEN_MIN && len <= Cfg::LEN_MAX && fast_sweep_supports(len, len, len);
+}
+
+int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                    int64_t n, int len, int32_t *d_scores)
+{
+    using C = Cfg;
+    if (n <= 0) return TRIALIGN_OK;
+    static_assert(sizeof(fast::StreamSmem<C>) + 64 <= 227 * 1024, "shared memory budget");
+    const size_t smem = sizeof(fast::StreamSmem<C>);
+    static bool attr_set[kMaxDevices] = {};
+    if (!attr_set[ctx->device]) {
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        attr_set[ctx->device] = true;
+    }
+    fast::StreamArgs A{};
+    A.a = d_a; A.b = d_b; A.c = d_c;
+    A.n = n; A.len = len; A.scores = d_scores;
+    A.nbj = (len + C::BJ - 1) / C::BJ;
+    A.nbk = (len + C::BK - 1) / C::BK;
+    A.pairs_total = (n + 1) / 2;
+    long long ppc, grid;
+    stream_plan(len, n, ctx->sm_count, ppc, grid);
+    A.pairs_per_cta = (int)ppc;
+    // face rings are private to a CTA; CTAs beyond one wave reuse nothing, so the rings are sized by the grid
+    A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
+    A.fk_ring = A.nbj + 1;
+    const size_t fj_bytes = (size_t)grid * 2 * A.fj_slot_words * 4;
+    const size_t fk_bytes = (size_t)grid * A.fk_ring * A.fk_slot_words * 4;
+    int rc = ctx->faces.reserve(fj_bytes + fk_bytes + 1024);
+    if (rc) return rc;
+    A.face_j = (uint32_t *)ctx->faces.ptr;
+    A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
+    const long long m = len;
+    A.base = (int)(-envelope_lo(m) + 32);
+    if (std::getenv("TRIALIGN_DEBUG"))
+        std::fprintf(stderr, "[trialign] K2S stream: len=%d blocks %dx%d grid=%lld pairs/cta=%lld faces=%.1f MB smem=%zu base=%d\n",
+                     len, A.nbj, A.nbk, grid, ppc, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
+    fast_stream_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+// the streaming kernel is used while its face rings stay small next to the device memory
+bool fast_stream_fits(int len, int64_t n, int sm_count)
+{
+    long long ppc, grid;
+    stream_plan(len, n, sm_count, ppc, grid);
+    return stream_face_bytes(len, grid) <= (8ll << 30);
+}
+
+}  // namespace trialign

@@ -43,6 +43,13 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
 int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                          int64_t n, int len, int32_t *d_scores);
 
+// K2S: streaming block-sweep kernel for batches of equal-length triples longer than 64 (fast_stream.cu): all blocks of
+// a CTA's pairs stream through the systolic array back to back.  Same exactness condition as K1 / K2.
+bool fast_stream_supports(int len);
+bool fast_stream_fits(int len, int64_t n, int sm_count);  // CTA-private face rings within the memory budget
+int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                    int64_t n, int len, int32_t *d_scores);
+
 // KT: traceback of one triple (traceback.cu).  d_out: 5 int32 (score, start cell i/j/k, number of columns); d_moves:
 // la+lb+lc bytes, forward order, bit0/1/2 = A/B/C advances.
 size_t traceback_dir_bytes(int la, int lb, int lc);

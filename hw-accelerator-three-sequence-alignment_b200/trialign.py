@@ -25,7 +25,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.environ.get("TRIALIGN_LIB") or os.path.join(_HERE, "lib", "libtrialign.so")  # override: development A/B builds
 
 BACKEND_AUTO, BACKEND_GPU, BACKEND_GPU_LITERAL, BACKEND_GPU_FAST = 0, 4, 5, 6
-PATH_NAMES = {0: "none", 1: "literal", 2: "fast_batch", 3: "fast_long", 4: "fast_then_literal", 5: "traceback"}
+PATH_NAMES = {0: "none", 1: "literal", 2: "fast_batch", 3: "fast_long", 4: "fast_then_literal", 5: "traceback", 6: "fast_stream"}
 
 _u8p = C.POINTER(C.c_uint8)
 _i32p = C.POINTER(C.c_int32)

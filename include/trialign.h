@@ -70,7 +70,8 @@ enum trialign_path {
     TRIALIGN_PATH_FAST_BATCH = 2,     /* K1: batched systolic kernel, two triples per 32-bit lane */
     TRIALIGN_PATH_FAST_LONG = 3,      /* K2: block-dataflow kernel for one long triple */
     TRIALIGN_PATH_FAST_THEN_LITERAL = 4, /* fast kernel ran, its range check failed, literal kernel re-ran */
-    TRIALIGN_PATH_TRACEBACK = 5       /* KT: literal plane sweep with a direction cube + backward walk */
+    TRIALIGN_PATH_TRACEBACK = 5,      /* KT: literal plane sweep with a direction cube + backward walk */
+    TRIALIGN_PATH_FAST_STREAM = 6     /* K2S: streaming block-sweep kernel for batches of triples longer than 64 */
 };
 
 int trialign_version(void);

@@ -332,3 +332,84 @@ extern "C" int emu_fast_sweep_batch(const uint8_t *a, const uint8_t *b, const ui
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2S (fast_stream.cuh): all blocks of a CTA's pairs streamed back to back, lagged barrier, faces in "global" memory.
+// Warps advance in a pseudo-random order (schedule_seed != 0: with bursts), at most two steps apart, exactly what the
+// kernel's mbarrier protocol allows.  Every emulated CTA gets poisoned shared memory and poisoned face rings.
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_stream.cuh"
+
+extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                               int pairs_per_cta, int schedule_seed, int32_t *scores)
+{
+    using C = StreamCfg;
+    if (len < C::LEN_MIN || len > C::LEN_MAX || n < 0 || pairs_per_cta < 1) return -1;
+    StreamArgs A{};
+    A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
+    A.nbj = (len + C::BJ - 1) / C::BJ;
+    A.nbk = (len + C::BK - 1) / C::BK;
+    A.pairs_total = (n + 1) / 2;
+    A.pairs_per_cta = pairs_per_cta;
+    A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
+    A.fk_ring = A.nbj + 1;
+    A.base = base;
+    const int n_ctas = (int)((A.pairs_total + pairs_per_cta - 1) / pairs_per_cta);
+    std::vector<uint32_t> fj((size_t)n_ctas * 2 * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)n_ctas * A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
+    A.face_j = fj.data(); A.face_k = fk.data();
+    auto S = std::make_unique<StreamSmem<C>>();
+    std::vector<StreamRegs<C>> R(C::NT);
+    std::vector<StreamConsts<C>> K(C::NT);
+    std::vector<StreamPos> pos(C::NT);
+    for (int cta = 0; cta < n_ctas; ++cta) {
+        const long long pair_base = (long long)cta * pairs_per_cta;
+        const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
+        const int tasks = P * A.nbj * A.nbk;
+        std::memset(S.get(), 0xA5, sizeof(StreamSmem<C>));
+        std::memset(R.data(), 0x5A, R.size() * sizeof(StreamRegs<C>));
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, -1);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, 0);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, -1);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            stream_thread_pos<C>(tid, tj, tk);
+            pos[tid] = stream_start_pos<C>(A, tj, tk);
+            if (tj == 0 || tk == 0) stream_edge_fetch<C>(*S, A, tj, tk, pos[tid], C::LAG & (C::NSLOT - 1));
+            stream_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, pos[tid], 0, false);
+        }
+        const int steps = (int)stream_total_steps<C>(A, P);
+        constexpr int NW = C::NT / 32;
+        std::vector<int> done(NW, -1);  // last finished step per warp
+        uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)schedule_seed ^ ((uint64_t)cta << 20);
+        int finished = 0;
+        while (finished < NW) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const int w = (int)((rng >> 33) % NW);
+            const int burst = schedule_seed ? 1 + (int)((rng >> 20) % 3) : 1;
+            for (int bi = 0; bi < burst; ++bi) {
+                const int s = done[w] + 1;
+                if (s > steps) break;
+                if (*std::min_element(done.begin(), done.end()) < s - 2) break;  // bar_wait(step s-2) would block
+                const int g_t = s / len, g_off = s % len;
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int tid = w * 32 + lane;
+                    int tj, tk;
+                    stream_thread_pos<C>(tid, tj, tk);
+                    stream_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, pos[tid]);
+                }
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int tid = w * 32 + lane;
+                    int tj, tk;
+                    stream_thread_pos<C>(tid, tj, tk);
+                    if (g_t < tasks) stream_uniform_actions<C>(*S, A, tid, cta, P, pair_base, g_t, g_off);
+                    stream_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, pos[tid], s + 1, true);
+                }
+                done[w] = s;
+                if (s == steps) ++finished;
+            }
+        }
+    }
+    return 0;
+}

@@ -150,3 +150,24 @@ def test_sweep_i_slab_pipeline(emu_sweep, ob, shape, n_slabs, n_ctas):
     assert rc == 0
     es, efin = ob.score(a, b, c, 16)
     assert int(out[0]) == es and out[1:].tolist() == efin.tolist()
+
+
+# ---- K2S: streaming block sweep for batches of triples longer than 64 (fast_stream.cuh) ----
+@pytest.mark.parametrize("ln,n,ppc", [(65, 3, 2), (100, 5, 2), (128, 4, 1), (130, 7, 4), (200, 5, 3), (256, 2, 1)])
+def test_stream_kernel_choreography(emu, ob, ln, n, ppc):
+    """All blocks of a CTA's pairs streamed back to back (task hand-over inside the array, faces through the rings,
+    staging of the next task while two are in flight), warps drifting in different pseudo-random orders."""
+    emu.emu_fast_stream.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    rng = np.random.default_rng(ln * 31 + n)
+    a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    for t in range(0, n, 2):  # mutated copies exercise large positive values
+        a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+    want = ob.score_batch(a, b, c, 16).tolist()
+    for seed in (0, 5, 12):
+        out = np.full(n, -99999, np.int32)
+        rc = emu.emu_fast_stream(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln,
+                                 2 * ln + 8 + 32, ppc, seed, out.ctypes.data_as(i32p))
+        assert rc == 0
+        assert out.tolist() == want, seed

@@ -157,18 +157,41 @@ def test_fast_long_kernel_shapes(gpu_ta, ob, shape):
         assert s == es and fin.tolist() == efin.tolist(), (shape, mutated)
 
 
-@pytest.mark.parametrize("ln,n", [(65, 7), (100, 12), (130, 5), (256, 6)])
-def test_fast_long_batch_kernel(gpu_ta, ob, ln, n):
+@pytest.mark.parametrize("ln,n", [(65, 7), (100, 12), (130, 5), (256, 6), (200, 601), (321, 3)])
+def test_fast_long_batch_kernels(gpu_ta, ob, ln, n, monkeypatch):
+    """Batches of triples longer than 64: the streaming block-sweep kernel K2S (default) and the per-block kernel
+    (TRIALIGN_K2=sweep, also the fallback for very long batches) against the oracle.  n = 601 gives every CTA several
+    pairs, so tasks of different pairs follow each other inside the array."""
     rng = np.random.default_rng(ln * 31 + n)
     a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
     b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
     c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
     for t in range(0, n, 2):
         a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+    want = {w: ob.score_batch(a, b, c, w).tolist() for w in (12, 16)}
     for w in (12, 16):
         got = gpu_ta.TriAlign(w).align_batch(a, b, c)
-        assert gpu_ta.last_path() == "fast_long"
-        assert got.tolist() == ob.score_batch(a, b, c, w).tolist(), (ln, n, w)
+        assert gpu_ta.last_path() == "fast_stream"
+        assert got.tolist() == want[w], (ln, n, w)
+    monkeypatch.setenv("TRIALIGN_K2", "sweep")
+    got = gpu_ta.TriAlign(16).align_batch(a, b, c)
+    assert gpu_ta.last_path() == "fast_long"
+    assert got.tolist() == want[16], (ln, n)
+
+
+def test_stream_kernel_extremes_and_repeats(gpu_ta, ob):
+    """All-equal sequences (largest values, 3L), all-mismatch (most negative), and the same launch repeated (face
+    rings and task buffers reused across launches)."""
+    L = 192
+    z = np.zeros((5, L), np.uint8)
+    o = np.ones((5, L), np.uint8)
+    t = np.full((5, L), 2, np.uint8)
+    eng = gpu_ta.TriAlign(16)
+    assert eng.align_batch(z, z, z).tolist() == [3 * L] * 5
+    assert gpu_ta.last_path() == "fast_stream"
+    want = ob.score_batch(z, o, t, 16).tolist()
+    for _ in range(3):
+        assert eng.align_batch(z, o, t).tolist() == want
 
 
 def test_range_checked_fast_path_and_literal_fallback(gpu_ta, ob, golden):
