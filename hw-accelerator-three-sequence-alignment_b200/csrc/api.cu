@@ -102,6 +102,15 @@ bool env_is(const char *name, const char *value)
     return e && std::strcmp(e, value) == 0;
 }
 
+// one long triple: K2L (fast_long.cu); TRIALIGN_K2L=old selects the first-generation kernel (fast_sweep.cu) for A/B runs
+int long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
+             int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol, const SlabLink *slab = nullptr)
+{
+    if (env_is("TRIALIGN_K2L", "old"))
+        return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_score, d_states, check_bits, d_viol, slab);
+    return fast_long2_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_score, d_states, check_bits, d_viol, slab);
+}
+
 bool backend_is_gpu(int backend)
 {
     return backend == TRIALIGN_BACKEND_AUTO || backend == TRIALIGN_BACKEND_GPU ||
@@ -133,7 +142,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         }
         if (n == 1 && fast_sweep_supports(la, lb, lc)) {
             ts.last_path = TRIALIGN_PATH_FAST_LONG;
-            return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, 0, nullptr);
+            return long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, 0, nullptr);
         }
         if (!d_finals && la == lb && lb == lc && fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count) &&
             !env_is("TRIALIGN_K2", "sweep")) {  // TRIALIGN_K2=sweep: the per-block kernel below, for A/B runs
@@ -152,7 +161,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         if (rc) return rc;
         int *d_viol = (int *)ctx->viol.ptr;
         TA_CUDA(cudaMemsetAsync(d_viol, 0, sizeof(int), st));
-        rc = fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, score_bits, d_viol);
+        rc = long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, score_bits, d_viol);
         if (rc) return rc;
         int viol = 0;
         TA_CUDA(cudaMemcpyAsync(&viol, d_viol, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -531,7 +540,7 @@ int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_
     link.out_state = out_state;
     link.out_flags = out_flags;
     ts.last_path = TRIALIGN_PATH_FAST_LONG;
-    return fast_sweep_long_run(ctx, (cudaStream_t)stream, d_a + i_begin, i_end - i_begin, d_b, lb, d_c, lc, d_out,
+    return long_run(ctx, (cudaStream_t)stream, d_a + i_begin, i_end - i_begin, d_b, lb, d_c, lc, d_out,
                                d_out ? d_out + 1 : nullptr, 0, nullptr, &link);
 }
 

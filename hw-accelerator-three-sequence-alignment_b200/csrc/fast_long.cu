@@ -1,0 +1,299 @@
+// fast_long.cu -- K2L launcher: block-sweep kernel for one long triple on the K1/K2S step engine (see fast_long.cuh).
+// Persistent CTAs claim (k-block-pair, j-block) tasks from a global counter in earliest-start order and stream block
+// faces through global memory, gated by per-task progress counters (release/acquire at GPU scope); the i-slab pipeline
+// over several GPUs hands the plane state of every task to the next GPU through peer memory (system scope).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "fast_long.cuh"
+#include "kernels.cuh"
+
+namespace trialign {
+
+namespace {
+
+__device__ __forceinline__ int ld_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int *p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// system scope: the flag / data may live in a peer GPU's memory (i-slab pipeline over NVLink)
+__device__ __forceinline__ int ld_acquire_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(int *p, int v)
+{
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// split-phase CTA barrier, one arrival per warp (as in fast_batch.cu)
+__device__ __forceinline__ void bar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_warp(uint64_t *bar)
+{
+    __syncwarp();  // orders the other lanes' shared-memory / global stores before lane 0's release
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+template <int LAG, bool CHECK>
+__global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
+{
+    using C = fast::Long2Cfg<LAG>;
+    // The thread that polls / releases the progress counters sits in a warp whose patch has the lightest block-edge
+    // duty (right edge only: a few face stores), so the MEMBAR of a release eats that warp's slack.
+    constexpr int kGateTid = 128;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::Long2Smem<C> &S = *reinterpret_cast<fast::Long2Smem<C> *>(smem_raw);
+    __shared__ __align__(8) uint64_t step_bar[2];
+    const int tid = threadIdx.x;
+    int tj, tk;
+    fast::stream_thread_pos<C>(tid, tj, tk);
+    if (tid == 0) {
+        bar_init(&step_bar[0], C::NT / 32);
+        bar_init(&step_bar[1], C::NT / 32);
+    }
+    fast::long2_load_a<C>(S, A, tid);
+    fast::Long2Regs<C> R;
+    fast::Long2Consts<C> K;
+    const int steps = fast::long2_task_steps<C>(A);
+    const bool edge = tj == 0 || tk == 0;
+    int g = 0;  // steps run by this CTA so far: the barrier phases continue across tasks
+
+    for (;;) {
+        __syncthreads();  // everybody is done with the previous task descriptor
+        if (tid == kGateTid) {
+            const unsigned long long t = atomicAdd(A.counter, 1ull);
+            if (t < (unsigned long long)A.tasks_total) {
+                fast::sweep_describe_long<C>(A, (long long)t, S.task);
+                // ring re-use: the previous tenants of the face slots must have been consumed (the ring sizes exceed
+                // the largest producer->consumer distance in claim order by more than the grid size, so every
+                // consumer waited for here was claimed long ago)
+                if ((long long)t >= A.fj_ring) {
+                    const int prev = A.order[t - A.fj_ring];
+                    if (prev % A.nbj + 1 < A.nbj)
+                        while (ld_acquire(A.progress + prev + 1) < fast::kProgressDone) __nanosleep(200);
+                }
+                if ((long long)t >= A.fk_ring) {
+                    const int prev = A.order[t - A.fk_ring];
+                    if (prev / A.nbj + 1 < A.nbkp)
+                        while (ld_acquire(A.progress + prev + A.nbj) < fast::kProgressDone) __nanosleep(200);
+                }
+                // i-slab pipeline: the previous slab (another GPU) must have delivered this task's plane-0 state
+                if (A.iface_in_flag)
+                    while (ld_acquire_sys(A.iface_in_flag + S.task.self_task) != A.epoch) __nanosleep(500);
+            } else {
+                S.task.valid = 0;
+            }
+        }
+        __syncthreads();
+        if (!S.task.valid) break;
+        fast::long2_load_bc<C>(S, A, tid);
+        __syncthreads();
+        fast::long2_build_tables<C>(S, tid);
+        fast::long2_init_thread<C>(R, S, tj, tk);
+        const fast::SweepTask &T = S.task;
+        const int *top_p = T.top_task >= 0 ? A.progress + T.top_task : nullptr;
+        const int *left_p = T.left_task >= 0 ? A.progress + T.left_task : nullptr;
+
+        // prologue: the halos of steps 0 and 1 are fetched here, and the first LAG iterations fetch before any barrier
+        // of this task has been waited for.  cert = last consumption step whose face rows are known to be complete.
+        int cert = -1000;
+        if (tid == kGateTid) {
+            for (;;) {
+                cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);
+                if (cert >= 1 + LAG) break;
+                __nanosleep(100);
+            }
+        }
+        __syncthreads();
+        if (edge) fast::long2_edge_fetch<C>(S, A, tj, tk, 0);
+        fast::ta_copy_commit();
+        fast::long2_thread_prepare<C>(R, K, S, A, tj, tk, 0, tid);
+
+#pragma unroll 1
+        for (int s = 0; s <= steps; ++s, ++g) {
+            // the gate thread certifies consumption step s + AHEAD before it arrives for step s: every edge thread
+            // fetches the halos of step x + 2 only after it has seen the arrivals of step x + 2 - AHEAD.  The
+            // producers' progress is sampled at the top of the step, so the load latency hides under the tile.
+            const int want = s + C::AHEAD < steps ? s + C::AHEAD : steps;
+            const bool need = tid == kGateTid && cert < want;
+            int tp = 0, lp = 0;
+            if (need) {
+                tp = top_p ? ld_acquire(top_p) : 0;
+                lp = left_p ? ld_acquire(left_p) : 0;
+            }
+            if (LAG == 2) {
+                if (g >= 2) bar_wait(&step_bar[g & 1], ((g - 2) >> 1) & 1);  // everybody has finished step s-2
+                // release: the edge threads' face stores of steps <= s-2 are ordered before the arrivals just observed
+                if (tid == kGateTid && s >= 2 && fast::long2_publish_now(A, s)) st_release(A.progress + T.self_task, s - 1);
+            }
+            fast::ta_copy_wait_prev();  // this thread's block-halo fetch for step s has landed
+            fast::long2_thread_step<C, CHECK>(R, K, S, A, tj, tk, s, tid);
+            if (need) {
+                cert = fast::long2_certified<C>(A, T, tp, lp);
+                while (cert < want) {
+                    __nanosleep(40);
+                    cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);
+                }
+            }
+            bar_arrive_warp(&step_bar[LAG == 2 ? (g & 1) : 0]);
+            fast::long2_thread_prepare<C>(R, K, S, A, tj, tk, s + 1, tid);
+            if (LAG == 1) {
+                bar_wait(&step_bar[0], g & 1);  // everybody has finished step s
+                if (tid == kGateTid && fast::long2_publish_now(A, s + 1)) st_release(A.progress + T.self_task, s + 1);
+            }
+        }
+        fast::ta_copy_wait();
+        __syncthreads();  // every thread's face / hand-over stores precede the final release
+        if (CHECK && R.viol) atomicOr(A.viol_flag, 1);
+        if (tid == kGateTid) {
+            st_release(A.progress + T.self_task, fast::kProgressDone);
+            if (A.iface_out_flag) {
+                __threadfence_system();
+                st_release_sys(A.iface_out_flag + T.self_task, A.epoch);
+            }
+        }
+    }
+}
+
+template <int LAG>
+int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, int la)
+{
+    using C = fast::Long2Cfg<LAG>;
+    static_assert(sizeof(fast::Long2Smem<C>) + 64 <= 227 * 1024, "shared memory budget");
+    const size_t smem = sizeof(fast::Long2Smem<C>);
+    static bool prepared[kMaxDevices][2] = {};
+    if (!prepared[ctx->device][check]) {
+        if (check) {
+            TA_CUDA(cudaFuncSetAttribute(long2_kernel<LAG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else {
+            TA_CUDA(cudaFuncSetAttribute(long2_kernel<LAG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        prepared[ctx->device][check] = true;
+    }
+    A.nbj = (A.lb + C::BJ - 1) / C::BJ;
+    A.nbkp = (A.lc + C::KSPAN - 1) / C::KSPAN;
+    A.tasks_total = (long long)A.nbj * A.nbkp;
+    int grid = ctx->sm_count;  // one persistent CTA per SM; all co-resident (spin-waits need that)
+    if (grid > A.tasks_total) grid = (int)A.tasks_total;
+    A.fj_slot_words = (long long)(la + C::PLAG + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(la + C::PLAG + 2) * C::FK_ROW_WORDS;
+    // claim order (earliest possible start first) and the face-ring sizes it needs
+    std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
+    for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
+    const int nbj = A.nbj, gate = A.gate;
+    std::stable_sort(order.begin(), order.end(), [nbj, gate](int x, int y) {
+        return fast::long2_order_key<C>(x % nbj, x / nbj, gate) < fast::long2_order_key<C>(y % nbj, y / nbj, gate);
+    });
+    for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;
+    int dist_j = 0, dist_k = 0;  // largest producer -> consumer distance in claim order
+    for (int t = 0; t < (int)A.tasks_total; ++t) {
+        if (t % nbj + 1 < nbj) dist_j = std::max(dist_j, pos_of[t + 1] - pos_of[t]);
+        if (t / nbj + 1 < A.nbkp) dist_k = std::max(dist_k, pos_of[t + nbj] - pos_of[t]);
+    }
+    A.fj_ring = (int)std::min<long long>(A.tasks_total, (long long)dist_j + 2 * grid + 2);
+    A.fk_ring = (int)std::min<long long>(A.tasks_total, (long long)dist_k + 2 * grid + 2);
+    const size_t fj_bytes = (size_t)A.fj_ring * A.fj_slot_words * 4, fk_bytes = (size_t)A.fk_ring * A.fk_slot_words * 4;
+    const size_t prog_bytes = (((size_t)A.tasks_total * sizeof(int) + 255) & ~(size_t)255);
+    const size_t ctl_bytes = 256 + prog_bytes;           // task counter, progress[]
+    const size_t ord_bytes = 2 * prog_bytes;             // order[], pos_of[]
+    int rc;
+    if ((rc = ctx->faces.reserve(fj_bytes + fk_bytes + 512))) return rc;
+    if ((rc = ctx->misc.reserve(ctl_bytes + ord_bytes))) return rc;
+    A.face_j = (uint32_t *)ctx->faces.ptr;
+    A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
+    A.counter = (unsigned long long *)ctx->misc.ptr;
+    A.progress = (int *)((char *)ctx->misc.ptr + 256);
+    int *d_order = (int *)((char *)ctx->misc.ptr + ctl_bytes);
+    int *d_pos = (int *)((char *)ctx->misc.ptr + ctl_bytes + prog_bytes);
+    A.order = d_order;
+    A.pos_of = d_pos;
+    TA_CUDA(cudaMemcpyAsync(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMemcpyAsync(d_pos, pos_of.data(), pos_of.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    TA_CUDA(cudaMemsetAsync(ctx->misc.ptr, 0, ctl_bytes, st));
+    if (std::getenv("TRIALIGN_DEBUG"))
+        std::fprintf(stderr, "[trialign] K2L: la=%d lag=%d gate=%d blocks %dx%d(pairs) tasks=%lld grid=%d faces=%.1f MB smem=%zu base=%d\n",
+                     la, LAG, A.gate, A.nbj, A.nbkp, A.tasks_total, grid, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
+    if (check) long2_kernel<LAG, true><<<grid, C::NT, smem, st>>>(A);
+    else long2_kernel<LAG, false><<<grid, C::NT, smem, st>>>(A);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+}  // namespace
+
+int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
+                   const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
+                   const SlabLink *slab)
+{
+    const bool check = check_bits > 0;
+    fast::SweepArgs A{};
+    A.a = d_a; A.b = d_b; A.c = d_c;
+    A.n = 1; A.la = la; A.lb = lb; A.lc = lc;
+    if (check) {
+        // candidates reach all+3 and (min all)-8; 45 / 60 cover the 15 unsampled planes between two samples
+        const int lim = 1 << (check_bits - 1);
+        A.check_hi = lim - 1 - 3 - 45;
+        A.check_lo = -lim + 8 + 60;
+        A.viol_flag = d_viol;
+    }
+    // LAG 1 (split-phase barrier, hop 17 / 33 steps between dependent tasks) is the default: measured faster than the
+    // lagged barrier (LAG 2) at L = 1,024 (416 vs 325 GCUPS, the sweep is dominated by the block-to-block pipeline
+    // fill) and at L = 8,192 (943 vs 860).  Long sweeps release their progress less often (a release is a MEMBAR.GPU).
+    // TRIALIGN_K2_LAG / TRIALIGN_K2_GATE override for experiments.
+    int lag = 1;
+    A.gate = la >= 4096 ? 16 : 4;
+    if (const char *e = std::getenv("TRIALIGN_K2_LAG")) {
+        const int v = std::atoi(e);
+        if (v == 1 || v == 2) lag = v;
+    }
+    if (const char *e = std::getenv("TRIALIGN_K2_GATE")) {
+        const int g = std::atoi(e);
+        if (g >= 1 && g <= 64 && (g & (g - 1)) == 0) A.gate = g;
+    }
+    A.out = d_score;
+    A.out_states = d_states;
+    const long long m0 = la < lb ? (la < lc ? la : lc) : (lb < lc ? lb : lc);
+    A.base = (int)(-envelope_lo(m0) + 32);
+    A.last_slab = 1;
+    if (slab) {  // planes i_begin+1 .. i_end of a triple of slab->la_total planes
+        const long long lt = slab->la_total;
+        const long long m = lt < lb ? (lt < lc ? lt : lc) : (lb < lc ? lb : lc);
+        A.base = (int)(-envelope_lo(m) + 32);
+        A.iface_in = (const uint32_t *)slab->in_state;
+        A.iface_in_flag = (const int *)slab->in_flags;
+        A.iface_out = (uint32_t *)slab->out_state;
+        A.iface_out_flag = (int *)slab->out_flags;
+        A.last_slab = slab->last ? 1 : 0;
+        A.epoch = slab->epoch;
+    }
+    return lag == 2 ? run_long2<2>(ctx, st, A, check, la) : run_long2<1>(ctx, st, A, check, la);
+}
+
+}  // namespace trialign

@@ -38,6 +38,11 @@ size_t fast_sweep_slab_flag_bytes(int lb, int lc);
 int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
                         const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
                         const SlabLink *slab = nullptr);
+// K2L (fast_long.cu): the same decomposition on the K1 / K2S step engine (split-phase or lagged mbarrier, block halos
+// prefetched by the edge threads); the default for one long triple.  Same arguments, same hand-over layout.
+int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
+                   const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
+                   const SlabLink *slab = nullptr);
 // check_bits > 0 selects the range-checked kernel: *d_viol (zeroed by the caller) becomes non-zero if some value came
 // close enough to the score_bits = check_bits limits that a wrap cannot be excluded.
 int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,

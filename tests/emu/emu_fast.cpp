@@ -413,3 +413,176 @@ extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// K2L (fast_long.cuh): one long triple on several emulated CTAs.  Every CTA runs the kernel's own protocol: the warps of
+// a CTA drift (a warp may run step s once every warp has finished step s-LAG), the gate warp cannot finish a step
+// before the producers' progress certifies the halo fetches AHEAD steps later, progress is published with the
+// kernel's rhythm.  CTAs and warps are advanced in a pseudo-random order.
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_long.cuh"
+
+namespace {
+
+template <class C>
+struct EmuCta2 {
+    std::unique_ptr<Long2Smem<C>> S{new Long2Smem<C>};
+    std::vector<Long2Regs<C>> R = std::vector<Long2Regs<C>>(C::NT);
+    std::vector<Long2Consts<C>> K = std::vector<Long2Consts<C>>(C::NT);
+    std::vector<int> done = std::vector<int>(C::NT / 32, -1);
+    bool has_task = false, prologue_done = false;
+};
+
+template <int LAG>
+int run_long2(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int base, int n_ctas,
+              int want_states, int32_t *out8, int check_bits, int *viol_out, const uint32_t *iface_in, uint32_t *iface_out,
+              int last_slab, int gate, int seed)
+{
+    using C = Long2Cfg<LAG>;
+    constexpr int NW = C::NT / 32, kGateWarp = 128 / 32;
+    if (la < 1 || lb < 1 || lc < 1 || la > C::LA_MAX || n_ctas < 1) return -1;
+    SweepArgs A{};
+    A.a = a; A.b = b; A.c = c; A.n = 1; A.la = la; A.lb = lb; A.lc = lc;
+    A.nbj = (lb + C::BJ - 1) / C::BJ;
+    A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
+    A.tasks_total = (long long)A.nbj * A.nbkp;
+    A.gate = gate;
+    A.fj_slot_words = (long long)(la + C::PLAG + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(la + C::PLAG + 2) * C::FK_ROW_WORDS;
+    A.fj_ring = (int)A.tasks_total;  // the emulation keeps every face (ring re-use is a launcher concern)
+    A.fk_ring = (int)A.tasks_total;
+    std::vector<uint32_t> fj((size_t)A.fj_ring * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
+    std::vector<int> prog((size_t)A.tasks_total, 0);
+    unsigned long long counter = 0;
+    std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
+    for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
+    const int nbj = A.nbj;
+    std::stable_sort(order.begin(), order.end(), [nbj, gate](int x, int y) {
+        return long2_order_key<C>(x % nbj, x / nbj, gate) < long2_order_key<C>(y % nbj, y / nbj, gate);
+    });
+    for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;
+    A.order = order.data(); A.pos_of = pos_of.data();
+    A.face_j = fj.data(); A.face_k = fk.data(); A.progress = prog.data(); A.counter = &counter;
+    A.out = out8; A.out_states = want_states ? out8 + 1 : nullptr; A.base = base;
+    A.iface_in = iface_in; A.iface_out = iface_out; A.last_slab = last_slab;
+    int viol = 0;
+    A.viol_flag = &viol;
+    const int lim = 1 << ((check_bits > 0 ? check_bits : 16) - 1);
+    A.check_hi = lim - 1 - 3 - 45;
+    A.check_lo = -lim + 8 + 60;
+    std::vector<EmuCta2<C>> ctas(n_ctas);
+    for (auto &cta : ctas) {
+        std::memset(cta.S.get(), 0xA5, sizeof(Long2Smem<C>));
+        for (int tid = 0; tid < C::NT; ++tid) long2_load_a<C>(*cta.S, A, tid);
+    }
+    const int steps = long2_task_steps<C>(A);
+    uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)seed;
+    long long finished = 0, idle = 0;
+    while (finished < A.tasks_total) {
+        rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+        auto &cta = ctas[(size_t)((rng >> 40) % (uint64_t)n_ctas)];
+        bool progressed = false;
+        if (!cta.has_task) {
+            if ((long long)counter < A.tasks_total) {
+                sweep_describe_long<C>(A, (long long)counter++, cta.S->task);
+                cta.has_task = true;
+                cta.prologue_done = false;
+                for (int tid = 0; tid < C::NT; ++tid) long2_load_bc<C>(*cta.S, A, tid);
+                for (int tid = 0; tid < C::NT; ++tid) long2_build_tables<C>(*cta.S, tid);
+                for (int tid = 0; tid < C::NT; ++tid) {
+                    int tj, tk;
+                    stream_thread_pos<C>(tid, tj, tk);
+                    long2_init_thread<C>(cta.R[tid], *cta.S, tj, tk);
+                }
+                std::fill(cta.done.begin(), cta.done.end(), -1);
+                progressed = true;
+            }
+        } else {
+            const SweepTask &T = cta.S->task;
+            const int tp = T.top_task >= 0 ? prog[T.top_task] : 0, lp = T.left_task >= 0 ? prog[T.left_task] : 0;
+            const int cert = long2_certified<C>(A, T, tp, lp);
+            if (!cta.prologue_done) {
+                if (cert >= 1 + LAG) {
+                    for (int tid = 0; tid < C::NT; ++tid) {
+                        int tj, tk;
+                        stream_thread_pos<C>(tid, tj, tk);
+                        if (tj == 0 || tk == 0) long2_edge_fetch<C>(*cta.S, A, tj, tk, 0);
+                        long2_thread_prepare<C>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, 0, tid);
+                    }
+                    cta.prologue_done = true;
+                    progressed = true;
+                }
+            } else {
+                const int w = (int)((rng >> 20) % NW);
+                const int s = cta.done[w] + 1;
+                const int mn = *std::min_element(cta.done.begin(), cta.done.end());
+                // LAG 2: step s needs everybody's step s-2; LAG 1: the wait at the end of step s-1 needs everybody's s-1
+                bool can = s <= steps && mn >= s - LAG;
+                const int want = s + C::AHEAD < steps ? s + C::AHEAD : steps;
+                if (can && w == kGateWarp && cert < want) can = false;  // the gate thread spins before its arrival
+                if (can) {
+                    if (w == kGateWarp) {  // publication, as the kernel orders it around the barrier waits
+                        if (LAG == 2 && s >= 2 && long2_publish_now(A, s)) prog[T.self_task] = s - 1;
+                        if (LAG == 1 && s >= 1 && long2_publish_now(A, s)) prog[T.self_task] = s;
+                    }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int tid = w * 32 + lane;
+                        int tj, tk;
+                        stream_thread_pos<C>(tid, tj, tk);
+                        long2_thread_step<C, true>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s, tid);
+                    }
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int tid = w * 32 + lane;
+                        int tj, tk;
+                        stream_thread_pos<C>(tid, tj, tk);
+                        long2_thread_prepare<C>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s + 1, tid);
+                    }
+                    cta.done[w] = s;
+                    progressed = true;
+                    if (*std::min_element(cta.done.begin(), cta.done.end()) == steps) {
+                        for (const auto &r : cta.R)
+                            if (r.viol) viol = 1;
+                        prog[T.self_task] = kProgressDone;
+                        cta.has_task = false;
+                        ++finished;
+                    }
+                }
+            }
+        }
+        if (progressed) idle = 0;
+        else if (++idle > 200000) return -2;  // deadlock
+    }
+    if (viol_out) *viol_out = viol;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int emu_fast_long2(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int base,
+                              int n_ctas, int lag, int gate, int seed, int32_t *out8, int check_bits, int *viol_out)
+{
+    if (lag == 1) return run_long2<1>(a, la, b, lb, c, lc, base, n_ctas, 1, out8, check_bits, viol_out, nullptr, nullptr, 1, gate, seed);
+    if (lag == 2) return run_long2<2>(a, la, b, lb, c, lc, base, n_ctas, 1, out8, check_bits, viol_out, nullptr, nullptr, 1, gate, seed);
+    return -1;
+}
+
+// the i-slab pipeline, slabs run one after the other (what n_slabs GPUs do concurrently, task by task)
+extern "C" int emu_fast_long2_slabs(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int base,
+                                    int n_ctas, int n_slabs, int lag, int32_t *out8)
+{
+    using C = Long2Cfg<1>;
+    const long long tasks = (long long)((lb + C::BJ - 1) / C::BJ) * ((lc + C::KSPAN - 1) / C::KSPAN);
+    std::vector<uint32_t> st[2];
+    st[0].assign((size_t)tasks * 4 * 16 * C::NT, 0xDEADBEEFu);
+    st[1] = st[0];
+    for (int g = 0; g < n_slabs; ++g) {
+        const int i0 = (int)((long long)la * g / n_slabs), i1 = (int)((long long)la * (g + 1) / n_slabs);
+        if (i1 <= i0) return -3;
+        const uint32_t *in = g > 0 ? st[(g - 1) & 1].data() : nullptr;
+        uint32_t *out = g + 1 < n_slabs ? st[g & 1].data() : nullptr;
+        const int rc = lag == 2 ? run_long2<2>(a + i0, i1 - i0, b, lb, c, lc, base, n_ctas, 1, out8, 0, nullptr, in, out, g + 1 == n_slabs, 4, g + 1)
+                                : run_long2<1>(a + i0, i1 - i0, b, lb, c, lc, base, n_ctas, 1, out8, 0, nullptr, in, out, g + 1 == n_slabs, 4, g + 1);
+        if (rc) return rc;
+    }
+    return 0;
+}

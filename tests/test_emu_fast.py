@@ -171,3 +171,73 @@ def test_stream_kernel_choreography(emu, ob, ln, n, ppc):
                                  2 * ln + 8 + 32, ppc, seed, out.ctypes.data_as(i32p))
         assert rc == 0
         assert out.tolist() == want, seed
+
+
+# ---- K2L: one long triple on the K1/K2S step engine (fast_long.cuh) ----
+@pytest.fixture(scope="module")
+def emu_long2(emu):
+    emu.emu_fast_long2.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                   i32p, C.c_int, C.POINTER(C.c_int)]
+    emu.emu_fast_long2_slabs.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    return emu
+
+
+def _long2(L, a, b, c, n_ctas, lag, gate=4, seed=1, check_bits=0):
+    a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (a, b, c))
+    out = np.zeros(8, np.int32)
+    viol = C.c_int(0)
+    base = 2 * min(len(a), len(b), len(c)) + 64
+    rc = L.emu_fast_long2(a.ctypes.data_as(u8p), len(a), b.ctypes.data_as(u8p), len(b), c.ctypes.data_as(u8p), len(c),
+                          base, n_ctas, lag, gate, seed, out.ctypes.data_as(i32p), check_bits, C.byref(viol))
+    assert rc == 0, "emulated CTAs deadlocked" if rc == -2 else rc
+    return int(out[0]), out[1:].tolist(), int(viol.value)
+
+
+@pytest.mark.parametrize("shape,n_ctas", [((5, 5, 5), 1), ((1, 5, 1), 1), ((20, 64, 64), 1), ((30, 64, 128), 1),
+                                          ((40, 70, 130), 2), ((33, 130, 200), 3), ((100, 200, 300), 4),
+                                          ((50, 129, 257), 5), ((10, 1, 1), 1), ((17, 260, 70), 2)])
+def test_long2_choreography(emu_long2, ob, shape, n_ctas):
+    """Both barrier lags, two publication rhythms, warps and CTAs advanced in pseudo-random order."""
+    la, lb, lc = shape
+    rng = np.random.default_rng(la * 7 + lb * 3 + lc)
+    for mutated in (True, False):
+        if mutated:
+            a, b, c = ob.mutated_triple(rng, max(shape))
+            a, b, c = a[:la], b[:lb], c[:lc]
+        else:
+            a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in shape)
+        es, efin = ob.score(a, b, c, 16)
+        for lag, gate, seed in ((1, 4, 1), (2, 4, 2), (2, 16, 3), (1, 8, 4)):
+            s, fin, _ = _long2(emu_long2, a, b, c, n_ctas, lag, gate, seed)
+            assert s == es and fin == efin.tolist(), (lag, gate, seed)
+
+
+def test_long2_range_check_is_sound_and_not_trigger_happy(emu_long2, ob):
+    rng = np.random.default_rng(77)
+    a, b, c = ob.mutated_triple(rng, 150, rate=0.02)        # nearly identical: all grows to ~3*150 = 450
+    _, _, (lo, hi) = ob.score(a, b, c, 32, want_range=True)
+    for lag in (1, 2):
+        for w in (9, 10, 11, 12):
+            lim = 1 << (w - 1)
+            _, _, viol = _long2(emu_long2, a, b, c, 2, lag, check_bits=w)
+            if hi + 3 > lim - 1 or lo - 4 < -lim:
+                assert viol, (w, lo, hi)                       # soundness: never miss a possible wrap
+            if hi + 3 + 45 + 12 <= lim - 1 and lo - 8 - 60 - 12 >= -lim:
+                assert not viol, (w, lo, hi)                   # and no false alarm when far from the limits
+        x, y, z = (rng.integers(0, 4, 150, dtype=np.uint8) for _ in range(3))
+        assert _long2(emu_long2, x, y, z, 2, lag, check_bits=10)[2] == 0
+
+
+@pytest.mark.parametrize("shape,n_slabs,n_ctas,lag", [((40, 70, 130), 2, 2, 1), ((64, 64, 64), 4, 1, 2),
+                                                      ((100, 129, 257), 3, 3, 1), ((37, 200, 140), 8, 2, 2)])
+def test_long2_i_slab_pipeline(emu_long2, ob, shape, n_slabs, n_ctas, lag):
+    la, lb, lc = shape
+    rng = np.random.default_rng(sum(shape) + n_slabs)
+    a, b, c = ob.mutated_triple(rng, max(shape))
+    a, b, c = (np.ascontiguousarray(x) for x in (a[:la], b[:lb], c[:lc]))
+    out = np.zeros(8, np.int32)
+    rc = emu_long2.emu_fast_long2_slabs(a.ctypes.data_as(u8p), la, b.ctypes.data_as(u8p), lb, c.ctypes.data_as(u8p), lc,
+                                        2 * min(shape) + 64, n_ctas, n_slabs, lag, out.ctypes.data_as(i32p))
+    assert rc == 0
+    es, efin = ob.score(a, b, c, 16)
+    assert int(out[0]) == es and out[1:].tolist() == efin.tolist()
