@@ -64,9 +64,8 @@ template <int LAG, bool CHECK>
 __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
 {
     using C = fast::Long2Cfg<LAG>;
-    // The thread that polls / releases the progress counters sits in a warp whose patch has the lightest block-edge
-    // duty (right edge only: a few face stores), so the MEMBAR of a release eats that warp's slack.
-    constexpr int kGateTid = 128;
+    // The thread that polls / releases the progress counters (A.gate_tid, see fast_long2_run)
+    const int kGateTid = A.gate_tid;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::Long2Smem<C> &S = *reinterpret_cast<fast::Long2Smem<C> *>(smem_raw);
     __shared__ __align__(8) uint64_t step_bar[2];
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             if (LAG == 2) {
                 if (g >= 2) bar_wait(&step_bar[g & 1], ((g - 2) >> 1) & 1);  // everybody has finished step s-2
                 // release: the edge threads' face stores of steps <= s-2 are ordered before the arrivals just observed
-                if (tid == kGateTid && s >= 2 && fast::long2_publish_now(A, s)) st_release(A.progress + T.self_task, s - 1);
+                if (tid == kGateTid && s >= 2 && fast::long2_publish_now<C>(A, s - 1)) st_release(A.progress + T.self_task, s - 1);
             }
             fast::ta_copy_wait_prev();  // this thread's block-halo fetch for step s has landed
             fast::long2_thread_step<C, CHECK>(R, K, S, A, tj, tk, s, tid);
@@ -165,7 +164,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             fast::long2_thread_prepare<C>(R, K, S, A, tj, tk, s + 1, tid);
             if (LAG == 1) {
                 bar_wait(&step_bar[0], g & 1);  // everybody has finished step s
-                if (tid == kGateTid && fast::long2_publish_now(A, s + 1)) st_release(A.progress + T.self_task, s + 1);
+                if (tid == kGateTid && fast::long2_publish_now<C>(A, s + 1)) st_release(A.progress + T.self_task, s + 1);
             }
         }
         fast::ta_copy_wait();
@@ -273,6 +272,9 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
         const int v = std::atoi(e);
         if (v == 1 || v == 2) lag = v;
     }
+    A.gate_tid = 128;
+    if (const char *e = std::getenv("TRIALIGN_K2_GATETID")) A.gate_tid = std::atoi(e) & 255;
+    if (const char *e = std::getenv("TRIALIGN_K2_EARLY")) A.early = std::atoi(e) ? 1 : 0;
     if (const char *e = std::getenv("TRIALIGN_K2_GATE")) {
         const int g = std::atoi(e);
         if (g >= 1 && g <= 64 && (g & (g - 1)) == 0) A.gate = g;

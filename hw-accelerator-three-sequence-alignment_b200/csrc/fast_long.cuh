@@ -471,8 +471,7 @@ TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem
 // at its step c the J-face row producer thread (15,tk) wrote at producer step c + LAG*15; thread (tj,0) consumes the
 // K-face row producer thread (tj,15) wrote at step c + LAG*15 + PLAG.
 //   long2_certified(): the last consumption step whose face rows are complete, given the producers' progress.
-//   Publication rhythm: every kEarlyGate steps during the first kEarlySteps steps of a task (tasks waiting to start need
-//   only HOP_J / HOP_K steps of their producer), every A.gate steps afterwards (a release is a MEMBAR.GPU).
+//   Publication rhythm: long2_publish_now().
 // ---------------------------------------------------------------------------------------------------------------
 template <class C>
 TA_HD int long2_certified(const SweepArgs &A, const SweepTask &T, int top_prog, int left_prog)
@@ -491,11 +490,17 @@ TA_HD int long2_certified(const SweepArgs &A, const SweepTask &T, int top_prog, 
 template <class C>
 TA_HD int long2_order_key(int bj, int bkp, int gate) { return (C::HOP_J + C::LAG + gate / 2) * bj + (C::HOP_K + C::LAG + gate / 2) * bkp; }
 
-// steps (counted from 0) after which the gate thread publishes the task's progress
-TA_HD bool long2_publish_now(const SweepArgs &A, int s)
+// Does the gate thread publish the task's progress once `done` steps are complete?  Every A.gate steps, plus the two
+// counts the tasks below / to the right are waiting for before they can start (their prologue needs HOP + 1 + LAG
+// steps).  A release is a MEMBAR.GPU with the task's face stores in flight, so there are as few as the hops allow.
+template <class C>
+TA_HD bool long2_publish_now(const SweepArgs &A, int done)
 {
-    const int gate = (s < kEarlySteps && A.gate > kEarlyGate) ? kEarlyGate : A.gate;
-    return (s & (gate - 1)) == 0;
+    if (A.early) {
+        const int gate = (done < kEarlySteps && A.gate > kEarlyGate) ? kEarlyGate : A.gate;
+        return (done & (gate - 1)) == 0;
+    }
+    return done == C::HOP_J + 1 + C::LAG || done == C::HOP_K + 1 + C::LAG || (done & (A.gate - 1)) == 0;
 }
 
 }  // namespace fast

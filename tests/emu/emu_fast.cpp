@@ -447,6 +447,7 @@ int run_long2(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t 
     A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
     A.tasks_total = (long long)A.nbj * A.nbkp;
     A.gate = gate;
+    A.early = seed & 1;  // both publication rhythms
     A.fj_slot_words = (long long)(la + C::PLAG + 2) * C::FJ_ROW_WORDS;
     A.fk_slot_words = (long long)(la + C::PLAG + 2) * C::FK_ROW_WORDS;
     A.fj_ring = (int)A.tasks_total;  // the emulation keeps every face (ring re-use is a launcher concern)
@@ -522,8 +523,8 @@ int run_long2(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t 
                 if (can && w == kGateWarp && cert < want) can = false;  // the gate thread spins before its arrival
                 if (can) {
                     if (w == kGateWarp) {  // publication, as the kernel orders it around the barrier waits
-                        if (LAG == 2 && s >= 2 && long2_publish_now(A, s)) prog[T.self_task] = s - 1;
-                        if (LAG == 1 && s >= 1 && long2_publish_now(A, s)) prog[T.self_task] = s;
+                        if (LAG == 2 && s >= 2 && long2_publish_now<C>(A, s - 1)) prog[T.self_task] = s - 1;
+                        if (LAG == 1 && s >= 1 && long2_publish_now<C>(A, s)) prog[T.self_task] = s;
                     }
                     for (int lane = 0; lane < 32; ++lane) {
                         const int tid = w * 32 + lane;
