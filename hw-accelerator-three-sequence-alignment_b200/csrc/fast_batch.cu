@@ -75,18 +75,31 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs 
     fast::BatchConsts<Cfg> K;
     fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, 0);
     const int steps = fast::batch_total_steps<Cfg>(P);
+    if (Cfg::LAG == 2) {
+        // Lagged barrier: everybody has finished step s-2 (even and odd steps use separate barriers, so the one waited
+        // on is at most one phase ahead of this thread's own arrivals).  Two register sets alternate (R -> R2 -> R) in
+        // a loop unrolled by two, so the loop-carried plane state needs no register moves; an odd extra step at the
+        // end runs on drained threads only.
+        fast::BatchRegs<Cfg> R2;
+#define TA_BATCH_STEP(RIN, ROUT, S_)                                                        \
+    do {                                                                                   \
+        const int s_ = (S_);                                                               \
+        if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                     \
+        fast::batch_thread_step<Cfg>(RIN, ROUT, K, S, A, tj, tk, s_, P, pair_base);        \
+        bar_arrive_warp(&step_bar[s_ & 1]);                                                \
+        fast::batch_uniform_actions<Cfg>(S, A, tid, s_, P, pair_base);                     \
+        fast::batch_thread_prepare<Cfg>(ROUT, K, S, A, tj, tk, s_ + 1);                    \
+    } while (0)
 #pragma unroll 1
-    for (int s = 0; s <= steps; ++s) {
-        if (Cfg::LAG == 2) {
-            // everybody has finished step s-2 (even and odd steps use separate barriers, so the one waited on is at
-            // most one phase ahead of this thread's own arrivals)
-            if (s >= 2) bar_wait(&step_bar[s & 1], ((s - 2) >> 1) & 1);
-            fast::batch_thread_step<Cfg>(R, K, S, A, tj, tk, s, P, pair_base);
-            bar_arrive_warp(&step_bar[s & 1]);
-            fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
-            fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, s + 1);
-        } else {
-            fast::batch_thread_step<Cfg>(R, K, S, A, tj, tk, s, P, pair_base);
+        for (int s = 0; s <= steps; s += 2) {
+            TA_BATCH_STEP(R, R2, s);
+            TA_BATCH_STEP(R2, R, s + 1);
+        }
+#undef TA_BATCH_STEP
+    } else {
+#pragma unroll 1
+        for (int s = 0; s <= steps; ++s) {
+            fast::batch_thread_step<Cfg>(R, R, K, S, A, tj, tk, s, P, pair_base);
             if (SPLIT) bar_arrive_warp(&step_bar[0]);
             fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
             fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, s + 1);

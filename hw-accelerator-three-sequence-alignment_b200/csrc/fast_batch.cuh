@@ -188,9 +188,11 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
 }
 
 // ---- one wavefront step of one thread: halos published at step s-1 -> tile -> publish for step s+1 ----
+// R = plane i-1 state (input), Rn = plane i state (output; may be R itself): the lagged-barrier kernel alternates two
+// register sets in a step loop unrolled by two, so that the loop-carried state needs no register moves.
 template <class C>
-TA_HD void batch_thread_step(BatchRegs<C> &R, const BatchConsts<C> &K, BatchSmem<C> &S, const BatchArgs &A, int tj,
-                             int tk, int s, int P, long long pair_base)
+TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
+                             const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int u = s - C::LAG * (tj + tk);
@@ -319,7 +321,8 @@ TA_HD void batch_thread_step(BatchRegs<C> &R, const BatchConsts<C> &K, BatchSmem
     for (int r = 0; r < RJ; ++r)
 #pragma unroll
         for (int c = 0; c < RK; ++c) {
-            R.all[r][c] = n_all[r][c]; R.wX[r][c] = n_wX[r][c]; R.u1[r][c] = n_u1[r][c]; R.u3[r][c] = n_u3[r][c];
+            Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
+            Rn.cBC[r][c] = R.cBC[r][c];
         }
 }
 

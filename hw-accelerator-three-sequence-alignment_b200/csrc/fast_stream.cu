@@ -64,28 +64,37 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArg
     fast::stream_stage_build<C>(S, tid, 0);
     __syncthreads();
 
-    fast::StreamRegs<C> R;
+    fast::StreamRegs<C> R, R2;
     fast::StreamConsts<C> K;
     fast::StreamPos pos = fast::stream_start_pos<C>(A, tj, tk);
     if (tj == 0 || tk == 0) fast::stream_edge_fetch<C>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1));
     fast::ta_copy_commit();
     fast::stream_thread_prepare<C>(R, K, S, A, tj, tk, pos, 0, false);
-    const int steps = (int)fast::stream_total_steps<C>(A, P);
+    const int steps = (int)fast::stream_total_steps<C>(A, P) | 1;  // an even number of steps: the loop runs two per turn
     int g_t = 0, g_off = 0;
+    // one step: wait until everybody has finished step s-2 (even and odd steps use separate barriers) and this thread's
+    // block-halo fetch for step s has landed | step | arrive | staging, next step's constants and halo fetch
+#define TA_STREAM_STEP(RIN, ROUT, S_)                                                              \
+    do {                                                                                          \
+        const int s_ = (S_);                                                                      \
+        if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                            \
+        fast::ta_copy_wait_prev();                                                                \
+        fast::stream_thread_step<C>(RIN, ROUT, K, S, A, tj, tk, s_, pos);                         \
+        bar_arrive_warp(&step_bar[s_ & 1]);                                                       \
+        if (g_t < tasks) fast::stream_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off); \
+        fast::stream_thread_prepare<C>(ROUT, K, S, A, tj, tk, pos, s_ + 1, true);                 \
+        if (++g_off == A.len) {                                                                   \
+            g_off = 0;                                                                            \
+            ++g_t;                                                                                \
+        }                                                                                         \
+    } while (0)
 #pragma unroll 1
-    for (int s = 0; s <= steps; ++s) {
-        // everybody has finished step s-2 (even and odd steps use separate barriers)
-        if (s >= 2) bar_wait(&step_bar[s & 1], ((s - 2) >> 1) & 1);
-        fast::ta_copy_wait_prev();  // this thread's block-halo fetch for step s has landed
-        fast::stream_thread_step<C>(R, K, S, A, tj, tk, s, pos);
-        bar_arrive_warp(&step_bar[s & 1]);
-        if (g_t < tasks) fast::stream_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off);
-        fast::stream_thread_prepare<C>(R, K, S, A, tj, tk, pos, s + 1, true);
-        if (++g_off == A.len) {
-            g_off = 0;
-            ++g_t;
-        }
+    for (int s = 0; s <= steps; s += 2) {
+        // two register sets alternate (R -> R2 -> R), so the loop-carried plane state needs no register moves
+        TA_STREAM_STEP(R, R2, s);
+        TA_STREAM_STEP(R2, R, s + 1);
     }
+#undef TA_STREAM_STEP
 }
 
 // contiguous chunks of pairs, one persistent CTA per SM (fill/drain once per CTA); the step counter stays below 2^30

@@ -314,9 +314,11 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
 }
 
 // ---- one wavefront step of one thread: halos published at step s-LAG -> tile -> publish for step s+LAG ----
+// R = plane i-1 state (input), Rn = plane i state (output; may be R itself).  The kernel alternates two register sets
+// (R -> Rn, Rn -> R) in a step loop unrolled by two, so that the loop-carried state needs no register moves.
 template <class C>
-TA_HD void stream_thread_step(StreamRegs<C> &R, const StreamConsts<C> &K, StreamSmem<C> &S, const StreamArgs &A, int tj,
-                              int tk, int s, const StreamPos &p)
+TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const StreamConsts<C> &K, StreamSmem<C> &S,
+                              const StreamArgs &A, int tj, int tk, int s, const StreamPos &p)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int j0 = tj * RJ, k0 = tk * RK;
@@ -447,7 +449,8 @@ TA_HD void stream_thread_step(StreamRegs<C> &R, const StreamConsts<C> &K, Stream
     for (int r = 0; r < RJ; ++r)
 #pragma unroll
         for (int c = 0; c < RK; ++c) {
-            R.all[r][c] = n_all[r][c]; R.wX[r][c] = n_wX[r][c]; R.u1[r][c] = n_u1[r][c]; R.u3[r][c] = n_u3[r][c];
+            Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
+            Rn.cBC[r][c] = R.cBC[r][c];
         }
 }
 

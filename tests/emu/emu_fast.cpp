@@ -51,7 +51,7 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
                 for (int tid = 0; tid < C::NT; ++tid) {
                     int tj, tk;
                     thread_pos<C>(tid, tj, tk);
-                    batch_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+                    batch_thread_step<C>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
                 }
                 for (int tid = C::NT - 1; tid >= 0; --tid) {
                     int tj, tk;
@@ -82,7 +82,7 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
                         const int tid = w * 32 + lane;
                         int tj, tk;
                         thread_pos<C>(tid, tj, tk);
-                        batch_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+                        batch_thread_step<C>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
                     }
                     for (int lane = 0; lane < 32; ++lane) {
                         const int tid = w * 32 + lane;
@@ -397,7 +397,7 @@ extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t
                     const int tid = w * 32 + lane;
                     int tj, tk;
                     stream_thread_pos<C>(tid, tj, tk);
-                    stream_thread_step<C>(R[tid], K[tid], *S, A, tj, tk, s, pos[tid]);
+                    stream_thread_step<C>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, pos[tid]);
                 }
                 for (int lane = 0; lane < 32; ++lane) {
                     const int tid = w * 32 + lane;
