@@ -134,39 +134,62 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         fast::ta_copy_commit();
         fast::long2_thread_prepare<C>(R, K, S, A, tj, tk, 0, tid);
 
+        // One step.  The gate thread certifies consumption step s + AHEAD before it arrives for step s: every edge
+        // thread fetches the halos of step x + 2 only after it has seen the arrivals of step x + 2 - AHEAD.  The
+        // producers' progress is sampled at the top of the step, so the load latency hides under the tile.
+#define TA_LONG_STEP(RARE, S_)                                                                                           \
+    do {                                                                                                                \
+        const int s_ = (S_);                                                                                            \
+        const int want = s_ + C::AHEAD < steps ? s_ + C::AHEAD : steps;                                                 \
+        const bool need = tid == kGateTid && cert < want;                                                               \
+        int tp = 0, lp = 0;                                                                                             \
+        if (need) {                                                                                                     \
+            tp = top_p ? ld_acquire(top_p) : 0;                                                                         \
+            lp = left_p ? ld_acquire(left_p) : 0;                                                                       \
+        }                                                                                                               \
+        if (LAG == 2) {                                                                                                 \
+            if (g >= 2) bar_wait(&step_bar[g & 1], ((g - 2) >> 1) & 1); /* everybody has finished step s-2 */           \
+            /* release: the face stores of steps <= s-2 are ordered before the arrivals just observed */                \
+            if (tid == kGateTid && s_ >= 2 && fast::long2_publish_now<C>(A, s_ - 1))                                    \
+                st_release(A.progress + T.self_task, s_ - 1);                                                           \
+        }                                                                                                               \
+        fast::ta_copy_wait_prev(); /* this thread's block-halo fetch for step s has landed */                           \
+        fast::long2_thread_step<C, CHECK, RARE>(R, R, K, S, A, tj, tk, s_, tid);                                       \
+        if (need) {                                                                                                     \
+            cert = fast::long2_certified<C>(A, T, tp, lp);                                                              \
+            while (cert < want) {                                                                                       \
+                __nanosleep(40);                                                                                        \
+                cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);  \
+            }                                                                                                           \
+        }                                                                                                               \
+        bar_arrive_warp(&step_bar[LAG == 2 ? (g & 1) : 0]);                                                             \
+        fast::long2_thread_prepare<C, RARE>(R, K, S, A, tj, tk, s_ + 1, tid);                                           \
+        if (LAG == 1) {                                                                                                 \
+            bar_wait(&step_bar[0], g & 1); /* everybody has finished step s */                                          \
+            if (tid == kGateTid && fast::long2_publish_now<C>(A, s_ + 1)) st_release(A.progress + T.self_task, s_ + 1); \
+        }                                                                                                               \
+        ++g;                                                                                                            \
+    } while (0)
+        // Three phases (long2_mid_*): head and tail share the full step; the middle -- nearly all steps of a long
+        // sweep -- runs a compact instantiation without the rare paths (plane-0 reset, range checks, score and final
+        // states, slab hand-over), which more than halves the loop body.  (K1 / K2S also alternate two register sets
+        // in a loop unrolled by two; here that doubled a 30 KB loop body and ran slower.)
+        {
+            int s = 0;
+            const int mid_begin = fast::long2_mid_begin<C>(A), mid_end = fast::long2_mid_end<C>(A);
 #pragma unroll 1
-        for (int s = 0; s <= steps; ++s, ++g) {
-            // the gate thread certifies consumption step s + AHEAD before it arrives for step s: every edge thread
-            // fetches the halos of step x + 2 only after it has seen the arrivals of step x + 2 - AHEAD.  The
-            // producers' progress is sampled at the top of the step, so the load latency hides under the tile.
-            const int want = s + C::AHEAD < steps ? s + C::AHEAD : steps;
-            const bool need = tid == kGateTid && cert < want;
-            int tp = 0, lp = 0;
-            if (need) {
-                tp = top_p ? ld_acquire(top_p) : 0;
-                lp = left_p ? ld_acquire(left_p) : 0;
-            }
-            if (LAG == 2) {
-                if (g >= 2) bar_wait(&step_bar[g & 1], ((g - 2) >> 1) & 1);  // everybody has finished step s-2
-                // release: the edge threads' face stores of steps <= s-2 are ordered before the arrivals just observed
-                if (tid == kGateTid && s >= 2 && fast::long2_publish_now<C>(A, s - 1)) st_release(A.progress + T.self_task, s - 1);
-            }
-            fast::ta_copy_wait_prev();  // this thread's block-halo fetch for step s has landed
-            fast::long2_thread_step<C, CHECK>(R, K, S, A, tj, tk, s, tid);
-            if (need) {
-                cert = fast::long2_certified<C>(A, T, tp, lp);
-                while (cert < want) {
-                    __nanosleep(40);
-                    cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);
+            for (int phase = 0; phase < 3; ++phase) {
+                if (phase == 1) {
+#pragma unroll 1
+                    for (; s <= mid_end; ++s) TA_LONG_STEP(false, s);
+                } else {
+                    const int end = (phase == 0 && mid_begin <= mid_end) ? mid_begin - 1 : steps;
+#pragma unroll 1
+                    for (; s <= end; ++s) TA_LONG_STEP(true, s);
                 }
             }
-            bar_arrive_warp(&step_bar[LAG == 2 ? (g & 1) : 0]);
-            fast::long2_thread_prepare<C>(R, K, S, A, tj, tk, s + 1, tid);
-            if (LAG == 1) {
-                bar_wait(&step_bar[0], g & 1);  // everybody has finished step s
-                if (tid == kGateTid && fast::long2_publish_now<C>(A, s + 1)) st_release(A.progress + T.self_task, s + 1);
-            }
         }
+#undef TA_LONG_STEP
         fast::ta_copy_wait();
         __syncthreads();  // every thread's face / hand-over stores precede the final release
         if (CHECK && R.viol) atomicOr(A.viol_flag, 1);

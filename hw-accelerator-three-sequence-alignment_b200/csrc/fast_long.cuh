@@ -82,6 +82,15 @@ TA_HD int long2_planes(const SweepArgs &A) { return A.la + C::PLAG; }           
 template <class C>
 TA_HD int long2_task_steps(const SweepArgs &A) { return A.la + C::PLAG + C::DEPTH - 1; }  // steps 0 .. this value
 
+// Middle phase of a task: steps long2_mid_begin .. long2_mid_end (may be empty).  There every thread has both halves
+// live (PLAG + 2 <= i0 <= la - 3), no half starts or finishes, and every face row fetched (two steps ahead) or stored
+// exists -- the step loop runs a compact instantiation (RARE = false) without the plane-0 reset, the range checks, the
+// score / final-state extraction and the slab hand-over.
+template <class C>
+TA_HD int long2_mid_begin(const SweepArgs &) { return C::DEPTH + C::PLAG + 1; }
+template <class C>
+TA_HD int long2_mid_end(const SweepArgs &A) { return A.la - 4; }
+
 // ---- once per CTA: the a symbols of both halves for every step offset ----
 template <class C>
 TA_HD void long2_load_a(Long2Smem<C> &S, const SweepArgs &A, int tid)
@@ -147,7 +156,8 @@ TA_HD void long2_init_thread(Long2Regs<C> &R, Long2Smem<C> &S, int tj, int tk)
 
 // ---- block-edge halos of consumption step c, into the edge slot that step reads.  Only thread (0,tk) / (tj,0) writes
 // and reads these entries (index 0 of the tj / tk dimension): cp.async + wait_group, no barrier involved. ----
-template <class C>
+// RARE = false: the caller guarantees that every face row asked for exists (steps of the middle phase, long2_mid_*).
+template <class C, bool RARE = true>
 TA_HD void long2_edge_fetch(Long2Smem<C> &S, const SweepArgs &A, int tj, int tk, int c)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
@@ -158,7 +168,7 @@ TA_HD void long2_edge_fetch(Long2Smem<C> &S, const SweepArgs &A, int tj, int tk,
         const int i = c - C::LAG * tk + 1;  // low-half plane of thread (0,tk) at step c
         const int k0 = tk * RK;
         if (T.fj_r) {
-            if (i >= 1 && i <= rows) {
+            if (!RARE || (i >= 1 && i <= rows)) {
                 const uint32_t *src = T.fj_r + (long long)i * C::FJ_ROW_WORDS + k0;
 #pragma unroll
                 for (int v = 0; v < 4; ++v) ta_copy16(&S.row[slot][v][0][k0], src + v * C::ROW_W);
@@ -180,7 +190,7 @@ TA_HD void long2_edge_fetch(Long2Smem<C> &S, const SweepArgs &A, int tj, int tk,
         const int j0 = tj * RJ;
         if (T.fk_r) {
             const int src_row = i + C::PLAG;  // the producer's high half is PLAG planes behind its row index
-            if (src_row >= 1 && src_row <= rows) {
+            if (!RARE || (src_row >= 1 && src_row <= rows)) {
                 const uint32_t *src = T.fk_r + (long long)src_row * C::FK_ROW_WORDS + j0;
 #pragma unroll
                 for (int v = 0; v < 4; ++v) ta_copy16(&S.col[slot][v][0][j0], src + v * C::COL_W);
@@ -208,7 +218,8 @@ TA_HD void long2_edge_fetch(Long2Smem<C> &S, const SweepArgs &A, int tj, int tk,
 
 // ---- the part of step s1 that does not depend on the neighbours: plane-0 reset, the step's constants, and the halo
 // fetch of step s1 + 1 ----
-template <class C>
+// RARE = false: steps of the middle phase (long2_mid_*), where no half starts and every face row exists.
+template <class C, bool RARE = true>
 TA_HD void long2_thread_prepare(Long2Regs<C> &R, Long2Consts<C> &K, Long2Smem<C> &S, const SweepArgs &A, int tj, int tk,
                                 int s1, int tid)
 {
@@ -219,7 +230,7 @@ TA_HD void long2_thread_prepare(Long2Regs<C> &R, Long2Consts<C> &K, Long2Smem<C>
     const int j0 = tj * RJ, k0 = tk * RK;
 
     // plane 0 is the all-zero border (PE override, src/PE_1cyc.v:164-178): reset the half whose plane 1 starts now
-    if (i0 == 1 || i1 == 1) {
+    if (RARE && (i0 == 1 || i1 == 1)) {
         const uint32_t keep = (i0 == 1 ? 0u : 0x0000FFFFu) | (i1 == 1 ? 0u : 0xFFFF0000u);
 #pragma unroll
         for (int r = 0; r < RJ; ++r)
@@ -255,14 +266,17 @@ TA_HD void long2_thread_prepare(Long2Regs<C> &R, Long2Consts<C> &K, Long2Smem<C>
         K.cAC[c] = S.tabK[code][k0 + c];
         K.tC[c] = S.tabK[code][64 + k0 + c];
     }
-    if (tj == 0 || tk == 0) long2_edge_fetch<C>(S, A, tj, tk, s1 + 1);
+    if (tj == 0 || tk == 0) long2_edge_fetch<C, RARE>(S, A, tj, tk, s1 + 1);
     ta_copy_commit();
 }
 
 // ---- one wavefront step of one thread ----
-template <class C, bool CHECK>
-TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem<C> &S, const SweepArgs &A, int tj,
-                             int tk, int s, int tid)
+// R = plane i-1 state (input), Rn = plane i state (output; may be R itself): the kernel alternates two register sets in
+// a step loop unrolled by two, so that the loop-carried state needs no register moves.
+// RARE = false: steps of the middle phase (long2_mid_*): both halves live, every face row in range, no half finishes.
+template <class C, bool CHECK, bool RARE = true>
+TA_HD void long2_thread_step(const Long2Regs<C> &R, Long2Regs<C> &Rn, const Long2Consts<C> &K, Long2Smem<C> &S,
+                             const SweepArgs &A, int tj, int tk, int s, int tid)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const SweepTask &T = S.task;
@@ -270,6 +284,8 @@ TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem
     const int i1 = i0 - C::PLAG;                // high-half plane
     const int j0 = tj * RJ, k0 = tk * RK;
     const int rs = (s + C::LAG) & (C::NSLOT - 1), ws = s & (C::NSLOT - 1);  // rs == (s - LAG) mod NSLOT
+
+    uint32_t viol = R.viol;
 
     // halos; index 0 of the tj / tk dimension is the block halo, filled by long2_edge_fetch
     uint32_t T_wY[RK], T_u1[RK], T_u2[RK + 1], T_all[RK + 1], L_wZ[RJ], L_u3[RJ], L_u2[RJ], L_all[RJ];
@@ -357,7 +373,7 @@ TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem
 
     // block faces to global memory, re-based to the consumer's frame (its halo row / column has local index 0)
     const int rows = long2_planes<C>(A);
-    if (tj == C::TJ - 1 && T.fj_w && i0 >= 1 && i0 <= rows) {
+    if (tj == C::TJ - 1 && T.fj_w && (!RARE || (i0 >= 1 && i0 <= rows))) {
         const uint32_t adj = rep(2 * C::BJ);
         uint32_t *dst = T.fj_w + (long long)i0 * C::FJ_ROW_WORDS + k0;
         ta_store4(dst + 0 * C::ROW_W, n_wY[RJ - 1][0] - adj, n_wY[RJ - 1][1] - adj, n_wY[RJ - 1][2] - adj, n_wY[RJ - 1][3] - adj);
@@ -365,7 +381,7 @@ TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem
         ta_store4(dst + 2 * C::ROW_W, R.u1[RJ - 1][0] - adj, R.u1[RJ - 1][1] - adj, R.u1[RJ - 1][2] - adj, R.u1[RJ - 1][3] - adj);
         ta_store4(dst + 3 * C::ROW_W, R.all[RJ - 1][0] - adj, R.all[RJ - 1][1] - adj, R.all[RJ - 1][2] - adj, R.all[RJ - 1][3] - adj);
     }
-    if (tk == C::TK - 1 && T.fk_w && i0 >= 1 && i0 <= rows) {
+    if (tk == C::TK - 1 && T.fk_w && (!RARE || (i0 >= 1 && i0 <= rows))) {
         // only the high half crosses to the next column pair (KSPAN columns to the right of this pair's origin)
         const uint32_t adj = (uint32_t)(2 * C::KSPAN) << 16;
         uint32_t *dst = T.fk_w + (long long)i0 * C::FK_ROW_WORDS + j0;
@@ -398,12 +414,13 @@ TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem
         const uint32_t hi_lim = (uint32_t)(h0 > 0xFFFF ? 0xFFFF : h0) | ((uint32_t)(h1 > 0xFFFF ? 0xFFFF : h1) << 16);
         const uint32_t lo_lim = (uint32_t)(l0 < 0 ? 0 : l0) | ((uint32_t)(l1 < 0 ? 0 : l1) << 16);
         const uint32_t bad = (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
-        const uint32_t live = ((i0 >= 1 && i0 <= A.la) ? 0x0000FFFFu : 0u) | ((i1 >= 1 && i1 <= A.la) ? 0xFFFF0000u : 0u);
-        R.viol |= bad & live;
+        const uint32_t live = !RARE ? 0xFFFFFFFFu
+                                    : ((i0 >= 1 && i0 <= A.la) ? 0x0000FFFFu : 0u) | ((i1 >= 1 && i1 <= A.la) ? 0xFFFF0000u : 0u);
+        viol |= bad & live;
     }
 
     // Score = max of the 7 states of cell (la,lb,lc) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
-    if (T.final_here && A.last_slab) {
+    if (RARE && T.final_here && A.last_slab) {
         const int jl = A.lb - T.bj * C::BJ;                 // 1..64
         const int kk = A.lc - T.bkp * C::KSPAN;             // 1..KSPAN
         const int hf = (kk - 1) / C::BK;                    // the half that holds column lc
@@ -441,13 +458,14 @@ TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem
     for (int r = 0; r < RJ; ++r)
 #pragma unroll
         for (int c = 0; c < RK; ++c) {
-            R.all[r][c] = n_all[r][c]; R.wX[r][c] = n_wX[r][c]; R.u1[r][c] = n_u1[r][c]; R.u3[r][c] = n_u3[r][c];
+            Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
         }
+    Rn.viol = viol;
 
     // i-slab hand-over: the half that has just finished the slab's last plane stores its state for the next slab,
     // re-based by the slab's 2*la so that the reader's plane index restarts at 0 (16-bit stores: the halves finish
     // PLAG steps apart)
-    if (A.iface_out && (i0 == A.la || i1 == A.la)) {
+    if (RARE && A.iface_out && (i0 == A.la || i1 == A.la)) {
         const uint32_t adj = rep((uint32_t)(2 * A.la));
         uint16_t *dst16 = reinterpret_cast<uint16_t *>(A.iface_out + (((long long)T.self_task * 4) * 16) * C::NT + tid);
         const int hsel = (i0 == A.la) ? 0 : 1;
@@ -456,7 +474,7 @@ TA_HD void long2_thread_step(Long2Regs<C> &R, const Long2Consts<C> &K, Long2Smem
 #pragma unroll
             for (int c = 0; c < RK; ++c) {
                 const long long w = (long long)(r * RK + c) * C::NT;  // word offset of this cell within a value plane
-                const uint32_t v0 = R.all[r][c] - adj, v1 = R.wX[r][c] - adj, v2 = R.u1[r][c] - adj, v3 = R.u3[r][c] - adj;
+                const uint32_t v0 = Rn.all[r][c] - adj, v1 = Rn.wX[r][c] - adj, v2 = Rn.u1[r][c] - adj, v3 = Rn.u3[r][c] - adj;
                 dst16[2 * (w + 0LL * 16 * C::NT) + hsel] = (uint16_t)(hsel ? v0 >> 16 : v0);
                 dst16[2 * (w + 1LL * 16 * C::NT) + hsel] = (uint16_t)(hsel ? v1 >> 16 : v1);
                 dst16[2 * (w + 2LL * 16 * C::NT) + hsel] = (uint16_t)(hsel ? v2 >> 16 : v2);

@@ -526,17 +526,21 @@ int run_long2(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t 
                         if (LAG == 2 && s >= 2 && long2_publish_now<C>(A, s - 1)) prog[T.self_task] = s - 1;
                         if (LAG == 1 && s >= 1 && long2_publish_now<C>(A, s)) prog[T.self_task] = s;
                     }
+                    // the kernel runs the compact instantiation (RARE = false) during the middle phase
+                    const bool mid = s >= long2_mid_begin<C>(A) && s <= long2_mid_end<C>(A);
                     for (int lane = 0; lane < 32; ++lane) {
                         const int tid = w * 32 + lane;
                         int tj, tk;
                         stream_thread_pos<C>(tid, tj, tk);
-                        long2_thread_step<C, true>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s, tid);
+                        if (mid) long2_thread_step<C, true, false>(cta.R[tid], cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s, tid);
+                        else long2_thread_step<C, true, true>(cta.R[tid], cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s, tid);
                     }
                     for (int lane = 0; lane < 32; ++lane) {
                         const int tid = w * 32 + lane;
                         int tj, tk;
                         stream_thread_pos<C>(tid, tj, tk);
-                        long2_thread_prepare<C>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s + 1, tid);
+                        if (mid) long2_thread_prepare<C, false>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s + 1, tid);
+                        else long2_thread_prepare<C, true>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s + 1, tid);
                     }
                     cta.done[w] = s;
                     progressed = true;

@@ -1,0 +1,9 @@
+mkdir -p gpurun_out
+one() { python bench.py --no-cpu "$@" 2>> gpurun_out/q_err.log | python -c "import sys,json,os; d=json.loads(sys.stdin.read()); print('%-10s %-44s %8.1f GCUPS %9.3f ms  %s cks=%s' % (os.environ.get('TAG',''), ' '.join(sys.argv[1:]), d['value'], d['ms_per_step'], d['config']['kernel_path'], d['config']['scores_checksum']))" "$@"; }
+: > gpurun_out/q_err.log
+{
+python tools/tiny_cases.py k2l 2>&1 | tail -1
+TAG=$1 one --steps 5 --warmup 3 --workload long1024
+TAG=$1 one --steps 2 --warmup 2 --workload long8192
+} > gpurun_out/long_quick.txt 2>&1
+cat gpurun_out/long_quick.txt; tail -3 gpurun_out/q_err.log
