@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         bar_init(&step_bar[1], C::NT / 32);
     }
     fast::long2_load_a<C>(S, A, tid);
-    fast::Long2Regs<C> R;
+    fast::Long2Regs<C> R, R2;
     fast::Long2Consts<C> K;
     const int steps = fast::long2_task_steps<C>(A);
     const bool edge = tj == 0 || tk == 0;
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         // One step.  The gate thread certifies consumption step s + AHEAD before it arrives for step s: every edge
         // thread fetches the halos of step x + 2 only after it has seen the arrivals of step x + 2 - AHEAD.  The
         // producers' progress is sampled at the top of the step, so the load latency hides under the tile.
-#define TA_LONG_STEP(RARE, S_)                                                                                           \
+#define TA_LONG_STEP(RARE, RIN, ROUT, S_)                                                                                     \
     do {                                                                                                                \
         const int s_ = (S_);                                                                                            \
         const int want = s_ + C::AHEAD < steps ? s_ + C::AHEAD : steps;                                                 \
@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
                 st_release(A.progress + T.self_task, s_ - 1);                                                           \
         }                                                                                                               \
         fast::ta_copy_wait_prev(); /* this thread's block-halo fetch for step s has landed */                           \
-        fast::long2_thread_step<C, CHECK, RARE>(R, R, K, S, A, tj, tk, s_, tid);                                       \
+        fast::long2_thread_step<C, CHECK, RARE>(RIN, ROUT, K, S, A, tj, tk, s_, tid);                                  \
         if (need) {                                                                                                     \
             cert = fast::long2_certified<C>(A, T, tp, lp);                                                              \
             while (cert < want) {                                                                                       \
@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             }                                                                                                           \
         }                                                                                                               \
         bar_arrive_warp(&step_bar[LAG == 2 ? (g & 1) : 0]);                                                             \
-        fast::long2_thread_prepare<C, RARE>(R, K, S, A, tj, tk, s_ + 1, tid);                                           \
+        fast::long2_thread_prepare<C, RARE>(ROUT, K, S, A, tj, tk, s_ + 1, tid);                                        \
         if (LAG == 1) {                                                                                                 \
             bar_wait(&step_bar[0], g & 1); /* everybody has finished step s */                                          \
             if (tid == kGateTid && fast::long2_publish_now<C>(A, s_ + 1)) st_release(A.progress + T.self_task, s_ + 1); \
@@ -176,16 +176,32 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         // in a loop unrolled by two; here that doubled a 30 KB loop body and ran slower.)
         {
             int s = 0;
-            const int mid_begin = fast::long2_mid_begin<C>(A), mid_end = fast::long2_mid_end<C>(A);
+            const int mid_begin = fast::long2_mid_begin<C>(A);
+            int mid_end = fast::long2_mid_end<C>(A);
+            // Experiment (TRIALIGN_K2_PP=1, unchecked kernel only): the middle loop unrolled by two over two alternating
+            // register sets, which removes the register moves of the loop-carried state (+4.5 % in K1 / K2S).  Here it
+            // gains nothing at L = 8,192 (1,131 vs 1,124 GCUPS) and loses a lot whenever tasks run in lock-step with
+            // their producers (1,024^3: 392 vs 492; 4,096 x 1,024^2: 536 vs 763), so it stays off.
+            const bool pingpong = !CHECK && A.pingpong;
+            if (pingpong && mid_begin <= mid_end && ((mid_end - mid_begin) & 1) == 0) --mid_end;  // even count
 #pragma unroll 1
             for (int phase = 0; phase < 3; ++phase) {
                 if (phase == 1) {
 #pragma unroll 1
-                    for (; s <= mid_end; ++s) TA_LONG_STEP(false, s);
+                    if (!CHECK && pingpong) {
+#pragma unroll 1
+                        for (; s <= mid_end; s += 2) {
+                            TA_LONG_STEP(false, R, R2, s);
+                            TA_LONG_STEP(false, R2, R, s + 1);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (; s <= mid_end; ++s) TA_LONG_STEP(false, R, R, s);
+                    }
                 } else {
                     const int end = (phase == 0 && mid_begin <= mid_end) ? mid_begin - 1 : steps;
 #pragma unroll 1
-                    for (; s <= end; ++s) TA_LONG_STEP(true, s);
+                    for (; s <= end; ++s) TA_LONG_STEP(true, R, R, s);
                 }
             }
         }
@@ -296,6 +312,8 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
         if (v == 1 || v == 2) lag = v;
     }
     A.gate_tid = 128;
+    A.pingpong = 0;
+    if (const char *e = std::getenv("TRIALIGN_K2_PP")) A.pingpong = std::atoi(e) ? 1 : 0;
     if (const char *e = std::getenv("TRIALIGN_K2_GATETID")) A.gate_tid = std::atoi(e) & 255;
     if (const char *e = std::getenv("TRIALIGN_K2_EARLY")) A.early = std::atoi(e) ? 1 : 0;
     if (const char *e = std::getenv("TRIALIGN_K2_GATE")) {

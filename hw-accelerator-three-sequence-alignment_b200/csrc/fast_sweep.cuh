@@ -67,6 +67,7 @@ struct SweepArgs {
     int gate;                     // LONG: steps between two progress releases in steady state (power of two)
     int gate_tid;                 // K2L: the thread that polls / releases the progress counters
     int early;                    // K2L: 1 = fine publication rhythm during a task's first steps (experiments)
+    int pingpong;                 // K2L: middle phase unrolled by two over two alternating register sets
     int *progress;                // LONG: [tasks_total] indexed by task id bj + nbj*bkp, zero-initialised
     const int *order;             // LONG: claim position -> task id (sorted by earliest possible start, sweep_order_key)
     const int *pos_of;            // LONG: task id -> claim position

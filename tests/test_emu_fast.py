@@ -195,7 +195,8 @@ def _long2(L, a, b, c, n_ctas, lag, gate=4, seed=1, check_bits=0):
 
 @pytest.mark.parametrize("shape,n_ctas", [((5, 5, 5), 1), ((1, 5, 1), 1), ((20, 64, 64), 1), ((30, 64, 128), 1),
                                           ((40, 70, 130), 2), ((33, 130, 200), 3), ((100, 200, 300), 4),
-                                          ((50, 129, 257), 5), ((10, 1, 1), 1), ((17, 260, 70), 2)])
+                                          ((50, 129, 257), 5), ((10, 1, 1), 1), ((17, 260, 70), 2),
+                                          ((260, 70, 130), 2)])  # long enough for the compact middle phase at both lags
 def test_long2_choreography(emu_long2, ob, shape, n_ctas):
     """Both barrier lags, two publication rhythms, warps and CTAs advanced in pseudo-random order."""
     la, lb, lc = shape
