@@ -136,6 +136,10 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     const bool want_fast = backend != TRIALIGN_BACKEND_GPU_LITERAL;
     // fast paths are used only where they are provably bit-exact: no candidate can wrap at score_bits
     if (want_fast && provably_wrap_free(la, lb, lc, score_bits)) {
+        if (!d_finals && la == lb && lb == lc && la <= 64 && fast_stream_supports(la) && env_is("TRIALIGN_K1", "stream")) {
+            ts.last_path = TRIALIGN_PATH_FAST_STREAM;  // experiment: K2S on a single block per pair (len 61..64)
+            return fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
+        }
         if (!d_finals && la == lb && lb == lc && fast_batch_supports(la)) {
             ts.last_path = TRIALIGN_PATH_FAST_BATCH;
             return fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);

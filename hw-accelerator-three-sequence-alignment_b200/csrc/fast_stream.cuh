@@ -42,7 +42,7 @@ struct StreamCfg {
     static constexpr int ROW_STRIDE = BK, COL_STRIDE = BJ + 4, CORNER_STRIDE = TK + 8;
     static constexpr int TABJ_STRIDE = 68, TABK_STRIDE = 128;
     static constexpr int SKEW = LAG * (TJ + TK - 2);
-    static constexpr int LEN_MIN = SKEW + 5;   // at most two tasks in flight; staging fits inside a task
+    static constexpr int LEN_MIN = SKEW + 1;   // at most two tasks in flight; staging fits inside a task
     static constexpr int LEN_MAX = 2048;       // a-codes of two pairs kept in shared memory
     static constexpr int LOAD_AT = 8, BUILD_AT = 16;  // steps after a task enters thread (0,0): stage the next one
     static constexpr int FJ_ROW_WORDS = 4 * ROW_STRIDE;  // one plane of a J face: {wY,u2,u1(old),all(old)} x 64 columns
@@ -83,7 +83,7 @@ struct StreamSmem {
     uint32_t tabMB[C::NBUF][16][C::TABJ_STRIDE];  // [buf][a code][j]  triple row constant {9,3}
     uint32_t tabK[C::NBUF][16][C::TABK_STRIDE];   // [buf][a code][k] pair constant, [64 + k] triple column constant {9,6}
     uint32_t bpk[C::NBUF][64], cpk[C::NBUF][64];  // [buf][pos]  b / c symbols of the block, one triple per half
-    uint8_t acode[2][C::LEN_MAX];                 // [pair parity][i]  a_lo | a_hi << 2
+    uint8_t acode[C::NBUF][C::LEN_MAX];           // [pair % NBUF][i]  a_lo | a_hi << 2 (a pair may be a single task)
     StreamTask task[C::NBUF];
 };
 
@@ -156,7 +156,7 @@ TA_HD void stream_stage_load(StreamSmem<C> &S, const StreamArgs &A, int tid, int
         T.valid = valid ? 1 : 0;
         T.bj = bj; T.bk = bk;
         T.pair = pair;
-        T.abuf = valid ? (p & 1) : 0;
+        T.abuf = valid ? (p % C::NBUF) : 0;
         T.final_here = valid && q == nblk - 1;
         uint32_t *fj = A.face_j + (long long)cta * 2 * A.fj_slot_words;
         uint32_t *fk = A.face_k + (long long)cta * A.fk_ring * A.fk_slot_words;
@@ -185,7 +185,7 @@ TA_HD void stream_stage_load(StreamSmem<C> &S, const StreamArgs &A, int tid, int
         for (int e = tid; e < A.len; e += C::NT) {
             const uint32_t a0 = (t0 < A.n) ? (A.a[t0 * A.len + e] & 3) : 0;
             const uint32_t a1 = (t1 < A.n) ? (A.a[t1 * A.len + e] & 3) : 0;
-            S.acode[p & 1][e] = (uint8_t)(a0 | (a1 << 2));
+            S.acode[p % C::NBUF][e] = (uint8_t)(a0 | (a1 << 2));
         }
     }
 }

@@ -153,7 +153,7 @@ def test_sweep_i_slab_pipeline(emu_sweep, ob, shape, n_slabs, n_ctas):
 
 
 # ---- K2S: streaming block sweep for batches of triples longer than 64 (fast_stream.cuh) ----
-@pytest.mark.parametrize("ln,n,ppc", [(65, 3, 2), (100, 5, 2), (128, 4, 1), (130, 7, 4), (200, 5, 3), (256, 2, 1)])
+@pytest.mark.parametrize("ln,n,ppc", [(61, 9, 5), (64, 7, 4), (65, 3, 2), (100, 5, 2), (128, 4, 1), (130, 7, 4), (200, 5, 3), (256, 2, 1)])
 def test_stream_kernel_choreography(emu, ob, ln, n, ppc):
     """All blocks of a CTA's pairs streamed back to back (task hand-over inside the array, faces through the rings,
     staging of the next task while two are in flight), warps drifting in different pseudo-random orders."""
