@@ -360,6 +360,8 @@ def run_ours(args, rank, world, local_rank):
             # DRAM bytes of one launch from the ncu capture, scaled by the number of triples when the captured launch
             # was a reduced batch (traffic is the input arrays + scores, linear in n)
             scale = float(n) / ks["triples_in_capture"] if ks.get("triples_in_capture") else 1.0
+            if slab:
+                scale = 1.0 / world  # every GPU of the i-slab pipeline sweeps 1/world of the planes (faces per plane are fixed)
             line["roofline"]["traffic"] = (ks["dram_bytes_read"] + ks["dram_bytes_write"]) * scale
             line["roofline"]["issued"] = {k: ks[k] for k in ("alu_pipe_pct", "issue_slot_pct", "warp_instr_per_cell_pair",
                                                               "alu_instr_per_cell_pair", "capture") if k in ks}
