@@ -11,6 +11,9 @@ from .trialign import (  # noqa: F401
     BACKEND_GPU_FAST,
     BACKEND_GPU_LITERAL,
     PATH_NAMES,
+    TRIPLE_RTL,
+    TRIPLE_SUM_OF_PAIRS,
+    Scoring,
     TriAlign,
     TriAlignError,
     build_library,

@@ -133,6 +133,11 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
                    int32_t *d_finals)
 {
     ThreadState &ts = tls();
+    if (ts.scoring_active) {  // non-RTL scoring parameters (*_ex entry points): the literal kernel evaluates them as given
+        if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
+        ts.last_path = TRIALIGN_PATH_LITERAL;
+        return literal_run(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals, &ts.scoring);
+    }
     const bool want_fast = backend != TRIALIGN_BACKEND_GPU_LITERAL;
     // fast paths are used only where they are provably bit-exact: no candidate can wrap at score_bits
     if (want_fast && provably_wrap_free(la, lb, lc, score_bits)) {
@@ -487,6 +492,8 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
     for (size_t g = 0; g < G; ++g) {
         const int64_t t0 = n * (int64_t)g / (int64_t)G, t1 = n * (int64_t)(g + 1) / (int64_t)G;
         th.emplace_back([&, g, t0, t1]() {
+            tls().scoring_active = ts.scoring_active;  // the *_ex scoring of the calling thread
+            tls().scoring = ts.scoring;
             if (t1 > t0)
                 rcs[g] = run_host_batch_on_device(devs[g], a + (size_t)t0 * len, b + (size_t)t0 * len,
                                                   c + (size_t)t0 * len, t1 - t0, len, len, len, score_bits,
@@ -507,6 +514,65 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
     }
     ts.last_seconds = worst;
     return TRIALIGN_OK;
+}
+
+// ---- explicit scoring parameters ----
+void trialign_scoring_rtl(trialign_scoring *sc)
+{
+    if (!sc) return;
+    sc->match = 1;       // src/PE_1cyc.v:53-56
+    sc->mismatch = -1;
+    sc->gap_open = 2;
+    sc->gap_extend = 1;
+    sc->triple_rule = TRIALIGN_TRIPLE_RTL;
+}
+
+namespace {
+
+int check_scoring(const trialign_scoring *sc, bool *is_rtl)
+{
+    if (!sc) return TRIALIGN_EINVAL;
+    if (sc->match < -1024 || sc->match > 1024 || sc->mismatch < -1024 || sc->mismatch > 1024) return TRIALIGN_EINVAL;
+    if (sc->gap_open < 0 || sc->gap_open > 1024 || sc->gap_extend < 0 || sc->gap_extend > 1024) return TRIALIGN_EINVAL;
+    if (sc->triple_rule != TRIALIGN_TRIPLE_RTL && sc->triple_rule != TRIALIGN_TRIPLE_SUM_OF_PAIRS) return TRIALIGN_EINVAL;
+    trialign_scoring rtl;
+    trialign_scoring_rtl(&rtl);
+    *is_rtl = std::memcmp(sc, &rtl, sizeof rtl) == 0;
+    return TRIALIGN_OK;
+}
+
+// sets the calling thread's scoring for the duration of one *_ex call
+struct ScopedScoring {
+    explicit ScopedScoring(const trialign_scoring &sc)
+    {
+        tls().scoring = sc;
+        tls().scoring_active = true;
+    }
+    ~ScopedScoring() { tls().scoring_active = false; }
+};
+
+}  // namespace
+
+int trialign_score_ex(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                      const trialign_scoring *scoring, unsigned devices, int32_t *score, int32_t final_states[7])
+{
+    bool is_rtl = false;
+    const int rc = check_scoring(scoring, &is_rtl);
+    if (rc) return rc;
+    if (is_rtl) return trialign_score(a, la, b, lb, c, lc, score_bits, TRIALIGN_BACKEND_AUTO, devices, score, final_states);
+    ScopedScoring scope(*scoring);
+    return trialign_score(a, la, b, lb, c, lc, score_bits, TRIALIGN_BACKEND_AUTO, devices, score, final_states);
+}
+
+int trialign_score_batch_ex(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len, int score_bits,
+                            const trialign_scoring *scoring, unsigned devices, int32_t *scores)
+{
+    bool is_rtl = false;
+    const int rc = check_scoring(scoring, &is_rtl);
+    if (rc) return rc;
+    if (is_rtl) return trialign_score_batch(a, b, c, n, len, score_bits, TRIALIGN_BACKEND_AUTO, devices, scores);
+    ScopedScoring scope(*scoring);
+    return trialign_score_batch(a, b, c, n, len, score_bits, TRIALIGN_BACKEND_AUTO, devices, scores);
 }
 
 int trialign_slab_buffer_bytes(int lb, int lc, int64_t *state_bytes, int64_t *flag_bytes)

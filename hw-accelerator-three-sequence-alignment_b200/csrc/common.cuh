@@ -19,6 +19,8 @@ struct ThreadState {
     double last_seconds = -1.0;
     double last_cells = 0.0;
     int last_path = TRIALIGN_PATH_NONE;
+    bool scoring_active = false;  // a *_ex entry point with non-RTL scoring is in progress on this thread
+    trialign_scoring scoring{};
 };
 ThreadState &tls();
 

@@ -11,7 +11,8 @@ namespace trialign {
 // KL: literal plane-sweep kernel, exact for any score_bits in [2,32] (literal_kernel.cu).
 // d_a/d_b/d_c are [n][la] / [n][lb] / [n][lc]; d_scores [n]; d_finals [n][7] or nullptr.
 int literal_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals);
+                int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals,
+                const trialign_scoring *scoring = nullptr);  // nullptr: the RTL's constants
 
 // K1: batched systolic kernel, two triples per 32-bit lane, len <= 64 (fast_batch.cu).  Exact only where no
 // candidate wraps at score_bits -- the dispatcher checks provably_wrap_free() first.

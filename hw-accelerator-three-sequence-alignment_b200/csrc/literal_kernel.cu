@@ -13,18 +13,41 @@ namespace trialign {
 
 namespace {
 
-// src/PE_1cyc.v:55-61
-constexpr int kMatch = 1, kMismatch = -1, kGO = 2, kGE = 1, kGO2 = 4, kGE2 = 2, kGOGE = 3;
-
-// cost subtracted per source state (M,Ix,Iy,Iz,Ixy,Iyz,Ixz); rows of SURVEY.md 8(a)
-__constant__ int c_cost[6][7] = {
-    {kGO2, kGE2, kGOGE, kGOGE, kGOGE, kGO2, kGOGE},  // Ix  <- (i-1,j,k)      :172-178
-    {kGO2, kGOGE, kGE2, kGOGE, kGOGE, kGOGE, kGO2},  // Iy  <- (i,j-1,k)      :180-186
-    {kGO2, kGOGE, kGOGE, kGE2, kGO2, kGOGE, kGOGE},  // Iz  <- (i,j,k-1)      :188-194
-    {kGO, kGE, kGE, kGO, kGE, kGO, kGO},             // Ixy <- (i-1,j-1,k)    :196-202
-    {kGO, kGO, kGE, kGE, kGO, kGE, kGO},             // Iyz <- (i,j-1,k-1)    :204-210
-    {kGO, kGE, kGO, kGE, kGO, kGO, kGE},             // Ixz <- (i-1,j,k-1)    :212-218
+// Scoring of one launch: the RTL's localparams (src/PE_1cyc.v:53-59) by default, or the values of the testbench's
+// commented-out .i_match / .i_mismatch / .i_gap_open / .i_gap_extend ports (src/TriAlign_tb.sv:220-224).
+// cost[m][q] = cost subtracted per source state q (M,Ix,Iy,Iz,Ixy,Iyz,Ixz) for destination Ix,Iy,Iz,Ixy,Iyz,Ixz; rows
+// of SURVEY.md 8(a) with GO2 = GO<<1, GE2 = GE<<1, GOGE = GO+GE (src/PE_1cyc.v:57-59).
+struct LitScoring {
+    int cost[6][7];
+    int match, mismatch;
+    int s3_all, s3_ab, s3_ne;  // temp_ABC of src/PE_1cyc.v:162: a=b=c / a=b!=c / a!=b
+    int sum_of_pairs;          // 1: S(a,b,c) = s(a,b)+s(b,c)+s(a,c) (pic/Algorithm.png) instead of temp_ABC
 };
+
+LitScoring make_scoring(const trialign_scoring *sc)
+{
+    const int M = sc ? sc->match : 1, X = sc ? sc->mismatch : -1, GO = sc ? sc->gap_open : 2, GE = sc ? sc->gap_extend : 1;
+    const int GO2 = GO * 2, GE2 = GE * 2, GOGE = GO + GE;
+    const int rows[6][7] = {
+        {GO2, GE2, GOGE, GOGE, GOGE, GO2, GOGE},  // Ix  <- (i-1,j,k)      :172-178
+        {GO2, GOGE, GE2, GOGE, GOGE, GOGE, GO2},  // Iy  <- (i,j-1,k)      :180-186
+        {GO2, GOGE, GOGE, GE2, GO2, GOGE, GOGE},  // Iz  <- (i,j,k-1)      :188-194
+        {GO, GE, GE, GO, GE, GO, GO},             // Ixy <- (i-1,j-1,k)    :196-202
+        {GO, GO, GE, GE, GO, GE, GO},             // Iyz <- (i,j-1,k-1)    :204-210
+        {GO, GE, GO, GE, GO, GO, GE},             // Ixz <- (i-1,j,k-1)    :212-218
+    };
+    LitScoring L;
+    for (int m = 0; m < 6; ++m)
+        for (int q = 0; q < 7; ++q) L.cost[m][q] = rows[m][q];
+    L.match = M;
+    L.mismatch = X;
+    // src/PE_1cyc.v:162 with Verilog precedence (`+` binds tighter than `<<`): MATCH*3 / (MATCH+MISMATCH)<<1 / MISMATCH*3
+    L.s3_all = 3 * M;
+    L.s3_ab = (M + X) * 2;
+    L.s3_ne = 3 * X;
+    L.sum_of_pairs = (sc && sc->triple_rule == TRIALIGN_TRIPLE_SUM_OF_PAIRS) ? 1 : 0;
+    return L;
+}
 
 __device__ __forceinline__ int wrapw(int x, int sh) { return (int)((unsigned)x << sh) >> sh; }
 
@@ -46,8 +69,8 @@ __device__ __forceinline__ int max7_from(const T *__restrict__ plane, size_t qst
 template <typename T>
 __global__ void __launch_bounds__(256)
 literal_plane_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, const uint8_t *__restrict__ c,
-                     int n, int la, int lb, int lc, int d, int sh, T *__restrict__ P0, const T *__restrict__ P1,
-                     const T *__restrict__ P2, const T *__restrict__ P3)
+                     int n, int la, int lb, int lc, int d, int sh, const LitScoring sc, T *__restrict__ P0,
+                     const T *__restrict__ P1, const T *__restrict__ P2, const T *__restrict__ P3)
 {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)n * lb * lc;
@@ -67,19 +90,19 @@ literal_plane_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ 
     const unsigned B = b[(size_t)t * lb + (j - 1)] & 3u;
     const unsigned C = c[(size_t)t * lc + (k - 1)] & 3u;
     // src/PE_1cyc.v:159-162 (with Verilog precedence: `+` binds tighter than `<<`)
-    const int sAB = (A == B) ? kMatch : kMismatch;
-    const int sBC = (B == C) ? kMatch : kMismatch;
-    const int sAC = (A == C) ? kMatch : kMismatch;
-    const int sABC = (A == B) ? ((B == C) ? kMatch * 3 : ((kMatch + kMismatch) << 1)) : kMismatch * 3;
+    const int sAB = (A == B) ? sc.match : sc.mismatch;
+    const int sBC = (B == C) ? sc.match : sc.mismatch;
+    const int sAC = (A == C) ? sc.match : sc.mismatch;
+    const int sABC = sc.sum_of_pairs ? sAB + sBC + sAC : ((A == B) ? ((B == C) ? sc.s3_all : sc.s3_ab) : sc.s3_ne);
     const bool first = (i == 1);
 
     const int vM = max7_from(P3, qstride, at - row - 1, first, nullptr, sABC, sh);    // (i-1,j-1,k-1)
-    const int vIx = max7_from(P1, qstride, at, first, c_cost[0], 0, sh);              // (i-1,j,k)
-    const int vIy = max7_from(P1, qstride, at - row, false, c_cost[1], 0, sh);        // (i,j-1,k)
-    const int vIz = max7_from(P1, qstride, at - 1, false, c_cost[2], 0, sh);          // (i,j,k-1)
-    const int vIxy = max7_from(P2, qstride, at - row, first, c_cost[3], sAB, sh);     // (i-1,j-1,k)
-    const int vIyz = max7_from(P2, qstride, at - row - 1, false, c_cost[4], sBC, sh); // (i,j-1,k-1)
-    const int vIxz = max7_from(P2, qstride, at - 1, first, c_cost[5], sAC, sh);       // (i-1,j,k-1)
+    const int vIx = max7_from(P1, qstride, at, first, sc.cost[0], 0, sh);              // (i-1,j,k)
+    const int vIy = max7_from(P1, qstride, at - row, false, sc.cost[1], 0, sh);        // (i,j-1,k)
+    const int vIz = max7_from(P1, qstride, at - 1, false, sc.cost[2], 0, sh);          // (i,j,k-1)
+    const int vIxy = max7_from(P2, qstride, at - row, first, sc.cost[3], sAB, sh);     // (i-1,j-1,k)
+    const int vIyz = max7_from(P2, qstride, at - row - 1, false, sc.cost[4], sBC, sh); // (i,j-1,k-1)
+    const int vIxz = max7_from(P2, qstride, at - 1, first, sc.cost[5], sAC, sh);       // (i-1,j,k-1)
 
     P0[0 * qstride + at] = (T)vM;
     P0[1 * qstride + at] = (T)vIx;
@@ -111,9 +134,11 @@ __global__ void literal_final_kernel(const T *__restrict__ P, int n, int lb, int
 
 template <typename T>
 int literal_run_t(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                  int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals)
+                  int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals,
+                  const trialign_scoring *scoring)
 {
     const int sh = 32 - score_bits;
+    const LitScoring sc = make_scoring(scoring);
     const size_t tri = (size_t)(lb + 1) * (lc + 1);
     const size_t per_triple = 4 * 7 * tri * sizeof(T);
     // chunk the batch so that the four rolling planes stay within ~3 GiB and the flat cell index within int range
@@ -133,7 +158,7 @@ int literal_run_t(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uin
         const unsigned blocks = (unsigned)((cells + 255) / 256);
         for (int d = 3; d <= la + lb + lc; ++d) {
             literal_plane_kernel<T><<<blocks, 256, 0, st>>>(
-                d_a + (size_t)t0 * la, d_b + (size_t)t0 * lb, d_c + (size_t)t0 * lc, nc, la, lb, lc, d, sh,
+                d_a + (size_t)t0 * la, d_b + (size_t)t0 * lb, d_c + (size_t)t0 * lc, nc, la, lb, lc, d, sh, sc,
                 base + (size_t)(d & 3) * plane_elems, base + (size_t)((d - 1) & 3) * plane_elems,
                 base + (size_t)((d - 2) & 3) * plane_elems, base + (size_t)((d - 3) & 3) * plane_elems);
             count_launch();
@@ -151,12 +176,13 @@ int literal_run_t(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uin
 }  // namespace
 
 int literal_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals)
+                int64_t n, int la, int lb, int lc, int score_bits, int32_t *d_scores, int32_t *d_finals,
+                const trialign_scoring *scoring)
 {
     if (n <= 0) return TRIALIGN_OK;
     if (score_bits <= 16)
-        return literal_run_t<int16_t>(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals);
-    return literal_run_t<int32_t>(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals);
+        return literal_run_t<int16_t>(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals, scoring);
+    return literal_run_t<int32_t>(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals, scoring);
 }
 
 }  // namespace trialign

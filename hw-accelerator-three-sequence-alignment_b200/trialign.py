@@ -31,6 +31,23 @@ _u8p = C.POINTER(C.c_uint8)
 _i32p = C.POINTER(C.c_int32)
 
 
+TRIPLE_RTL, TRIPLE_SUM_OF_PAIRS = 0, 1
+
+
+class Scoring(C.Structure):
+    """``trialign_scoring``: the values the testbench's commented-out .i_match / .i_mismatch / .i_gap_open /
+    .i_gap_extend ports would carry (src/TriAlign_tb.sv:220-224); defaults = the PE localparams (src/PE_1cyc.v:53-56)."""
+
+    _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32),
+                ("triple_rule", C.c_int32)]
+
+    def __init__(self, match=1, mismatch=-1, gap_open=2, gap_extend=1, triple_rule=TRIPLE_RTL):
+        super().__init__(match, mismatch, gap_open, gap_extend, triple_rule)
+
+    def as_list(self):
+        return [self.match, self.mismatch, self.gap_open, self.gap_extend, self.triple_rule]
+
+
 class TriAlignError(RuntimeError):
     def __init__(self, rc: int, what: str):
         self.rc = rc
@@ -85,6 +102,14 @@ def library() -> C.CDLL:
     L.trialign_align.restype = C.c_int
     L.trialign_score_batch.argtypes = [_u8p, _u8p, _u8p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p]
     L.trialign_score_batch.restype = C.c_int
+    L.trialign_scoring_rtl.argtypes = [C.POINTER(Scoring)]
+    L.trialign_scoring_rtl.restype = None
+    L.trialign_score_ex.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.POINTER(Scoring), C.c_uint,
+                                    _i32p, _i32p]
+    L.trialign_score_ex.restype = C.c_int
+    L.trialign_score_batch_ex.argtypes = [_u8p, _u8p, _u8p, C.c_int64, C.c_int, C.c_int, C.POINTER(Scoring), C.c_uint,
+                                          _i32p]
+    L.trialign_score_batch_ex.restype = C.c_int
     L.trialign_score_batch_dev.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
                                            C.c_int, C.c_void_p, C.c_void_p]
     L.trialign_score_batch_dev.restype = C.c_int
@@ -182,16 +207,24 @@ def _devmask(devices: Optional[Sequence[int]]) -> int:
 class TriAlign:
     """One configured aligner, the counterpart of a ``TRIALIGN #(.SCORE_BITS(W))`` instance."""
 
-    def __init__(self, score_bits: int = 12, backend: int = BACKEND_AUTO, devices: Optional[Sequence[int]] = None):
+    def __init__(self, score_bits: int = 12, backend: int = BACKEND_AUTO, devices: Optional[Sequence[int]] = None,
+                 scoring: Optional[Scoring] = None):
         self.score_bits = int(score_bits)
         self.backend = int(backend)
         self.devices = list(devices) if devices else None
+        self.scoring = scoring  # None: the RTL's constants through the plain entry points
 
     # -- host-memory entry points (these are what the reference-side binding would call) --
     def align(self, A, B, C_, return_states: bool = False):
         a, b, c = _u8(A), _u8(B), _u8(C_)
         s = C.c_int32(0)
         fin = np.zeros(7, np.int32)
+        if self.scoring is not None:
+            rc = library().trialign_score_ex(_p(a, _u8p), a.size, _p(b, _u8p), b.size, _p(c, _u8p), c.size,
+                                             self.score_bits, C.byref(self.scoring), _devmask(self.devices),
+                                             C.byref(s), _p(fin, _i32p))
+            _check(rc, "trialign_score_ex")
+            return (int(s.value), fin) if return_states else int(s.value)
         rc = library().trialign_score(_p(a, _u8p), a.size, _p(b, _u8p), b.size, _p(c, _u8p), c.size,
                                       self.score_bits, self.backend, _devmask(self.devices), C.byref(s),
                                       _p(fin, _i32p))
@@ -232,6 +265,11 @@ class TriAlign:
             raise ValueError("align_batch wants three [n][len] arrays of identical shape")
         n, ln = a.shape
         out = np.zeros(n, np.int32)
+        if self.scoring is not None:
+            rc = library().trialign_score_batch_ex(_p(a, _u8p), _p(b, _u8p), _p(c, _u8p), n, ln, self.score_bits,
+                                                   C.byref(self.scoring), _devmask(self.devices), _p(out, _i32p))
+            _check(rc, "trialign_score_batch_ex")
+            return out
         rc = library().trialign_score_batch(_p(a, _u8p), _p(b, _u8p), _p(c, _u8p), n, ln, self.score_bits,
                                             self.backend, _devmask(self.devices), _p(out, _i32p))
         _check(rc, "trialign_score_batch")

@@ -75,6 +75,23 @@ enum trialign_path {
 };
 
 int trialign_version(void);
+/* Scoring parameters.  The RTL hard-wires them as PE localparams (src/PE_1cyc.v:53-59: MATCH=1,
+ * MISMATCH=-1, GO=2, GE=1; GO2 = GO<<1, GE2 = GE<<1, GOGE = GO+GE derive from them) and its testbench carries the intent
+ * to make them inputs: the commented-out ports .i_match / .i_mismatch / .i_gap_extend / .i_gap_open
+ * (src/TriAlign_tb.sv:220-224).  The *_ex entry points take them as arguments. */
+enum trialign_triple_rule {
+    TRIALIGN_TRIPLE_RTL = 0,          /* temp_ABC exactly as src/PE_1cyc.v:162 parses: 3*MATCH if a=b=c,
+                                         (MATCH+MISMATCH)<<1 if a=b!=c, 3*MISMATCH whenever a!=b */
+    TRIALIGN_TRIPLE_SUM_OF_PAIRS = 1  /* the paper's S(a,b,c) = s(a,b)+s(b,c)+s(a,c) (pic/Algorithm.png) */
+};
+typedef struct trialign_scoring {
+    int32_t match;       /* MATCH: score of an equal pair */
+    int32_t mismatch;    /* MISMATCH: score of an unequal pair (signed: the RTL's is -1) */
+    int32_t gap_open;    /* GO: cost of opening a gap in one sequence (>= 0) */
+    int32_t gap_extend;  /* GE: cost of extending it (>= 0) */
+    int32_t triple_rule; /* enum trialign_triple_rule */
+} trialign_scoring;
+
 const char *trialign_strerror(int rc);
 const char *trialign_last_cuda_error(void); /* thread-local text of the last CUDA failure, "" if none */
 int trialign_device_count(void);            /* 0 when no driver / no device; never negative */
@@ -84,6 +101,16 @@ int trialign_device_count(void);            /* 0 when no driver / no device; nev
  * Any zero length gives score 0 (the cell lies on a zero boundary plane). */
 int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                    int backend, unsigned devices, int32_t *score, int32_t final_states[7]);
+
+/* The same with explicit scoring parameters.  trialign_scoring_rtl() fills in the RTL's constants; with exactly those
+ * the call is identical to trialign_score / trialign_score_batch (all kernels).  Any other setting runs the literal
+ * kernel (every candidate wrapped to score_bits before the signed max, as the RTL's datapath would with other
+ * localparams); |match|, |mismatch|, gap_open, gap_extend <= 1024, gap costs >= 0, else TRIALIGN_EINVAL. */
+void trialign_scoring_rtl(trialign_scoring *sc);
+int trialign_score_ex(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                      const trialign_scoring *scoring, unsigned devices, int32_t *score, int32_t final_states[7]);
+int trialign_score_batch_ex(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len, int score_bits,
+                            const trialign_scoring *scoring, unsigned devices, int32_t *scores);
 
 /* Uniform-length batch, structure of arrays: a/b/c are [n][len] row-major host bytes, scores is [n].
  * With several bits set in `devices` the batch is split contiguously across those GPUs (no exchange). */

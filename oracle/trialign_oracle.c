@@ -354,3 +354,66 @@ int oracle_hw_threads(void)
     return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Explicit scoring parameters: the values the testbench's commented-out .i_match / .i_mismatch /
+ * .i_gap_open / .i_gap_extend ports would feed (TriAlign_tb.sv:220-224) in place of the PE localparams (PE_1cyc.v:53-59).
+ * Table-driven and independent of pe_cell(): destination state m reads the predecessor cell at offset kDelta[m],
+ * subtracts kCostSym[m][q] per source state q, adds the move's substitution score; every candidate is wrapped to
+ * score_bits before the signed max (PE_1cyc.v:127-133).
+ * ------------------------------------------------------------------------------------------------------------------ */
+enum { C_0 = 0, C_GO, C_GE, C_GO2, C_GE2, C_GOGE };
+static const int kCostSym[7][7] = {
+    {C_0, C_0, C_0, C_0, C_0, C_0, C_0},                      /* M   PE_1cyc.v:164-170 */
+    {C_GO2, C_GE2, C_GOGE, C_GOGE, C_GOGE, C_GO2, C_GOGE},    /* Ix  :172-178 */
+    {C_GO2, C_GOGE, C_GE2, C_GOGE, C_GOGE, C_GOGE, C_GO2},    /* Iy  :180-186 */
+    {C_GO2, C_GOGE, C_GOGE, C_GE2, C_GO2, C_GOGE, C_GOGE},    /* Iz  :188-194 */
+    {C_GO, C_GE, C_GE, C_GO, C_GE, C_GO, C_GO},               /* Ixy :196-202 */
+    {C_GO, C_GO, C_GE, C_GE, C_GO, C_GE, C_GO},               /* Iyz :204-210 */
+    {C_GO, C_GE, C_GO, C_GE, C_GO, C_GO, C_GE},               /* Ixz :212-218 */
+};
+
+int oracle_score_ex(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                    const int32_t scoring[5], int32_t *score, int32_t final_states[7])
+{
+    if (bad_args(a, la, b, lb, c, lc, score_bits) || !score || !scoring) return -1;
+    const int32_t M = scoring[0], X = scoring[1], go = scoring[2], ge = scoring[3], rule = scoring[4];
+    const int32_t costv[6] = {0, go, ge, go << 1, ge << 1, go + ge};  /* PE_1cyc.v:57-59 */
+    const int sh = 32 - score_bits;
+    int32_t fin[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (la > 0 && lb > 0 && lc > 0) {
+        const size_t sk = 7, sj = (size_t)(lc + 1) * sk, si = (size_t)(lb + 1) * sj;
+        int32_t *buf = (int32_t *)calloc(2 * si, sizeof(int32_t)); /* planes i-1 and i; borders stay 0 */
+        if (!buf) return -2;
+        for (int i = 1; i <= la; ++i) {
+            int32_t *cur = buf + (size_t)(i & 1) * si, *prev = buf + (size_t)((i - 1) & 1) * si;
+            if (i == 1) memset(prev, 0, si * sizeof(int32_t)); /* PE override: plane 0 is all-zero (PE_1cyc.v:164-178) */
+            for (int j = 1; j <= lb; ++j)
+                for (int k = 1; k <= lc; ++k) {
+                    const unsigned A = a[i - 1] & 3u, B = b[j - 1] & 3u, C = c[k - 1] & 3u;
+                    const int32_t sAB = A == B ? M : X, sBC = B == C ? M : X, sAC = A == C ? M : X;
+                    const int32_t s3 = rule ? sAB + sBC + sAC
+                                            : (A == B ? (B == C ? M * 3 : (int32_t)((uint32_t)(M + X) << 1)) : X * 3);
+                    const int32_t add[7] = {s3, 0, 0, 0, sAB, sBC, sAC};
+                    for (int m = 0; m < 7; ++m) {
+                        const int32_t *src = (kDelta[m][0] ? prev : cur) + (size_t)(j - kDelta[m][1]) * sj +
+                                             (size_t)(k - kDelta[m][2]) * sk;
+                        int32_t best = INT32_MIN;
+                        for (int q = 0; q < 7; ++q) {
+                            const int32_t cand = wrapw((uint32_t)src[q] - (uint32_t)costv[kCostSym[m][q]] + (uint32_t)add[m], sh);
+                            if (cand > best) best = cand;
+                        }
+                        cur[(size_t)j * sj + (size_t)k * sk + m] = best;
+                    }
+                }
+        }
+        memcpy(fin, buf + (size_t)(la & 1) * si + (size_t)lb * sj + (size_t)lc * sk, sizeof fin);
+        free(buf);
+    }
+    int32_t best = fin[0];
+    for (int q = 1; q < 7; ++q)
+        if (fin[q] > best) best = fin[q];
+    *score = best;
+    if (final_states) memcpy(final_states, fin, sizeof fin);
+    return 0;
+}

@@ -55,6 +55,14 @@ int oracle_cube(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_
 int oracle_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                  int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves);
 
+/* The recurrence with explicit scoring parameters: scoring[5] = {MATCH, MISMATCH, GO, GE, rule}
+ * with GO2 = GO<<1, GE2 = GE<<1, GOGE = GO+GE as PE_1cyc.v:57-59 derives them; rule 0 = temp_ABC as PE_1cyc.v:162 parses
+ * (3*MATCH / (MATCH+MISMATCH)<<1 / 3*MISMATCH), rule 1 = sum of pairs s(a,b)+s(b,c)+s(a,c) (pic/Algorithm.png).
+ * Written independently of pe_cell() above (table-driven: destination state -> predecessor offset, cost row, score),
+ * so that {1,-1,2,1,0} must reproduce oracle_score() exactly -- tests/test_oracle.py checks that. */
+int oracle_score_ex(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
+                    const int32_t scoring[5], int32_t *score, int32_t final_states[7]);
+
 /* Synthetic symbol generator of SURVEY.md 8(d): splitmix64 finaliser, top 2 bits. */
 void oracle_synth(uint64_t seed, int64_t triple, int which, int len, uint8_t *out);
 

@@ -96,6 +96,21 @@ def score(a, b, c, score_bits: int = 12, want_range: bool = False):
     return int(s.value), fin
 
 
+def score_ex(a, b, c, score_bits: int, scoring):
+    """Recurrence with explicit scoring [MATCH, MISMATCH, GO, GE, rule] -> (score, final_states[7])."""
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    s = C.c_int32()
+    fin = np.zeros(7, np.int32)
+    sc = np.array(list(scoring), np.int32)
+    L = lib()
+    L.oracle_score_ex.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, i32p, C.POINTER(C.c_int32), i32p]
+    rc = L.oracle_score_ex(_ptr(a, u8p), len(a), _ptr(b, u8p), len(b), _ptr(c, u8p), len(c), score_bits,
+                           _ptr(sc, i32p), C.byref(s), _ptr(fin, i32p))
+    if rc:
+        raise ValueError(f"oracle_score_ex rc={rc}")
+    return int(s.value), fin
+
+
 def score_mt(a, b, c, score_bits: int = 12, threads: int = 0):
     a, b, c = _u8(a), _u8(b), _u8(c)
     s = C.c_int32()

@@ -372,3 +372,34 @@ def test_all_triples_of_186_sequences_is_the_million_triple_batch(gpu_ta):
     pick = np.concatenate([np.arange(0, 4096), np.arange(1 << 20, (1 << 20) + 2048), np.arange(got.size - 4096, got.size)])
     want = eng.align_batch(seqs[idx[pick, 0]], seqs[idx[pick, 1]], seqs[idx[pick, 2]])
     assert got[pick].tolist() == want.tolist()
+
+
+# ---- explicit scoring parameters (trialign_score_ex / trialign_score_batch_ex) ----
+@pytest.mark.parametrize("sc", [(1, -1, 2, 1, 0), (2, -1, 2, 1, 0), (2, 1, 2, 1, 0), (1, -1, 2, 1, 1), (5, -4, 10, 1, 1),
+                                (3, -2, 0, 0, 0), (1, -3, 4, 2, 1)])
+def test_explicit_scoring_matches_the_oracle(gpu_ta, ob, sc):
+    """(2, 1, 2, 1) are the testbench's own unused MATCH/MISMATCH/GAP_OPEN/GAP_EXTEND localparams
+    (src/TriAlign_tb.sv:37-40); rule 1 is the paper's sum of pairs.  Also at widths where candidates wrap."""
+    rng = np.random.default_rng(sum(abs(x) for x in sc) + 100 * sc[4])
+    scoring = gpu_ta.Scoring(*sc)
+    for shape, w in [((30, 30, 30), 12), ((64, 64, 64), 12), ((20, 33, 9), 16), ((40, 40, 40), 7), ((25, 70, 66), 10)]:
+        a, b, c = ob.mutated_triple(rng, max(shape), rate=0.12)
+        a, b, c = a[:shape[0]], b[:shape[1]], c[:shape[2]]
+        s, fin = gpu_ta.TriAlign(w, scoring=scoring).align(a, b, c, return_states=True)
+        es, efin = ob.score_ex(a, b, c, w, sc)
+        assert s == es and fin.tolist() == efin.tolist(), (sc, shape, w, gpu_ta.last_path())
+    assert gpu_ta.last_path() == ("literal" if sc != (1, -1, 2, 1, 0) else gpu_ta.last_path())
+    n, ln = 9, 48
+    A = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    B = A.copy()
+    B[:, ::5] = rng.integers(0, 4, B[:, ::5].shape, dtype=np.uint8)
+    Cc = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    got = gpu_ta.TriAlign(12, scoring=scoring).align_batch(A, B, Cc)
+    assert got.tolist() == [ob.score_ex(A[t], B[t], Cc[t], 12, sc)[0] for t in range(n)]
+
+
+def test_rtl_scoring_through_the_ex_entry_points_uses_the_fast_kernels(gpu_ta, ob):
+    a, b, c = gpu_ta.synth_batch(0x5EED0002, 0, 64, 64)
+    got = gpu_ta.TriAlign(12, scoring=gpu_ta.Scoring()).align_batch(a, b, c)
+    assert gpu_ta.last_path() == "fast_batch"
+    assert got.tolist() == ob.score_batch(a, b, c, 12).tolist()

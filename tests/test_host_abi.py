@@ -209,3 +209,24 @@ def test_tb_generator_reproduces_the_shipped_testbench(ta, tmp_path):
     out2 = mk.rewrite_testbench(tb, open(p).read(), 40, 24, 16, 10)
     assert "localparam A_LENGTH = 40;" in out2 and "localparam B_LENGTH = 24;" in out2 and "localparam C_LENGTH = 16;" in out2
     assert "localparam SCORE_BITS = 10;" in out2 and "seqA_ram[1][31:28] <= " in out2
+
+
+def test_scoring_struct_defaults_and_argument_errors(ta):
+    """trialign_scoring_rtl fills in the PE localparams (src/PE_1cyc.v:53-56); out-of-range parameters are refused
+    before any device work (codes, not crashes)."""
+    import ctypes as C
+
+    L = ta.library()
+    sc = ta.Scoring(0, 0, 0, 0, 7)
+    L.trialign_scoring_rtl(C.byref(sc))
+    assert sc.as_list() == [1, -1, 2, 1, 0] and ta.Scoring().as_list() == [1, -1, 2, 1, 0]
+    a = np.zeros(4, np.uint8)
+    s = C.c_int32(0)
+    u8p = C.POINTER(C.c_uint8)
+    for bad in (ta.Scoring(gap_open=-1), ta.Scoring(match=5000), ta.Scoring(triple_rule=2), ta.Scoring(gap_extend=2000)):
+        rc = L.trialign_score_ex(a.ctypes.data_as(u8p), 4, a.ctypes.data_as(u8p), 4, a.ctypes.data_as(u8p), 4, 12,
+                                 C.byref(bad), 0, C.byref(s), None)
+        assert rc == -1
+    rc = L.trialign_score_ex(a.ctypes.data_as(u8p), 4, a.ctypes.data_as(u8p), 4, a.ctypes.data_as(u8p), 4, 12, None, 0,
+                             C.byref(s), None)
+    assert rc == -1

@@ -203,3 +203,39 @@ def test_traceback_golden_paths(ob, golden):
         assert s == case["score"], case["name"]
         assert list(start) == case["traceback"]["start"], case["name"]
         assert "".join(str(int(m)) for m in moves) == case["traceback"]["moves"], case["name"]
+
+
+# ---- explicit scoring parameters ----
+def test_score_ex_with_rtl_constants_is_the_literal_oracle(ob, golden):
+    """oracle_score_ex is written independently of pe_cell() (table-driven); with the PE localparams
+    {MATCH=1, MISMATCH=-1, GO=2, GE=1, temp_ABC rule} it must reproduce oracle_score on score and all 7 states,
+    including where candidates wrap."""
+    import numpy as np
+
+    rng = np.random.default_rng(21)
+    d = golden["dat"]
+    s, fin = ob.score_ex(d["A"], d["B"], d["C"], 12, [1, -1, 2, 1, 0])
+    assert s == 1 and fin.tolist() == [-1, 1, -4, -5, 1, -7, -2]
+    for shape, w in [((9, 9, 9), 12), ((24, 24, 24), 7), ((17, 5, 30), 12), ((40, 33, 21), 8), ((30, 30, 30), 5)]:
+        a, b, c = ob.mutated_triple(rng, max(shape), rate=0.1)
+        a, b, c = a[:shape[0]], b[:shape[1]], c[:shape[2]]
+        s, fin = ob.score_ex(a, b, c, w, [1, -1, 2, 1, 0])
+        es, efin = ob.score(a, b, c, w)
+        assert s == es and fin.tolist() == efin.tolist(), (shape, w)
+
+
+def test_score_ex_sum_of_pairs_is_symmetric_and_rtl_rule_is_not(ob, golden):
+    """The paper's S(a,b,c) does not care which sequence plays which role; the RTL's temp_ABC does (SURVEY.md 8(a) a3:
+    the dat/ triple scores 1, 0, 1, -4, 0, -4 over the six role permutations)."""
+    import itertools
+
+    d = golden["dat"]
+    seqs = [d["A"], d["B"], d["C"]]
+    rtl = [ob.score_ex(seqs[p[0]], seqs[p[1]], seqs[p[2]], 12, [1, -1, 2, 1, 0])[0] for p in itertools.permutations(range(3))]
+    assert sorted(rtl) == sorted([1, 0, 1, -4, 0, -4])
+    sop = {ob.score_ex(seqs[p[0]], seqs[p[1]], seqs[p[2]], 12, [1, -1, 2, 1, 1])[0] for p in itertools.permutations(range(3))}
+    assert len(sop) == 1
+    # identical sequences: every column is a three-way match worth 3*MATCH under both rules
+    x = seqs[0][:20]
+    assert ob.score_ex(x, x, x, 12, [2, -1, 3, 1, 0])[0] == 3 * 2 * 20
+    assert ob.score_ex(x, x, x, 12, [2, -1, 3, 1, 1])[0] == 3 * 2 * 20
