@@ -12,6 +12,7 @@
 // Works for any score_bits in [2,32] (it follows the wrapped values, like the RTL would).  The direction cube limits
 // the size: la*lb*lc*4 bytes must fit the device (4.3 GB at 1024^3); longer triples need checkpointed recomputation,
 // which is not built.
+#include <algorithm>
 #include <climits>
 
 #include "kernels.cuh"
@@ -22,27 +23,38 @@ namespace {
 
 constexpr int kGO = 2, kGE = 1, kGO2 = 4, kGE2 = 2, kGOGE = 3;  // src/PE_1cyc.v:55-61
 
+// The wiring tables are local constants of forceinline functions: with the destination state and the port unrolled,
+// every look-up folds at compile time and a predecessor value is a plain register reference.  (As __constant__ arrays
+// they were run-time loads followed by 7-way select chains: ~7x the instructions per cell.)
 // state order M,Ix,Iy,Iz,Ixy,Iyz,Ixz; ports in the order G4, G1_A, G1_B, G3_A, G2_A, G2_B, G3_B
-__constant__ int c_port_src[8][7] = {
-    {0, 1, 2, 3, 4, 5, 6},  // M   src/PE_1cyc.v:139
-    {1, 0, 5, 2, 4, 6, 3},  // Ix  :140
-    {2, 0, 6, 1, 4, 5, 3},  // Iy  :141
-    {3, 0, 4, 1, 6, 5, 2},  // Iz  :142
-    {2, 0, 6, 5, 4, 1, 3},  // Ixy :143
-    {3, 0, 4, 5, 6, 1, 2},  // Iyz :144
-    {3, 0, 4, 5, 6, 1, 2},  // Ixz :145
-    {6, 0, 1, 4, 2, 3, 5},  // FINAL_MAX src/TriAlign_1cyc.v:141-142
-};
+__host__ __device__ __forceinline__ int port_src(int dest, int port)
+{
+    const int t[8][7] = {
+        {0, 1, 2, 3, 4, 5, 6},  // M   src/PE_1cyc.v:139
+        {1, 0, 5, 2, 4, 6, 3},  // Ix  :140
+        {2, 0, 6, 1, 4, 5, 3},  // Iy  :141
+        {3, 0, 4, 1, 6, 5, 2},  // Iz  :142
+        {2, 0, 6, 5, 4, 1, 3},  // Ixy :143
+        {3, 0, 4, 5, 6, 1, 2},  // Iyz :144
+        {3, 0, 4, 5, 6, 1, 2},  // Ixz :145
+        {6, 0, 1, 4, 2, 3, 5},  // FINAL_MAX src/TriAlign_1cyc.v:141-142
+    };
+    return t[dest][port];
+}
 // cost subtracted by destination (row) and source (column); src/PE_1cyc.v:164-218, SURVEY.md 8(a)
-__constant__ int c_cost[7][7] = {
-    {0, 0, 0, 0, 0, 0, 0},
-    {kGO2, kGE2, kGOGE, kGOGE, kGOGE, kGO2, kGOGE},
-    {kGO2, kGOGE, kGE2, kGOGE, kGOGE, kGOGE, kGO2},
-    {kGO2, kGOGE, kGOGE, kGE2, kGO2, kGOGE, kGOGE},
-    {kGO, kGE, kGE, kGO, kGE, kGO, kGO},
-    {kGO, kGO, kGE, kGE, kGO, kGE, kGO},
-    {kGO, kGE, kGO, kGE, kGO, kGO, kGE},
-};
+__host__ __device__ __forceinline__ int move_cost(int dest, int q)
+{
+    const int t[7][7] = {
+        {0, 0, 0, 0, 0, 0, 0},
+        {kGO2, kGE2, kGOGE, kGOGE, kGOGE, kGO2, kGOGE},
+        {kGO2, kGOGE, kGE2, kGOGE, kGOGE, kGOGE, kGO2},
+        {kGO2, kGOGE, kGOGE, kGE2, kGO2, kGOGE, kGOGE},
+        {kGO, kGE, kGE, kGO, kGE, kGO, kGO},
+        {kGO, kGO, kGE, kGE, kGO, kGE, kGO},
+        {kGO, kGE, kGO, kGE, kGO, kGO, kGE},
+    };
+    return t[dest][q];
+}
 
 __device__ __forceinline__ int wrapw(int x, int sh) { return (int)((unsigned)x << sh) >> sh; }
 
@@ -57,38 +69,47 @@ __device__ __forceinline__ int max7_port(const int g[7])
 }
 
 // one destination state: value and winning source state
-__device__ __forceinline__ void dest_state(int dest, const int *__restrict__ plane, size_t qstride, size_t idx, bool zero,
+template <typename T>
+__device__ __forceinline__ void dest_state(int dest, const T *__restrict__ plane, size_t qstride, size_t idx, bool zero,
                                            int add, int sh, int &value, unsigned &src)
 {
     int p[7], g[7];
 #pragma unroll
-    for (int q = 0; q < 7; ++q) p[q] = zero ? 0 : plane[q * qstride + idx];
+    for (int q = 0; q < 7; ++q) p[q] = zero ? 0 : (int)plane[q * qstride + idx];
 #pragma unroll
     for (int port = 0; port < 7; ++port) {
-        int q = c_port_src[dest][port], pv = 0;
-#pragma unroll
-        for (int x = 0; x < 7; ++x) pv = (x == q) ? p[x] : pv;  // keeps p[] in registers
-        g[port] = wrapw((int)((unsigned)pv - (unsigned)c_cost[dest][q] + (unsigned)add), sh);
+        const int q = port_src(dest, port);  // compile-time: dest and port are unrolled
+        g[port] = wrapw((int)((unsigned)p[q] - (unsigned)move_cost(dest, q) + (unsigned)add), sh);
     }
     const int port = max7_port(g);
     int v = g[0];
+    unsigned sq = (unsigned)port_src(dest, 0);
 #pragma unroll
-    for (int x = 1; x < 7; ++x) v = (x == port) ? g[x] : v;
+    for (int x = 1; x < 7; ++x) {
+        v = (x == port) ? g[x] : v;
+        sq = (x == port) ? (unsigned)port_src(dest, x) : sq;
+    }
     value = v;
-    src = (unsigned)c_port_src[dest][port];
+    src = sq;
 }
 
+// One anti-diagonal plane d = i+j+k.  The grid covers only the rows j that hold cells of the plane (blockIdx.y, from
+// j_lo) and, per row, the k interval with 1 <= i <= la (blockIdx.x from the row's first k): about half of the lb x lc
+// threads a full-plane launch would start.  T = int16 where score_bits <= 16 (halves the plane traffic).
+template <typename T>
 __global__ void __launch_bounds__(256)
 trace_plane_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b, const uint8_t *__restrict__ c, int la,
-                   int lb, int lc, int d, int sh, int *__restrict__ P0, const int *__restrict__ P1,
-                   const int *__restrict__ P2, const int *__restrict__ P3, uint32_t *__restrict__ dir)
+                   int lb, int lc, int d, int sh, int j_lo, T *__restrict__ P0, const T *__restrict__ P1,
+                   const T *__restrict__ P2, const T *__restrict__ P3, uint32_t *__restrict__ dir)
 {
-    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= (long long)lb * lc) return;
-    const int k = (int)(e % lc) + 1;
-    const int j = (int)(e / lc) + 1;
+    const int j = j_lo + (int)blockIdx.y;
+    if (j > lb) return;
+    int k_lo = d - j - la;  // i = d - j - k <= la
+    if (k_lo < 1) k_lo = 1;
+    const int k = k_lo + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+    if (k > lc) return;
     const int i = d - j - k;
-    if (i < 1 || i > la) return;
+    if (i < 1) return;
     const size_t row = (size_t)(lc + 1);
     const size_t qstride = (size_t)(lb + 1) * row;
     const size_t at = (size_t)j * row + k;
@@ -109,23 +130,30 @@ trace_plane_kernel(const uint8_t *__restrict__ a, const uint8_t *__restrict__ b,
     unsigned word = 0;
 #pragma unroll
     for (int q = 0; q < 7; ++q) {
-        P0[q * qstride + at] = v[q];
+        P0[q * qstride + at] = (T)v[q];
         word |= s[q] << (3 * q);
     }
     dir[((size_t)(i - 1) * lb + (j - 1)) * lc + (k - 1)] = word;
 }
 
 // out[0] = score, out[1..3] = start cell, out[4] = number of columns; moves[] in forward order
-__global__ void trace_walk_kernel(const uint32_t *__restrict__ dir, const int *__restrict__ Pfin, int la, int lb, int lc,
+template <typename T>
+__global__ void trace_walk_kernel(const uint32_t *__restrict__ dir, const T *__restrict__ Pfin, int la, int lb, int lc,
                                   int32_t *__restrict__ out, uint8_t *__restrict__ moves)
 {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     const size_t row = (size_t)(lc + 1), qstride = (size_t)(lb + 1) * row, at = (size_t)lb * row + lc;
     int g[7];
-    for (int port = 0; port < 7; ++port) g[port] = Pfin[c_port_src[7][port] * qstride + at];
-    int port = max7_port(g);
-    out[0] = g[port];
-    int state = c_port_src[7][port];
+#pragma unroll
+    for (int port = 0; port < 7; ++port) g[port] = (int)Pfin[port_src(7, port) * qstride + at];
+    const int port = max7_port(g);
+    int state = port_src(7, 0), best = g[0];
+#pragma unroll
+    for (int x = 1; x < 7; ++x) {
+        best = (x == port) ? g[x] : best;
+        state = (x == port) ? port_src(7, x) : state;
+    }
+    out[0] = best;
     int i = la, j = lb, k = lc, n = 0;
     while (i > 0 && j > 0 && k > 0) {
         // M=7 (all advance), Ix=1 (A), Iy=2 (B), Iz=4 (C), Ixy=3, Iyz=6, Ixz=5
@@ -149,32 +177,54 @@ __global__ void trace_walk_kernel(const uint32_t *__restrict__ dir, const int *_
 
 size_t traceback_dir_bytes(int la, int lb, int lc) { return (size_t)la * lb * lc * sizeof(uint32_t); }
 
+namespace {
+
+template <typename T>
+int traceback_run_t(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
+                    const uint8_t *d_c, int lc, int score_bits, int32_t *d_out, uint8_t *d_moves)
+{
+    const int sh = 32 - score_bits;
+    const size_t plane_elems = 7 * (size_t)(lb + 1) * (lc + 1);
+    int rc = ctx->planes.reserve(4 * plane_elems * sizeof(T));
+    if (rc) return rc;
+    if ((rc = ctx->dirs.reserve(traceback_dir_bytes(la, lb, lc)))) return rc;
+    T *base = (T *)ctx->planes.ptr;
+    uint32_t *dir = (uint32_t *)ctx->dirs.ptr;
+    TA_CUDA(cudaMemsetAsync(base, 0, 4 * plane_elems * sizeof(T), st));
+    for (int d = 3; d <= la + lb + lc; ++d) {
+        // rows with cells of this plane: 1 <= i = d-j-k <= la for some k in [1,lc]
+        const int j_lo = std::max(1, d - la - lc), j_hi = std::min(lb, d - 2);
+        if (j_hi < j_lo) continue;
+        // widest k interval of a row: [max(1, d-j-la), min(lc, d-j-1)]
+        int width = 0;
+        for (int j : {j_lo, j_hi, std::min(j_hi, std::max(j_lo, d - la - 1)), std::min(j_hi, std::max(j_lo, d - lc - 1))}) {
+            const int k0 = std::max(1, d - j - la), k1 = std::min(lc, d - j - 1);
+            width = std::max(width, k1 - k0 + 1);
+        }
+        if (width < 1) continue;
+        const dim3 grid((unsigned)((width + 255) / 256), (unsigned)(j_hi - j_lo + 1));
+        trace_plane_kernel<T><<<grid, 256, 0, st>>>(d_a, d_b, d_c, la, lb, lc, d, sh, j_lo, base + (size_t)(d & 3) * plane_elems,
+                                                    base + (size_t)((d - 1) & 3) * plane_elems,
+                                                    base + (size_t)((d - 2) & 3) * plane_elems,
+                                                    base + (size_t)((d - 3) & 3) * plane_elems, dir);
+        count_launch();
+    }
+    TA_CUDA(cudaGetLastError());
+    trace_walk_kernel<T><<<1, 32, 0, st>>>(dir, base + (size_t)((la + lb + lc) & 3) * plane_elems, la, lb, lc, d_out, d_moves);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+}  // namespace
+
 // d_out: 5 int32 (score, start i/j/k, columns); d_moves: la+lb+lc bytes
 int traceback_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
                   const uint8_t *d_c, int lc, int score_bits, int32_t *d_out, uint8_t *d_moves)
 {
-    const int sh = 32 - score_bits;
-    const size_t plane_elems = 7 * (size_t)(lb + 1) * (lc + 1);
-    int rc = ctx->planes.reserve(4 * plane_elems * sizeof(int));
-    if (rc) return rc;
-    if ((rc = ctx->dirs.reserve(traceback_dir_bytes(la, lb, lc)))) return rc;
-    int *base = (int *)ctx->planes.ptr;
-    uint32_t *dir = (uint32_t *)ctx->dirs.ptr;
-    TA_CUDA(cudaMemsetAsync(base, 0, 4 * plane_elems * sizeof(int), st));
-    const long long cells = (long long)lb * lc;
-    const unsigned blocks = (unsigned)((cells + 255) / 256);
-    for (int d = 3; d <= la + lb + lc; ++d) {
-        trace_plane_kernel<<<blocks, 256, 0, st>>>(d_a, d_b, d_c, la, lb, lc, d, sh, base + (size_t)(d & 3) * plane_elems,
-                                                   base + (size_t)((d - 1) & 3) * plane_elems,
-                                                   base + (size_t)((d - 2) & 3) * plane_elems,
-                                                   base + (size_t)((d - 3) & 3) * plane_elems, dir);
-        count_launch();
-    }
-    TA_CUDA(cudaGetLastError());
-    trace_walk_kernel<<<1, 32, 0, st>>>(dir, base + (size_t)((la + lb + lc) & 3) * plane_elems, la, lb, lc, d_out, d_moves);
-    count_launch();
-    TA_CUDA(cudaGetLastError());
-    return TRIALIGN_OK;
+    if (score_bits <= 16)
+        return traceback_run_t<int16_t>(ctx, st, d_a, la, d_b, lb, d_c, lc, score_bits, d_out, d_moves);
+    return traceback_run_t<int32_t>(ctx, st, d_a, la, d_b, lb, d_c, lc, score_bits, d_out, d_moves);
 }
 
 }  // namespace trialign
