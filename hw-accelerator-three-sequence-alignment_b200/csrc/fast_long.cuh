@@ -189,8 +189,12 @@ TA_HD void long2_edge_fetch(Long2Smem<C> &S, const SweepArgs &A, int tj, int tk,
         const int i = c - C::LAG * tj + 1;  // low-half plane of thread (tj,0) at step c
         const int j0 = tj * RJ;
         if (T.fk_r) {
-            const int src_row = i + C::PLAG;  // the producer's high half is PLAG planes behind its row index
-            if (!RARE || (src_row >= 1 && src_row <= rows)) {
+            // the producer's high half is PLAG planes behind its row index.  Beyond the last plane (i > la) the low half
+            // is dead but must stay BOUNDED while the high half is still live (32-bit adds carry from the low lane into
+            // the high one, fast_core.cuh): it keeps consuming the last row instead of whatever the slot held.
+            int src_row = i + C::PLAG;
+            if (RARE && src_row > rows) src_row = rows;
+            if (!RARE || src_row >= 1) {
                 const uint32_t *src = T.fk_r + (long long)src_row * C::FK_ROW_WORDS + j0;
 #pragma unroll
                 for (int v = 0; v < 4; ++v) ta_copy16(&S.col[slot][v][0][j0], src + v * C::COL_W);

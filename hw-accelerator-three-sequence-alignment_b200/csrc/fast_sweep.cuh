@@ -333,7 +333,10 @@ TA_HD void sweep_edge_fetch(SweepSmem<C> &S, const SweepArgs &A, int tj, int tk,
         const int i = s + 2 - tj;  // low-half plane of thread (tj,0) at step s+1
         const int j0 = tj * RJ;
         if (T.fk_r) {
-            const int src_row = i + C::LAG;  // LONG: the producer's high half is LAG planes behind its row index
+            // LONG: the producer's high half is LAG planes behind its row index; beyond the last plane the dead low half
+            // keeps consuming the last row, so that it stays bounded while the high half is live (fast_long.cuh)
+            int src_row = i + C::LAG;
+            if (C::LONG && src_row > rows) src_row = rows;
             if (src_row >= 1 && src_row <= rows) {
                 const uint32_t *src = T.fk_r + (long long)src_row * C::FK_ROW_WORDS + j0;
 #pragma unroll

@@ -473,7 +473,7 @@ int run_long2(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t 
     A.check_lo = -lim + 8 + 60;
     std::vector<EmuCta2<C>> ctas(n_ctas);
     for (auto &cta : ctas) {
-        std::memset(cta.S.get(), 0xA5, sizeof(Long2Smem<C>));
+        std::memset(cta.S.get(), (seed & 2) ? 0xFF : 0x00, sizeof(Long2Smem<C>));  // nasty poison: a dead lane must never disturb a live one
         for (int tid = 0; tid < C::NT; ++tid) long2_load_a<C>(*cta.S, A, tid);
     }
     const int steps = long2_task_steps<C>(A);

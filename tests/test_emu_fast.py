@@ -213,6 +213,23 @@ def test_long2_choreography(emu_long2, ob, shape, n_ctas):
             assert s == es and fin == efin.tolist(), (lag, gate, seed)
 
 
+@pytest.mark.parametrize("shape", [(1, 154, 350), (1, 130, 365), (2, 70, 300), (3, 64, 129), (1, 64, 256)])
+def test_long2_dead_low_half_stays_bounded(emu_long2, ob, shape):
+    """Very short sweeps (la < 16) on as many CTAs as tasks, shared memory pre-filled with 0xFF / 0x00: after plane la
+    the low half of a word is dead while the high half (16 planes behind) is still live; a dead lane fed from an
+    unwritten halo slot would carry into the live one (found by tools/stress_gpu.py on the GPU)."""
+    la, lb, lc = shape
+    rng = np.random.default_rng(sum(shape))
+    tasks = ((lb + 63) // 64) * ((lc + 127) // 128)
+    for rate in (0.01, 0.2, 0.75):
+        a, b, c = ob.mutated_triple(rng, max(shape), rate=rate)
+        a, b, c = a[:la], b[:lb], c[:lc]
+        es, efin = ob.score(a, b, c, 16)
+        for lag, seed in ((1, 2), (1, 5), (2, 3), (2, 4)):
+            s, fin, _ = _long2(emu_long2, a, b, c, tasks, lag, 4, seed)
+            assert s == es and fin == efin.tolist(), (rate, lag, seed)
+
+
 def test_long2_range_check_is_sound_and_not_trigger_happy(emu_long2, ob):
     rng = np.random.default_rng(77)
     a, b, c = ob.mutated_triple(rng, 150, rate=0.02)        # nearly identical: all grows to ~3*150 = 450

@@ -403,3 +403,27 @@ def test_rtl_scoring_through_the_ex_entry_points_uses_the_fast_kernels(gpu_ta, o
     got = gpu_ta.TriAlign(12, scoring=gpu_ta.Scoring()).align_batch(a, b, c)
     assert gpu_ta.last_path() == "fast_batch"
     assert got.tolist() == ob.score_batch(a, b, c, 12).tolist()
+
+
+def test_fast_kernels_agree_with_the_literal_kernel_on_random_shapes(gpu_ta):
+    """A short run of tools/stress_gpu.py: K1 / K2S / K2L against the literal kernel (two independent GPU implementations)
+    over random shapes, including very short sweeps of long b, c (la < 16: the case where a dead low half once carried
+    into the live high half)."""
+    import subprocess
+    import sys
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run([sys.executable, os.path.join(root, "tools", "stress_gpu.py"), "12"], capture_output=True, text=True)
+    assert proc.returncode == 0 and "stress ok" in proc.stdout, proc.stdout[-2000:] + proc.stderr[-2000:]
+    eng = gpu_ta.TriAlign(12)
+    lit = gpu_ta.TriAlign(12, backend=gpu_ta.BACKEND_GPU_LITERAL)
+    rng = np.random.default_rng(4)
+    for la, lb, lc in [(1, 154, 350), (1, 130, 365), (2, 70, 300), (3, 64, 129), (1, 64, 256), (5, 400, 400)]:
+        a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in (la, lb, lc))
+        b[:la] = a  # some real matches
+        for _ in range(3):  # shared memory of the SMs holds whatever the previous launches left
+            f = eng.align(a, b, c, return_states=True)
+            assert gpu_ta.last_path() == "fast_long"
+            g = lit.align(a, b, c, return_states=True)
+            assert f[0] == g[0] and f[1].tolist() == g[1].tolist(), (la, lb, lc)
