@@ -401,8 +401,10 @@ TA_HD void long2_thread_step(const Long2Regs<C> &R, Long2Regs<C> &Rn, const Long
     }
 
     // Run-time wrap check (used when wrap-freedom at score_bits cannot be proved a priori), see fast_sweep.cuh: `all`
-    // moves by at most +3 / -4 per plane, so sampling every 16th plane with 45 / 60 margins bounds every plane.
-    if (CHECK && (i0 & 15) == 0) {
+    // moves by at most +3 / -4 per plane, so sampling every 16th plane of a cell with 45 / 60 margins bounds every
+    // plane.  Sampled on every 16th STEP: warp-uniform (sampling by plane index made 11 of 16 steps of a warp diverge
+    // into this block, its lanes having 11 different skews).
+    if (CHECK && (s & 15) == 0) {
         uint32_t mx = n_all[0][0], mn = n_all[0][0];
 #pragma unroll
         for (int r = 0; r < RJ; ++r)
