@@ -1,0 +1,10 @@
+mkdir -p gpurun_out
+one() { python bench.py --no-cpu "$@" 2>> gpurun_out/u_err.log | python -c "import sys,json,os; d=json.loads(sys.stdin.read()); print('%-10s %-50s %8.1f GCUPS %9.3f ms  %s cks=%s' % (os.environ.get('TAG',''), ' '.join(sys.argv[1:]), d['value'], d['ms_per_step'], d['config']['kernel_path'], d['config']['scores_checksum']))" "$@"; }
+: > gpurun_out/u_err.log
+{
+python tools/tiny_cases.py k2b 2>&1 | tail -1
+TAG=k2s one --steps 3 --warmup 3 --workload batch256 --triples 8192
+TAG=k2s one --steps 2 --warmup 3 --workload batch256 --triples 32768
+python -m pytest tests -m gpu -x -q -k "batch_kernels or stream or properties" 2>&1 | tail -2
+} > gpurun_out/k2s_quick.txt 2>&1
+cat gpurun_out/k2s_quick.txt; tail -3 gpurun_out/u_err.log
