@@ -228,7 +228,11 @@ def run_ours(args, rank, world, local_rank):
         a1, b1, c1 = da[0], db[0], dc[0]
         if slab:
             # config 5: i-slab pipeline, rank g computes planes (la*g/N, la*(g+1)/N] and hands block states to rank g+1
-            pipe = ta.SlabPipeline(length, length, score_bits=w, device=local_rank)
+            # (TRIALIGN_MULTI=slab), or the column pipeline: rank g sweeps all planes of its block-column range and streams
+            # the faces crossing the range edge to rank g+1 while it runs
+            use_cols = os.environ.get("TRIALIGN_MULTI", "slab") == "cols"
+            pipe = (ta.ColumnPipeline(length, length, length, score_bits=w, device=local_rank) if use_cols
+                    else ta.SlabPipeline(length, length, score_bits=w, device=local_rank))
             sync_t = torch.zeros(1, device=dev)
 
             def step():
@@ -343,7 +347,7 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "u16x2 (packed 16-bit integer lanes)" if path.startswith("fast") else "int16/int32",
             "data": "synthetic",
             "config": {"workload": args.workload, "baseline_config": cfg, "triples_per_gpu": n, "length": length,
-                       "parallelism": ("i-slab pipeline over %d GPUs, NVLink peer stores" % world) if slab else ("batch shard per GPU, no exchange" if world > 1 else "single GPU"),
+                       "parallelism": (("column pipeline" if os.environ.get("TRIALIGN_MULTI", "slab") == "cols" else "i-slab pipeline") + " over %d GPUs, NVLink peer stores" % world) if slab else ("batch shard per GPU, no exchange" if world > 1 else "single GPU"),
                        "score_bits": w, "kernel_path": path, "l2": "inputs (3 x n x len bytes) larger than L2" if 3 * n * length > 126e6 else "inputs smaller than L2; compute-bound kernel, no reuse across steps assumed",
                        "reduced": reduced, "scores_checksum": checksum},
             "gpu_launches": launches,

@@ -37,4 +37,4 @@ from .trialign import (  # noqa: F401
     write_seq_dat,
     write_tb_init,
 )
-from .parallel import SlabPipeline, shard_range, slab_range  # noqa: E402,F401
+from .parallel import ColumnPipeline, SlabPipeline, col_range, shard_range, slab_range  # noqa: E402,F401

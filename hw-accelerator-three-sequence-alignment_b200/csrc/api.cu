@@ -614,6 +614,47 @@ int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_
                                d_out ? d_out + 1 : nullptr, 0, nullptr, &link);
 }
 
+int trialign_cols_buffer_bytes(int la, int lb, int64_t *face_bytes, int64_t *prog_bytes)
+{
+    if (la < 1 || lb < 1 || !face_bytes || !prog_bytes) return TRIALIGN_EINVAL;
+    *face_bytes = (int64_t)fast_long2_col_face_bytes(la, lb);
+    *prog_bytes = (int64_t)fast_long2_col_prog_bytes(lb);
+    return TRIALIGN_OK;
+}
+
+int trialign_cols_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
+                            int lc, int c_begin, int c_end, const void *in_face, const void *in_prog, void *out_face,
+                            void *out_prog, int epoch, int score_bits, int32_t *d_out, void *stream)
+{
+    if (la < 1 || lb < 1 || lc < 1 || score_bits < 2 || score_bits > 32 || !d_a || !d_b || !d_c) return TRIALIGN_EINVAL;
+    if (c_begin < 0 || c_end <= c_begin || c_end > lc || (c_begin % 128) != 0) return TRIALIGN_EINVAL;
+    if (c_end < lc && (c_end % 128) != 0) return TRIALIGN_EINVAL;  // ranges are whole block-column pairs
+    if ((c_begin > 0) != (in_face != nullptr) || (in_face != nullptr) != (in_prog != nullptr)) return TRIALIGN_EINVAL;
+    if ((c_end < lc) != (out_face != nullptr) || (out_face != nullptr) != (out_prog != nullptr)) return TRIALIGN_EINVAL;
+    if (c_end == lc && !d_out) return TRIALIGN_EINVAL;
+    if (epoch < 1 || epoch > 2047) return TRIALIGN_EINVAL;
+    ThreadState &ts = tls();
+    ts.last_seconds = -1.0;
+    ts.last_cells = (double)la * lb * (c_end - c_begin);
+    ts.last_path = TRIALIGN_PATH_NONE;
+    if (!provably_wrap_free(la, lb, lc, score_bits) || !fast_sweep_supports(la, lb, lc)) return TRIALIGN_EINEXACT;
+    DeviceCtx *ctx = nullptr;
+    int rc = get_ctx(device, &ctx);
+    if (rc) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    ColLink link;
+    link.lc_total = lc;
+    link.last = (c_end == lc);
+    link.epoch = epoch;
+    link.in_face = in_face;
+    link.in_prog = in_prog;
+    link.out_face = out_face;
+    link.out_prog = out_prog;
+    ts.last_path = TRIALIGN_PATH_FAST_LONG;
+    return fast_long2_run(ctx, (cudaStream_t)stream, d_a, la, d_b, lb, d_c + c_begin, c_end - c_begin, d_out,
+                          d_out ? d_out + 1 : nullptr, 0, nullptr, nullptr, &link);
+}
+
 int trialign_device_alloc(int device, int64_t bytes, void **dptr)
 {
     if (bytes <= 0 || !dptr) return TRIALIGN_EINVAL;

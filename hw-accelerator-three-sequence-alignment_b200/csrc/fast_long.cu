@@ -60,7 +60,21 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-template <int LAG, bool CHECK>
+// progress word of the column pipeline: epoch << 20 | steps (0xFFFFF = task finished); a word of another epoch reads 0
+__device__ __forceinline__ int col_decode(int v, int epoch)
+{
+    if ((v >> 20) != epoch) return 0;
+    const int steps = v & 0xFFFFF;
+    return steps == 0xFFFFF ? fast::kProgressDone : steps;
+}
+__device__ __forceinline__ int col_encode(int steps, int epoch)
+{
+    return (epoch << 20) | (steps >= fast::kProgressDone ? 0xFFFFF : steps);
+}
+
+// COLS: the column-pipeline variant (faces and progress words of the range edges in peer memory); a separate
+// instantiation, so that the single-GPU / i-slab kernels compile exactly as without it.
+template <int LAG, bool CHECK, bool COLS = false>
 __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
 {
     using C = fast::Long2Cfg<LAG>;
@@ -89,6 +103,12 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             const unsigned long long t = atomicAdd(A.counter, 1ull);
             if (t < (unsigned long long)A.tasks_total) {
                 fast::sweep_describe_long<C>(A, (long long)t, S.task);
+                // column pipeline: the first / last local column pair exchanges its K face with a neighbour GPU
+                if (COLS && A.cface_in && S.task.bkp == 0) {
+                    S.task.fk_r = A.cface_in + (long long)S.task.bj * A.fk_slot_words;
+                    S.task.left_task = -2 - S.task.bj;  // <= -2: gated by the peer-written progress word of block row bj
+                }
+                if (COLS && A.cface_out && S.task.bkp == A.nbkp - 1) S.task.fk_w = A.cface_out + (long long)S.task.bj * A.fk_slot_words;
                 // ring re-use: the previous tenants of the face slots must have been consumed (the ring sizes exceed
                 // the largest producer->consumer distance in claim order by more than the grid size, so every
                 // consumer waited for here was claimed long ago)
@@ -117,14 +137,26 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         fast::long2_init_thread<C>(R, S, tj, tk);
         const fast::SweepTask &T = S.task;
         const int *top_p = T.top_task >= 0 ? A.progress + T.top_task : nullptr;
-        const int *left_p = T.left_task >= 0 ? A.progress + T.left_task : nullptr;
+        const bool left_remote = COLS && T.left_task <= -2;
+        const int *left_p = T.left_task >= 0 ? A.progress + T.left_task : (left_remote ? A.cprog_in + (-2 - T.left_task) : nullptr);
+        int *const right_p = (COLS && A.cprog_out && T.bkp == A.nbkp - 1) ? A.cprog_out + T.bj : nullptr;  // peer memory
+        // producers' progress: the left one may be a word another GPU writes (system scope, epoch-tagged)
+        auto load_left = [&]() {
+            if (COLS && left_remote) return col_decode(ld_acquire_sys(left_p), A.epoch);
+            return ld_acquire(left_p);
+        };
+        // publication of this task's progress: locally, and to the right neighbour GPU for the last local column
+        auto publish = [&](int done) {
+            st_release(A.progress + T.self_task, done);
+            if (COLS && right_p) st_release_sys(right_p, col_encode(done, A.epoch));
+        };
 
         // prologue: the halos of steps 0 and 1 are fetched here, and the first LAG iterations fetch before any barrier
         // of this task has been waited for.  cert = last consumption step whose face rows are known to be complete.
         int cert = -1000;
         if (tid == kGateTid) {
             for (;;) {
-                cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);
+                cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? load_left() : 0);
                 if (cert >= 1 + LAG) break;
                 __nanosleep(100);
             }
@@ -145,13 +177,13 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         int tp = 0, lp = 0;                                                                                             \
         if (need) {                                                                                                     \
             tp = top_p ? ld_acquire(top_p) : 0;                                                                         \
-            lp = left_p ? ld_acquire(left_p) : 0;                                                                       \
+            lp = left_p ? load_left() : 0;                                                                              \
         }                                                                                                               \
         if (LAG == 2) {                                                                                                 \
             if (g >= 2) bar_wait(&step_bar[g & 1], ((g - 2) >> 1) & 1); /* everybody has finished step s-2 */           \
             /* release: the face stores of steps <= s-2 are ordered before the arrivals just observed */                \
             if (tid == kGateTid && s_ >= 2 && fast::long2_publish_now<C>(A, s_ - 1))                                    \
-                st_release(A.progress + T.self_task, s_ - 1);                                                           \
+                publish(s_ - 1);                                                                                        \
         }                                                                                                               \
         fast::ta_copy_wait_prev(); /* this thread's block-halo fetch for step s has landed */                           \
         fast::long2_thread_step<C, CHECK, RARE>(RIN, ROUT, K, S, A, tj, tk, s_, tid);                                  \
@@ -159,14 +191,14 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             cert = fast::long2_certified<C>(A, T, tp, lp);                                                              \
             while (cert < want) {                                                                                       \
                 __nanosleep(40);                                                                                        \
-                cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? ld_acquire(left_p) : 0);  \
+                cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? load_left() : 0);         \
             }                                                                                                           \
         }                                                                                                               \
         bar_arrive_warp(&step_bar[LAG == 2 ? (g & 1) : 0]);                                                             \
         fast::long2_thread_prepare<C, RARE>(ROUT, K, S, A, tj, tk, s_ + 1, tid);                                        \
         if (LAG == 1) {                                                                                                 \
             bar_wait(&step_bar[0], g & 1); /* everybody has finished step s */                                          \
-            if (tid == kGateTid && fast::long2_publish_now<C>(A, s_ + 1)) st_release(A.progress + T.self_task, s_ + 1); \
+            if (tid == kGateTid && fast::long2_publish_now<C>(A, s_ + 1)) publish(s_ + 1);                              \
         }                                                                                                               \
         ++g;                                                                                                            \
     } while (0)
@@ -210,7 +242,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         __syncthreads();  // every thread's face / hand-over stores precede the final release
         if (CHECK && R.viol) atomicOr(A.viol_flag, 1);
         if (tid == kGateTid) {
-            st_release(A.progress + T.self_task, fast::kProgressDone);
+            publish(fast::kProgressDone);
             if (A.iface_out_flag) {
                 __threadfence_system();
                 st_release_sys(A.iface_out_flag + T.self_task, A.epoch);
@@ -220,19 +252,22 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
 }
 
 template <int LAG>
-int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, int la)
+int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, int la, bool cols = false)
 {
     using C = fast::Long2Cfg<LAG>;
     static_assert(sizeof(fast::Long2Smem<C>) + 64 <= 227 * 1024, "shared memory budget");
     const size_t smem = sizeof(fast::Long2Smem<C>);
-    static bool prepared[kMaxDevices][2] = {};
-    if (!prepared[ctx->device][check]) {
-        if (check) {
+    static bool prepared[kMaxDevices][3] = {};
+    const int variant = cols ? 2 : (check ? 1 : 0);
+    if (!prepared[ctx->device][variant]) {
+        if (cols) {
+            TA_CUDA(cudaFuncSetAttribute(long2_kernel<1, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        } else if (check) {
             TA_CUDA(cudaFuncSetAttribute(long2_kernel<LAG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         } else {
             TA_CUDA(cudaFuncSetAttribute(long2_kernel<LAG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
-        prepared[ctx->device][check] = true;
+        prepared[ctx->device][variant] = true;
     }
     A.nbj = (A.lb + C::BJ - 1) / C::BJ;
     A.nbkp = (A.lc + C::KSPAN - 1) / C::KSPAN;
@@ -244,8 +279,11 @@ int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, in
     // claim order (earliest possible start first) and the face-ring sizes it needs
     std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
     for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
-    const int nbj = A.nbj, gate = A.gate;
-    std::stable_sort(order.begin(), order.end(), [nbj, gate](int x, int y) {
+    const int nbj = A.nbj, gate = A.gate, nbkp = A.nbkp;
+    std::stable_sort(order.begin(), order.end(), [nbj, gate, nbkp, cols](int x, int y) {
+        // column pipeline: row-major, so that the last local column of the first block rows -- what the right
+        // neighbour GPU is waiting for -- is swept first (in earliest-start order it would come last)
+        if (cols) return (x % nbj) * nbkp + x / nbj < (y % nbj) * nbkp + y / nbj;
         return fast::long2_order_key<C>(x % nbj, x / nbj, gate) < fast::long2_order_key<C>(y % nbj, y / nbj, gate);
     });
     for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;
@@ -277,7 +315,8 @@ int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, in
     if (std::getenv("TRIALIGN_DEBUG"))
         std::fprintf(stderr, "[trialign] K2L: la=%d lag=%d gate=%d blocks %dx%d(pairs) tasks=%lld grid=%d faces=%.1f MB smem=%zu base=%d\n",
                      la, LAG, A.gate, A.nbj, A.nbkp, A.tasks_total, grid, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
-    if (check) long2_kernel<LAG, true><<<grid, C::NT, smem, st>>>(A);
+    if (cols) long2_kernel<1, false, true><<<grid, C::NT, smem, st>>>(A);
+    else if (check) long2_kernel<LAG, true><<<grid, C::NT, smem, st>>>(A);
     else long2_kernel<LAG, false><<<grid, C::NT, smem, st>>>(A);
     count_launch();
     TA_CUDA(cudaGetLastError());
@@ -286,9 +325,21 @@ int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, in
 
 }  // namespace
 
+size_t fast_long2_col_face_bytes(int la, int lb)
+{
+    using C = fast::Long2Cfg<1>;
+    const size_t nbj = (size_t)(lb + C::BJ - 1) / C::BJ;
+    return nbj * (size_t)(la + C::PLAG + 2) * C::FK_ROW_WORDS * sizeof(uint32_t);
+}
+size_t fast_long2_col_prog_bytes(int lb)
+{
+    using C = fast::Long2Cfg<1>;
+    return (size_t)((lb + C::BJ - 1) / C::BJ) * sizeof(int);
+}
+
 int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
                    const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
-                   const SlabLink *slab)
+                   const SlabLink *slab, const ColLink *col)
 {
     const bool check = check_bits > 0;
     fast::SweepArgs A{};
@@ -335,6 +386,19 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
         A.iface_out_flag = (int *)slab->out_flags;
         A.last_slab = slab->last ? 1 : 0;
         A.epoch = slab->epoch;
+    }
+    if (col) {  // block-column pairs [first, first + lc/128) of a triple of col->lc_total columns (c points at them)
+        const long long lt = col->lc_total;
+        const long long m = la < lb ? (la < lt ? la : lt) : (lb < lt ? lb : lt);
+        A.base = (int)(-envelope_lo(m) + 32);
+        A.cface_in = (const uint32_t *)col->in_face;
+        A.cprog_in = (const int *)col->in_prog;
+        A.cface_out = (uint32_t *)col->out_face;
+        A.cprog_out = (int *)col->out_prog;
+        A.last_slab = col->last ? 1 : 0;
+        A.epoch = col->epoch;
+        if (check) return TRIALIGN_EINEXACT;  // the column pipeline needs an input that is provably wrap-free
+        return run_long2<1>(ctx, st, A, false, la, true);  // LAG 1: the boundary faces are laid out for PLAG = 16
     }
     return lag == 2 ? run_long2<2>(ctx, st, A, check, la) : run_long2<1>(ctx, st, A, check, la);
 }

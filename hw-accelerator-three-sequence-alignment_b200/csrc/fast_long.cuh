@@ -503,7 +503,7 @@ TA_HD int long2_certified(const SweepArgs &A, const SweepTask &T, int top_prog, 
     const int total = long2_task_steps<C>(A) + 1;  // steps 0..steps
     int cert = kCertifiedAll;
     if (T.top_task >= 0 && top_prog < total) cert = top_prog - C::HOP_J;
-    if (T.left_task >= 0 && left_prog < total) {
+    if (T.left_task != -1 && left_prog < total) {  // <= -2: a block row of the left neighbour GPU (column pipeline)
         const int c2 = left_prog - C::HOP_K;
         cert = c2 < cert ? c2 : cert;
     }

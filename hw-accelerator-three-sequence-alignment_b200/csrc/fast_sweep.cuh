@@ -81,7 +81,16 @@ struct SweepArgs {
     uint32_t *iface_out;
     const int *iface_in_flag;
     int *iface_out_flag;
-    int last_slab;                // emit the score (the slab ends at plane la of the whole triple)
+    // column pipeline (K2L, several GPUs): this launch sweeps a contiguous range of block-column pairs of the triple (c
+    // already points at the range's first column, lc = its columns).  The K faces crossing the range's left edge come
+    // from the left neighbour GPU (cface_in, cprog_in: on this GPU, written by the peer), those crossing its right edge go
+    // to the right neighbour (cface_out, cprog_out: peer pointers): one face slot and one progress word per block row.
+    // Progress words are tagged (epoch << 20 | steps, 0xFFFFF = done), so that runs repeat without clearing.
+    const uint32_t *cface_in;
+    const int *cprog_in;
+    uint32_t *cface_out;
+    int *cprog_out;
+    int last_slab;                // emit the score (the launch holds cell (la,lb,lc) of the whole triple)
     int epoch;                    // value the hand-over flags take in this run (lets runs repeat without clearing)
     int32_t *out;                 // BATCH: scores[n]; LONG: out[0] = score
     int32_t *out_states;          // LONG: 7 final-cell states (or nullptr)

@@ -41,9 +41,23 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
                         const SlabLink *slab = nullptr);
 // K2L (fast_long.cu): the same decomposition on the K1 / K2S step engine (split-phase or lagged mbarrier, block halos
 // prefetched by the edge threads); the default for one long triple.  Same arguments, same hand-over layout.
+// column pipeline of one long triple over several GPUs: a launch sweeps ALL planes of a contiguous range of block-column
+// pairs; the K faces crossing the range's edges stream to / from the neighbour GPUs through peer memory, gated by
+// epoch-tagged progress words at system scope.  in_* live on this GPU, out_* are peer pointers.
+struct ColLink {
+    int lc_total;          // columns of the whole triple
+    int last;              // this range holds column lc_total: emit the score
+    int epoch;             // tag of this run's progress words (1 .. 2047)
+    const void *in_face;   // nullptr for the first range
+    const void *in_prog;
+    void *out_face;        // nullptr for the last range
+    void *out_prog;
+};
+size_t fast_long2_col_face_bytes(int la, int lb);
+size_t fast_long2_col_prog_bytes(int lb);
 int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
                    const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
-                   const SlabLink *slab = nullptr);
+                   const SlabLink *slab = nullptr, const ColLink *col = nullptr);
 // check_bits > 0 selects the range-checked kernel: *d_viol (zeroed by the caller) becomes non-zero if some value came
 // close enough to the score_bits = check_bits limits that a wrap cannot be excluded.
 int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,

@@ -29,6 +29,16 @@ def slab_range(la: int, rank: int, world: int) -> Tuple[int, int]:
     return (la * rank) // world, (la * (rank + 1)) // world
 
 
+def col_range(lc: int, rank: int, world: int) -> Tuple[int, int]:
+    """Columns [c_begin, c_end) of C that rank `rank` sweeps in the column pipeline: whole block-column pairs (128
+    columns), split as evenly as the pair count allows."""
+    pairs = (lc + 127) // 128
+    if world < 1 or not (0 <= rank < world) or pairs < world:
+        raise ValueError("need at least one block-column pair (128 columns) per rank")
+    p0, p1 = (pairs * rank) // world, (pairs * (rank + 1)) // world
+    return 128 * p0, min(lc, 128 * p1)
+
+
 def exchange_objects(obj, group=None) -> List:
     """all_gather of a small picklable object (IPC handles, shapes) over the given process group."""
     import torch.distributed as dist
@@ -107,3 +117,74 @@ class SlabPipeline:
             if p:
                 L.trialign_device_free(self.device, C.c_void_p(p))
         self.next_state = self.next_flags = self.state = self.flags = None
+
+
+class ColumnPipeline:
+    """Column pipeline for one long triple (trialign_cols_score_dev): rank g sweeps all planes of its block-column
+    range; the K faces crossing a range edge stream into rank g+1's memory (CUDA IPC mapping) while the sweep runs.
+    Build once per (la, lb, lc); a run must have finished on every rank before the next one starts (e.g. a
+    stream-ordered all_reduce between runs)."""
+
+    def __init__(self, la: int, lb: int, lc: int, score_bits: int = 16, device: Optional[int] = None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.device = torch.cuda.current_device() if device is None else device
+        self.la, self.lb, self.lc, self.score_bits = la, lb, lc, score_bits
+        self.c_begin, self.c_end = col_range(lc, self.rank, self.world)
+        self.epoch = 0
+        L = _ta.library()
+        fb, pb = C.c_int64(0), C.c_int64(0)
+        _ta._check(L.trialign_cols_buffer_bytes(la, lb, C.byref(fb), C.byref(pb)), "trialign_cols_buffer_bytes")
+        self.face = self.prog = None
+        handles = None
+        if self.rank > 0:  # boundary buffers of THIS rank, written by rank-1 through its peer mapping
+            pf, pp = C.c_void_p(), C.c_void_p()
+            _ta._check(L.trialign_device_alloc(self.device, fb.value, C.byref(pf)), "trialign_device_alloc")
+            _ta._check(L.trialign_device_alloc(self.device, max(pb.value, 256), C.byref(pp)), "trialign_device_alloc")
+            self.face, self.prog = pf.value, pp.value
+            hf, hp = (C.c_ubyte * 64)(), (C.c_ubyte * 64)()
+            _ta._check(L.trialign_ipc_export(C.c_void_p(self.face), hf), "trialign_ipc_export")
+            _ta._check(L.trialign_ipc_export(C.c_void_p(self.prog), hp), "trialign_ipc_export")
+            handles = (bytes(hf), bytes(hp))
+        everyone = exchange_objects(handles, group)
+        self.next_face = self.next_prog = None
+        if self.rank + 1 < self.world:
+            hf, hp = everyone[self.rank + 1]
+            pf, pp = C.c_void_p(), C.c_void_p()
+            _ta._check(L.trialign_ipc_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hf), C.byref(pf)), "trialign_ipc_open")
+            _ta._check(L.trialign_ipc_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hp), C.byref(pp)), "trialign_ipc_open")
+            self.next_face, self.next_prog = pf.value, pp.value
+
+    def run(self, A, B, C_, out=None, stream=None):
+        """A, B, C_: uint8 CUDA tensors holding the WHOLE sequences on every rank.  Returns the int32[8] result tensor
+        (score + 7 final states), meaningful on the last rank only."""
+        import torch
+
+        if out is None:
+            out = torch.zeros(8, dtype=torch.int32, device=A.device)
+        st = stream if stream is not None else torch.cuda.current_stream(A.device)
+        self.epoch = self.epoch % 2047 + 1
+        rc = _ta.library().trialign_cols_score_dev(
+            self.device, C.c_void_p(A.data_ptr()), A.numel(), C.c_void_p(B.data_ptr()), B.numel(),
+            C.c_void_p(C_.data_ptr()), C_.numel(), self.c_begin, self.c_end,
+            C.c_void_p(self.face) if self.rank > 0 else None,
+            C.c_void_p(self.prog) if self.rank > 0 else None,
+            C.c_void_p(self.next_face) if self.next_face else None,
+            C.c_void_p(self.next_prog) if self.next_prog else None,
+            self.epoch, self.score_bits, C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
+        _ta._check(rc, "trialign_cols_score_dev")
+        return out
+
+    def close(self):
+        L = _ta.library()
+        for p in (self.next_face, self.next_prog):
+            if p:
+                L.trialign_ipc_close(C.c_void_p(p))
+        for p in (self.face, self.prog):
+            if p:
+                L.trialign_device_free(self.device, C.c_void_p(p))
+        self.next_face = self.next_prog = self.face = self.prog = None

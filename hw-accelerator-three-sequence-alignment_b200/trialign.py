@@ -141,6 +141,12 @@ def library() -> C.CDLL:
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                           C.c_void_p, C.c_void_p]
     L.trialign_slab_score_dev.restype = C.c_int
+    L.trialign_cols_buffer_bytes.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.trialign_cols_buffer_bytes.restype = C.c_int
+    L.trialign_cols_score_dev.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                          C.c_void_p, C.c_void_p]
+    L.trialign_cols_score_dev.restype = C.c_int
     L.trialign_device_alloc.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
     L.trialign_device_alloc.restype = C.c_int
     L.trialign_device_free.argtypes = [C.c_int, C.c_void_p]

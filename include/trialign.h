@@ -160,6 +160,18 @@ int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_
                             int lc, int i_begin, int i_end, const void *in_state, const void *in_flags,
                             void *out_state, void *out_flags, int epoch, int score_bits, int32_t *d_out,
                             void *stream);
+/* Column pipeline, the second multi-GPU decomposition of one long triple: rank g sweeps ALL planes of a contiguous range
+ * of block-column pairs (columns c_begin .. c_end-1 of C; multiples of 128 except at the end); the block faces that
+ * cross a range edge stream to the right neighbour's memory while the sweep runs (one face slot and one epoch-tagged
+ * progress word per 64-row block, sizes from trialign_cols_buffer_bytes), so every GPU works on the same planes a few
+ * block hops apart instead of waiting for whole slabs.  in_* = this rank's own buffers (NULL on the first rank),
+ * out_* = the next rank's buffers as mapped with trialign_ipc_open() (NULL on the last rank).  epoch in 1..2047 must
+ * differ between consecutive runs; a run must have finished on every rank before the next one starts.  Only the last
+ * rank writes d_out (int32[8]).  Requires an input that is provably wrap-free at score_bits (else EINEXACT). */
+int trialign_cols_buffer_bytes(int la, int lb, int64_t *face_bytes, int64_t *prog_bytes);
+int trialign_cols_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
+                            int lc, int c_begin, int c_end, const void *in_face, const void *in_prog, void *out_face,
+                            void *out_prog, int epoch, int score_bits, int32_t *d_out, void *stream);
 /* Hand-over buffers must be whole cudaMalloc allocations (IPC handles name allocations, not sub-ranges). */
 int trialign_device_alloc(int device, int64_t bytes, void **dptr); /* zero-filled */
 int trialign_device_free(int device, void *dptr);

@@ -458,7 +458,10 @@ int run_long2(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t 
     std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
     for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
     const int nbj = A.nbj;
-    std::stable_sort(order.begin(), order.end(), [nbj, gate](int x, int y) {
+    const int nbkp = A.nbkp;
+    const bool row_major = (seed & 4) != 0;  // the column pipeline's claim order (fast_long.cu)
+    std::stable_sort(order.begin(), order.end(), [nbj, gate, nbkp, row_major](int x, int y) {
+        if (row_major) return (x % nbj) * nbkp + x / nbj < (y % nbj) * nbkp + y / nbj;
         return long2_order_key<C>(x % nbj, x / nbj, gate) < long2_order_key<C>(y % nbj, y / nbj, gate);
     });
     for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;

@@ -45,6 +45,12 @@ def _worker(rank, world, port, q):
         spans = par.exchange_objects((i0, i1))
         assert spans[0][0] == 0 and spans[-1][1] == la
         assert all(spans[g][1] == spans[g + 1][0] for g in range(world - 1))
+        # 2b. column pipeline: whole block-column pairs (128 columns) per rank, tiling C
+        for lc in (8192, 1000, 128 * world, 128 * world + 5):
+            c0, c1 = ta.col_range(lc, rank, world)
+            cols = par.exchange_objects((c0, c1))
+            assert cols[0][0] == 0 and cols[-1][1] == lc
+            assert all(cols[g][1] == cols[g + 1][0] and cols[g][1] % 128 == 0 for g in range(world - 1))
         # 3. the set-up exchange: every rank > 0 publishes two 64-byte handles, rank g maps those of rank g+1
         mine = (bytes([rank] * 64), bytes([rank + 100] * 64)) if rank > 0 else None
         everyone = par.exchange_objects(mine)
@@ -84,3 +90,7 @@ def test_partition_edge_cases():
         ta.slab_range(3, 0, 4)
     with pytest.raises(ValueError):
         ta.shard_range(10, 4, 4)
+    assert [ta.col_range(8192, r, 8) for r in range(8)][5] == (5120, 6144)
+    assert [ta.col_range(300, r, 3) for r in range(3)] == [(0, 128), (128, 256), (256, 300)]
+    with pytest.raises(ValueError):
+        ta.col_range(300, 0, 4)  # three column pairs cannot feed four ranks

@@ -260,6 +260,51 @@ def test_i_slab_pipeline_back_to_back_on_one_gpu(gpu_ta, ob, shape, n_slabs):
             L.trialign_device_free(0, pf)
 
 
+@pytest.mark.parametrize("shape,n_ranges", [((300, 200, 260), 2), ((200, 130, 700), 3), ((512, 512, 1024), 8),
+                                            ((64, 300, 1000), 4)])
+def test_column_pipeline_back_to_back_on_one_gpu(gpu_ta, ob, shape, n_ranges):
+    """The column pipeline (trialign_cols_score_dev) with the ranges run one after the other on a single GPU: each
+    range reads the boundary faces and progress words the previous one wrote; result must equal the single-pass score.
+    Run twice with different epochs over the same buffers."""
+    import ctypes as C
+
+    import torch
+
+    la, lb, lc = shape
+    rng = np.random.default_rng(sum(shape))
+    a, b, c = ob.mutated_triple(rng, max(shape))
+    a, b, c = a[:la], b[:lb], c[:lc]
+    L = gpu_ta.library()
+    fb, pb = C.c_int64(0), C.c_int64(0)
+    assert L.trialign_cols_buffer_bytes(la, lb, C.byref(fb), C.byref(pb)) == 0
+    bufs = []
+    for _ in range(n_ranges - 1):
+        pf, pp = C.c_void_p(), C.c_void_p()
+        assert L.trialign_device_alloc(0, fb.value, C.byref(pf)) == 0
+        assert L.trialign_device_alloc(0, max(pb.value, 256), C.byref(pp)) == 0
+        bufs.append((pf, pp))
+    da, db, dc = (torch.from_numpy(x.copy()).cuda() for x in (a, b, c))
+    out = torch.zeros(8, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    es, efin = ob.score_mt(a, b, c, 16)
+    try:
+        for epoch in (1, 2):
+            out.zero_()
+            for g in range(n_ranges):
+                c0, c1 = gpu_ta.col_range(lc, g, n_ranges)
+                src = bufs[g - 1] if g > 0 else (None, None)
+                dst = bufs[g] if g + 1 < n_ranges else (None, None)
+                rc = L.trialign_cols_score_dev(0, da.data_ptr(), la, db.data_ptr(), lb, dc.data_ptr(), lc, c0, c1,
+                                               src[0], src[1], dst[0], dst[1], epoch, 16, out.data_ptr(), st)
+                assert rc == 0, rc
+            torch.cuda.synchronize()
+            assert out.cpu().numpy().tolist() == [es] + efin.tolist()
+    finally:
+        for pf, pp in bufs:
+            L.trialign_device_free(0, pf)
+            L.trialign_device_free(0, pp)
+
+
 def test_fast_kernels_agree_with_literal_kernel_beyond_oracle_sizes(gpu_ta):
     """At sizes the CPU oracle cannot reach in seconds, the factored block-sweep kernel and the literal plane-sweep
     kernel (two independent implementations) must agree; identical sequences must score 3L."""
