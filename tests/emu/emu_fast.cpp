@@ -594,3 +594,197 @@ extern "C" int emu_fast_long2_slabs(const uint8_t *a, int la, const uint8_t *b, 
     }
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column pipeline (fast_long.cu, COLS kernels): several emulated GPUs run CONCURRENTLY, each sweeping a range of
+// block-column pairs with its own task counter, claim order (row-major), face rings and progress array; the K faces
+// and epoch-tagged progress words of the range edges live in the right neighbour's "memory".  The descriptor overrides,
+// the tagged progress words and the publication mirror the kernel body (long2_kernel<1,false,true>).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+int emu_col_decode(int v, int epoch)
+{
+    if ((v >> 20) != epoch) return 0;
+    const int steps = v & 0xFFFFF;
+    return steps == 0xFFFFF ? kProgressDone : steps;
+}
+int emu_col_encode(int steps, int epoch) { return (epoch << 20) | (steps >= kProgressDone ? 0xFFFFF : steps); }
+
+struct EmuGpu {
+    using C = Long2Cfg<1>;
+    SweepArgs A{};
+    std::vector<uint32_t> fj, fk, cface;  // cface / cprog: boundary buffers of THIS gpu (written by the left neighbour)
+    std::vector<int> prog, cprog, order, pos_of;
+    unsigned long long counter = 0;
+    std::vector<EmuCta2<C>> ctas;
+    long long finished = 0;
+};
+
+}  // namespace
+
+extern "C" int emu_fast_long2_cols(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int base,
+                                   int n_ctas, int n_ranges, int seed, int epochs, int32_t *out8)
+{
+    using C = Long2Cfg<1>;
+    constexpr int NW = C::NT / 32, kGateWarp = 128 / 32;
+    const int pairs = (lc + 127) / 128;
+    if (la < 1 || lb < 1 || lc < 1 || n_ranges < 1 || pairs < n_ranges || n_ctas < 1) return -1;
+    const int nbj = (lb + C::BJ - 1) / C::BJ;
+    const long long slot_k = (long long)(la + C::PLAG + 2) * C::FK_ROW_WORDS;
+    std::vector<EmuGpu> gpus(n_ranges);
+    for (int g = 0; g < n_ranges; ++g) {
+        EmuGpu &G = gpus[g];
+        const int p0 = pairs * g / n_ranges, p1 = pairs * (g + 1) / n_ranges;
+        const int c0 = 128 * p0, c1 = std::min(lc, 128 * p1);
+        SweepArgs &A = G.A;
+        A.a = a; A.b = b; A.c = c + c0; A.n = 1; A.la = la; A.lb = lb; A.lc = c1 - c0;
+        A.nbj = nbj;
+        A.nbkp = (A.lc + C::KSPAN - 1) / C::KSPAN;
+        A.tasks_total = (long long)A.nbj * A.nbkp;
+        A.gate = 4;
+        A.fj_slot_words = (long long)(la + C::PLAG + 2) * C::FJ_ROW_WORDS;
+        A.fk_slot_words = slot_k;
+        A.fj_ring = A.fk_ring = (int)A.tasks_total;
+        G.fj.assign((size_t)A.fj_ring * A.fj_slot_words, 0xDEADBEEFu);
+        G.fk.assign((size_t)A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
+        G.prog.assign((size_t)A.tasks_total, 0);
+        G.order.resize((size_t)A.tasks_total);
+        G.pos_of.resize((size_t)A.tasks_total);
+        for (int t = 0; t < (int)A.tasks_total; ++t) G.order[t] = t;
+        const int nbkp = A.nbkp;
+        std::stable_sort(G.order.begin(), G.order.end(), [nbj, nbkp](int x, int y) {
+            return (x % nbj) * nbkp + x / nbj < (y % nbj) * nbkp + y / nbj;  // row-major (fast_long.cu, cols)
+        });
+        for (int p = 0; p < (int)A.tasks_total; ++p) G.pos_of[G.order[p]] = p;
+        A.order = G.order.data(); A.pos_of = G.pos_of.data();
+        A.face_j = G.fj.data(); A.face_k = G.fk.data(); A.progress = G.prog.data(); A.counter = &G.counter;
+        A.out = out8; A.out_states = out8 + 1; A.base = base;
+        A.last_slab = g + 1 == n_ranges;
+        if (g > 0) {
+            G.cface.assign((size_t)nbj * slot_k, 0xDEADBEEFu);
+            G.cprog.assign((size_t)nbj, 0);
+        }
+        G.ctas.resize(n_ctas);
+    }
+    for (int g = 0; g < n_ranges; ++g) {
+        SweepArgs &A = gpus[g].A;
+        if (g > 0) { A.cface_in = gpus[g].cface.data(); A.cprog_in = gpus[g].cprog.data(); }
+        if (g + 1 < n_ranges) { A.cface_out = gpus[g + 1].cface.data(); A.cprog_out = gpus[g + 1].cprog.data(); }
+    }
+    uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)seed;
+    for (int epoch = 1; epoch <= epochs; ++epoch) {
+        for (auto &G : gpus) {
+            G.A.epoch = epoch;
+            G.counter = 0;
+            G.finished = 0;
+            std::fill(G.prog.begin(), G.prog.end(), 0);  // the launcher clears the local progress array
+            for (auto &cta : G.ctas) {
+                std::memset(cta.S.get(), (seed & 2) ? 0xFF : 0x00, sizeof(Long2Smem<C>));
+                for (int tid = 0; tid < C::NT; ++tid) long2_load_a<C>(*cta.S, G.A, tid);
+                cta.has_task = false;
+            }
+        }
+        out8[0] = -99999;
+        const int steps = long2_task_steps<C>(gpus[0].A);
+        long long idle = 0;
+        auto all_done = [&]() {
+            for (auto &G : gpus)
+                if (G.finished < G.A.tasks_total) return false;
+            return true;
+        };
+        while (!all_done()) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            // skewed choice of the GPU: later ranges sometimes run far ahead of / behind their producers
+            EmuGpu &G = gpus[(size_t)((rng >> 44) % (uint64_t)n_ranges)];
+            SweepArgs &A = G.A;
+            auto &cta = G.ctas[(size_t)((rng >> 40) % (uint64_t)n_ctas) % G.ctas.size()];
+            bool progressed = false;
+            if (!cta.has_task) {
+                if ((long long)G.counter < A.tasks_total) {
+                    SweepTask &T = cta.S->task;
+                    sweep_describe_long<C>(A, (long long)G.counter++, T);
+                    if (A.cface_in && T.bkp == 0) {
+                        T.fk_r = A.cface_in + (long long)T.bj * A.fk_slot_words;
+                        T.left_task = -2 - T.bj;
+                    }
+                    if (A.cface_out && T.bkp == A.nbkp - 1) T.fk_w = A.cface_out + (long long)T.bj * A.fk_slot_words;
+                    cta.has_task = true;
+                    cta.prologue_done = false;
+                    for (int tid = 0; tid < C::NT; ++tid) long2_load_bc<C>(*cta.S, A, tid);
+                    for (int tid = 0; tid < C::NT; ++tid) long2_build_tables<C>(*cta.S, tid);
+                    for (int tid = 0; tid < C::NT; ++tid) {
+                        int tj, tk;
+                        stream_thread_pos<C>(tid, tj, tk);
+                        long2_init_thread<C>(cta.R[tid], *cta.S, tj, tk);
+                    }
+                    std::fill(cta.done.begin(), cta.done.end(), -1);
+                    progressed = true;
+                }
+            } else {
+                const SweepTask &T = cta.S->task;
+                const int tp = T.top_task >= 0 ? G.prog[T.top_task] : 0;
+                const int lp = T.left_task >= 0 ? G.prog[T.left_task]
+                                                : (T.left_task <= -2 ? emu_col_decode(G.cprog[-2 - T.left_task], A.epoch) : 0);
+                int *right_p = (A.cprog_out && T.bkp == A.nbkp - 1) ? A.cprog_out + T.bj : nullptr;
+                auto publish = [&](int done) {
+                    G.prog[T.self_task] = done;
+                    if (right_p) *right_p = emu_col_encode(done, A.epoch);
+                };
+                const int cert = long2_certified<C>(A, T, tp, lp);
+                if (!cta.prologue_done) {
+                    if (cert >= 2) {
+                        for (int tid = 0; tid < C::NT; ++tid) {
+                            int tj, tk;
+                            stream_thread_pos<C>(tid, tj, tk);
+                            if (tj == 0 || tk == 0) long2_edge_fetch<C>(*cta.S, A, tj, tk, 0);
+                            long2_thread_prepare<C>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, 0, tid);
+                        }
+                        cta.prologue_done = true;
+                        progressed = true;
+                    }
+                } else {
+                    const int w = (int)((rng >> 20) % NW);
+                    const int s = cta.done[w] + 1;
+                    const int mn = *std::min_element(cta.done.begin(), cta.done.end());
+                    bool can = s <= steps && mn >= s - 1;
+                    const int want = s + C::AHEAD < steps ? s + C::AHEAD : steps;
+                    if (can && w == kGateWarp && cert < want) can = false;
+                    if (can) {
+                        if (w == kGateWarp && s >= 1 && long2_publish_now<C>(A, s)) publish(s);
+                        const bool mid = s >= long2_mid_begin<C>(A) && s <= long2_mid_end<C>(A);
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int tid = w * 32 + lane;
+                            int tj, tk;
+                            stream_thread_pos<C>(tid, tj, tk);
+                            if (mid) long2_thread_step<C, false, false>(cta.R[tid], cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s, tid);
+                            else long2_thread_step<C, false, true>(cta.R[tid], cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s, tid);
+                        }
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int tid = w * 32 + lane;
+                            int tj, tk;
+                            stream_thread_pos<C>(tid, tj, tk);
+                            if (mid) long2_thread_prepare<C, false>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s + 1, tid);
+                            else long2_thread_prepare<C, true>(cta.R[tid], cta.K[tid], *cta.S, A, tj, tk, s + 1, tid);
+                        }
+                        cta.done[w] = s;
+                        progressed = true;
+                        if (*std::min_element(cta.done.begin(), cta.done.end()) == steps) {
+                            publish(kProgressDone);
+                            cta.has_task = false;
+                            ++G.finished;
+                        }
+                    }
+                }
+            }
+            if (progressed) idle = 0;
+            else if (++idle > 400000) return -2;  // deadlock
+        }
+        if (epoch < epochs) {
+            // the face buffers are reused by the next epoch without clearing; poison them to catch a read that was not
+            // certified in its own epoch
+            for (auto &G : gpus) std::fill(G.cface.begin(), G.cface.end(), 0xDEADBEEFu);
+        }
+    }
+    return 0;
+}

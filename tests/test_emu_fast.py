@@ -259,3 +259,25 @@ def test_long2_i_slab_pipeline(emu_long2, ob, shape, n_slabs, n_ctas, lag):
     assert rc == 0
     es, efin = ob.score(a, b, c, 16)
     assert int(out[0]) == es and out[1:].tolist() == efin.tolist()
+
+
+@pytest.mark.parametrize("shape,n_ranges,n_ctas", [((40, 70, 300), 2, 2), ((33, 130, 520), 4, 2), ((100, 64, 1000), 8, 1),
+                                                   ((1, 100, 400), 3, 3), ((60, 200, 700), 3, 4)])
+def test_long2_column_pipeline_concurrent_ranges(emu_long2, ob, shape, n_ranges, n_ctas):
+    """The multi-GPU column pipeline: several emulated GPUs run at the same time, each sweeping a block-column range
+    with its own counter / claim order / rings, boundary faces and epoch-tagged progress words in the neighbour's
+    memory; two epochs over the same buffers (the faces poisoned in between).  A consumer that is not gated by its
+    remote producer reads poison here."""
+    emu_long2.emu_fast_long2_cols.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                              C.c_int, C.c_int, i32p]
+    la, lb, lc = shape
+    rng = np.random.default_rng(sum(shape) + n_ranges)
+    a, b, c = ob.mutated_triple(rng, max(shape))
+    a, b, c = (np.ascontiguousarray(x) for x in (a[:la], b[:lb], c[:lc]))
+    es, efin = ob.score(a, b, c, 16)
+    for seed in (1, 2, 7):
+        out = np.zeros(8, np.int32)
+        rc = emu_long2.emu_fast_long2_cols(a.ctypes.data_as(u8p), la, b.ctypes.data_as(u8p), lb, c.ctypes.data_as(u8p), lc,
+                                           2 * min(shape) + 64, n_ctas, n_ranges, seed, 2, out.ctypes.data_as(i32p))
+        assert rc == 0, "emulated GPUs deadlocked" if rc == -2 else rc
+        assert int(out[0]) == es and out[1:].tolist() == efin.tolist(), seed
