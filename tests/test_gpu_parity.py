@@ -472,3 +472,17 @@ def test_fast_kernels_agree_with_the_literal_kernel_on_random_shapes(gpu_ta):
             assert gpu_ta.last_path() == "fast_long"
             g = lit.align(a, b, c, return_states=True)
             assert f[0] == g[0] and f[1].tolist() == g[1].tolist(), (la, lb, lc)
+
+
+def test_explicit_scoring_fixture(gpu_ta):
+    """tests/golden/golden_scoring.json (generated by make_golden_scoring.py from oracle_score_ex) through the C ABI."""
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_scoring.json")) as f:
+        g = json.load(f)
+    for case in g["cases"]:
+        eng = gpu_ta.TriAlign(case["score_bits"], scoring=gpu_ta.Scoring(*case["scoring"]))
+        s, fin = eng.align(np.array(case["a"], np.uint8), np.array(case["b"], np.uint8), np.array(case["c"], np.uint8),
+                           return_states=True)
+        assert s == case["score"] and fin.tolist() == case["final_states"], (case["name"], case["scoring"])

@@ -239,3 +239,15 @@ def test_score_ex_sum_of_pairs_is_symmetric_and_rtl_rule_is_not(ob, golden):
     x = seqs[0][:20]
     assert ob.score_ex(x, x, x, 12, [2, -1, 3, 1, 0])[0] == 3 * 2 * 20
     assert ob.score_ex(x, x, x, 12, [2, -1, 3, 1, 1])[0] == 3 * 2 * 20
+
+
+def test_score_ex_reproduces_the_committed_scoring_fixture(ob):
+    import json
+    import os
+
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_scoring.json")) as f:
+        g = json.load(f)
+    assert len(g["cases"]) == 40
+    for case in g["cases"]:
+        s, fin = ob.score_ex(case["a"], case["b"], case["c"], case["score_bits"], case["scoring"])
+        assert s == case["score"] and fin.tolist() == case["final_states"], (case["name"], case["scoring"])
