@@ -1,15 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- 3D-GCUPS of the three-sequence alignment hot path on B200 (contract in the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--opt name=value]
 
-A "step" is one pass of the hot path over one batch of synthetic ACGT triples.  Default workload (N=1) is
-BASELINE.json configs[1]: 1M triples of length 64, SCORE_BITS=12 (the testbench value), on one GPU.  Under torchrun
-(N>1) every rank processes its own 1M-triple shard (independent triples, no data-path collective) -> weak scaling.
-`value` times the device-resident call (inputs already in HBM); `e2e` times the host-pointer C-ABI call with pinned
-host buffers, H2D and D2H copies inside the timed region.
+A "step" is one pass of the hot path over one batch of synthetic ACGT triples.
+
+Top-level line = BASELINE.json configs[1] (`batch64`): 1M triples of length 64, SCORE_BITS=12 (the testbench value) per
+GPU; under torchrun (N>1) every rank processes its own 1M-triple shard (independent triples, no data-path collective)
+-> weak scaling.  `value` times the device-resident call (inputs already in HBM); `e2e` times the host-pointer C-ABI
+call with pinned host buffers, H2D and D2H copies inside the timed region.
+
+`secondary` (same JSON line) carries the other BASELINE configs so that the driver's run exercises them too:
+    N = 1 : long1024 (config 3, W=12), batch256 (config 4, all 262,144 triples), long8192 (config 5's triple on one GPU)
+    N > 1 : batch256 as a 262,144-triple TOTAL split over the ranks (config 4 as written, strong scaling) and long8192
+            through the multi-GPU pipeline (config 5, strong scaling; the 1-GPU rate is measured on rank 0 in the same
+            run so that the efficiency has its own denominator), plus the single-process host-pointer call
+            trialign_score(devices = all N GPUs) as its e2e.
+Every workload's result is compared with the committed oracle goldens (tests/golden/golden.json, golden_long.json;
+the timed batch64 scores also with the scores the cpu_baseline leg computes for the same triples): a mismatch is
+reported in `parity` and the process EXITS NON-ZERO.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -18,11 +30,13 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (ROOT, os.path.join(ROOT, "tests")):
+for _p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-OPS_PER_CELL = 91  # 49 adds + 42 max per cell update (PE_1cyc.v:164-218, :22-28) -- SURVEY.md 8(d)
+OPS_PER_CELL = 91     # 49 adds + 42 max per cell update (PE_1cyc.v:164-218, :22-28) -- SURVEY.md 8(d)
+MIN_ALU_PER_PAIR = 12  # ALU-pipe instructions the factored update needs per cell pair (fast_core.cuh)
+SMS, ALU_LANES_PER_CLK = 148, 64
 
 WORKLOADS = {
     # name: (BASELINE config index, triples per GPU, length, score_bits)
@@ -33,29 +47,49 @@ WORKLOADS = {
 }
 
 
+def csrc_hash():
+    """Hash of the kernel sources; profiles/ncu_kernel_stats.json records the one its captures were taken from."""
+    d = os.path.join(ROOT, "hw-accelerator-three-sequence-alignment_b200", "csrc")
+    h = hashlib.sha256()
+    for name in sorted(os.listdir(d)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(name.encode())
+            with open(os.path.join(d, name), "rb") as f:
+                h.update(f.read())
+    return h.hexdigest()[:16]
+
+
 def kernel_stats(workload):
-    """Per-launch DRAM traffic and issued-instruction utilisation of the dominant kernel, taken from the committed
-    `ncu --set full` captures (profiles/ncu_kernel_stats.json); never measured under this process."""
+    """Per-launch DRAM traffic and issued-instruction mix of the dominant kernel from the committed `ncu --set full`
+    captures (profiles/ncu_kernel_stats.json, written by tools/ncu_stats.py; never measured under this process)."""
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_kernel_stats.json")) as f:
-            return json.load(f).get(workload)
+            doc = json.load(f)
+        ks = doc.get(workload)
+        if ks is not None:
+            ks = dict(ks)
+            ks["stale"] = ks.get("csrc_hash", doc.get("csrc_hash")) != csrc_hash()
+        return ks
     except Exception:
         return None
 
 
-def alu_peak():
-    """Measured integer-ALU peak (tools/alu_microbench.cu on this pool's B200), else the nominal figure."""
-    path = os.path.join(ROOT, "profiles", "alu_peak.json")
+def golden_short():
+    with open(os.path.join(ROOT, "tests", "golden", "golden.json")) as f:
+        return json.load(f)["synth"]
+
+
+def golden_long():
     try:
-        with open(path) as f:
-            d = json.load(f)
-        return float(d["peak_s16x2_lane_ops_per_s"]), "measured (profiles/alu_peak.json: 148 SMs x 64 lanes/clk x 2 (s16x2) x measured clock)"
+        import long_cases
+
+        return long_cases.load()
     except Exception:
-        return 148 * 64 * 2 * 1.965e9, "nominal (148 SMs x 64 lanes/clk x 2 x 1.965 GHz)"
+        return {}
 
 
 class ClockSampler:
-    """Samples nvidia-smi during the timed region (B200_PROFILING.md's clocks line)."""
+    """Samples nvidia-smi during a timed region (B200_PROFILING.md's clocks line)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -75,6 +109,7 @@ class ClockSampler:
             self.t.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
@@ -116,7 +151,8 @@ def host_threads():
 
 
 def cpu_baseline(length, score_bits, target_s=22.0):
-    """Times the CPU oracle (kind 'port': O1, all host threads) and the RTL cycle model on a bounded sample."""
+    """Times the CPU oracle (kind 'port': O1, all host threads) and the RTL cycle model on a bounded sample.
+    Returns (json object, oracle scores of the sample) -- the sample is triples 0..n-1 of the batch64 seed."""
     import numpy as np
 
     import oracle_bindings as ob
@@ -134,7 +170,7 @@ def cpu_baseline(length, score_bits, target_s=22.0):
     n = int(max(probe_n, min(1 << 18, target_s * rate / per)))
     a, b, c = ob.synth_batch(0x5EED0002, 0, n, L)
     t0 = time.perf_counter()
-    ob.score_batch(a, b, c, score_bits, threads)
+    scores = ob.score_batch(a, b, c, score_bits, threads)
     dt = time.perf_counter() - t0
     out = {"value": n * per / dt / 1e9, "unit": "GCUPS", "cores": threads, "kind": "port",
            "sample": f"{n} synthetic triples of length {L}, W={score_bits}, functional oracle O1 (OpenMP over triples), {dt:.1f} s"}
@@ -158,7 +194,7 @@ def cpu_baseline(length, score_bits, target_s=22.0):
                               "sample": f"{m} triples of length 64, {dt:.1f} s"}
     except Exception as e:  # pragma: no cover
         out["rtl_sim"] = {"error": str(e)}
-    return out
+    return out, (scores if L == length else None)
 
 
 def run_reference(args, rank, world):
@@ -199,181 +235,340 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def run_ours(args, rank, world, local_rank):
-    import numpy as np
-    import torch
+# ------------------------------------------------------------------------------------------------------------------
+class Runner:
+    """Shared timing harness of one process (one rank)."""
 
-    import trialign_b200 as ta
+    def __init__(self, rank, world, local_rank):
+        import torch
 
-    cfg, n_full, length, w = WORKLOADS[args.workload]
-    n = args.triples if args.triples else n_full
-    reduced = bool(args.triples and args.triples != n_full)
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
+        self.torch = torch
+        self.rank, self.world, self.local_rank = rank, world, local_rank
+        torch.cuda.set_device(local_rank)
+        self.dev = torch.device("cuda", local_rank)
+        self.dist = None
+        if world > 1:
+            import torch.distributed as dist
 
-        dist.init_process_group("nccl", device_id=dev)
-    eng = ta.TriAlign(score_bits=w, devices=[local_rank])
-    seed = 0x5EED0000 + cfg
-    single = length > 256  # one long triple (configs 3 and 5) instead of a batch
-    slab = single and world > 1
-    scaling = "strong" if slab else "weak"
-    first = 0 if single else rank * n  # batch: each rank owns a contiguous shard of independent triples
-    da, db, dc = ta.synth_batch_cuda(seed, first, n, length, device=local_rank)
-    cells_step = float(n) * float(length) ** 3
-    if single:
-        out = torch.zeros(8, dtype=torch.int32, device=dev)
-        a1, b1, c1 = da[0], db[0], dc[0]
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.dist = dist
+            # host-side barrier for phases in which only rank 0 uses the GPUs (an NCCL barrier would park a spinning
+            # kernel on every waiting rank's GPU, which rank 0's single-process multi-GPU call also needs)
+            self.cpu_group = dist.new_group(backend="gloo")
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def host_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist is not None:
+            self.dist.barrier(group=self.cpu_group)
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.int64, device=self.dev)
+        if self.dist is not None:
+            self.dist.all_reduce(t)
+        return int(t.item())
+
+    def time_steps(self, step, steps, warmup, ta, collective=True):
+        """W warm-up steps, then K steps bracketed by barrier + synchronize, CUDA events on the launching stream,
+        max over ranks.  collective=False: only this rank runs (the others wait at the caller's barrier)."""
+        torch = self.torch
+        sync = self.barrier if collective else torch.cuda.synchronize
+        for _ in range(max(warmup, 3)):
+            step()
+        sync()
+        sampler = ClockSampler(self.local_rank).start() if self.rank == 0 else None
+        l0 = ta.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        sync()
+        launches = ta.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        if collective:
+            ms = self.max_over_ranks(ms)
+        clocks = sampler.stop() if sampler else None
+        return ms / steps, launches, clocks
+
+    def time_host(self, fn, steps, collective=True):
+        """e2e: host-pointer calls, wall clock around `steps` synchronous calls after one untimed call."""
+        fn()
+        if collective:
+            self.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        self.torch.cuda.synchronize()
+        s = (time.perf_counter() - t0) / steps
+        return self.max_over_ranks(s) if collective else s
+
+
+def roofline(workload, cells_per_s_per_gpu, clocks, world=1, slab=False, n=None):
+    """Integer-ALU roofline of the dominant (only) kernel of a step.
+    frac = ALU-pipe instructions the kernel ISSUES per second / what the pipe can issue: (alu instr per cell pair from
+    the committed ncu capture, else the static minimum 12) x cell pairs/s / (148 SMs x 64 lanes/clk x SM clock).
+    `literal_equivalent` keeps SURVEY.md 8(d)'s figure (the RTL's 91 lane-ops per cell against the packed-lane peak),
+    which exceeds 1 because the factored update needs far fewer operations."""
+    ks = kernel_stats(workload)
+    clk_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = SMS * ALU_LANES_PER_CLK * clk_mhz * 1e6            # ALU-pipe lane-instructions / s
+    alu_per_pair = float(ks["alu_instr_per_cell_pair"]) if ks and "alu_instr_per_cell_pair" in ks else float(MIN_ALU_PER_PAIR)
+    pairs = cells_per_s_per_gpu / 2.0
+    achieved = alu_per_pair * pairs
+    out = {"bound": "int_alu", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "T ALU-pipe lane-instr/s",
+           "frac": achieved / peak, "traffic": None,
+           "alu_instr_per_cell_pair": alu_per_pair,
+           "alu_instr_source": ("ncu capture " + ks.get("capture", "")) if ks and "alu_instr_per_cell_pair" in ks else "static minimum (fast_core.cuh)",
+           "frac_min_ops": MIN_ALU_PER_PAIR * pairs / peak,
+           "peak_source": f"148 SMs x 64 ALU lanes/clk (profiles/alu_peak.json: 2.0 warp-instr/clk/SM measured) x {clk_mhz:.0f} MHz sampled during the timed region",
+           "literal_equivalent": {"ops_per_cell": OPS_PER_CELL, "frac": cells_per_s_per_gpu * OPS_PER_CELL / (2 * peak),
+                                  "note": "RTL's 49 adds + 42 max per cell against the packed s16x2 lane peak; > 1 because the factored update issues 12 ALU instructions per cell PAIR"}}
+    if ks:
+        scale = 1.0
+        if ks.get("triples_in_capture") and n:
+            scale = float(n) / ks["triples_in_capture"]
         if slab:
-            # config 5: i-slab pipeline, rank g computes planes (la*g/N, la*(g+1)/N] and hands block states to rank g+1
-            # (TRIALIGN_MULTI=slab), or the column pipeline: rank g sweeps all planes of its block-column range and streams
-            # the faces crossing the range edge to rank g+1 while it runs
-            use_cols = os.environ.get("TRIALIGN_MULTI", "slab") == "cols"
-            pipe = (ta.ColumnPipeline(length, length, length, score_bits=w, device=local_rank) if use_cols
-                    else ta.SlabPipeline(length, length, score_bits=w, device=local_rank))
-            sync_t = torch.zeros(1, device=dev)
+            scale = 1.0 / world
+        out["traffic"] = (ks["dram_bytes_read"] + ks["dram_bytes_write"]) * scale
+        out["issued"] = {k: ks[k] for k in ("alu_pipe_pct", "issue_slot_pct", "warp_instr_per_cell_pair",
+                                             "alu_instr_per_cell_pair", "capture", "csrc_hash", "stale") if k in ks}
+    return out
 
-            def step():
-                pipe.run(a1, b1, c1, out=out)
-                dist.all_reduce(sync_t)  # stream-ordered: nobody starts run k+1 before every rank finished run k
-            cells_step /= world  # per rank; the job total is restored below
-        else:
-            def step():
-                eng.align_cuda(a1, b1, c1, out=out)
-    else:
-        out = torch.empty(n, dtype=torch.int32, device=dev)
 
-        def step():
-            eng.align_batch_cuda(da, db, dc, out=out)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    path = ta.last_path()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    l0 = ta.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    barrier()
-    launches = ta.launch_count() - l0
-    ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    clocks = sampler.stop() if rank == 0 else None
-    if slab:  # the score lives on the last rank
-        res = out[:1].clone().to(torch.int64)
-        if rank != world - 1:
-            res.zero_()
-        dist.all_reduce(res)
-        checksum = int(res.item())
-    else:
-        checksum = int(out[0].item()) if single else int(out.sum().item())
-
-    # ---- e2e: host buffers through the C ABI (H2D + kernels + D2H inside the timed region) ----
+def run_batch(R, ta, name, steps, warmup, n_per_rank, first, golden_scores, want_cpu, parity, total_strong=None):
+    """Batch workload on this rank's GPU: device-resident timing + host-pointer e2e + golden comparison."""
     import ctypes as C
 
+    torch = R.torch
+    cfg, _, length, w = WORKLOADS[name]
+    seed = 0x5EED0000 + cfg
+    eng = ta.TriAlign(score_bits=w, devices=[R.local_rank])
+    da, db, dc = ta.synth_batch_cuda(seed, first, n_per_rank, length, device=R.local_rank)
+    out = torch.empty(n_per_rank, dtype=torch.int32, device=R.dev)
+
+    def step():
+        eng.align_batch_cuda(da, db, dc, out=out)
+
+    ms, launches, clocks = R.time_steps(step, steps, warmup, ta)
+    path = ta.last_path()
+    checksum = R.sum_over_ranks(int(out.sum().item()))
+    head = out[:64].cpu().tolist() if R.rank == 0 else []
+    # golden: the first scores of the batch against tests/golden/golden.json (rank 0 owns triple 0)
+    if R.rank == 0 and golden_scores:
+        k = min(len(golden_scores), len(head))
+        ok = head[:k] == golden_scores[:k]
+        parity.append({"workload": name, "against": "tests/golden/golden.json", "checked": k, "ok": ok})
+    # e2e through the C ABI with pinned host buffers
     L = ta.library()
     u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
     ha, hb, hc = (x.cpu().pin_memory() for x in (da, db, dc))
-    if slab:
-        # the pipeline has no host-pointer form; e2e = device run + staging of the three sequences and the result
-        hres = torch.empty(8, dtype=torch.int32).pin_memory()
+    hout = torch.empty(n_per_rank, dtype=torch.int32).pin_memory()
 
-        def e2e_step():
-            da.copy_(ha, non_blocking=True); db.copy_(hb, non_blocking=True); dc.copy_(hc, non_blocking=True)
-            step()
-            hres.copy_(out, non_blocking=True)
-            torch.cuda.synchronize()
-        h2d, d2h = 3 * length, 32
-    elif single:
+    def e2e_step():
+        rc = L.trialign_score_batch(C.cast(ha.data_ptr(), u8p), C.cast(hb.data_ptr(), u8p), C.cast(hc.data_ptr(), u8p),
+                                    n_per_rank, length, w, 0, 1 << R.local_rank, C.cast(hout.data_ptr(), i32p))
+        if rc:
+            raise RuntimeError(f"trialign_score_batch rc={rc}")
+
+    e2e_s = R.time_host(e2e_step, max(1, min(steps, 5)))
+    same = bool((hout == out.cpu()).all().item())
+    same = R.sum_over_ranks(0 if same else 1) == 0
+    if R.rank == 0:
+        parity.append({"workload": name, "against": "e2e host-pointer call == device-resident call", "checked": n_per_rank * R.world, "ok": same})
+    cells_rank = float(n_per_rank) * float(length) ** 3
+    res = {"workload": name, "baseline_config": cfg, "value": cells_rank * R.world / (ms / 1e3) / 1e9, "unit": "GCUPS",
+           "ms_per_step": ms, "steps": steps, "warmup": max(warmup, 3), "scaling": "strong" if total_strong else "weak",
+           "triples_per_gpu": n_per_rank, "triples_total": n_per_rank * R.world, "length": length, "score_bits": w,
+           "kernel_path": path, "gpu_launches": launches, "scores_checksum": checksum, "clocks": clocks,
+           "e2e": {"value": cells_rank * R.world / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": 3 * n_per_rank * length,
+                   "d2h_bytes_per_step": 4 * n_per_rank},
+           "roofline": roofline(name, cells_rank / (ms / 1e3), clocks, n=n_per_rank)}
+    res["_scores_dev"] = out if want_cpu else None
+    return res
+
+
+def run_long(R, ta, name, steps, warmup, parity, multi):
+    """One long triple.  multi=False: this rank's GPU alone (only rank 0 runs; the others wait).  multi=True: the
+    pipeline over all ranks (one process per GPU, CUDA-IPC peer buffers), plus -- on rank 0 -- the single-process
+    host-pointer call over all GPUs as e2e."""
+    import ctypes as C
+
+    import long_cases
+
+    torch = R.torch
+    cfg, _, length, w = WORKLOADS[name]
+    seed = 0x5EED0000 + cfg
+    gl = golden_long()
+    want = None
+    if length == 1024:
+        for e in golden_short():
+            if e.get("single") and e["len"] == 1024 and e["score_bits"] == w:
+                want = (e["score"], e["final_states"], "tests/golden/golden.json")
+    elif "config5_8192_w16" in gl and length == 8192:
+        e = gl["config5_8192_w16"]
+        want = (e["score"], e["final_states"], "tests/golden/golden_long.json")
+    a, b, c = long_cases.build_case(ta.synth, seed, "synth", (length, length, length))
+    da, db, dc = (torch.from_numpy(x).to(R.dev) for x in (a, b, c))
+    out = torch.zeros(8, dtype=torch.int32, device=R.dev)
+    eng = ta.TriAlign(score_bits=w, devices=[R.local_rank])
+    cells = float(length) ** 3
+    active = multi or R.rank == 0
+    mode = "single GPU"
+    if multi:
+        use_cols = ta.get_option("multi") == "cols"
+        pipe = (ta.ColumnPipeline(length, length, length, score_bits=w, device=R.local_rank) if use_cols
+                else ta.SlabPipeline(length, length, score_bits=w, device=R.local_rank))
+        mode = ("column pipeline" if use_cols else "i-slab pipeline") + f" over {R.world} GPUs, NVLink peer stores"
+
+        def step():
+            pipe.run(da, db, dc, out=out)  # ends with a stream-ordered all_reduce: runs never overlap across ranks
+    else:
+        def step():
+            eng.align_cuda(da, db, dc, out=out)
+
+    ms = launches = clocks = None
+    if active:
+        ms, launches, clocks = R.time_steps(step, steps, warmup, ta, collective=multi)
+    path = ta.last_path() if active else None
+    R.host_barrier()
+    if multi:  # the score lives on the last rank
+        res = out.clone().to(torch.int64)
+        if R.rank != R.world - 1:
+            res.zero_()
+        R.dist.all_reduce(res)
+        got = res.cpu().tolist()
+        pipe.close()
+        R.host_barrier()
+    else:
+        got = out.cpu().tolist()
+    e2e = None
+    if R.rank == 0:
+        if want:
+            ok = got[0] == want[0] and got[1:8] == list(want[1])
+            parity.append({"workload": name + (f"@{R.world}gpu" if multi else "@1gpu"), "against": want[2],
+                           "checked": 8, "ok": ok, "got": got[0], "want": want[0]})
+        else:
+            parity.append({"workload": name, "against": "no golden committed for this shape", "checked": 0, "ok": True})
+        # e2e: trialign_score with host pointers (multi: ONE process drives all GPUs of the mask)
+        L = ta.library()
+        u8p = C.POINTER(C.c_uint8)
+        ha, hb, hc = (torch.from_numpy(x).pin_memory() for x in (a, b, c))
         hs = C.c_int32(0)
+        fin = (C.c_int32 * 7)()
+        mask = (1 << R.world) - 1 if multi else 1 << R.local_rank
 
         def e2e_step():
             rc = L.trialign_score(C.cast(ha.data_ptr(), u8p), length, C.cast(hb.data_ptr(), u8p), length,
-                                  C.cast(hc.data_ptr(), u8p), length, w, 0, 1 << local_rank, C.byref(hs), None)
+                                  C.cast(hc.data_ptr(), u8p), length, w, 0, mask, C.byref(hs), fin)
             if rc:
-                raise RuntimeError(f"trialign_score rc={rc}")
-        h2d, d2h = 3 * length, 4
+                raise RuntimeError(f"trialign_score rc={rc}: {ta.library().trialign_last_cuda_error().decode()}")
+
+        e2e_s = R.time_host(e2e_step, max(1, min(steps, 3)), collective=False)
+        used = ta.last_devices()
+        ok = [int(hs.value)] + list(fin) == got
+        parity.append({"workload": name + " e2e", "against": "host-pointer trialign_score(devices mask) == device-resident run",
+                       "checked": 8, "ok": ok, "devices_used": used})
+        e2e = {"value": cells / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": 3 * length * used, "d2h_bytes_per_step": 32,
+               "call": f"trialign_score(devices=0x{mask:x}) from one process", "devices_used": used}
+    R.host_barrier()
+    if R.rank != 0:
+        return None
+    world = R.world if multi else 1
+    return {"workload": name, "baseline_config": cfg, "value": cells / (ms / 1e3) / 1e9, "unit": "GCUPS", "n_gpus": world,
+            "ms_per_step": ms, "steps": steps, "warmup": max(warmup, 3), "scaling": "strong" if multi else "n/a (one GPU)",
+            "length": length, "score_bits": w, "parallelism": mode, "kernel_path": path, "gpu_launches": launches,
+            "score": got[0], "final_states": got[1:8], "clocks": clocks, "e2e": e2e,
+            "roofline": roofline(name, cells / world / (ms / 1e3), clocks, world=world, slab=multi)}
+
+
+def run_ours(args, rank, world, local_rank):
+    import trialign_b200 as ta
+
+    ta.apply_option_args(args.opt)
+    R = Runner(rank, world, local_rank)
+    parity = []
+    gs = {e["config"]: e for e in golden_short() if not e.get("single")}
+
+    if args.workload != "batch64" or args.triples:
+        # development mode: one workload, no secondary block
+        cfg, n_full, length, w = WORKLOADS[args.workload]
+        if length > 256:
+            main = run_long(R, ta, args.workload, args.steps, args.warmup, parity, multi=world > 1)
+        else:
+            n = args.triples or n_full
+            main = run_batch(R, ta, args.workload, args.steps, args.warmup, n, rank * n, gs.get(cfg, {}).get("scores"), False, parity)
+        secondary = []
     else:
-        hout = torch.empty(n, dtype=torch.int32).pin_memory()
-
-        def e2e_step():
-            rc = L.trialign_score_batch(C.cast(ha.data_ptr(), u8p), C.cast(hb.data_ptr(), u8p), C.cast(hc.data_ptr(), u8p),
-                                        n, length, w, 0, 1 << local_rank, C.cast(hout.data_ptr(), i32p))
-            if rc:
-                raise RuntimeError(f"trialign_score_batch rc={rc}")
-        h2d, d2h = 3 * n * length, 4 * n
-
-    e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
-    if single and not slab and int(hs.value) != checksum:
-        raise RuntimeError("e2e score differs from the device-resident score")
-    if not single and int(hout.sum().item()) != checksum:
-        raise RuntimeError("e2e scores differ from the device-resident scores")
+        main = run_batch(R, ta, "batch64", args.steps, args.warmup, 1 << 20, rank * (1 << 20), gs[2]["scores"], world == 1, parity)
+        secondary = []
+        if not args.no_secondary:
+            ssteps = max(2, min(args.steps, 5))
+            if world == 1:
+                secondary.append(run_long(R, ta, "long1024", ssteps, 3, parity, multi=False))
+                secondary.append(run_batch(R, ta, "batch256", 2, 3, 1 << 18, 0, gs[4]["scores"], False, parity))
+                secondary.append(run_long(R, ta, "long8192", min(ssteps, 3), 3, parity, multi=False))
+            else:
+                n = (1 << 18) // world  # config 4 as written: 262,144 triples in total, contiguous split
+                secondary.append(run_batch(R, ta, "batch256", 2, 3, n, rank * n, gs[4]["scores"], False, parity, total_strong=True))
+                one = run_long(R, ta, "long8192", 2, 3, parity, multi=False)   # rank 0 alone: the efficiency's denominator
+                many = run_long(R, ta, "long8192", min(ssteps, 3), 3, parity, multi=True)
+                if rank == 0:
+                    many["one_gpu_value"] = one["value"]
+                    many["strong_scaling_efficiency"] = many["value"] / (world * one["value"])
+                    secondary.append(many)
 
     if rank == 0:
-        per_step_s = ms_max / 1e3 / args.steps
-        gcups = cells_step * world / per_step_s / 1e9
-        peak, peak_how = alu_peak()
-        achieved = cells_step / per_step_s * OPS_PER_CELL  # per GPU, the dominant (only) kernel of the step
+        scores_dev = main.pop("_scores_dev", None)
+        for s in secondary:
+            if s:
+                s.pop("_scores_dev", None)
         line = {
-            "metric": "3D-GCUPS", "value": gcups, "unit": "GCUPS", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": per_step_s * 1e3, "higher_is_better": True, "scaling": scaling,
-            "vs_baseline": None, "dtype": "u16x2 (packed 16-bit integer lanes)" if path.startswith("fast") else "int16/int32",
+            "metric": "3D-GCUPS", "value": main["value"], "unit": "GCUPS", "n_gpus": main.get("n_gpus", world), "steps": main["steps"],
+            "warmup": main["warmup"], "ms_per_step": main["ms_per_step"], "higher_is_better": True,
+            "scaling": main["scaling"] if main["scaling"] in ("weak", "strong") else "weak",
+            "vs_baseline": None, "dtype": "u16x2 (packed 16-bit integer lanes)" if str(main["kernel_path"]).startswith("fast") else "int16/int32",
             "data": "synthetic",
-            "config": {"workload": args.workload, "baseline_config": cfg, "triples_per_gpu": n, "length": length,
-                       "parallelism": (("column pipeline" if os.environ.get("TRIALIGN_MULTI", "slab") == "cols" else "i-slab pipeline") + " over %d GPUs, NVLink peer stores" % world) if slab else ("batch shard per GPU, no exchange" if world > 1 else "single GPU"),
-                       "score_bits": w, "kernel_path": path, "l2": "inputs (3 x n x len bytes) larger than L2" if 3 * n * length > 126e6 else "inputs smaller than L2; compute-bound kernel, no reuse across steps assumed",
-                       "reduced": reduced, "scores_checksum": checksum},
-            "gpu_launches": launches,
-            "e2e": {"value": cells_step * world / e2e_s / 1e9, "unit": "GCUPS", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h},
-            "roofline": {"bound": "int_alu", "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "Tlane-op/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_how,
-                         "algorithmic_ops_per_cell": OPS_PER_CELL,
-                         "note": "achieved counts the RTL's 91 lane-ops per cell; the factored kernel issues fewer (see DESIGN.md), so frac can exceed 1"},
-            "clocks": clocks,
+            "config": {"workload": main["workload"], "baseline_config": main["baseline_config"],
+                       "triples_per_gpu": main.get("triples_per_gpu", 1), "length": main["length"],
+                       "parallelism": main.get("parallelism") or ("batch shard per GPU, no exchange" if world > 1 else "single GPU"),
+                       "score_bits": main["score_bits"], "kernel_path": main["kernel_path"],
+                       "l2": ("inputs (3 x n x len bytes) larger than L2" if 3 * main.get("triples_per_gpu", 1) * main["length"] > 126e6
+                              else "inputs smaller than L2; compute-bound kernel, no reuse across steps assumed"),
+                       "reduced": bool(args.triples), "scores_checksum": main.get("scores_checksum", main.get("score")),
+                       "options": args.opt or []},
+            "gpu_launches": main["gpu_launches"], "e2e": main["e2e"], "roofline": main["roofline"], "clocks": main["clocks"],
         }
-        ks = kernel_stats(args.workload)
-        if ks:
-            # DRAM bytes of one launch from the ncu capture, scaled by the number of triples when the captured launch
-            # was a reduced batch (traffic is the input arrays + scores, linear in n)
-            scale = float(n) / ks["triples_in_capture"] if ks.get("triples_in_capture") else 1.0
-            if slab:
-                scale = 1.0 / world  # every GPU of the i-slab pipeline sweeps 1/world of the planes (faces per plane are fixed)
-            line["roofline"]["traffic"] = (ks["dram_bytes_read"] + ks["dram_bytes_write"]) * scale
-            line["roofline"]["issued"] = {k: ks[k] for k in ("alu_pipe_pct", "issue_slot_pct", "warp_instr_per_cell_pair",
-                                                              "alu_instr_per_cell_pair", "capture") if k in ks}
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline(length, w)
+        if world == 1 and not args.no_cpu and main["workload"] == "batch64":
+            base, oracle_scores = cpu_baseline(64, 12)
+            line["cpu_baseline"] = base
+            if oracle_scores is not None and scores_dev is not None and not args.triples:
+                k = len(oracle_scores)
+                got = scores_dev[:k].cpu().numpy()
+                ok = bool((got == oracle_scores).all())
+                parity.append({"workload": "batch64", "against": "oracle O1 scores of the cpu_baseline sample (same seed, triples 0..n-1)",
+                               "checked": int(k), "ok": ok})
+        line["secondary"] = [s for s in secondary if s]
+        line["parity"] = parity
+        line["parity_checked"] = int(sum(p["checked"] for p in parity))
+        line["parity_ok"] = all(p["ok"] for p in parity)
         print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    bad = R.sum_over_ranks(0 if (rank != 0 or all(p["ok"] for p in parity)) else 1)
+    if R.dist is not None:
+        R.dist.destroy_process_group()
+    if bad:
+        sys.exit(3)  # a score differs from the committed golden: the run is invalid
 
 
 def main():
@@ -385,6 +580,8 @@ def main():
     ap.add_argument("--workload", default="batch64", choices=sorted(WORKLOADS))
     ap.add_argument("--triples", type=int, default=0, help="override triples per GPU (development only; marks the line reduced)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary workloads")
+    ap.add_argument("--opt", action="append", help="library option name=value (trialign_set_option), development only")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -19,6 +19,10 @@ from .trialign import (  # noqa: F401
     build_library,
     device_count,
     format_alignment,
+    apply_option_args,
+    get_option,
+    last_devices,
+    set_option,
     last_path,
     last_timing,
     launch_count,

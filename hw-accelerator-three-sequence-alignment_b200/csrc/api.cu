@@ -4,8 +4,12 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <thread>
 #include <vector>
+
+#include <nvtx3/nvToolsExt.h>
 
 #include "kernels.cuh"
 
@@ -65,6 +69,54 @@ void Scratch::release()
     bytes = 0;
 }
 
+NvtxRange::NvtxRange(const char *name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
+
+// ---- run-time options (trialign_set_option) ----
+// Every experiment switch of the kernels is an explicit option of the library; nothing is read from the environment.
+static const char *const kOptionNames[] = {
+    "debug",       // 1: launch geometry of the fast kernels on stderr
+    "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l (default) | stream (K2S on len <= 64)
+    "k2",          // "sweep": first-generation per-block kernel for batches longer than 64 (A/B runs)
+    "k2l",         // "old": first-generation kernel for one long triple (A/B runs)
+    "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate",  // K2L experiment parameters (fast_long.cu)
+    "multi",       // one long triple on several GPUs: "slab" (i-slab pipeline, default) | "cols" (column pipeline)
+    "multi_min",   // smallest la (slab) / lc (cols) per GPU for which the multi-GPU pipeline is used (default 64 / 128)
+};
+static std::mutex g_opt_mu;
+static std::map<std::string, std::string> g_opts;
+
+static bool option_known(const char *name)
+{
+    for (const char *n : kOptionNames)
+        if (std::strcmp(n, name) == 0) return true;
+    return false;
+}
+
+int opt_int(const char *name, int dflt)
+{
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    auto it = g_opts.find(name);
+    if (it == g_opts.end() || it->second.empty()) return dflt;
+    char *end = nullptr;
+    const long v = std::strtol(it->second.c_str(), &end, 10);
+    return (end && *end == 0) ? (int)v : dflt;
+}
+
+bool opt_is(const char *name, const char *value)
+{
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    auto it = g_opts.find(name);
+    return it != g_opts.end() && it->second == value;
+}
+
+static std::string opt_str(const char *name)
+{
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    auto it = g_opts.find(name);
+    return it == g_opts.end() ? std::string() : it->second;
+}
+
 static DeviceCtx g_ctx[kMaxDevices];
 static std::mutex g_ctx_mu;
 
@@ -87,6 +139,7 @@ int get_ctx(int device, DeviceCtx **out)
         TA_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
         TA_CUDA(cudaEventCreate(&c.ev0));
         TA_CUDA(cudaEventCreate(&c.ev1));
+        TA_CUDA(cudaEventCreateWithFlags(&c.scratch_ev, cudaEventDisableTiming));
         TA_CUDA(cudaDeviceGetAttribute(&c.sm_count, cudaDevAttrMultiProcessorCount, device));
         c.ready = true;
     }
@@ -96,17 +149,11 @@ int get_ctx(int device, DeviceCtx **out)
 
 namespace {
 
-bool env_is(const char *name, const char *value)
-{
-    const char *e = std::getenv(name);
-    return e && std::strcmp(e, value) == 0;
-}
-
-// one long triple: K2L (fast_long.cu); TRIALIGN_K2L=old selects the first-generation kernel (fast_sweep.cu) for A/B runs
+// one long triple: K2L (fast_long.cu); option k2l=old selects the first-generation kernel (fast_sweep.cu) for A/B runs
 int long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
              int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol, const SlabLink *slab = nullptr)
 {
-    if (env_is("TRIALIGN_K2L", "old"))
+    if (opt_is("k2l", "old"))
         return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_score, d_states, check_bits, d_viol, slab);
     return fast_long2_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_score, d_states, check_bits, d_viol, slab);
 }
@@ -141,7 +188,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     const bool want_fast = backend != TRIALIGN_BACKEND_GPU_LITERAL;
     // fast paths are used only where they are provably bit-exact: no candidate can wrap at score_bits
     if (want_fast && provably_wrap_free(la, lb, lc, score_bits)) {
-        if (!d_finals && la == lb && lb == lc && la <= 64 && fast_stream_supports(la) && env_is("TRIALIGN_K1", "stream")) {
+        if (!d_finals && la == lb && lb == lc && la <= 64 && fast_stream_supports(la) && opt_is("k1", "stream")) {
             ts.last_path = TRIALIGN_PATH_FAST_STREAM;  // experiment: K2S on a single block per pair (len 61..64)
             return fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
         }
@@ -154,7 +201,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
             return long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, 0, nullptr);
         }
         if (!d_finals && la == lb && lb == lc && fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count) &&
-            !env_is("TRIALIGN_K2", "sweep")) {  // TRIALIGN_K2=sweep: the per-block kernel below, for A/B runs
+            !opt_is("k2", "sweep")) {  // option k2=sweep: the per-block kernel below, for A/B runs
             ts.last_path = TRIALIGN_PATH_FAST_STREAM;
             return fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
         }
@@ -201,6 +248,7 @@ int run_host_batch_on_device(int device, const uint8_t *a, const uint8_t *b, con
                              int lb, int lc, int score_bits, int backend, int32_t *scores, int32_t *finals,
                              double *seconds)
 {
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
@@ -214,22 +262,206 @@ int run_host_batch_on_device(int device, const uint8_t *a, const uint8_t *b, con
     uint8_t *d_a = (uint8_t *)ctx->seq.ptr, *d_b = d_a + up(na), *d_c = d_b + up(nb);
     int32_t *d_scores = (int32_t *)ctx->out.ptr;
     int32_t *d_finals = finals ? d_scores + n_pad : nullptr;
-    TA_CUDA(cudaMemcpyAsync(d_a, a, na, cudaMemcpyHostToDevice, st));
-    TA_CUDA(cudaMemcpyAsync(d_b, b, nb, cudaMemcpyHostToDevice, st));
-    TA_CUDA(cudaMemcpyAsync(d_c, c, nc, cudaMemcpyHostToDevice, st));
+    ScratchLease lease(ctx, st);
+    {
+        NvtxRange r("trialign:h2d");
+        TA_CUDA(cudaMemcpyAsync(d_a, a, na, cudaMemcpyHostToDevice, st));
+        TA_CUDA(cudaMemcpyAsync(d_b, b, nb, cudaMemcpyHostToDevice, st));
+        TA_CUDA(cudaMemcpyAsync(d_c, c, nc, cudaMemcpyHostToDevice, st));
+    }
     TA_CUDA(cudaEventRecord(ctx->ev0, st));
-    rc = dispatch_batch(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, backend, d_scores, d_finals);
+    {
+        NvtxRange r("trialign:kernels");
+        rc = dispatch_batch(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, backend, d_scores, d_finals);
+    }
     if (rc) {
         cudaStreamSynchronize(st);
         return rc;
     }
     TA_CUDA(cudaEventRecord(ctx->ev1, st));
-    TA_CUDA(cudaMemcpyAsync(scores, d_scores, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (finals) TA_CUDA(cudaMemcpyAsync(finals, d_finals, (size_t)n * 7 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    TA_CUDA(cudaStreamSynchronize(st));
+    {
+        NvtxRange r("trialign:d2h");
+        TA_CUDA(cudaMemcpyAsync(scores, d_scores, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        if (finals) TA_CUDA(cudaMemcpyAsync(finals, d_finals, (size_t)n * 7 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(cudaStreamSynchronize(st));
+    }
     float ms = 0.f;
     TA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     if (seconds) *seconds = (double)ms * 1e-3;
+    return TRIALIGN_OK;
+}
+
+std::vector<int> devices_of(unsigned mask)
+{
+    std::vector<int> devs;
+    for (int d = 0; d < kMaxDevices; ++d)
+        if (mask & (1u << d)) devs.push_back(d);
+    if (devs.empty()) devs.push_back(0);
+    return devs;
+}
+
+// Limits of one K2L launch over `planes` planes of a triple whose whole extent is (la_total, lb, lc): the launch keeps
+// its own planes' a symbols in shared memory, the 16-bit potential range depends on the whole triple.
+bool long_launch_supports(int planes, int la_total, int lb, int lc)
+{
+    return planes >= 1 && planes <= la_total && fast_sweep_supports(planes, lb, lc) &&
+           fast_long_range_ok(planes, la_total, lb, lc);
+}
+
+// ---- ONE long triple on several GPUs from ONE process (the drop-in form of SURVEY.md 8(e)(2)) ----
+// The calling thread drives every GPU of the mask: peer access g -> g+1, one stream per device, the hand-over buffers of
+// the i-slab pipeline (or the boundary faces of the column pipeline) live on the receiving GPU and are written by the
+// sending GPU's kernel through NVLink.  Kernels are launched upstream first; each spins only on flags its upstream
+// neighbour -- already launched -- raises, so the chain always drains.  All streams are synchronised before returning,
+// which is also what keeps a run from overwriting hand-over slots its predecessor's consumers have not read.
+struct MultiPipe {
+    std::vector<int> devs;
+    std::vector<void *> state, flags;   // [g] buffers on device g (g >= 1), written by g-1
+    std::vector<size_t> state_bytes, flag_bytes;
+    int epoch = 0;
+    bool peers_ready = false;
+};
+std::mutex g_multi_mu;
+std::map<unsigned, std::unique_ptr<MultiPipe>> g_multi;
+
+int multi_reserve(MultiPipe &mp, size_t g, size_t sbytes, size_t fbytes)
+{
+    if (mp.state_bytes[g] >= sbytes && mp.flag_bytes[g] >= fbytes) return TRIALIGN_OK;
+    TA_CUDA(cudaSetDevice(mp.devs[g]));
+    TA_CUDA(cudaDeviceSynchronize());
+    if (mp.state[g]) cudaFree(mp.state[g]);
+    if (mp.flags[g]) cudaFree(mp.flags[g]);
+    mp.state[g] = mp.flags[g] = nullptr;
+    mp.state_bytes[g] = mp.flag_bytes[g] = 0;
+    TA_CUDA(cudaMalloc(&mp.state[g], sbytes));
+    TA_CUDA(cudaMalloc(&mp.flags[g], fbytes));
+    TA_CUDA(cudaMemset(mp.flags[g], 0, fbytes));
+    mp.state_bytes[g] = sbytes;
+    mp.flag_bytes[g] = fbytes;
+    return TRIALIGN_OK;
+}
+
+int run_host_triple_multi(const std::vector<int> &devs, unsigned mask, bool cols, const uint8_t *a, int la,
+                          const uint8_t *b, int lb, const uint8_t *c, int lc, int32_t *score, int32_t fin[7],
+                          double *seconds)
+{
+    DeviceGuard guard;
+    const size_t G = devs.size();
+    std::lock_guard<std::mutex> mlk(g_multi_mu);
+    std::unique_ptr<MultiPipe> &slot = g_multi[mask | (cols ? 0x80000000u : 0u)];
+    if (!slot) {
+        slot.reset(new MultiPipe);
+        slot->devs = devs;
+        slot->state.assign(G, nullptr);
+        slot->flags.assign(G, nullptr);
+        slot->state_bytes.assign(G, 0);
+        slot->flag_bytes.assign(G, 0);
+    }
+    MultiPipe &mp = *slot;
+    std::vector<DeviceCtx *> ctx(G, nullptr);
+    int rc;
+    for (size_t g = 0; g < G; ++g)
+        if ((rc = get_ctx(devs[g], &ctx[g]))) return rc;
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (size_t g = 0; g < G; ++g) locks.emplace_back(ctx[g]->mu);  // ascending device order: no lock cycle
+    if (!mp.peers_ready) {
+        for (size_t g = 0; g + 1 < G; ++g) {
+            int ok = 0;
+            TA_CUDA(cudaDeviceCanAccessPeer(&ok, devs[g], devs[g + 1]));
+            if (!ok) return TRIALIGN_EUNSUPPORTED;
+            TA_CUDA(cudaSetDevice(devs[g]));
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devs[g + 1], 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+        }
+        mp.peers_ready = true;
+    }
+    size_t sbytes, fbytes;
+    if (cols) {
+        sbytes = fast_long2_col_face_bytes(la, lb);
+        fbytes = std::max<size_t>(fast_long2_col_prog_bytes(lb), 256);
+    } else {
+        sbytes = fast_sweep_slab_state_bytes(lb, lc);
+        fbytes = fast_sweep_slab_flag_bytes(lb, lc);
+    }
+    for (size_t g = 1; g < G; ++g)
+        if ((rc = multi_reserve(mp, g, sbytes, fbytes))) return rc;
+    mp.epoch = mp.epoch % 2047 + 1;  // 1..2047: the column pipeline tags its progress words with 11 bits
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const int pairs = (lc + 127) / 128;
+    std::vector<int32_t *> d_out(G, nullptr);
+    for (size_t g = 0; g < G; ++g) {
+        TA_CUDA(cudaSetDevice(devs[g]));
+        cudaStream_t st = ctx[g]->stream;
+        if ((rc = ctx[g]->seq.reserve(up(la) + up(lb) + up(lc) + 256))) return rc;
+        if ((rc = ctx[g]->out.reserve(256))) return rc;
+        uint8_t *d_a = (uint8_t *)ctx[g]->seq.ptr, *d_b = d_a + up(la), *d_c = d_b + up(lb);
+        d_out[g] = (int32_t *)ctx[g]->out.ptr;
+        ScratchLease lease(ctx[g], st);
+        {
+            NvtxRange r("trialign:h2d");
+            TA_CUDA(cudaMemcpyAsync(d_a, a, la, cudaMemcpyHostToDevice, st));
+            TA_CUDA(cudaMemcpyAsync(d_b, b, lb, cudaMemcpyHostToDevice, st));
+            TA_CUDA(cudaMemcpyAsync(d_c, c, lc, cudaMemcpyHostToDevice, st));
+        }
+        TA_CUDA(cudaEventRecord(ctx[g]->ev0, st));
+        NvtxRange r("trialign:kernels");
+        const bool last = g + 1 == G;
+        if (cols) {
+            const int c0 = 128 * (int)((size_t)pairs * g / G), c1 = last ? lc : 128 * (int)((size_t)pairs * (g + 1) / G);
+            ColLink link;
+            link.lc_total = lc;
+            link.last = last;
+            link.epoch = mp.epoch;
+            link.in_face = g ? mp.state[g] : nullptr;
+            link.in_prog = g ? mp.flags[g] : nullptr;
+            link.out_face = last ? nullptr : mp.state[g + 1];
+            link.out_prog = last ? nullptr : mp.flags[g + 1];
+            rc = fast_long2_run(ctx[g], st, d_a, la, d_b, lb, d_c + c0, c1 - c0, d_out[g], d_out[g] + 1, 0, nullptr,
+                                nullptr, &link);
+        } else {
+            const int i0 = (int)((long long)la * g / G), i1 = (int)((long long)la * (g + 1) / G);
+            SlabLink link;
+            link.la_total = la;
+            link.last = last;
+            link.epoch = mp.epoch;
+            link.in_state = g ? mp.state[g] : nullptr;
+            link.in_flags = g ? mp.flags[g] : nullptr;
+            link.out_state = last ? nullptr : mp.state[g + 1];
+            link.out_flags = last ? nullptr : mp.flags[g + 1];
+            rc = fast_long2_run(ctx[g], st, d_a + i0, i1 - i0, d_b, lb, d_c, lc, d_out[g], d_out[g] + 1, 0, nullptr,
+                                &link);
+        }
+        if (rc) break;
+        TA_CUDA(cudaEventRecord(ctx[g]->ev1, st));
+    }
+    if (rc) {  // drain whatever was launched (upstream kernels finish on their own)
+        for (size_t g = 0; g < G; ++g) {
+            cudaSetDevice(devs[g]);
+            cudaStreamSynchronize(ctx[g]->stream);
+        }
+        return rc;
+    }
+    int32_t res[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    {
+        NvtxRange r("trialign:d2h");
+        TA_CUDA(cudaSetDevice(devs[G - 1]));
+        TA_CUDA(cudaMemcpyAsync(res, d_out[G - 1], sizeof res, cudaMemcpyDeviceToHost, ctx[G - 1]->stream));
+        for (size_t g = 0; g < G; ++g) {
+            TA_CUDA(cudaSetDevice(devs[g]));
+            TA_CUDA(cudaStreamSynchronize(ctx[g]->stream));
+        }
+    }
+    double worst = 0.0;
+    for (size_t g = 0; g < G; ++g) {
+        float ms = 0.f;
+        TA_CUDA(cudaSetDevice(devs[g]));
+        TA_CUDA(cudaEventElapsedTime(&ms, ctx[g]->ev0, ctx[g]->ev1));
+        worst = std::max(worst, (double)ms * 1e-3);
+    }
+    *score = res[0];
+    std::memcpy(fin, res + 1, 7 * sizeof(int32_t));
+    if (seconds) *seconds = worst;
     return TRIALIGN_OK;
 }
 
@@ -251,7 +483,7 @@ const char *trialign_strerror(int rc)
     case TRIALIGN_ECUDA: return "CUDA error (see trialign_last_cuda_error)";
     case TRIALIGN_EIO: return "file I/O error";
     case TRIALIGN_EPARSE: return "malformed input file";
-    case TRIALIGN_EUNSUPPORTED: return "backend not part of libtrialign (CPU checkers live under oracle/)";
+    case TRIALIGN_EUNSUPPORTED: return "not supported: a backend outside libtrialign (CPU checkers live under oracle/), or a size beyond a kernel's limits";
     case TRIALIGN_ENODEVICE: return "no usable CUDA device";
     case TRIALIGN_ECAPACITY: return "output buffer too small";
     case TRIALIGN_EINEXACT: return "fast kernels cannot be proven bit-exact for this input";
@@ -271,6 +503,24 @@ int trialign_device_count(void)
     return count < 0 ? 0 : count;
 }
 
+int trialign_set_option(const char *name, const char *value)
+{
+    if (!name || !option_known(name)) return TRIALIGN_EINVAL;
+    std::lock_guard<std::mutex> lk(g_opt_mu);
+    if (!value || !value[0]) g_opts.erase(name);
+    else g_opts[name] = value;
+    return TRIALIGN_OK;
+}
+
+int trialign_get_option(const char *name, char *buf, int cap)
+{
+    if (!name || !option_known(name) || !buf || cap < 1) return TRIALIGN_EINVAL;
+    const std::string v = opt_str(name);
+    if ((int)v.size() + 1 > cap) return TRIALIGN_ECAPACITY;
+    std::memcpy(buf, v.c_str(), v.size() + 1);
+    return TRIALIGN_OK;
+}
+
 int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c, int64_t n,
                              int len, int score_bits, int backend, int32_t *d_scores, void *stream)
 {
@@ -283,7 +533,9 @@ int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b,
     ts.last_seconds = -1.0;
     ts.last_cells = (double)n * len * len * len;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_devices = 1;
     if (n == 0) return TRIALIGN_OK;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     if ((rc = get_ctx(device, &ctx))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -292,6 +544,7 @@ int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b,
         return TRIALIGN_OK;
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ScratchLease lease(ctx, st);
     return dispatch_batch(ctx, st, d_a, d_b, d_c, n, len, len, len, score_bits, backend, d_scores, nullptr);
 }
 
@@ -306,6 +559,8 @@ int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_
     ts.last_seconds = -1.0;
     ts.last_cells = (double)la * lb * lc;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_devices = 1;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     if ((rc = get_ctx(device, &ctx))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -314,6 +569,7 @@ int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_
         return TRIALIGN_OK;
     }
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ScratchLease lease(ctx, st);
     return dispatch_batch(ctx, st, d_a, d_b, d_c, 1, la, lb, lc, score_bits, backend, d_out, d_out + 1);
 }
 
@@ -337,8 +593,34 @@ int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     }
     int32_t fin[7];
     double sec = -1.0;
-    rc = run_host_batch_on_device(first_device(devices), a, b, c, 1, la, lb, lc, score_bits, backend, score, fin,
-                                  &sec);
+    const std::vector<int> devs = devices_of(devices);
+    const int have = trialign_device_count();
+    for (int d : devs)
+        if (d >= have) return TRIALIGN_EINVAL;
+    ts.last_devices = 1;
+    // several GPUs in the mask: the triple is split as an i-slab (or column) pipeline when it is long enough for every
+    // GPU to get whole blocks and the fast kernels are provably bit-exact for it; otherwise the first GPU serves it alone
+    // (trialign_last_devices() tells which happened)
+    if (devs.size() > 1 && backend != TRIALIGN_BACKEND_GPU_LITERAL && !ts.scoring_active &&
+        provably_wrap_free(la, lb, lc, score_bits)) {
+        const int G = (int)devs.size();
+        const bool cols = opt_is("multi", "cols");
+        bool ok;
+        if (cols) ok = lc >= opt_int("multi_min", 128) * G && lc >= 128 * G && long_launch_supports(la, la, lb, lc);
+        else ok = la >= opt_int("multi_min", 64) * G && la >= G && long_launch_supports((la + G - 1) / G, la, lb, lc);
+        if (ok) {
+            rc = run_host_triple_multi(devs, devices, cols, a, la, b, lb, c, lc, score, fin, &sec);
+            if (rc != TRIALIGN_EUNSUPPORTED) {  // EUNSUPPORTED: no peer access between neighbours -> one GPU below
+                if (rc) return rc;
+                if (final_states) std::memcpy(final_states, fin, sizeof fin);
+                ts.last_seconds = sec;
+                ts.last_path = TRIALIGN_PATH_FAST_LONG;
+                ts.last_devices = G;
+                return TRIALIGN_OK;
+            }
+        }
+    }
+    rc = run_host_batch_on_device(devs[0], a, b, c, 1, la, lb, lc, score_bits, backend, score, fin, &sec);
     if (rc) return rc;
     if (final_states) std::memcpy(final_states, fin, sizeof fin);
     ts.last_seconds = sec;
@@ -346,6 +628,50 @@ int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
 }
 
 int64_t trialign_triple_count(int nseq) { return nseq < 3 ? 0 : (int64_t)all_triples_count(nseq); }
+
+namespace {
+// triples [t_begin, t_end) of the set on one device: upload the set once, gather chunk by chunk, score, copy back
+int all_triples_on_device(int device, const uint8_t *seqs, int nseq, int len, int score_bits, int backend,
+                          int64_t t_begin, int64_t t_end, int32_t *scores, double *seconds)
+{
+    DeviceGuard guard;
+    DeviceCtx *ctx = nullptr;
+    int rc;
+    if ((rc = get_ctx(device, &ctx))) return rc;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaStream_t st = ctx->stream;
+    const int64_t total = t_end - t_begin;
+    // chunks of at most 2^20 triples bound the staging arrays (3 x chunk x len bytes) whatever nseq is
+    const int64_t chunk = total < (1 << 20) ? total : (1 << 20);
+    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+    const size_t set_bytes = up((size_t)nseq * len), arr = up((size_t)chunk * len);
+    if ((rc = ctx->seq.reserve(set_bytes + 3 * arr + 256))) return rc;
+    if ((rc = ctx->out.reserve((size_t)chunk * sizeof(int32_t)))) return rc;
+    uint8_t *d_set = (uint8_t *)ctx->seq.ptr, *d_a = d_set + set_bytes, *d_b = d_a + arr, *d_c = d_b + arr;
+    int32_t *d_scores = (int32_t *)ctx->out.ptr;
+    ScratchLease lease(ctx, st);
+    {
+        NvtxRange r("trialign:h2d");
+        TA_CUDA(cudaMemcpyAsync(d_set, seqs, (size_t)nseq * len, cudaMemcpyHostToDevice, st));
+    }
+    TA_CUDA(cudaEventRecord(ctx->ev0, st));
+    for (int64_t t0 = t_begin; t0 < t_end; t0 += chunk) {
+        const int64_t cnt = t_end - t0 < chunk ? t_end - t0 : chunk;
+        if ((rc = all_triples_gather(st, d_set, nseq, len, t0, cnt, d_a, d_b, d_c)) ||
+            (rc = dispatch_batch(ctx, st, d_a, d_b, d_c, cnt, len, len, len, score_bits, backend, d_scores, nullptr))) {
+            cudaStreamSynchronize(st);
+            return rc;
+        }
+        TA_CUDA(cudaMemcpyAsync(scores + t0, d_scores, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    }
+    TA_CUDA(cudaEventRecord(ctx->ev1, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    TA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    if (seconds) *seconds = (double)ms * 1e-3;
+    return TRIALIGN_OK;
+}
+}  // namespace
 
 int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score_bits, int backend, unsigned devices,
                                int32_t *scores)
@@ -359,41 +685,51 @@ int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score
     ts.last_seconds = -1.0;
     ts.last_cells = (double)total * len * len * len;
     ts.last_path = TRIALIGN_PATH_NONE;
-    if (trialign_device_count() == 0) return TRIALIGN_ENODEVICE;
+    ts.last_devices = 1;
+    const int have = trialign_device_count();
+    if (have == 0) return TRIALIGN_ENODEVICE;
     if (total == 0) return TRIALIGN_OK;
     if (len == 0) {
         std::memset(scores, 0, (size_t)total * sizeof(int32_t));
         ts.last_seconds = 0.0;
         return TRIALIGN_OK;
     }
-    DeviceCtx *ctx = nullptr;
-    if ((rc = get_ctx(first_device(devices), &ctx))) return rc;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    cudaStream_t st = ctx->stream;
-    // chunks of at most 2^20 triples bound the staging arrays (3 x chunk x len bytes) whatever nseq is
-    const int64_t chunk = total < (1 << 20) ? total : (1 << 20);
-    auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    const size_t set_bytes = up((size_t)nseq * len), arr = up((size_t)chunk * len);
-    if ((rc = ctx->seq.reserve(set_bytes + 3 * arr + 256))) return rc;
-    if ((rc = ctx->out.reserve((size_t)chunk * sizeof(int32_t)))) return rc;
-    uint8_t *d_set = (uint8_t *)ctx->seq.ptr, *d_a = d_set + set_bytes, *d_b = d_a + arr, *d_c = d_b + arr;
-    int32_t *d_scores = (int32_t *)ctx->out.ptr;
-    TA_CUDA(cudaMemcpyAsync(d_set, seqs, (size_t)nseq * len, cudaMemcpyHostToDevice, st));
-    TA_CUDA(cudaEventRecord(ctx->ev0, st));
-    for (int64_t t0 = 0; t0 < total; t0 += chunk) {
-        const int64_t cnt = total - t0 < chunk ? total - t0 : chunk;
-        if ((rc = all_triples_gather(st, d_set, nseq, len, t0, cnt, d_a, d_b, d_c)) ||
-            (rc = dispatch_batch(ctx, st, d_a, d_b, d_c, cnt, len, len, len, score_bits, backend, d_scores, nullptr))) {
-            cudaStreamSynchronize(st);
-            return rc;
-        }
-        TA_CUDA(cudaMemcpyAsync(scores + t0, d_scores, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    std::vector<int> devs = devices_of(devices);
+    for (int d : devs)
+        if (d >= have) return TRIALIGN_EINVAL;
+    if ((int64_t)devs.size() > total) devs.resize((size_t)total);
+    if (devs.size() == 1) {
+        double sec = -1.0;
+        rc = all_triples_on_device(devs[0], seqs, nseq, len, score_bits, backend, 0, total, scores, &sec);
+        ts.last_seconds = sec;
+        return rc;
     }
-    TA_CUDA(cudaEventRecord(ctx->ev1, st));
-    TA_CUDA(cudaStreamSynchronize(st));
-    float ms = 0.f;
-    TA_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ts.last_seconds = (double)ms * 1e-3;
+    // contiguous ranges of the triple list, one host thread per device, no exchange
+    const size_t G = devs.size();
+    std::vector<int> rcs(G, 0), paths(G, 0);
+    std::vector<double> secs(G, -1.0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    for (size_t g = 0; g < G; ++g) {
+        const int64_t t0 = total * (int64_t)g / (int64_t)G, t1 = total * (int64_t)(g + 1) / (int64_t)G;
+        th.emplace_back([&, g, t0, t1]() {
+            rcs[g] = all_triples_on_device(devs[g], seqs, nseq, len, score_bits, backend, t0, t1, scores, &secs[g]);
+            paths[g] = tls().last_path;
+            errs[g] = tls().cuda_error;
+        });
+    }
+    for (auto &t : th) t.join();
+    double worst = 0.0;
+    for (size_t g = 0; g < G; ++g) {
+        if (rcs[g]) {
+            ts.cuda_error = errs[g];
+            return rcs[g];
+        }
+        worst = std::max(worst, secs[g]);
+        if (paths[g] > ts.last_path) ts.last_path = paths[g];
+    }
+    ts.last_seconds = worst;
+    ts.last_devices = (int)G;
     return TRIALIGN_OK;
 }
 
@@ -414,11 +750,16 @@ int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
         ts.last_seconds = 0.0;
         return TRIALIGN_OK;
     }
+    // the traceback runs on ONE GPU, the first of the mask (the direction cube is not partitioned)
+    if (first_device(devices) >= trialign_device_count()) return TRIALIGN_EINVAL;
+    ts.last_devices = 1;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(first_device(devices), &ctx);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaStream_t st = ctx->stream;
+    ScratchLease lease(ctx, st);
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const size_t total = (size_t)la + lb + lc;
     if ((rc = ctx->seq.reserve(up(la) + up(lb) + up(lc) + 256))) return rc;
@@ -471,12 +812,11 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
         ts.last_seconds = 0.0;
         return TRIALIGN_OK;
     }
-    std::vector<int> devs;
-    for (int d = 0; d < kMaxDevices; ++d)
-        if (devices & (1u << d)) devs.push_back(d);
-    if (devs.empty()) devs.push_back(0);
+    std::vector<int> devs = devices_of(devices);
     for (int d : devs)
         if (d >= have) return TRIALIGN_EINVAL;
+    if ((int64_t)devs.size() > n) devs.resize((size_t)n);
+    ts.last_devices = (int)devs.size();
     if (devs.size() == 1) {
         double sec = -1.0;
         rc = run_host_batch_on_device(devs[0], a, b, c, n, len, len, len, score_bits, backend, scores, nullptr, &sec);
@@ -592,15 +932,22 @@ int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_
     if ((i_begin > 0) != (in_state != nullptr) || (in_state != nullptr) != (in_flags != nullptr)) return TRIALIGN_EINVAL;
     if ((i_end < la) != (out_state != nullptr) || (out_state != nullptr) != (out_flags != nullptr)) return TRIALIGN_EINVAL;
     if (i_end == la && !d_out) return TRIALIGN_EINVAL;
+    if (epoch < 1) return TRIALIGN_EINVAL;  // 0 is what freshly allocated flags hold
     ThreadState &ts = tls();
     ts.last_seconds = -1.0;
     ts.last_cells = (double)(i_end - i_begin) * lb * lc;
     ts.last_path = TRIALIGN_PATH_NONE;
-    if (!provably_wrap_free(la, lb, lc, score_bits) || !fast_sweep_supports(la, lb, lc)) return TRIALIGN_EINEXACT;
+    ts.last_devices = 1;
+    if (!provably_wrap_free(la, lb, lc, score_bits)) return TRIALIGN_EINEXACT;
+    // size limits apply to the slab's own planes (their a symbols live in shared memory) and to the 16-bit range of the
+    // whole triple -- not to la, so the pipeline takes triples longer than one launch could
+    if (!long_launch_supports(i_end - i_begin, la, lb, lc)) return TRIALIGN_EUNSUPPORTED;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ScratchLease lease(ctx, (cudaStream_t)stream);
     SlabLink link;
     link.la_total = la;
     link.last = (i_end == la);
@@ -637,11 +984,15 @@ int trialign_cols_score_dev(int device, const uint8_t *d_a, int la, const uint8_
     ts.last_seconds = -1.0;
     ts.last_cells = (double)la * lb * (c_end - c_begin);
     ts.last_path = TRIALIGN_PATH_NONE;
-    if (!provably_wrap_free(la, lb, lc, score_bits) || !fast_sweep_supports(la, lb, lc)) return TRIALIGN_EINEXACT;
+    ts.last_devices = 1;
+    if (!provably_wrap_free(la, lb, lc, score_bits)) return TRIALIGN_EINEXACT;
+    if (!long_launch_supports(la, la, lb, lc)) return TRIALIGN_EUNSUPPORTED;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
     std::lock_guard<std::mutex> lk(ctx->mu);
+    ScratchLease lease(ctx, (cudaStream_t)stream);
     ColLink link;
     link.lc_total = lc;
     link.last = (c_end == lc);
@@ -658,6 +1009,7 @@ int trialign_cols_score_dev(int device, const uint8_t *d_a, int la, const uint8_
 int trialign_device_alloc(int device, int64_t bytes, void **dptr)
 {
     if (bytes <= 0 || !dptr) return TRIALIGN_EINVAL;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
@@ -669,6 +1021,7 @@ int trialign_device_alloc(int device, int64_t bytes, void **dptr)
 int trialign_device_free(int device, void *dptr)
 {
     if (!dptr) return TRIALIGN_EINVAL;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
@@ -689,6 +1042,7 @@ int trialign_ipc_export(const void *dptr, unsigned char handle[64])
 int trialign_ipc_open(int device, const unsigned char handle[64], void **dptr)
 {
     if (!handle || !dptr) return TRIALIGN_EINVAL;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
@@ -711,6 +1065,7 @@ int trialign_synth_batch_dev(int device, uint64_t seed, int64_t first, int64_t n
     if (n < 0 || len < 0 || first < 0) return TRIALIGN_EINVAL;
     if (n == 0 || len == 0) return TRIALIGN_OK;
     if (!d_a || !d_b || !d_c) return TRIALIGN_EINVAL;
+    DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
     int rc = get_ctx(device, &ctx);
     if (rc) return rc;
@@ -726,6 +1081,8 @@ int trialign_last_timing(double *seconds, double *cells)
 }
 
 int trialign_last_path(void) { return tls().last_path; }
+
+int trialign_last_devices(void) { return tls().last_devices; }
 
 int64_t trialign_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -19,6 +19,7 @@ struct ThreadState {
     double last_seconds = -1.0;
     double last_cells = 0.0;
     int last_path = TRIALIGN_PATH_NONE;
+    int last_devices = 0;         // GPUs that served the last compute call of this thread
     bool scoring_active = false;  // a *_ex entry point with non-RTL scoring is in progress on this thread
     trialign_scoring scoring{};
 };
@@ -31,6 +32,29 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
         cudaError_t e__ = (expr);                                                \
         if (e__ != cudaSuccess) return ::trialign::cuda_fail(e__, #expr, __FILE__, __LINE__); \
     } while (0)
+
+// ---- run-time options (trialign_set_option): experiment switches live here, never in the environment ----
+// Known names: see kOptionNames in api.cu.  opt_int() returns dflt when the option is unset or not a number.
+int opt_int(const char *name, int dflt);
+bool opt_is(const char *name, const char *value);
+inline bool opt_debug() { return opt_int("debug", 0) != 0; }
+
+// ---- keeps the calling thread's current CUDA device unchanged across an entry point ----
+struct DeviceGuard {
+    int saved = -1;
+    DeviceGuard() { if (cudaGetDevice(&saved) != cudaSuccess) { cudaGetLastError(); saved = -1; } }
+    ~DeviceGuard() { if (saved >= 0) cudaSetDevice(saved); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+
+// ---- NVTX ranges around the phases of the host-pointer entry points (H2D / kernels / D2H) ----
+struct NvtxRange {
+    explicit NvtxRange(const char *name);
+    ~NvtxRange();
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 extern std::atomic<int64_t> g_launches;
 inline void count_launch(int64_t k = 1) { g_launches.fetch_add(k, std::memory_order_relaxed); }
@@ -54,10 +78,35 @@ struct DeviceCtx {
     Scratch seq, out, planes, faces, misc;
     Scratch dirs;        // direction cube of the traceback path
     Scratch viol;        // range-check flag of the checked fast path (never reallocated by the kernels)
+    Scratch flagged;     // per-triple range-check flags + compaction buffers of the checked batch path
+    // Stream ordering of the shared scratch buffers: every enqueue that touches them records scratch_ev on its stream;
+    // a later enqueue on ANOTHER stream first waits for that event (ScratchLease), so two calls in flight on different
+    // streams never run kernels against the same faces / planes / progress words.  Guarded by mu.
+    cudaEvent_t scratch_ev = nullptr;
+    cudaStream_t scratch_stream = nullptr;
+    bool scratch_used = false;
+};
+
+// Taken (with ctx->mu held) around every enqueue that uses the context's scratch buffers.
+struct ScratchLease {
+    DeviceCtx *ctx;
+    cudaStream_t st;
+    ScratchLease(DeviceCtx *c, cudaStream_t s) : ctx(c), st(s)
+    {
+        if (ctx->scratch_used && ctx->scratch_stream != st) cudaStreamWaitEvent(st, ctx->scratch_ev, 0);
+    }
+    ~ScratchLease()
+    {
+        cudaEventRecord(ctx->scratch_ev, st);
+        ctx->scratch_stream = st;
+        ctx->scratch_used = true;
+    }
+    ScratchLease(const ScratchLease &) = delete;
+    ScratchLease &operator=(const ScratchLease &) = delete;
 };
 
 constexpr int kMaxDevices = 32;
-int get_ctx(int device, DeviceCtx **ctx);  // sets the current device, creates stream/events on first use
+int get_ctx(int device, DeviceCtx **ctx);  // sets the current device (callers hold a DeviceGuard), creates stream/events on first use
 
 // wrap-free envelope of the recurrence: with zero borders every state of cell (i,j,k)
 // lies in [-(2*m+5), 3*m] with m = min(i,j,k) (at most m three-way matches; gap chains from the zero border lose

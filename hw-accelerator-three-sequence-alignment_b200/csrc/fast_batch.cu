@@ -1,5 +1,6 @@
 // fast_batch.cu -- K1 launcher: CTA-wide systolic kernel for batches of short triples (see fast_batch.cuh).
 #include <cstdlib>
+#include <cstring>
 
 #include "fast_batch.cuh"
 #include "kernels.cuh"
@@ -135,7 +136,7 @@ int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant
     if (ppc > (1 << 20)) ppc = 1 << 20;  // keep the step counter far from int overflow
     A.pairs_per_cta = (int)ppc;
     const long long grid = (A.pairs_total + ppc - 1) / ppc;
-    if (std::getenv("TRIALIGN_DEBUG"))
+    if (opt_debug())
         std::fprintf(stderr, "[trialign] K1: variant=%d threads=%d grid=%lld pairs/cta=%lld smem=%zu\n", variant, Cfg::NT,
                      grid, ppc, smem);
     kernel<<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
@@ -150,17 +151,18 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
                    int64_t n, int len, int32_t *d_scores)
 {
     if (n <= 0) return TRIALIGN_OK;
-    // TRIALIGN_K1 selects a variant for comparison: "256" / "512" threads per CTA; suffix "m" = split-phase mbarrier
-    // instead of __syncthreads, suffix "l" = lagged barrier (LAG 2), e.g. TRIALIGN_K1=512m.
-    static const int variant = []() {
-        const char *e = std::getenv("TRIALIGN_K1");
-        if (!e || !e[0]) return 4;  // default: 256 threads, lagged barrier (measured fastest)
-        int v = 0;
-        if (e[0] == '5') v = 2;
-        if (e[1] && e[2] && e[3] == 'm') v |= 1;
-        if (e[1] && e[2] && e[3] == 'l') v |= 4;
-        return v;
-    }();
+    // option k1 selects a variant for comparison: "256" / "512" threads per CTA; suffix "m" = split-phase mbarrier
+    // instead of __syncthreads, suffix "l" = lagged barrier (LAG 2), e.g. k1=512m.  Default: 256l (measured fastest).
+    int variant = 4;
+    {
+        char e[8] = {0};
+        if (trialign_get_option("k1", e, sizeof e) == TRIALIGN_OK && e[0] && std::strcmp(e, "stream") != 0) {
+            variant = 0;
+            if (e[0] == '5') variant = 2;
+            if (e[1] && e[2] && e[3] == 'm') variant |= 1;
+            if (e[1] && e[2] && e[3] == 'l') variant |= 4;
+        }
+    }
     fast::BatchArgs A;
     A.a = d_a; A.b = d_b; A.c = d_c;
     A.n = n; A.len = len; A.scores = d_scores;

@@ -312,7 +312,7 @@ int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, in
     TA_CUDA(cudaMemcpyAsync(d_order, order.data(), order.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     TA_CUDA(cudaMemcpyAsync(d_pos, pos_of.data(), pos_of.size() * sizeof(int), cudaMemcpyHostToDevice, st));
     TA_CUDA(cudaMemsetAsync(ctx->misc.ptr, 0, ctl_bytes, st));
-    if (std::getenv("TRIALIGN_DEBUG"))
+    if (opt_debug())
         std::fprintf(stderr, "[trialign] K2L: la=%d lag=%d gate=%d blocks %dx%d(pairs) tasks=%lld grid=%d faces=%.1f MB smem=%zu base=%d\n",
                      la, LAG, A.gate, A.nbj, A.nbkp, A.tasks_total, grid, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
     if (cols) long2_kernel<1, false, true><<<grid, C::NT, smem, st>>>(A);
@@ -355,20 +355,18 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
     // LAG 1 (split-phase barrier, hop 17 / 33 steps between dependent tasks) is the default: measured faster than the
     // lagged barrier (LAG 2) at L = 1,024 (416 vs 325 GCUPS, the sweep is dominated by the block-to-block pipeline
     // fill) and at L = 8,192 (943 vs 860).  Long sweeps release their progress less often (a release is a MEMBAR.GPU).
-    // TRIALIGN_K2_LAG / TRIALIGN_K2_GATE override for experiments.
+    // Options k2_lag / k2_gate (trialign_set_option) override for experiments.
     int lag = 1;
     A.gate = la >= 4096 ? 16 : 4;
-    if (const char *e = std::getenv("TRIALIGN_K2_LAG")) {
-        const int v = std::atoi(e);
+    {
+        const int v = opt_int("k2_lag", 0);
         if (v == 1 || v == 2) lag = v;
     }
-    A.gate_tid = 128;
-    A.pingpong = 0;
-    if (const char *e = std::getenv("TRIALIGN_K2_PP")) A.pingpong = std::atoi(e) ? 1 : 0;
-    if (const char *e = std::getenv("TRIALIGN_K2_GATETID")) A.gate_tid = std::atoi(e) & 255;
-    if (const char *e = std::getenv("TRIALIGN_K2_EARLY")) A.early = std::atoi(e) ? 1 : 0;
-    if (const char *e = std::getenv("TRIALIGN_K2_GATE")) {
-        const int g = std::atoi(e);
+    A.gate_tid = opt_int("k2_gatetid", 128) & 255;
+    A.pingpong = opt_int("k2_pp", 0) ? 1 : 0;
+    A.early = opt_int("k2_early", 0) ? 1 : 0;
+    {
+        const int g = opt_int("k2_gate", 0);
         if (g >= 1 && g <= 64 && (g & (g - 1)) == 0) A.gate = g;
     }
     A.out = d_score;

@@ -156,7 +156,7 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
     A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
     const long long m = len;
     A.base = (int)(-envelope_lo(m) + 32);
-    if (std::getenv("TRIALIGN_DEBUG"))
+    if (opt_debug())
         std::fprintf(stderr, "[trialign] K2S stream: len=%d blocks %dx%d grid=%lld pairs/cta=%lld faces=%.1f MB smem=%zu base=%d\n",
                      len, A.nbj, A.nbk, grid, ppc, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
     fast_stream_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);

@@ -214,13 +214,19 @@ size_t fast_sweep_slab_flag_bytes(int lb, int lc)
     return (size_t)tasks * sizeof(int);
 }
 
+bool fast_long_range_ok(int planes, int la_total, int lb, int lc)
+{
+    if (planes < 1 || la_total < planes || lb < 1 || lc < 1) return false;
+    const long long m = la_total < lb ? (la_total < lc ? la_total : lc) : (lb < lc ? lb : lc);
+    const long long base = -envelope_lo(m) + 32;
+    const long long top = base + envelope_hi(m) + 9 + 2 * ((long long)planes + LongCfg::LAG + LongCfg::DEPTH + 64 + 128) + 600;
+    return top < 65535;
+}
+
 bool fast_sweep_supports(int la, int lb, int lc)
 {
     if (la < 1 || lb < 1 || lc < 1 || la > LongCfg::LA_MAX - 64) return false;
-    const long long m = la < lb ? (la < lc ? la : lc) : (lb < lc ? lb : lc);
-    const long long base = -envelope_lo(m) + 32;
-    const long long top = base + envelope_hi(m) + 9 + 2 * ((long long)la + LongCfg::LAG + LongCfg::DEPTH + 64 + 128) + 600;
-    return top < 65535;
+    return fast_long_range_ok(la, la, lb, lc);
 }
 
 static int sweep_base(int la, int lb, int lc)
@@ -253,10 +259,10 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
     A.nbj = (lb + C::BJ - 1) / C::BJ;
     A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
     A.tasks_total = (long long)A.nbj * A.nbkp;
-    // long sweeps release their progress less often (see fast_sweep.cuh); TRIALIGN_K2_GATE overrides for experiments
+    // long sweeps release their progress less often (see fast_sweep.cuh); option k2_gate overrides for experiments
     A.gate = la >= 4096 ? 16 : 8;
-    if (const char *e = std::getenv("TRIALIGN_K2_GATE")) {
-        const int g = std::atoi(e);
+    {
+        const int g = opt_int("k2_gate", 0);
         if (g >= 1 && g <= 64 && (g & (g - 1)) == 0) A.gate = g;
     }
     int grid = ctx->sm_count;  // one persistent CTA per SM; all co-resident (spin-waits need that)
@@ -308,7 +314,7 @@ int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int
         A.epoch = slab->epoch;
     }
     TA_CUDA(cudaMemsetAsync(ctx->misc.ptr, 0, ctl_bytes, st));
-    if (std::getenv("TRIALIGN_DEBUG"))
+    if (opt_debug())
         std::fprintf(stderr, "[trialign] K2 long: la=%d blocks %dx%d(pairs) tasks=%lld grid=%d faces=%.1f MB base=%d\n", la,
                      A.nbj, A.nbkp, A.tasks_total, grid, (fj_bytes + fk_bytes) / 1e6, A.base);
     if (check) sweep_long_kernel<true><<<grid, C::NT, smem, st>>>(A);
@@ -345,7 +351,7 @@ int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, co
     A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
     A.out = d_scores;
     A.base = sweep_base(len, len, len);
-    if (std::getenv("TRIALIGN_DEBUG"))
+    if (opt_debug())
         std::fprintf(stderr, "[trialign] K2 batch: len=%d blocks %dx%d grid=%d faces=%.1f MB base=%d\n", len, A.nbj, A.nbkp,
                      grid, (fj_bytes + fk_bytes) / 1e6, A.base);
     sweep_batch_kernel<<<grid, C::NT, smem, st>>>(A);

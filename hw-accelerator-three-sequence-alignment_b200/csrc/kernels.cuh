@@ -23,6 +23,8 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
 // K2: block-sweep kernels for long triples (fast_sweep.cu); same exactness condition as K1 plus the 16-bit envelope
 // checked by fast_sweep_supports().
 bool fast_sweep_supports(int la, int lb, int lc);
+// 16-bit range of a launch over `planes` planes of a triple of la_total x lb x lc (i-slab pipeline: planes < la_total)
+bool fast_long_range_ok(int planes, int la_total, int lb, int lc);
 // i-slab pipeline of one long triple over several GPUs: a launch computes planes (i_begin, i_begin+la] and hands the
 // plane state of every block task to the next slab.  in_* live on this GPU, out_* may be peer memory.
 struct SlabLink {

@@ -49,7 +49,12 @@ def exchange_objects(obj, group=None) -> List:
 
 
 class SlabPipeline:
-    """i-slab pipeline for one long triple; build once per (lb, lc), call run() as often as needed."""
+    """i-slab pipeline for one long triple; build once per (lb, lc), call run() as often as needed.
+
+    There is ONE hand-over slot per block task: run r+1 may overwrite a slot on rank g+1 only after that rank's run r
+    has consumed it.  run() therefore ends with a stream-ordered all_reduce over the group (nobody's next run starts
+    before every rank's kernels of this run have finished); pass sync=False only when the caller orders the runs itself.
+    """
 
     def __init__(self, lb: int, lc: int, score_bits: int = 16, device: Optional[int] = None, group=None):
         import torch
@@ -61,6 +66,7 @@ class SlabPipeline:
         self.device = torch.cuda.current_device() if device is None else device
         self.lb, self.lc, self.score_bits = lb, lc, score_bits
         self.epoch = 0
+        self._sync = torch.zeros(1, device=torch.device("cuda", self.device))
         L = _ta.library()
         sb, fb = C.c_int64(0), C.c_int64(0)
         _ta._check(L.trialign_slab_buffer_bytes(lb, lc, C.byref(sb), C.byref(fb)), "trialign_slab_buffer_bytes")
@@ -86,10 +92,11 @@ class SlabPipeline:
             _ta._check(L.trialign_ipc_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hf), C.byref(pf)), "trialign_ipc_open")
             self.next_state, self.next_flags = ps.value, pf.value
 
-    def run(self, A, B, C_, out=None, stream=None):
+    def run(self, A, B, C_, out=None, stream=None, sync=True):
         """A, B, C_: uint8 CUDA tensors holding the WHOLE sequences on every rank.  Returns the int32[8] result tensor
         (score + 7 final states), meaningful on the last rank only."""
         import torch
+        import torch.distributed as dist
 
         la = A.numel()
         i0, i1 = slab_range(la, self.rank, self.world)
@@ -106,6 +113,9 @@ class SlabPipeline:
             C.c_void_p(self.next_flags) if self.next_flags else None,
             self.epoch, self.score_bits, C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
         _ta._check(rc, "trialign_slab_score_dev")
+        if sync:
+            with torch.cuda.stream(st):
+                dist.all_reduce(self._sync, group=self.group)
         return out
 
     def close(self):
@@ -122,8 +132,8 @@ class SlabPipeline:
 class ColumnPipeline:
     """Column pipeline for one long triple (trialign_cols_score_dev): rank g sweeps all planes of its block-column
     range; the K faces crossing a range edge stream into rank g+1's memory (CUDA IPC mapping) while the sweep runs.
-    Build once per (la, lb, lc); a run must have finished on every rank before the next one starts (e.g. a
-    stream-ordered all_reduce between runs)."""
+    Build once per (la, lb, lc); a run must have finished on every rank before the next one starts: run() ends with a
+    stream-ordered all_reduce over the group unless sync=False."""
 
     def __init__(self, la: int, lb: int, lc: int, score_bits: int = 16, device: Optional[int] = None, group=None):
         import torch
@@ -136,6 +146,7 @@ class ColumnPipeline:
         self.la, self.lb, self.lc, self.score_bits = la, lb, lc, score_bits
         self.c_begin, self.c_end = col_range(lc, self.rank, self.world)
         self.epoch = 0
+        self._sync = torch.zeros(1, device=torch.device("cuda", self.device))
         L = _ta.library()
         fb, pb = C.c_int64(0), C.c_int64(0)
         _ta._check(L.trialign_cols_buffer_bytes(la, lb, C.byref(fb), C.byref(pb)), "trialign_cols_buffer_bytes")
@@ -159,10 +170,11 @@ class ColumnPipeline:
             _ta._check(L.trialign_ipc_open(self.device, (C.c_ubyte * 64).from_buffer_copy(hp), C.byref(pp)), "trialign_ipc_open")
             self.next_face, self.next_prog = pf.value, pp.value
 
-    def run(self, A, B, C_, out=None, stream=None):
+    def run(self, A, B, C_, out=None, stream=None, sync=True):
         """A, B, C_: uint8 CUDA tensors holding the WHOLE sequences on every rank.  Returns the int32[8] result tensor
         (score + 7 final states), meaningful on the last rank only."""
         import torch
+        import torch.distributed as dist
 
         if out is None:
             out = torch.zeros(8, dtype=torch.int32, device=A.device)
@@ -177,6 +189,9 @@ class ColumnPipeline:
             C.c_void_p(self.next_prog) if self.next_prog else None,
             self.epoch, self.score_bits, C.c_void_p(out.data_ptr()), C.c_void_p(st.cuda_stream))
         _ta._check(rc, "trialign_cols_score_dev")
+        if sync:
+            with torch.cuda.stream(st):
+                dist.all_reduce(self._sync, group=self.group)
         return out
 
     def close(self):

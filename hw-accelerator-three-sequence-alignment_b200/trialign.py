@@ -160,6 +160,11 @@ def library() -> C.CDLL:
     L.trialign_last_timing.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.trialign_last_timing.restype = C.c_int
     L.trialign_last_path.restype = C.c_int
+    L.trialign_last_devices.restype = C.c_int
+    L.trialign_set_option.argtypes = [C.c_char_p, C.c_char_p]
+    L.trialign_set_option.restype = C.c_int
+    L.trialign_get_option.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
+    L.trialign_get_option.restype = C.c_int
     L.trialign_launch_count.restype = C.c_int64
     _lib = L
     return L
@@ -192,6 +197,32 @@ def launch_count() -> int:
 
 def last_path() -> str:
     return PATH_NAMES.get(int(library().trialign_last_path()), "?")
+
+
+def last_devices() -> int:
+    """GPUs that served the last compute call of this thread (a device mask with several bits may still be served by
+    one GPU when the input does not qualify for the multi-GPU pipeline)."""
+    return int(library().trialign_last_devices())
+
+
+def set_option(name: str, value=None) -> None:
+    """Run-time option of the library (kernel A/B variants, gate intervals, multi-GPU decomposition); None restores
+    the default.  The library never reads the environment."""
+    v = None if value is None else str(value).encode()
+    _check(library().trialign_set_option(name.encode(), v), f"trialign_set_option({name})")
+
+
+def get_option(name: str) -> str:
+    buf = C.create_string_buffer(64)
+    _check(library().trialign_get_option(name.encode(), buf, 64), f"trialign_get_option({name})")
+    return buf.value.decode()
+
+
+def apply_option_args(pairs) -> None:
+    """Helper for the tools' `--opt name=value` flags."""
+    for kv in pairs or []:
+        k, _, v = kv.partition("=")
+        set_option(k, v or None)
 
 
 def last_timing() -> Tuple[float, float]:

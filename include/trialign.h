@@ -47,7 +47,8 @@ enum trialign_rc {
     TRIALIGN_ECUDA = -3,        /* a CUDA call failed; see trialign_last_cuda_error() */
     TRIALIGN_EIO = -4,          /* file could not be opened / read / written */
     TRIALIGN_EPARSE = -5,       /* dat file holds something other than digits 0-3 and line ends */
-    TRIALIGN_EUNSUPPORTED = -6, /* backend not part of the product (CPU checkers live under oracle/) */
+    TRIALIGN_EUNSUPPORTED = -6, /* backend not part of the product (CPU checkers live under oracle/), or a size beyond a
+                                   kernel's limits (e.g. more than 8,192 planes in one slab launch) */
     TRIALIGN_ENODEVICE = -7,    /* no usable CUDA device */
     TRIALIGN_ECAPACITY = -8,    /* output buffer too small */
     TRIALIGN_EINEXACT = -9      /* TRIALIGN_BACKEND_GPU_FAST forced, but wrap-freedom could not be established */
@@ -96,9 +97,22 @@ const char *trialign_strerror(int rc);
 const char *trialign_last_cuda_error(void); /* thread-local text of the last CUDA failure, "" if none */
 int trialign_device_count(void);            /* 0 when no driver / no device; never negative */
 
-/* One triple.  a/b/c: host bytes.  score_bits in [2,32].  devices: bitmask of CUDA ordinals (0 = device 0).
+/* Run-time options: the experiment switches of the kernels (A/B variants, gate intervals, multi-GPU decomposition).
+ * Nothing in the library reads the environment; a caller that wants a non-default kernel says so explicitly.
+ * Names: debug, k1, k2, k2l, k2_lag, k2_pp, k2_gatetid, k2_early, k2_gate, multi ("slab" | "cols"), multi_min.
+ * value NULL or "" restores the default.  Unknown names give TRIALIGN_EINVAL.  Process-wide, thread-safe. */
+int trialign_set_option(const char *name, const char *value);
+int trialign_get_option(const char *name, char *buf, int cap); /* "" when unset */
+
+/* One triple.  a/b/c: host bytes.  score_bits in [2,32].  devices: bitmask of CUDA ordinals (0 = device 0); a bit
+ * beyond trialign_device_count() gives TRIALIGN_EINVAL.
  * final_states (may be NULL) receives the 7 states of cell (la,lb,lc) in the order M,Ix,Iy,Iz,Ixy,Iyz,Ixz.
- * Any zero length gives score 0 (the cell lies on a zero boundary plane). */
+ * Any zero length gives score 0 (the cell lies on a zero boundary plane).
+ * Several bits set: the calling thread drives all of those GPUs (peer access, one stream per device) and the triple is
+ * split as an i-slab pipeline -- GPU g computes planes (la*g/G, la*(g+1)/G] and hands the plane state of every block to
+ * GPU g+1 through NVLink peer stores (option multi=cols: the column pipeline instead) -- provided every GPU gets at least
+ * 64 planes and the fast kernels are provably bit-exact for the input; otherwise the first GPU of the mask serves the
+ * call alone.  trialign_last_devices() reports how many GPUs did. */
 int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                    int backend, unsigned devices, int32_t *score, int32_t final_states[7]);
 
@@ -119,7 +133,11 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
 
 /* Device-resident variants: every pointer is device memory on CUDA ordinal `device`, work is enqueued on
  * `stream` (a cudaStream_t; NULL = legacy default stream) and the call returns without synchronising unless
- * the range check of the fast path forces a literal re-run.  d_scores is [n] int32. */
+ * the range check of the fast path forces a literal re-run.  d_scores is [n] int32.
+ * The calling thread's current CUDA device is left unchanged.  Calls on one device share that device's scratch
+ * buffers (block faces, progress words): a call enqueued on another stream than its predecessor first waits (on the
+ * device, cudaStreamWaitEvent) for the predecessor's kernels, so calls in flight on different streams are safe but run
+ * one after the other. */
 int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c, int64_t n,
                              int len, int score_bits, int backend, int32_t *d_scores, void *stream);
 /* d_out: int32[8] = score followed by the 7 final states. */
@@ -130,6 +148,7 @@ int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_
  * instances' commented-out `act` outputs would select (src/PE_1cyc.v:12,22-30,139-145; SURVEY.md 8(f).2 -- the RTL
  * itself ships score-only).  The path runs from the border cell start[] = (i0,j0,k0) (one of them 0: all three border
  * planes are zero, src/TriAlign_1cyc.v:156-181, so the symbols before it are unaligned and free) to (la,lb,lc).
+ * The traceback runs on ONE GPU: the first of the `devices` mask (the direction cube is not partitioned).
  * moves[0..*n_moves): one byte per alignment column, first column first: bit0 = A advances, bit1 = B, bit2 = C
  * (7 = three symbols aligned / state M, 1 = Ix, 2 = Iy, 4 = Iz, 3 = Ixy, 6 = Iyz, 5 = Ixz).  *score equals
  * trialign_score()'s.  cap < *n_moves gives ECAPACITY (cap = la+lb+lc always suffices); the direction cube needs
@@ -141,7 +160,8 @@ int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
  * all triples of its input -- the workload behind "a million short triples": 186 sequences give 1,055,240).
  * seqs: [nseq][len] symbols, uploaded once; the C(nseq,3) triples are laid out on the device and scored by the batch
  * kernels.  scores[t] belongs to the t-th triple (x < y < z) in lexicographic order with roles A = x, B = y, C = z
- * (the RTL's score is not symmetric in the roles, src/PE_1cyc.v:162); trialign_triple_count(nseq) = C(nseq,3) entries. */
+ * (the RTL's score is not symmetric in the roles, src/PE_1cyc.v:162); trialign_triple_count(nseq) = C(nseq,3) entries.
+ * With several bits set in `devices` the triple list is split contiguously across those GPUs (no exchange). */
 int64_t trialign_triple_count(int nseq);
 int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score_bits, int backend, unsigned devices,
                                int32_t *scores);
@@ -152,9 +172,13 @@ int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score
  * hand-over buffers (state + one int flag per block task) live on the RECEIVING GPU; the sender writes them through a
  * peer mapping (NVLink), so there is no host round trip and no collective.  Sizes come from
  * trialign_slab_buffer_bytes(); in_* = this rank's own buffers (NULL on the first rank), out_* = the next rank's
- * buffers as mapped with trialign_ipc_open() (NULL on the last rank).  `epoch` must differ between consecutive runs
- * that reuse the buffers (flags are compared for equality, never cleared).  Only the last rank writes d_out
- * (int32[8]: score + 7 final states).  Requires an input that is provably wrap-free at score_bits (else EINEXACT). */
+ * buffers as mapped with trialign_ipc_open() (NULL on the last rank).  `epoch` >= 1 must differ between consecutive runs
+ * that reuse the buffers (flags are compared for equality, never cleared), and -- there is ONE hand-over slot per block
+ * task -- run r+1 may only be enqueued on rank g once run r has finished on rank g+1 (parallel.SlabPipeline.run() orders
+ * the runs with a stream-ordered collective; trialign_score() with a device mask synchronises every GPU before it
+ * returns).  Only the last rank writes d_out (int32[8]: score + 7 final states).  Requires an input that is provably
+ * wrap-free at score_bits (else EINEXACT); a slab of more than 8,192 planes, or a triple whose values leave the 16-bit
+ * potential range, gives EUNSUPPORTED (la itself may exceed 8,192: the limit is per slab). */
 int trialign_slab_buffer_bytes(int lb, int lc, int64_t *state_bytes, int64_t *flag_bytes);
 int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
                             int lc, int i_begin, int i_end, const void *in_state, const void *in_flags,
@@ -213,6 +237,7 @@ int trialign_synth_batch_dev(int device, uint64_t seed, int64_t first, int64_t n
 /* Bookkeeping of the last compute call made by this thread. */
 int trialign_last_timing(double *seconds, double *cells); /* device time of the kernels only, cells = sum la*lb*lc */
 int trialign_last_path(void);                             /* enum trialign_path */
+int trialign_last_devices(void);                          /* GPUs that served the last call (0 before any call) */
 int64_t trialign_launch_count(void);                      /* kernels launched by this process so far */
 
 #ifdef __cplusplus

@@ -308,6 +308,98 @@ int oracle_score_mt(const uint8_t *a, int la, const uint8_t *b, int lb, const ui
     return 0;
 }
 
+/* Same function again, scheduled like the RTL's slicing (TriAlign_1cyc.v:127-140,289-335): the (j,k) plane is cut into
+ * blk x blk blocks, every block is swept over all i with two small rolling planes (cache resident), and the block's last
+ * row / last column of every plane i are parked in face memories for the blocks below / to the right (the z-face and
+ * y-face SRAMs; the corner cell the RTL routes through border_00, :149,175-181, travels as element 0 of a face row).
+ * Blocks on one anti-diagonal bj+bk are independent -> OpenMP over them; faces of two anti-diagonals are live.
+ * Every cell still goes through the literal pe_cell().  Used for the long golden vectors (8192^3 in ~20 min). */
+int oracle_score_blocked(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
+                         int score_bits, int threads, int blk, int32_t *score, int32_t final_states[7])
+{
+    if (bad_args(a, la, b, lb, c, lc, score_bits) || !score || blk < 1) return -1;
+    const int sh = 32 - score_bits;
+    int32_t fin[7] = {0, 0, 0, 0, 0, 0, 0};
+    int rc = 0;
+    if (la > 0 && lb > 0 && lc > 0) {
+        const int nbj = (lb + blk - 1) / blk, nbk = (lc + blk - 1) / blk;
+        const size_t frow = (size_t)(blk + 1) * 7;             /* one face row: corner + blk cells, 7 states */
+        const size_t fsz = (size_t)(la + 1) * frow;            /* one face: planes 0..la */
+        /* J faces (last row of a block, read by block bj+1) and K faces (last column, read by bk+1), [parity][bj] */
+        int32_t *jf = (int32_t *)calloc((size_t)2 * nbj * fsz, sizeof(int32_t));
+        int32_t *kf = (int32_t *)calloc((size_t)2 * nbj * fsz, sizeof(int32_t));
+        if (!jf || !kf) { free(jf); free(kf); return -2; }
+#ifdef _OPENMP
+        if (threads <= 0) threads = omp_get_max_threads();
+#else
+        threads = 1;
+#endif
+        const size_t prow = (size_t)(blk + 1) * 7, pplane = (size_t)(blk + 1) * prow;
+        for (int d = 0; d <= nbj + nbk - 2; ++d) {
+            int blo = d - (nbk - 1); if (blo < 0) blo = 0;
+            int bhi = d < nbj - 1 ? d : nbj - 1;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
+#endif
+            for (int bj = blo; bj <= bhi; ++bj) {
+                const int bk = d - bj;
+                const int j0 = bj * blk, k0 = bk * blk;
+                const int nj = lb - j0 < blk ? lb - j0 : blk, nk = lc - k0 < blk ? lc - k0 : blk;
+                int32_t *pl = (int32_t *)calloc(2 * pplane, sizeof(int32_t));
+                if (!pl) {
+#ifdef _OPENMP
+#pragma omp atomic write
+#endif
+                    rc = -2;
+                    continue;
+                }
+                /* inbound: J face of (bj-1,bk) and K face of (bj,bk-1), both written on anti-diagonal d-1 */
+                const int32_t *jin = bj > 0 ? jf + ((size_t)((d - 1) & 1) * nbj + (bj - 1)) * fsz : NULL;
+                const int32_t *kin = bk > 0 ? kf + ((size_t)((d - 1) & 1) * nbj + bj) * fsz : NULL;
+                int32_t *jout = jf + ((size_t)(d & 1) * nbj + bj) * fsz;
+                int32_t *kout = kf + ((size_t)(d & 1) * nbj + bj) * fsz;
+                int32_t *prev = pl, *cur = pl + pplane;   /* plane 0 is all zero (PE first-symbol override) */
+                for (int i = 1; i <= la; ++i) {
+                    const unsigned A = a[i - 1] & 3u;
+                    /* halos of plane i: local row 0 = global row j0, local column 0 = global column k0 */
+                    if (jin) memcpy(cur, jin + (size_t)i * frow, (size_t)(nk + 1) * 7 * sizeof(int32_t));
+                    else memset(cur, 0, (size_t)(nk + 1) * 7 * sizeof(int32_t));
+                    for (int j = 1; j <= nj; ++j) {
+                        if (kin) memcpy(cur + j * prow, kin + (size_t)i * frow + (size_t)j * 7, 7 * sizeof(int32_t));
+                        else memset(cur + j * prow, 0, 7 * sizeof(int32_t));
+                    }
+                    if (!jin && kin) memcpy(cur, kin + (size_t)i * frow, 7 * sizeof(int32_t)); /* corner via the K face */
+                    for (int j = 1; j <= nj; ++j) {
+                        const unsigned B = b[j0 + j - 1] & 3u;
+                        for (int k = 1; k <= nk; ++k) {
+                            const unsigned C = c[k0 + k - 1] & 3u;
+                            pe_cell(cur + j * prow + (size_t)k * 7, prev + (j - 1) * prow + (size_t)(k - 1) * 7,
+                                    prev + j * prow + (size_t)k * 7, cur + (j - 1) * prow + (size_t)k * 7,
+                                    cur + j * prow + (size_t)(k - 1) * 7, prev + (j - 1) * prow + (size_t)k * 7,
+                                    cur + (j - 1) * prow + (size_t)(k - 1) * 7, prev + j * prow + (size_t)(k - 1) * 7,
+                                    A, B, C, sh);
+                        }
+                    }
+                    /* outbound faces: last row incl. its column-0 halo, last column incl. its row-0 halo */
+                    memcpy(jout + (size_t)i * frow, cur + (size_t)nj * prow, (size_t)(nk + 1) * 7 * sizeof(int32_t));
+                    for (int j = 0; j <= nj; ++j)
+                        memcpy(kout + (size_t)i * frow + (size_t)j * 7, cur + j * prow + (size_t)nk * 7,
+                               7 * sizeof(int32_t));
+                    int32_t *t = prev; prev = cur; cur = t;
+                }
+                if (bj == nbj - 1 && bk == nbk - 1) memcpy(fin, prev + nj * prow + (size_t)nk * 7, sizeof fin);
+                free(pl);
+            }
+            if (rc) break;
+        }
+        free(jf); free(kf);
+        if (rc) return rc;
+    }
+    *score = max7(fin[TA_IXZ], fin[TA_M], fin[TA_IX], fin[TA_IXY], fin[TA_IY], fin[TA_IZ], fin[TA_IYZ]);
+    if (final_states) memcpy(final_states, fin, sizeof fin);
+    return 0;
+}
+
 int oracle_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len,
                        int score_bits, int threads, int32_t *scores)
 {

@@ -38,6 +38,11 @@ int oracle_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8
 int oracle_score_mt(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
                     int score_bits, int threads, int32_t *score, int32_t final_states[7]);
 
+/* Same function, scheduled like the RTL's slicing (blk x blk blocks of the (j,k) plane swept over all i, faces parked
+ * between blocks; TriAlign_1cyc.v:127-140): cache resident, OpenMP over the blocks of an anti-diagonal.  blk e.g. 64. */
+int oracle_score_blocked(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
+                         int score_bits, int threads, int blk, int32_t *score, int32_t final_states[7]);
+
 /* Uniform-length batch, structure of arrays [n][len]; OpenMP over triples. */
 int oracle_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len,
                        int score_bits, int threads, int32_t *scores);

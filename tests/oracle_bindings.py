@@ -52,6 +52,9 @@ def lib() -> C.CDLL:
         L.oracle_score.restype = C.c_int
         L.oracle_score_mt.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, i32p, i32p]
         L.oracle_score_mt.restype = C.c_int
+        L.oracle_score_blocked.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p,
+                                           i32p]
+        L.oracle_score_blocked.restype = C.c_int
         L.oracle_score_batch.argtypes = [u8p, u8p, u8p, C.c_int64, C.c_int, C.c_int, C.c_int, i32p]
         L.oracle_score_batch.restype = C.c_int
         L.oracle_cube.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, i32p]
@@ -119,6 +122,18 @@ def score_mt(a, b, c, score_bits: int = 12, threads: int = 0):
                                threads, C.byref(s), _ptr(fin, i32p))
     if rc:
         raise ValueError(f"oracle_score_mt rc={rc}")
+    return int(s.value), fin
+
+
+def score_blocked(a, b, c, score_bits: int = 12, threads: int = 0, blk: int = 128):
+    """O1 on the RTL's slicing schedule (blk x blk blocks swept over all i): the fast form for long triples."""
+    a, b, c = _u8(a), _u8(b), _u8(c)
+    s = C.c_int32()
+    fin = np.zeros(7, np.int32)
+    rc = lib().oracle_score_blocked(_ptr(a, u8p), len(a), _ptr(b, u8p), len(b), _ptr(c, u8p), len(c), score_bits,
+                                    threads, blk, C.byref(s), _ptr(fin, i32p))
+    if rc:
+        raise ValueError(f"oracle_score_blocked rc={rc}")
     return int(s.value), fin
 
 

@@ -158,9 +158,9 @@ def test_fast_long_kernel_shapes(gpu_ta, ob, shape):
 
 
 @pytest.mark.parametrize("ln,n", [(65, 7), (100, 12), (130, 5), (256, 6), (200, 601), (321, 3)])
-def test_fast_long_batch_kernels(gpu_ta, ob, ln, n, monkeypatch):
+def test_fast_long_batch_kernels(gpu_ta, ob, ln, n):
     """Batches of triples longer than 64: the streaming block-sweep kernel K2S (default) and the per-block kernel
-    (TRIALIGN_K2=sweep, also the fallback for very long batches) against the oracle.  n = 601 gives every CTA several
+    (option k2=sweep, also the fallback for very long batches) against the oracle.  n = 601 gives every CTA several
     pairs, so tasks of different pairs follow each other inside the array."""
     rng = np.random.default_rng(ln * 31 + n)
     a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
@@ -173,9 +173,12 @@ def test_fast_long_batch_kernels(gpu_ta, ob, ln, n, monkeypatch):
         got = gpu_ta.TriAlign(w).align_batch(a, b, c)
         assert gpu_ta.last_path() == "fast_stream"
         assert got.tolist() == want[w], (ln, n, w)
-    monkeypatch.setenv("TRIALIGN_K2", "sweep")
-    got = gpu_ta.TriAlign(16).align_batch(a, b, c)
-    assert gpu_ta.last_path() == "fast_long"
+    gpu_ta.set_option("k2", "sweep")
+    try:
+        got = gpu_ta.TriAlign(16).align_batch(a, b, c)
+        assert gpu_ta.last_path() == "fast_long"
+    finally:
+        gpu_ta.set_option("k2", None)
     assert got.tolist() == want[16], (ln, n)
 
 

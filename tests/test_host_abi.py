@@ -230,3 +230,32 @@ def test_scoring_struct_defaults_and_argument_errors(ta):
     rc = L.trialign_score_ex(a.ctypes.data_as(u8p), 4, a.ctypes.data_as(u8p), 4, a.ctypes.data_as(u8p), 4, 12, None, 0,
                              C.byref(s), None)
     assert rc == -1
+
+
+def test_options_are_explicit_and_checked(ta):
+    """Experiment switches are library options (trialign_set_option), never environment variables."""
+    assert ta.get_option("k2_gate") == ""
+    ta.set_option("k2_gate", 8)
+    assert ta.get_option("k2_gate") == "8"
+    ta.set_option("k2_gate", None)
+    assert ta.get_option("k2_gate") == ""
+    with pytest.raises(ta.TriAlignError) as ei:
+        ta.set_option("no_such_option", "1")
+    assert ei.value.rc == -1
+    L = ta.library()
+    assert L.trialign_set_option(None, b"1") == -1
+    buf = C.create_string_buffer(2)
+    ta.set_option("multi", "cols")
+    assert L.trialign_get_option(b"multi", buf, 2) == -8  # ECAPACITY
+    ta.set_option("multi", None)
+    # the product sources do not read the environment
+    src = os.path.join(ROOT, "hw-accelerator-three-sequence-alignment_b200", "csrc")
+    for name in os.listdir(src):
+        with open(os.path.join(src, name)) as f:
+            assert "getenv" not in f.read(), name
+
+
+def test_last_devices_before_any_call(ta):
+    assert ta.last_devices() >= 0
+    assert ta.library().trialign_slab_score_dev(0, None, 1, None, 1, None, 1, 0, 1, None, None, None, None, 0, 16, None,
+                                                None) == -1

@@ -1,5 +1,7 @@
 """CPU tests of the checkers themselves: O1 (functional oracle) against the frozen golden vectors and against
 O2 (cycle-accurate RTL model), plus the survey-derived known answers of SURVEY.md 8(c)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -251,3 +253,37 @@ def test_score_ex_reproduces_the_committed_scoring_fixture(ob):
     for case in g["cases"]:
         s, fin = ob.score_ex(case["a"], case["b"], case["c"], case["score_bits"], case["scoring"])
         assert s == case["score"] and fin.tolist() == case["final_states"], (case["name"], case["scoring"])
+
+
+def test_blocked_oracle_equals_serial(ob):
+    """oracle_score_blocked (the RTL's slicing as a CPU schedule, used for the long goldens) against the serial form:
+    ragged shapes, block sizes that do and do not divide the lengths, wrap cases, several threads."""
+    rng = np.random.default_rng(20261019)
+    for (la, lb, lc) in [(1, 1, 1), (5, 9, 3), (17, 33, 29), (64, 64, 64), (65, 63, 70), (100, 37, 129)]:
+        for w in (7, 9, 12, 16):
+            for blk in (1, 3, 8, 64):
+                a, b, c = ob.mutated_triple(rng, max(la, lb, lc))
+                a, b, c = a[:la], b[:lb], c[:lc]
+                s, fin = ob.score(a, b, c, w)
+                s2, fin2 = ob.score_blocked(a, b, c, w, 3, blk)
+                assert s == s2 and fin.tolist() == fin2.tolist(), (la, lb, lc, w, blk)
+
+
+def test_long_golden_file_is_reproducible(ob, ta):
+    """tests/golden/golden_long.json: inputs rebuild identically from the oracle's and the product's generator, and the
+    smallest case re-computes to the frozen score."""
+    import sys as _sys
+    _sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import long_cases
+
+    cases = long_cases.load()
+    assert "pipe_1500_w16" in cases
+    for name, e in cases.items():
+        a, b, c = long_cases.build_case(ob.synth, e["seed"], e["kind"], [min(n, 2000) for n in e["lens"]])
+        a2, b2, c2 = long_cases.build_case(ta.synth, e["seed"], e["kind"], [min(n, 2000) for n in e["lens"]])
+        assert a.tolist() == a2.tolist() and b.tolist() == b2.tolist() and c.tolist() == c2.tolist()
+        assert a[:16].tolist() == e["first_symbols"]["A"] and c[:16].tolist() == e["first_symbols"]["C"], name
+    e = cases["long_1024_mut_w12"]
+    a, b, c = long_cases.build_case(ob.synth, e["seed"], e["kind"], e["lens"])
+    s, fin = ob.score_blocked(a[:300], b[:300], c[:300], 12, 0, 64)
+    assert (s, fin.tolist()) == (ob.score_mt(a[:300], b[:300], c[:300], 12)[0], ob.score_mt(a[:300], b[:300], c[:300], 12)[1].tolist())
