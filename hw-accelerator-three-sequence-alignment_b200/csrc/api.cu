@@ -79,7 +79,7 @@ static const char *const kOptionNames[] = {
     "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l (default) | stream (K2S on len <= 64)
     "k2",          // "sweep": first-generation per-block kernel for batches longer than 64 (A/B runs)
     "k2l",         // "old": first-generation kernel for one long triple (A/B runs)
-    "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate",  // K2L experiment parameters (fast_long.cu)
+    "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate", "k2_rgate",  // K2L experiment parameters (fast_long.cu)
     "multi",       // one long triple on several GPUs: "slab" (i-slab pipeline, default) | "cols" (column pipeline)
     "multi_min",   // smallest la (slab) / lc (cols) per GPU for which the multi-GPU pipeline is used (default 64 / 128)
 };

@@ -39,8 +39,10 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-template <class Cfg, bool SPLIT>
-__global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel(fast::BatchArgs A)
+// MINB = CTAs per SM the register budget is set for: 2 (<= 128 registers, a few words spilled) lets two CTAs cover each
+// other's barrier waits and fixed-latency stalls (4 warps per scheduler instead of 2).
+template <class Cfg, bool SPLIT, int MINB = 1>
+__global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchArgs A)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
@@ -116,12 +118,12 @@ bool fast_batch_supports(int len) { return len >= 1 && len <= 64; }
 
 namespace {
 
-template <class Cfg, bool SPLIT>
+template <class Cfg, bool SPLIT, int MINB = 1>
 int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant)
 {
-    static_assert(sizeof(fast::BatchSmem<Cfg>) <= 227 * 1024, "shared memory budget");
+    static_assert(MINB * (sizeof(fast::BatchSmem<Cfg>) + 1024 + 64) <= 228 * 1024, "shared memory budget");
     const size_t smem = sizeof(fast::BatchSmem<Cfg>);
-    auto kernel = fast_batch_kernel<Cfg, SPLIT>;
+    auto kernel = fast_batch_kernel<Cfg, SPLIT, MINB>;
     static bool attr_set[kMaxDevices] = {};
     if (!attr_set[ctx->device]) {
         TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -130,15 +132,18 @@ int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant
         attr_set[ctx->device] = true;
     }
     // one persistent CTA per SM; contiguous chunks so that the fill/drain is paid once per CTA
-    const long long slots = ctx->sm_count;
+    const long long slots = (long long)ctx->sm_count * MINB;
     long long ppc = (A.pairs_total + slots - 1) / slots;
     if (ppc < 1) ppc = 1;
     if (ppc > (1 << 20)) ppc = 1 << 20;  // keep the step counter far from int overflow
     A.pairs_per_cta = (int)ppc;
     const long long grid = (A.pairs_total + ppc - 1) / ppc;
-    if (opt_debug())
-        std::fprintf(stderr, "[trialign] K1: variant=%d threads=%d grid=%lld pairs/cta=%lld smem=%zu\n", variant, Cfg::NT,
-                     grid, ppc, smem);
+    if (opt_debug()) {
+        int occ = -1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, Cfg::NT, smem);
+        std::fprintf(stderr, "[trialign] K1: variant=%d threads=%d grid=%lld pairs/cta=%lld smem=%zu ctas/sm=%d\n", variant,
+                     Cfg::NT, grid, ppc, smem, occ);
+    }
     kernel<<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
     count_launch();
     TA_CUDA(cudaGetLastError());
@@ -161,6 +166,7 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
             if (e[0] == '5') variant = 2;
             if (e[1] && e[2] && e[3] == 'm') variant |= 1;
             if (e[1] && e[2] && e[3] == 'l') variant |= 4;
+            if (e[1] && e[2] && e[3] == 'm' && e[4] == '2') variant = 8;  // 256m2: two CTAs per SM
         }
     }
     fast::BatchArgs A;
@@ -174,6 +180,7 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     case 2: return launch_batch<Cfg512, false>(ctx, st, A, variant);
     case 3: return launch_batch<Cfg512, true>(ctx, st, A, variant);
     case 4: return launch_batch<Cfg256L, true>(ctx, st, A, variant);
+    case 8: return launch_batch<Cfg256, true, 2>(ctx, st, A, variant);
     default: return launch_batch<Cfg256, false>(ctx, st, A, variant);
     }
 }

@@ -146,9 +146,15 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             return ld_acquire(left_p);
         };
         // publication of this task's progress: locally, and to the right neighbour GPU for the last local column
+        // The remote word is released at system scope -- a MEMBAR.SYS that waits for the acknowledgements of the face
+        // rows stored into the neighbour's memory over NVLink, several microseconds with the CTA held at its next
+        // barrier -- so it follows a coarser rhythm (A.rgate steps) than the local one; the count the neighbour's first
+        // task is waiting for (HOP_K + 1 + LAG) goes out at once.
         auto publish = [&](int done) {
             st_release(A.progress + T.self_task, done);
-            if (COLS && right_p) st_release_sys(right_p, col_encode(done, A.epoch));
+            if (COLS && right_p &&
+                (done >= fast::kProgressDone || (done & (A.rgate - 1)) == 0 || done == C::HOP_K + 1 + LAG))
+                st_release_sys(right_p, col_encode(done, A.epoch));
         };
 
         // prologue: the halos of steps 0 and 1 are fetched here, and the first LAG iterations fetch before any barrier
@@ -369,6 +375,12 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
         const int g = opt_int("k2_gate", 0);
         if (g >= 1 && g <= 64 && (g & (g - 1)) == 0) A.gate = g;
     }
+    A.rgate = 128;  // column pipeline: steps between two system-scope releases of a boundary task's progress
+    {
+        const int g = opt_int("k2_rgate", 0);
+        if (g >= A.gate && g <= 4096 && (g & (g - 1)) == 0) A.rgate = g;
+    }
+    if (A.rgate < A.gate) A.rgate = A.gate;
     A.out = d_score;
     A.out_states = d_states;
     const long long m0 = la < lb ? (la < lc ? la : lc) : (lb < lc ? lb : lc);

@@ -65,6 +65,7 @@ struct SweepArgs {
     long long fj_slot_words, fk_slot_words;
     int fj_ring, fk_ring;         // LONG: global ring sizes; BATCH: per-CTA ring sizes
     int gate;                     // LONG: steps between two progress releases in steady state (power of two)
+    int rgate;                    // K2L column pipeline: steps between two system-scope releases to the neighbour GPU
     int gate_tid;                 // K2L: the thread that polls / releases the progress counters
     int early;                    // K2L: 1 = fine publication rhythm during a task's first steps (experiments)
     int pingpong;                 // K2L: middle phase unrolled by two over two alternating register sets

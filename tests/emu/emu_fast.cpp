@@ -643,6 +643,7 @@ extern "C" int emu_fast_long2_cols(const uint8_t *a, int la, const uint8_t *b, i
         A.nbkp = (A.lc + C::KSPAN - 1) / C::KSPAN;
         A.tasks_total = (long long)A.nbj * A.nbkp;
         A.gate = 4;
+        A.rgate = (seed & 4) ? 4 : 32;  // remote publication rhythm (fast_long.cu: 128 by default)
         A.fj_slot_words = (long long)(la + C::PLAG + 2) * C::FJ_ROW_WORDS;
         A.fk_slot_words = slot_k;
         A.fj_ring = A.fk_ring = (int)A.tasks_total;
@@ -727,9 +728,10 @@ extern "C" int emu_fast_long2_cols(const uint8_t *a, int la, const uint8_t *b, i
                 const int lp = T.left_task >= 0 ? G.prog[T.left_task]
                                                 : (T.left_task <= -2 ? emu_col_decode(G.cprog[-2 - T.left_task], A.epoch) : 0);
                 int *right_p = (A.cprog_out && T.bkp == A.nbkp - 1) ? A.cprog_out + T.bj : nullptr;
-                auto publish = [&](int done) {
+                auto publish = [&](int done) {  // mirrors the kernel: the remote word follows the coarser rgate rhythm
                     G.prog[T.self_task] = done;
-                    if (right_p) *right_p = emu_col_encode(done, A.epoch);
+                    if (right_p && (done >= kProgressDone || (done & (A.rgate - 1)) == 0 || done == C::HOP_K + 1 + C::LAG))
+                        *right_p = emu_col_encode(done, A.epoch);
                 };
                 const int cert = long2_certified<C>(A, T, tp, lp);
                 if (!cta.prologue_done) {

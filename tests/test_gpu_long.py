@@ -150,7 +150,9 @@ def test_single_process_multi_gpu_triple(gpu_ta, name, multi):
             for rep in range(3):
                 s, fin = eng.align(a, b, c, return_states=True)
                 assert (s, fin.tolist()) == (e["score"], e["final_states"]), (name, multi, g, rep)
-                assert gpu_ta.last_devices() == g
+                # the column pipeline needs a 128-column block pair per GPU; shorter inputs are served by one GPU
+                want_g = g if (multi == "slab" or e["lens"][2] >= 128 * g) else 1
+                assert gpu_ta.last_devices() == want_g
             assert torch.cuda.current_device() == 0
     finally:
         gpu_ta.set_option("multi", None)
