@@ -22,6 +22,7 @@ from .trialign import (  # noqa: F401
     apply_option_args,
     get_option,
     last_devices,
+    last_flagged,
     set_option,
     last_path,
     last_timing,

@@ -230,6 +230,45 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         ts.last_path = TRIALIGN_PATH_FAST_THEN_LITERAL;
         return literal_run(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals);
     }
+    // A batch whose wrap-freedom cannot be proved from the length: the range-checked batch kernels flag, per triple,
+    // values that came near the score_bits limits; only the flagged triples are re-scored by the literal kernel.
+    if (want_fast && !d_finals && la == lb && lb == lc && score_bits >= 6 && score_bits <= 16 &&
+        (fast_batch_supports(la) || (fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count)))) {
+        const int64_t pairs = (n + 1) / 2;
+        const size_t flag_bytes = (((size_t)pairs * sizeof(int)) + 255) & ~(size_t)255;
+        const size_t list_bytes = (((size_t)n * sizeof(int)) + 255) & ~(size_t)255;
+        int rc = ctx->flagged.reserve(256 + flag_bytes + list_bytes);
+        if (rc) return rc;
+        int *d_count = (int *)ctx->flagged.ptr;
+        int *d_flags = (int *)((char *)ctx->flagged.ptr + 256);
+        int *d_list = (int *)((char *)ctx->flagged.ptr + 256 + flag_bytes);
+        TA_CUDA(cudaMemsetAsync(d_flags, 0, flag_bytes, st));
+        const bool k1 = fast_batch_supports(la);
+        rc = k1 ? fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags)
+                : fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags);
+        if (rc) return rc;
+        if ((rc = fixup_compact(st, d_flags, n, d_list, d_count))) return rc;
+        int count = 0;
+        TA_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        TA_CUDA(cudaStreamSynchronize(st));
+        ts.last_flagged += count;
+        if (count == 0) {
+            ts.last_path = k1 ? TRIALIGN_PATH_FAST_BATCH : TRIALIGN_PATH_FAST_STREAM;
+            return TRIALIGN_OK;
+        }
+        if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
+        // gather -> literal -> scatter; the staging arrays live behind the planes of the literal kernel's own scratch
+        const size_t arr = (((size_t)count * la) + 255) & ~(size_t)255;
+        const size_t sc_bytes = (((size_t)count * sizeof(int32_t)) + 255) & ~(size_t)255;
+        if ((rc = ctx->misc.reserve(3 * arr + sc_bytes))) return rc;
+        uint8_t *g_a = (uint8_t *)ctx->misc.ptr, *g_b = g_a + arr, *g_c = g_b + arr;
+        int32_t *g_scores = (int32_t *)(g_c + arr);
+        if ((rc = fixup_gather(st, d_a, d_b, d_c, la, d_list, count, g_a, g_b, g_c))) return rc;
+        if ((rc = literal_run(ctx, st, g_a, g_b, g_c, count, la, la, la, score_bits, g_scores, nullptr))) return rc;
+        if ((rc = fixup_scatter(st, g_scores, d_list, count, d_scores))) return rc;
+        ts.last_path = TRIALIGN_PATH_FAST_THEN_LITERAL;
+        return TRIALIGN_OK;
+    }
     if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
     ts.last_path = TRIALIGN_PATH_LITERAL;
     return literal_run(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals);
@@ -533,6 +572,7 @@ int trialign_score_batch_dev(int device, const uint8_t *d_a, const uint8_t *d_b,
     ts.last_seconds = -1.0;
     ts.last_cells = (double)n * len * len * len;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     ts.last_devices = 1;
     if (n == 0) return TRIALIGN_OK;
     DeviceGuard guard;
@@ -559,6 +599,7 @@ int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_
     ts.last_seconds = -1.0;
     ts.last_cells = (double)la * lb * lc;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     ts.last_devices = 1;
     DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
@@ -584,6 +625,7 @@ int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     ts.last_seconds = -1.0;
     ts.last_cells = (double)la * lb * lc;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     if (trialign_device_count() == 0) return TRIALIGN_ENODEVICE;
     if (la == 0 || lb == 0 || lc == 0) {
         *score = 0;
@@ -685,6 +727,7 @@ int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score
     ts.last_seconds = -1.0;
     ts.last_cells = (double)total * len * len * len;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     ts.last_devices = 1;
     const int have = trialign_device_count();
     if (have == 0) return TRIALIGN_ENODEVICE;
@@ -709,6 +752,7 @@ int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score
     std::vector<int> rcs(G, 0), paths(G, 0);
     std::vector<double> secs(G, -1.0);
     std::vector<std::string> errs(G);
+    std::vector<int64_t> flagged(G, 0);
     std::vector<std::thread> th;
     for (size_t g = 0; g < G; ++g) {
         const int64_t t0 = total * (int64_t)g / (int64_t)G, t1 = total * (int64_t)(g + 1) / (int64_t)G;
@@ -716,6 +760,7 @@ int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score
             rcs[g] = all_triples_on_device(devs[g], seqs, nseq, len, score_bits, backend, t0, t1, scores, &secs[g]);
             paths[g] = tls().last_path;
             errs[g] = tls().cuda_error;
+            flagged[g] = tls().last_flagged;
         });
     }
     for (auto &t : th) t.join();
@@ -727,6 +772,7 @@ int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score
         }
         worst = std::max(worst, secs[g]);
         if (paths[g] > ts.last_path) ts.last_path = paths[g];
+        ts.last_flagged += flagged[g];
     }
     ts.last_seconds = worst;
     ts.last_devices = (int)G;
@@ -742,6 +788,7 @@ int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     ts.last_seconds = -1.0;
     ts.last_cells = (double)la * lb * lc;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     if (trialign_device_count() == 0) return TRIALIGN_ENODEVICE;
     *n_moves = 0;
     start[0] = la; start[1] = lb; start[2] = lc;
@@ -804,6 +851,7 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
     ts.last_seconds = -1.0;
     ts.last_cells = (double)n * len * len * len;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     const int have = trialign_device_count();
     if (have == 0) return TRIALIGN_ENODEVICE;
     if (n == 0) return TRIALIGN_OK;
@@ -828,6 +876,7 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
     std::vector<int> rcs(G, 0), paths(G, 0);
     std::vector<double> secs(G, -1.0);
     std::vector<std::string> errs(G);
+    std::vector<int64_t> flagged(G, 0);
     std::vector<std::thread> th;
     for (size_t g = 0; g < G; ++g) {
         const int64_t t0 = n * (int64_t)g / (int64_t)G, t1 = n * (int64_t)(g + 1) / (int64_t)G;
@@ -840,6 +889,7 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
                                                   backend, scores + t0, nullptr, &secs[g]);
             paths[g] = tls().last_path;
             errs[g] = tls().cuda_error;
+            flagged[g] = tls().last_flagged;
         });
     }
     for (auto &t : th) t.join();
@@ -851,6 +901,7 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
         }
         worst = std::max(worst, secs[g]);
         if (paths[g] > ts.last_path) ts.last_path = paths[g];
+        ts.last_flagged += flagged[g];
     }
     ts.last_seconds = worst;
     return TRIALIGN_OK;
@@ -937,6 +988,7 @@ int trialign_slab_score_dev(int device, const uint8_t *d_a, int la, const uint8_
     ts.last_seconds = -1.0;
     ts.last_cells = (double)(i_end - i_begin) * lb * lc;
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     ts.last_devices = 1;
     if (!provably_wrap_free(la, lb, lc, score_bits)) return TRIALIGN_EINEXACT;
     // size limits apply to the slab's own planes (their a symbols live in shared memory) and to the 16-bit range of the
@@ -984,6 +1036,7 @@ int trialign_cols_score_dev(int device, const uint8_t *d_a, int la, const uint8_
     ts.last_seconds = -1.0;
     ts.last_cells = (double)la * lb * (c_end - c_begin);
     ts.last_path = TRIALIGN_PATH_NONE;
+    ts.last_flagged = 0;
     ts.last_devices = 1;
     if (!provably_wrap_free(la, lb, lc, score_bits)) return TRIALIGN_EINEXACT;
     if (!long_launch_supports(la, la, lb, lc)) return TRIALIGN_EUNSUPPORTED;
@@ -1083,6 +1136,8 @@ int trialign_last_timing(double *seconds, double *cells)
 int trialign_last_path(void) { return tls().last_path; }
 
 int trialign_last_devices(void) { return tls().last_devices; }
+
+int64_t trialign_last_flagged(void) { return tls().last_flagged; }
 
 int64_t trialign_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

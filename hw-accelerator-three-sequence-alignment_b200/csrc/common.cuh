@@ -20,6 +20,7 @@ struct ThreadState {
     double last_cells = 0.0;
     int last_path = TRIALIGN_PATH_NONE;
     int last_devices = 0;         // GPUs that served the last compute call of this thread
+    int64_t last_flagged = 0;     // triples the range-checked batch path re-scored on the literal kernel (last call)
     bool scoring_active = false;  // a *_ex entry point with non-RTL scoring is in progress on this thread
     trialign_scoring scoring{};
 };

@@ -66,7 +66,14 @@ struct BatchArgs {
     long long pairs_total;     // ceil(n/2)
     int pairs_per_cta;         // contiguous chunk per CTA
     int base;                  // potential base (common.cuh envelope), < 2^15
+    // range-checked variant (CHECK kernels, used when wrap-freedom at score_bits cannot be proved from the length):
+    // every sampled `all` must lie in [check_lo, check_hi]; pair_flags[pair] gets bit 0 / bit 1 set when the low / high
+    // triple of the pair came too close to the score_bits limits (the dispatcher re-runs those on the literal kernel)
+    int check_lo, check_hi;
+    int *pair_flags;
 };
+
+constexpr int kBatchCheckEvery = 8;  // steps between two range samples: `all` moves by at most +3 / -4 per plane
 
 template <class C>
 struct BatchSmem {
@@ -85,6 +92,7 @@ template <class C>
 struct BatchRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
     uint32_t cBC[C::RJ][C::RK];                                                        // per-cell constant
+    uint32_t viol;                                                                     // CHECK: range violations of the current pair
 };
 
 // Constants of the step a thread is about to run (a_i against the tile's rows / columns), fetched one step ahead in
@@ -119,7 +127,10 @@ TA_HD void load_pair_sequences(BatchSmem<C> &S, const BatchArgs &A, int tid, lon
         const int which = e >> 7, half = (e >> 6) & 1, pos = e & 63;
         const long long t = 2 * pair + half;
         const uint8_t *src = which == 0 ? A.a : (which == 1 ? A.b : A.c);
-        uint8_t v = 0;
+        // positions beyond len are padding: b gets code 4, c code 5 -- they match nothing, not even each other, so
+        // padded cells decay instead of growing like a run of matches (keeps the range check free of false alarms;
+        // real cells never depend on padded ones)
+        uint8_t v = which == 0 ? 0 : (uint8_t)(3 + which);
         if (t < A.n && pos < A.len) v = src[t * A.len + pos] & 3;  // PE keeps bits [1:0] (src/PE_1cyc.v:63-66)
         S.seq[buf][which][half][pos] = v;
     }
@@ -171,6 +182,7 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
                 const uint32_t nbc = neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]);
                 R.cBC[r][c] = pair_const(nbc);
             }
+        R.viol = 0;
     }
 
     const int code = S.acode[buf][i - 1];
@@ -190,7 +202,8 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
 // ---- one wavefront step of one thread: halos published at step s-1 -> tile -> publish for step s+1 ----
 // R = plane i-1 state (input), Rn = plane i state (output; may be R itself): the lagged-barrier kernel alternates two
 // register sets in a step loop unrolled by two, so that the loop-carried state needs no register moves.
-template <class C>
+// CHECK: the run-time range check (see BatchArgs), sampled every kBatchCheckEvery-th step (warp-uniform).
+template <class C, bool CHECK = false>
 TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
                              const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base)
 {
@@ -302,6 +315,36 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
         S.col[ws][1][tk][j0 + r] = n_u2[r][RK - 1];
     }
 
+    uint32_t viol = R.viol;
+    if (CHECK) {
+        if ((s & (kBatchCheckEvery - 1)) == 0 && i <= A.len) {
+            // only cells of the real triple count: padding (j or k beyond len) decays without bound of its own
+            uint32_t mx = 0u, mn = 0xFFFFFFFFu;
+#pragma unroll
+            for (int r = 0; r < RJ; ++r)
+#pragma unroll
+                for (int c = 0; c < RK; ++c)
+                    if (j0 + r < A.len && k0 + c < A.len) {
+                        mx = vmax2(mx, n_all[r][c]);
+                        mn = vmin2(mn, n_all[r][c]);
+                    }
+            // true value = stored - phi(cell); phi grows by 2 per row / column inside the tile
+            const int ph = A.base + 2 * (i + j0 + 1 + k0 + 1), slack = 2 * (RJ + RK - 2);
+            const int h = ph + A.check_hi, l = ph + A.check_lo + slack;
+            const uint32_t hi_lim = rep((uint32_t)(h > 0xFFFF ? 0xFFFF : h)), lo_lim = rep((uint32_t)(l < 0 ? 0 : l));
+            viol |= (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
+        }
+        // the pair leaves this thread: report
+        if (i == C::L && viol != 0 && u >= 0 && p < P) {
+            const int bits = ((viol & 0xFFFFu) ? 1 : 0) | ((viol >> 16) ? 2 : 0);
+#if defined(__CUDA_ARCH__)
+            atomicOr(A.pair_flags + (pair_base + p), bits);
+#else
+            A.pair_flags[pair_base + p] |= bits;
+#endif
+        }
+    }
+
     // Score = max of the 7 states of cell (len,len,len) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
     if (i == A.len && u >= 0 && p < P && tj == (A.len - 1) / RJ && tk == (A.len - 1) / RK) {
         const int rf = (A.len - 1) % RJ, cf = (A.len - 1) % RK;
@@ -324,6 +367,7 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
             Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
             Rn.cBC[r][c] = R.cBC[r][c];
         }
+    Rn.viol = viol;
 }
 
 // Steps a CTA needs for P pairs, and the CTA-uniform actions of global step s.

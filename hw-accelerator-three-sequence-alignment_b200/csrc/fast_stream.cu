@@ -38,6 +38,7 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
+template <bool CHECK>
 __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArgs A)
 {
     using C = Cfg;
@@ -65,6 +66,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArg
     __syncthreads();
 
     fast::StreamRegs<C> R, R2;
+    R.viol = R2.viol = 0;
     fast::StreamConsts<C> K;
     fast::StreamPos pos = fast::stream_start_pos<C>(A, tj, tk);
     if (tj == 0 || tk == 0) fast::stream_edge_fetch<C>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1));
@@ -79,7 +81,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArg
         const int s_ = (S_);                                                                      \
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                            \
         fast::ta_copy_wait_prev();                                                                \
-        fast::stream_thread_step<C>(RIN, ROUT, K, S, A, tj, tk, s_, pos);                         \
+        fast::stream_thread_step<C, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, pos);                  \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                       \
         if (g_t < tasks) fast::stream_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off); \
         fast::stream_thread_prepare<C>(ROUT, K, S, A, tj, tk, pos, s_ + 1, true);                 \
@@ -122,7 +124,7 @@ bool fast_stream_supports(int len)
 }
 
 int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                    int64_t n, int len, int32_t *d_scores)
+                    int64_t n, int len, int32_t *d_scores, int check_bits, int *d_pair_flags)
 {
     using C = Cfg;
     if (n <= 0) return TRIALIGN_OK;
@@ -130,8 +132,11 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
     const size_t smem = sizeof(fast::StreamSmem<C>);
     static bool attr_set[kMaxDevices] = {};
     if (!attr_set[ctx->device]) {
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
         attr_set[ctx->device] = true;
     }
@@ -159,7 +164,15 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
     if (opt_debug())
         std::fprintf(stderr, "[trialign] K2S stream: len=%d blocks %dx%d grid=%lld pairs/cta=%lld faces=%.1f MB smem=%zu base=%d\n",
                      len, A.nbj, A.nbk, grid, ppc, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
-    fast_stream_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
+    if (check_bits > 0) {
+        const int lim = 1 << (check_bits - 1), gap = fast::kStreamCheckEvery - 1;
+        A.check_hi = lim - 1 - 3 - 3 * gap;
+        A.check_lo = -lim + 8 + 4 * gap;
+        A.pair_flags = d_pair_flags;
+        fast_stream_kernel<true><<<(unsigned)grid, C::NT, smem, st>>>(A);
+    } else {
+        fast_stream_kernel<false><<<(unsigned)grid, C::NT, smem, st>>>(A);
+    }
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TRIALIGN_OK;

@@ -72,7 +72,13 @@ struct StreamArgs {
     int fk_ring;                  // nbj + 1
     int32_t *scores;              // [n]
     int base;                     // potential base
+    // range-checked variant (CHECK kernels), as in fast_batch.cuh: sampled `all` in [check_lo, check_hi], else
+    // pair_flags[pair] gets bit 0 / 1 set for the low / high triple
+    int check_lo, check_hi;
+    int *pair_flags;
 };
+
+constexpr int kStreamCheckEvery = 16;  // steps between two range samples (`all` moves by at most +3 / -4 per plane)
 
 template <class C>
 struct StreamSmem {
@@ -91,6 +97,7 @@ template <class C>
 struct StreamRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
     uint32_t cBC[C::RJ][C::RK];                                                        // per-cell (b,c) constant
+    uint32_t viol;                                                                     // CHECK: violations of the current task
 };
 
 template <class C>
@@ -291,6 +298,7 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
                 R.all[r][c] = z; R.wX[r][c] = z; R.u1[r][c] = z; R.u3[r][c] = z;
                 R.cBC[r][c] = pair_const(neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]));
             }
+        R.viol = 0;
     }
     const int code = S.acode[S.task[buf].abuf][p.i - 1];
     TA_CHECK(code >= 0 && code < 16);
@@ -316,7 +324,8 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
 // ---- one wavefront step of one thread: halos published at step s-LAG -> tile -> publish for step s+LAG ----
 // R = plane i-1 state (input), Rn = plane i state (output; may be R itself).  The kernel alternates two register sets
 // (R -> Rn, Rn -> R) in a step loop unrolled by two, so that the loop-carried state needs no register moves.
-template <class C>
+// CHECK: the run-time range check (see StreamArgs), sampled every kStreamCheckEvery-th step (warp-uniform).
+template <class C, bool CHECK = false>
 TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const StreamConsts<C> &K, StreamSmem<C> &S,
                               const StreamArgs &A, int tj, int tk, int s, const StreamPos &p)
 {
@@ -424,6 +433,35 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
         }
     }
 
+    uint32_t viol = R.viol;
+    if (CHECK) {
+        if ((s & (kStreamCheckEvery - 1)) == 0) {
+            uint32_t mx = n_all[0][0], mn = n_all[0][0];
+#pragma unroll
+            for (int r = 0; r < RJ; ++r)
+#pragma unroll
+                for (int c = 0; c < RK; c += 2) {
+                    mx = vmax3(mx, n_all[r][c], n_all[r][c + 1]);
+                    mn = vmin3(mn, n_all[r][c], n_all[r][c + 1]);
+                }
+            const int ph = A.base + 2 * (p.i + j0 + 1 + k0 + 1), slack = 2 * (RJ + RK - 2);
+            const int h = ph + A.check_hi, l = ph + A.check_lo + slack;
+            const uint32_t hi_lim = rep((uint32_t)(h > 0xFFFF ? 0xFFFF : h)), lo_lim = rep((uint32_t)(l < 0 ? 0 : l));
+            viol |= (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
+        }
+        if (p.i == A.len && viol != 0) {  // the task leaves this thread: report
+            const StreamTask &T = S.task[p.buf];
+            if (T.valid) {
+                const int bits = ((viol & 0xFFFFu) ? 1 : 0) | ((viol >> 16) ? 2 : 0);
+#if defined(__CUDA_ARCH__)
+                atomicOr(A.pair_flags + T.pair, bits);
+#else
+                A.pair_flags[T.pair] |= bits;
+#endif
+            }
+        }
+    }
+
     // Score = max of the 7 states of cell (len,len,len) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
     if (p.i == A.len) {
         const int jl = A.len - (A.nbj - 1) * C::BJ, kl = A.len - (A.nbk - 1) * C::BK;  // 1..64, in the last block
@@ -452,6 +490,7 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
             Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
             Rn.cBC[r][c] = R.cBC[r][c];
         }
+    Rn.viol = viol;
 }
 
 // global steps a CTA runs for P pairs: steps 0 .. this value

@@ -17,8 +17,10 @@ int literal_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8
 // K1: batched systolic kernel, two triples per 32-bit lane, len <= 64 (fast_batch.cu).  Exact only where no
 // candidate wraps at score_bits -- the dispatcher checks provably_wrap_free() first.
 bool fast_batch_supports(int len);
+// check_bits > 0: the range-checked variant; d_pair_flags[(n+1)/2] (zeroed by the caller) gets bit 0 / 1 set for the
+// low / high triple of a pair whose values came too close to the score_bits = check_bits limits.
 int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                   int64_t n, int len, int32_t *d_scores);
+                   int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr);
 
 // K2: block-sweep kernels for long triples (fast_sweep.cu); same exactness condition as K1 plus the 16-bit envelope
 // checked by fast_sweep_supports().
@@ -70,7 +72,14 @@ int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, co
 bool fast_stream_supports(int len);
 bool fast_stream_fits(int len, int64_t n, int sm_count);  // CTA-private face rings within the memory budget
 int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                    int64_t n, int len, int32_t *d_scores);
+                    int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr);
+
+// flagged-triple plumbing of the checked batch path (batch_fixup.cu): compaction of the per-pair flags into a list of
+// triple indices, gather of those triples into contiguous arrays, scatter of their re-computed scores
+int fixup_compact(cudaStream_t st, const int *d_pair_flags, int64_t n, int *d_list, int *d_count);
+int fixup_gather(cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c, int len, const int *d_list,
+                 int count, uint8_t *g_a, uint8_t *g_b, uint8_t *g_c);
+int fixup_scatter(cudaStream_t st, const int32_t *g_scores, const int *d_list, int count, int32_t *d_scores);
 
 // KT: traceback of one triple (traceback.cu).  d_out: 5 int32 (score, start cell i/j/k, number of columns); d_moves:
 // la+lb+lc bytes, forward order, bit0/1/2 = A/B/C advances.

@@ -161,6 +161,7 @@ def library() -> C.CDLL:
     L.trialign_last_timing.restype = C.c_int
     L.trialign_last_path.restype = C.c_int
     L.trialign_last_devices.restype = C.c_int
+    L.trialign_last_flagged.restype = C.c_int64
     L.trialign_set_option.argtypes = [C.c_char_p, C.c_char_p]
     L.trialign_set_option.restype = C.c_int
     L.trialign_get_option.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
@@ -203,6 +204,11 @@ def last_devices() -> int:
     """GPUs that served the last compute call of this thread (a device mask with several bits may still be served by
     one GPU when the input does not qualify for the multi-GPU pipeline)."""
     return int(library().trialign_last_devices())
+
+
+def last_flagged() -> int:
+    """Triples of the last batch call that the range check handed to the literal kernel."""
+    return int(library().trialign_last_flagged())
 
 
 def set_option(name: str, value=None) -> None:

@@ -70,7 +70,9 @@ enum trialign_path {
     TRIALIGN_PATH_LITERAL = 1,        /* plane-sweep literal kernel */
     TRIALIGN_PATH_FAST_BATCH = 2,     /* K1: batched systolic kernel, two triples per 32-bit lane */
     TRIALIGN_PATH_FAST_LONG = 3,      /* K2: block-dataflow kernel for one long triple */
-    TRIALIGN_PATH_FAST_THEN_LITERAL = 4, /* fast kernel ran, its range check failed, literal kernel re-ran */
+    TRIALIGN_PATH_FAST_THEN_LITERAL = 4, /* range-checked fast kernel ran; the triples whose values came near the
+                                            score_bits limits (all of a single-triple call, only the flagged ones of a
+                                            batch: trialign_last_flagged) were re-scored by the literal kernel */
     TRIALIGN_PATH_TRACEBACK = 5,      /* KT: literal plane sweep with a direction cube + backward walk */
     TRIALIGN_PATH_FAST_STREAM = 6     /* K2S: streaming block-sweep kernel for batches of triples longer than 64 */
 };
@@ -238,6 +240,8 @@ int trialign_synth_batch_dev(int device, uint64_t seed, int64_t first, int64_t n
 int trialign_last_timing(double *seconds, double *cells); /* device time of the kernels only, cells = sum la*lb*lc */
 int trialign_last_path(void);                             /* enum trialign_path */
 int trialign_last_devices(void);                          /* GPUs that served the last call (0 before any call) */
+int64_t trialign_last_flagged(void);                      /* triples of the last batch call that the range check sent to
+                                                             the literal kernel (path FAST_THEN_LITERAL) */
 int64_t trialign_launch_count(void);                      /* kernels launched by this process so far */
 
 #ifdef __cplusplus

@@ -82,8 +82,9 @@ def test_exactness_envelope_boundary(gpu_ta, ob, w):
             got = eng.align_batch(A, B, Cc)
             path = gpu_ta.last_path()
             assert got.tolist() == ob.score_batch(A, B, Cc, w).tolist(), (w, L, path)
-            if L > m:
-                assert path == "literal", (w, L, path)
+            if L > m:  # never the unchecked kernels: the range-checked ones (w >= 6), flagged triples re-run literally
+                assert path in ("literal", "fast_then_literal", "fast_batch", "fast_stream"), (w, L, path)
+                assert path != "literal", (w, L, path)  # every length here is within K1's or K2S's reach
 
 
 def test_two_streams_share_a_device_safely(gpu_ta, ob):
@@ -123,6 +124,57 @@ def test_wide_score_bits_use_the_fast_kernels(gpu_ta, ob):
     got = gpu_ta.TriAlign(score_bits=20).align_batch(A, A[::-1].copy(), A)
     assert gpu_ta.last_path() == "fast_batch"
     assert got.tolist() == ob.score_batch(A, A[::-1].copy(), A, 20).tolist()
+
+
+def test_range_checked_batch_path_reruns_only_flagged_triples(gpu_ta, ob):
+    """Batches whose wrap-freedom cannot be proved from the length (W=8 at len 64: 3*64 > 127): the range-checked K1
+    flags, per triple, values near the limits; only those go to the literal kernel.  Random triples stay far from the
+    limits, identical ones wrap for real."""
+    rng = np.random.default_rng(808)
+    n, L = 301, 64
+    A, B, Cc = (rng.integers(0, 4, (n, L), dtype=np.uint8) for _ in range(3))
+    hot = [0, 7, 150, 299, 300]
+    for t in hot:
+        B[t] = A[t]
+        Cc[t] = A[t]
+    eng = gpu_ta.TriAlign(score_bits=8)
+    got = eng.align_batch(A, B, Cc)
+    assert gpu_ta.last_path() == "fast_then_literal"
+    assert len(hot) <= gpu_ta.last_flagged() <= 3 * len(hot) + 10
+    want = ob.score_batch(A, B, Cc, 8)
+    assert got.tolist() == want.tolist()
+    assert want[0] != 192  # the identical triple really wrapped at 8 bits
+    # forced fast backend refuses instead of guessing
+    with pytest.raises(gpu_ta.TriAlignError) as ei:
+        gpu_ta.TriAlign(score_bits=8, backend=gpu_ta.BACKEND_GPU_FAST).align_batch(A, B, Cc)
+    assert ei.value.rc == -9
+    # no false alarms from the padding beyond len, nor from random data: nothing flagged, no literal launch
+    for Ls in (41, 50, 64):
+        X, Y, Z = (rng.integers(0, 4, (77, Ls), dtype=np.uint8) for _ in range(3))
+        got = eng.align_batch(X, Y, Z)
+        assert gpu_ta.last_path() == "fast_batch" and gpu_ta.last_flagged() == 0, Ls
+        assert got.tolist() == ob.score_batch(X, Y, Z, 8).tolist()
+    # W=7: everything above len 19 is checked; mutated triples reach the limits often
+    X, Y, Z = (np.stack(t) for t in zip(*[ob.mutated_triple(rng, 48) for _ in range(40)]))
+    got = gpu_ta.TriAlign(score_bits=7).align_batch(X, Y, Z)
+    assert got.tolist() == ob.score_batch(X, Y, Z, 7).tolist()
+    assert gpu_ta.last_flagged() > 0
+
+
+def test_range_checked_stream_path(gpu_ta, ob):
+    """The same for batches longer than 64 (K2S): W=10 at len 200 (3*200 > 511)."""
+    rng = np.random.default_rng(909)
+    n, L = 9, 200
+    A, B, Cc = (rng.integers(0, 4, (n, L), dtype=np.uint8) for _ in range(3))
+    B[3] = A[3]
+    Cc[3] = A[3]          # 600 > 511: wraps
+    B[8], Cc[8] = A[8], A[8]
+    got = gpu_ta.TriAlign(score_bits=10).align_batch(A, B, Cc)
+    assert gpu_ta.last_path() == "fast_then_literal" and 2 <= gpu_ta.last_flagged() <= 4
+    assert got.tolist() == ob.score_batch(A, B, Cc, 10).tolist()
+    got = gpu_ta.TriAlign(score_bits=10).align_batch(A[:3], B[:3], Cc[:3])
+    assert gpu_ta.last_path() == "fast_stream" and gpu_ta.last_flagged() == 0
+    assert got.tolist() == ob.score_batch(A[:3], B[:3], Cc[:3], 10).tolist()
 
 
 # ---- several GPUs ----
