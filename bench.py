@@ -427,9 +427,8 @@ def run_long(R, ta, name, steps, warmup, parity, multi):
     active = multi or R.rank == 0
     mode = "single GPU"
     if multi:
-        use_cols = ta.get_option("multi") == "cols"
-        pipe = (ta.ColumnPipeline(length, length, length, score_bits=w, device=R.local_rank) if use_cols
-                else ta.SlabPipeline(length, length, score_bits=w, device=R.local_rank))
+        pipe = ta.make_pipeline(length, length, length, score_bits=w, device=R.local_rank)  # trialign_multi_plan's choice
+        use_cols = isinstance(pipe, ta.ColumnPipeline)
         mode = ("column pipeline" if use_cols else "i-slab pipeline") + f" over {R.world} GPUs, NVLink peer stores"
 
         def step():
@@ -515,8 +514,9 @@ def run_ours(args, rank, world, local_rank):
         secondary = []
         if not args.no_secondary:
             ssteps = max(2, min(args.steps, 5))
+            lsteps = 100  # long1024 takes 2.3 ms per step: enough steps for the clock sampler to see the load
             if world == 1:
-                secondary.append(run_long(R, ta, "long1024", ssteps, 3, parity, multi=False))
+                secondary.append(run_long(R, ta, "long1024", lsteps, 3, parity, multi=False))
                 secondary.append(run_batch(R, ta, "batch256", 2, 3, 1 << 18, 0, gs[4]["scores"], False, parity))
                 secondary.append(run_long(R, ta, "long8192", min(ssteps, 3), 3, parity, multi=False))
             else:

@@ -23,6 +23,7 @@ from .trialign import (  # noqa: F401
     get_option,
     last_devices,
     last_flagged,
+    multi_plan,
     set_option,
     last_path,
     last_timing,
@@ -42,4 +43,4 @@ from .trialign import (  # noqa: F401
     write_seq_dat,
     write_tb_init,
 )
-from .parallel import ColumnPipeline, SlabPipeline, col_range, shard_range, slab_range  # noqa: E402,F401
+from .parallel import ColumnPipeline, SlabPipeline, col_range, make_pipeline, shard_range, slab_range  # noqa: E402,F401

@@ -79,8 +79,8 @@ static const char *const kOptionNames[] = {
     "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l (default) | stream (K2S on len <= 64)
     "k2",          // "sweep": first-generation per-block kernel for batches longer than 64 (A/B runs)
     "k2l",         // "old": first-generation kernel for one long triple (A/B runs)
-    "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate", "k2_rgate",  // K2L experiment parameters (fast_long.cu)
-    "multi",       // one long triple on several GPUs: "slab" (i-slab pipeline, default) | "cols" (column pipeline)
+    "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate", "k2_rgate", "k2_cols_order",  // K2L experiment parameters (fast_long.cu)
+    "multi",       // one long triple on several GPUs: "slab" (i-slab pipeline) | "cols" (column pipeline); default: auto
     "multi_min",   // smallest la (slab) / lc (cols) per GPU for which the multi-GPU pipeline is used (default 64 / 128)
 };
 static std::mutex g_opt_mu;
@@ -337,6 +337,22 @@ std::vector<int> devices_of(unsigned mask)
         if (mask & (1u << d)) devs.push_back(d);
     if (devs.empty()) devs.push_back(0);
     return devs;
+}
+
+// How one long triple is spread over G GPUs: 0 = not at all (first GPU alone), 1 = i-slab pipeline, 2 = column pipeline.
+// Measured on 8192^3 (W=16): 2 GPUs slab 255 ms / cols 269, 4 GPUs 143 / 140, 8 GPUs 81.3 / 78.3 -- the slab pipeline
+// pays (G-1) task durations of fill plus the set-up of G times as many tasks, the column pipeline a lag of one block row
+// per GPU plus coarser waves; columns win from 4 GPUs on when every GPU gets at least two block-column pairs.
+bool long_launch_supports(int planes, int la_total, int lb, int lc);
+int multi_plan(int la, int lb, int lc, int score_bits, int G)
+{
+    if (G < 2 || !provably_wrap_free(la, lb, lc, score_bits)) return 0;
+    const bool cols_ok = lc >= opt_int("multi_min", 128) * G && lc >= 128 * G && long_launch_supports(la, la, lb, lc);
+    const bool slab_ok = la >= opt_int("multi_min", 64) * G && la >= G && long_launch_supports((la + G - 1) / G, la, lb, lc);
+    if (opt_is("multi", "cols")) return cols_ok ? 2 : 0;
+    if (opt_is("multi", "slab")) return slab_ok ? 1 : 0;
+    if (cols_ok && G >= 4 && lc >= 256 * G && la >= 2048) return 2;
+    return slab_ok ? 1 : (cols_ok ? 2 : 0);
 }
 
 // Limits of one K2L launch over `planes` planes of a triple whose whole extent is (la_total, lb, lc): the launch keeps
@@ -643,15 +659,11 @@ int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     // several GPUs in the mask: the triple is split as an i-slab (or column) pipeline when it is long enough for every
     // GPU to get whole blocks and the fast kernels are provably bit-exact for it; otherwise the first GPU serves it alone
     // (trialign_last_devices() tells which happened)
-    if (devs.size() > 1 && backend != TRIALIGN_BACKEND_GPU_LITERAL && !ts.scoring_active &&
-        provably_wrap_free(la, lb, lc, score_bits)) {
+    if (devs.size() > 1 && backend != TRIALIGN_BACKEND_GPU_LITERAL && !ts.scoring_active) {
         const int G = (int)devs.size();
-        const bool cols = opt_is("multi", "cols");
-        bool ok;
-        if (cols) ok = lc >= opt_int("multi_min", 128) * G && lc >= 128 * G && long_launch_supports(la, la, lb, lc);
-        else ok = la >= opt_int("multi_min", 64) * G && la >= G && long_launch_supports((la + G - 1) / G, la, lb, lc);
-        if (ok) {
-            rc = run_host_triple_multi(devs, devices, cols, a, la, b, lb, c, lc, score, fin, &sec);
+        const int plan = multi_plan(la, lb, lc, score_bits, G);
+        if (plan) {
+            rc = run_host_triple_multi(devs, devices, plan == 2, a, la, b, lb, c, lc, score, fin, &sec);
             if (rc != TRIALIGN_EUNSUPPORTED) {  // EUNSUPPORTED: no peer access between neighbours -> one GPU below
                 if (rc) return rc;
                 if (final_states) std::memcpy(final_states, fin, sizeof fin);
@@ -964,6 +976,13 @@ int trialign_score_batch_ex(const uint8_t *a, const uint8_t *b, const uint8_t *c
     if (is_rtl) return trialign_score_batch(a, b, c, n, len, score_bits, TRIALIGN_BACKEND_AUTO, devices, scores);
     ScopedScoring scope(*scoring);
     return trialign_score_batch(a, b, c, n, len, score_bits, TRIALIGN_BACKEND_AUTO, devices, scores);
+}
+
+int trialign_multi_plan(int la, int lb, int lc, int score_bits, int n_devices)
+{
+    if (la < 0 || lb < 0 || lc < 0 || score_bits < 2 || score_bits > 32 || n_devices < 1) return TRIALIGN_EINVAL;
+    if (la == 0 || lb == 0 || lc == 0) return 0;
+    return multi_plan(la, lb, lc, score_bits, n_devices);
 }
 
 int trialign_slab_buffer_bytes(int lb, int lc, int64_t *state_bytes, int64_t *flag_bytes)

@@ -286,10 +286,14 @@ int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, in
     std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
     for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
     const int nbj = A.nbj, gate = A.gate, nbkp = A.nbkp;
-    std::stable_sort(order.begin(), order.end(), [nbj, gate, nbkp, cols](int x, int y) {
-        // column pipeline: row-major, so that the last local column of the first block rows -- what the right
-        // neighbour GPU is waiting for -- is swept first (in earliest-start order it would come last)
-        if (cols) return (x % nbj) * nbkp + x / nbj < (y % nbj) * nbkp + y / nbj;
+    // Column pipeline: row-major claims, so that every GPU works on the same band of block rows at the same time and the
+    // last local column of a row -- what the right neighbour waits for -- follows its first column within 8 claims.
+    // Earliest-start order (option k2_cols_order=diag) is 2 % faster for a range by itself (65.9 vs 67.3 ms per eighth of
+    // 8192^3), but tilts the sweep: column 7 trails column 0 by 0.7 wave, the neighbour trails by as much, and 8 GPUs
+    // take 96 ms instead of 78 (tools/sim_cols_schedule.py models both).
+    const bool row_major = cols && !opt_is("k2_cols_order", "diag");
+    std::stable_sort(order.begin(), order.end(), [nbj, gate, nbkp, row_major](int x, int y) {
+        if (row_major) return (x % nbj) * nbkp + x / nbj < (y % nbj) * nbkp + y / nbj;
         return fast::long2_order_key<C>(x % nbj, x / nbj, gate) < fast::long2_order_key<C>(y % nbj, y / nbj, gate);
     });
     for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;

@@ -48,6 +48,19 @@ def exchange_objects(obj, group=None) -> List:
     return out
 
 
+def make_pipeline(la: int, lb: int, lc: int, score_bits: int = 16, device: Optional[int] = None, group=None):
+    """The pipeline trialign_score() itself would use for this triple on the group's GPUs (trialign_multi_plan):
+    a SlabPipeline or a ColumnPipeline; raises if the triple does not qualify for either."""
+    import torch.distributed as dist
+
+    plan = _ta.multi_plan(la, lb, lc, score_bits, dist.get_world_size(group))
+    if plan == "cols":
+        return ColumnPipeline(la, lb, lc, score_bits=score_bits, device=device, group=group)
+    if plan == "slab":
+        return SlabPipeline(lb, lc, score_bits=score_bits, device=device, group=group)
+    raise ValueError("the triple does not qualify for a multi-GPU pipeline (too short, or not provably wrap-free)")
+
+
 class SlabPipeline:
     """i-slab pipeline for one long triple; build once per (lb, lc), call run() as often as needed.
 

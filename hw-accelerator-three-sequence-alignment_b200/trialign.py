@@ -162,6 +162,8 @@ def library() -> C.CDLL:
     L.trialign_last_path.restype = C.c_int
     L.trialign_last_devices.restype = C.c_int
     L.trialign_last_flagged.restype = C.c_int64
+    L.trialign_multi_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.trialign_multi_plan.restype = C.c_int
     L.trialign_set_option.argtypes = [C.c_char_p, C.c_char_p]
     L.trialign_set_option.restype = C.c_int
     L.trialign_get_option.argtypes = [C.c_char_p, C.c_char_p, C.c_int]
@@ -204,6 +206,13 @@ def last_devices() -> int:
     """GPUs that served the last compute call of this thread (a device mask with several bits may still be served by
     one GPU when the input does not qualify for the multi-GPU pipeline)."""
     return int(library().trialign_last_devices())
+
+
+def multi_plan(la: int, lb: int, lc: int, score_bits: int, n_devices: int) -> str:
+    """How one long triple is spread over n_devices GPUs: "single", "slab" or "cols" (trialign_multi_plan)."""
+    rc = int(library().trialign_multi_plan(la, lb, lc, score_bits, n_devices))
+    _check(min(rc, 0), "trialign_multi_plan")
+    return ("single", "slab", "cols")[rc]
 
 
 def last_flagged() -> int:

@@ -101,7 +101,7 @@ int trialign_device_count(void);            /* 0 when no driver / no device; nev
 
 /* Run-time options: the experiment switches of the kernels (A/B variants, gate intervals, multi-GPU decomposition).
  * Nothing in the library reads the environment; a caller that wants a non-default kernel says so explicitly.
- * Names: debug, k1, k2, k2l, k2_lag, k2_pp, k2_gatetid, k2_early, k2_gate, k2_rgate, multi ("slab" | "cols"), multi_min.
+ * Names: debug, k1, k2, k2l, k2_lag, k2_pp, k2_gatetid, k2_early, k2_gate, k2_rgate, k2_cols_order, multi ("slab" | "cols"; default: chosen by trialign_multi_plan), multi_min.
  * value NULL or "" restores the default.  Unknown names give TRIALIGN_EINVAL.  Process-wide, thread-safe. */
 int trialign_set_option(const char *name, const char *value);
 int trialign_get_option(const char *name, char *buf, int cap); /* "" when unset */
@@ -112,9 +112,10 @@ int trialign_get_option(const char *name, char *buf, int cap); /* "" when unset 
  * Any zero length gives score 0 (the cell lies on a zero boundary plane).
  * Several bits set: the calling thread drives all of those GPUs (peer access, one stream per device) and the triple is
  * split as an i-slab pipeline -- GPU g computes planes (la*g/G, la*(g+1)/G] and hands the plane state of every block to
- * GPU g+1 through NVLink peer stores (option multi=cols: the column pipeline instead) -- provided every GPU gets at least
- * 64 planes and the fast kernels are provably bit-exact for the input; otherwise the first GPU of the mask serves the
- * call alone.  trialign_last_devices() reports how many GPUs did. */
+ * GPU g+1 through NVLink peer stores -- or, from 4 GPUs on, as a column pipeline (GPU g sweeps all planes of a range of
+ * block columns and streams the boundary faces to GPU g+1; trialign_multi_plan tells which) -- provided every GPU gets
+ * at least 64 planes / 128 columns and the fast kernels are provably bit-exact for the input; otherwise the first GPU
+ * of the mask serves the call alone.  trialign_last_devices() reports how many GPUs did. */
 int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                    int backend, unsigned devices, int32_t *score, int32_t final_states[7]);
 
@@ -167,6 +168,12 @@ int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
 int64_t trialign_triple_count(int nseq);
 int trialign_score_all_triples(const uint8_t *seqs, int nseq, int len, int score_bits, int backend, unsigned devices,
                                int32_t *scores);
+
+/* How trialign_score() would spread one long triple over n_devices GPUs: 0 = first GPU alone (too short, or not provably
+ * wrap-free), 1 = i-slab pipeline, 2 = column pipeline (option multi = slab | cols forces one; the default picks columns
+ * from 4 GPUs on when every GPU gets at least two 128-column block pairs).  One process per GPU (below) should follow
+ * the same plan; parallel.make_pipeline() does. */
+int trialign_multi_plan(int la, int lb, int lc, int score_bits, int n_devices);
 
 /* ---- i-slab pipeline: ONE long triple over several GPUs, one process per GPU ----
  * Rank g computes planes (i_begin, i_end] of the cube for every (j,k) block and hands the plane-i_end state of each

@@ -654,8 +654,11 @@ extern "C" int emu_fast_long2_cols(const uint8_t *a, int la, const uint8_t *b, i
         G.pos_of.resize((size_t)A.tasks_total);
         for (int t = 0; t < (int)A.tasks_total; ++t) G.order[t] = t;
         const int nbkp = A.nbkp;
-        std::stable_sort(G.order.begin(), G.order.end(), [nbj, nbkp](int x, int y) {
-            return (x % nbj) * nbkp + x / nbj < (y % nbj) * nbkp + y / nbj;  // row-major (fast_long.cu, cols)
+        const bool row_major = (seed & 1) == 0;  // both claim orders of fast_long.cu (default: earliest start first)
+        const int gate = A.gate;
+        std::stable_sort(G.order.begin(), G.order.end(), [nbj, nbkp, row_major, gate](int x, int y) {
+            if (row_major) return (x % nbj) * nbkp + x / nbj < (y % nbj) * nbkp + y / nbj;
+            return long2_order_key<C>(x % nbj, x / nbj, gate) < long2_order_key<C>(y % nbj, y / nbj, gate);
         });
         for (int p = 0; p < (int)A.tasks_total; ++p) G.pos_of[G.order[p]] = p;
         A.order = G.order.data(); A.pos_of = G.pos_of.data();
