@@ -76,9 +76,7 @@ NvtxRange::~NvtxRange() { nvtxRangePop(); }
 // Every experiment switch of the kernels is an explicit option of the library; nothing is read from the environment.
 static const char *const kOptionNames[] = {
     "debug",       // 1: launch geometry of the fast kernels on stderr
-    "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l (default) | stream (K2S on len <= 64)
-    "k2",          // "sweep": first-generation per-block kernel for batches longer than 64 (A/B runs)
-    "k2l",         // "old": first-generation kernel for one long triple (A/B runs)
+    "k1",          // K1 variant for A/B runs: 256 | 256m | 256m2 | 512 | 512m | 256l (default) | stream (K2S on len <= 64)
     "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate", "k2_rgate", "k2_cols_order",  // K2L experiment parameters (fast_long.cu)
     "multi",       // one long triple on several GPUs: "slab" (i-slab pipeline) | "cols" (column pipeline); default: auto
     "multi_min",   // smallest la (slab) / lc (cols) per GPU for which the multi-GPU pipeline is used (default 64 / 128)
@@ -149,12 +147,10 @@ int get_ctx(int device, DeviceCtx **out)
 
 namespace {
 
-// one long triple: K2L (fast_long.cu); option k2l=old selects the first-generation kernel (fast_sweep.cu) for A/B runs
+// one long triple: K2L (fast_long.cu)
 int long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb, const uint8_t *d_c,
              int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol, const SlabLink *slab = nullptr)
 {
-    if (opt_is("k2l", "old"))
-        return fast_sweep_long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_score, d_states, check_bits, d_viol, slab);
     return fast_long2_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_score, d_states, check_bits, d_viol, slab);
 }
 
@@ -196,23 +192,29 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
             ts.last_path = TRIALIGN_PATH_FAST_BATCH;
             return fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
         }
-        if (n == 1 && fast_sweep_supports(la, lb, lc)) {
+        if (n == 1 && fast_long_supports(la, lb, lc)) {
             ts.last_path = TRIALIGN_PATH_FAST_LONG;
             return long_run(ctx, st, d_a, la, d_b, lb, d_c, lc, d_scores, d_finals, 0, nullptr);
         }
-        if (!d_finals && la == lb && lb == lc && fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count) &&
-            !opt_is("k2", "sweep")) {  // option k2=sweep: the per-block kernel below, for A/B runs
+        if (!d_finals && la == lb && lb == lc && fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count)) {
             ts.last_path = TRIALIGN_PATH_FAST_STREAM;
             return fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
         }
-        if (!d_finals && la == lb && lb == lc && fast_sweep_supports(la, lb, lc)) {
+        // batches of very long triples (beyond K2S's 2,048, or whose CTA-private face rings would not fit): every
+        // triple is a full-GPU job of its own for K2L, one launch after the other
+        if (!d_finals && fast_long_supports(la, lb, lc)) {
             ts.last_path = TRIALIGN_PATH_FAST_LONG;
-            return fast_sweep_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
+            for (int64_t t = 0; t < n; ++t) {
+                const int rc = long_run(ctx, st, d_a + t * la, la, d_b + t * lb, lb, d_c + t * lc, lc, d_scores + t,
+                                        nullptr, 0, nullptr);
+                if (rc) return rc;
+            }
+            return TRIALIGN_OK;
         }
     }
     // One long triple whose wrap-freedom cannot be proved from the lengths: run the fast kernel with its run-time
     // range check, and fall back to the literal kernel only if some value came near the score_bits limits.
-    if (want_fast && n == 1 && score_bits >= 10 && score_bits <= 16 && fast_sweep_supports(la, lb, lc)) {
+    if (want_fast && n == 1 && score_bits >= 10 && score_bits <= 16 && fast_long_supports(la, lb, lc)) {
         int rc = ctx->viol.reserve(256);
         if (rc) return rc;
         int *d_viol = (int *)ctx->viol.ptr;
@@ -359,7 +361,7 @@ int multi_plan(int la, int lb, int lc, int score_bits, int G)
 // its own planes' a symbols in shared memory, the 16-bit potential range depends on the whole triple.
 bool long_launch_supports(int planes, int la_total, int lb, int lc)
 {
-    return planes >= 1 && planes <= la_total && fast_sweep_supports(planes, lb, lc) &&
+    return planes >= 1 && planes <= la_total && fast_long_supports(planes, lb, lc) &&
            fast_long_range_ok(planes, la_total, lb, lc);
 }
 
@@ -436,8 +438,8 @@ int run_host_triple_multi(const std::vector<int> &devs, unsigned mask, bool cols
         sbytes = fast_long2_col_face_bytes(la, lb);
         fbytes = std::max<size_t>(fast_long2_col_prog_bytes(lb), 256);
     } else {
-        sbytes = fast_sweep_slab_state_bytes(lb, lc);
-        fbytes = fast_sweep_slab_flag_bytes(lb, lc);
+        sbytes = fast_long_slab_state_bytes(lb, lc);
+        fbytes = fast_long_slab_flag_bytes(lb, lc);
     }
     for (size_t g = 1; g < G; ++g)
         if ((rc = multi_reserve(mp, g, sbytes, fbytes))) return rc;
@@ -988,8 +990,8 @@ int trialign_multi_plan(int la, int lb, int lc, int score_bits, int n_devices)
 int trialign_slab_buffer_bytes(int lb, int lc, int64_t *state_bytes, int64_t *flag_bytes)
 {
     if (lb < 1 || lc < 1 || !state_bytes || !flag_bytes) return TRIALIGN_EINVAL;
-    *state_bytes = (int64_t)fast_sweep_slab_state_bytes(lb, lc);
-    *flag_bytes = (int64_t)fast_sweep_slab_flag_bytes(lb, lc);
+    *state_bytes = (int64_t)fast_long_slab_state_bytes(lb, lc);
+    *flag_bytes = (int64_t)fast_long_slab_flag_bytes(lb, lc);
     return TRIALIGN_OK;
 }
 

@@ -315,8 +315,9 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
         S.col[ws][1][tk][j0 + r] = n_u2[r][RK - 1];
     }
 
-    uint32_t viol = R.viol;
+    uint32_t viol = 0;
     if (CHECK) {
+        viol = R.viol;
         if ((s & (kBatchCheckEvery - 1)) == 0 && i <= A.len) {
             // only cells of the real triple count: padding (j or k beyond len) decays without bound of its own
             uint32_t mx = 0u, mn = 0xFFFFFFFFu;
@@ -367,7 +368,7 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
             Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
             Rn.cBC[r][c] = R.cBC[r][c];
         }
-    Rn.viol = viol;
+    if (CHECK) Rn.viol = viol;
 }
 
 // Steps a CTA needs for P pairs, and the CTA-uniform actions of global step s.

@@ -335,6 +335,41 @@ int run_long2(DeviceCtx *ctx, cudaStream_t st, fast::SweepArgs A, bool check, in
 
 }  // namespace
 
+// ---- limits and hand-over sizes (host) ----
+// 16-bit envelope of the fast kernels: stored value = v + 2*(i + jl + kl) + base, block-local jl, kl <= 64 / 128.
+// `planes` = planes of ONE launch (an i-slab of a longer triple keeps only its own a symbols in shared memory and
+// restarts its plane potential); the value envelope depends on the whole triple (la_total).
+bool fast_long_range_ok(int planes, int la_total, int lb, int lc)
+{
+    using C = fast::Long2Cfg<1>;
+    if (planes < 1 || la_total < planes || lb < 1 || lc < 1) return false;
+    const long long m = la_total < lb ? (la_total < lc ? la_total : lc) : (lb < lc ? lb : lc);
+    const long long base = -envelope_lo(m) + 32;
+    const long long top = base + envelope_hi(m) + 9 + 2 * ((long long)planes + 2 * C::PLAG + 2 * C::DEPTH + 64 + 128) + 600;
+    return top < 65535;
+}
+
+bool fast_long_supports(int la, int lb, int lc)
+{
+    using C = fast::Long2Cfg<1>;
+    if (la < 1 || lb < 1 || lc < 1 || la > C::LA_MAX - 64) return false;
+    return fast_long_range_ok(la, la, lb, lc);
+}
+
+// i-slab hand-over: per block task the plane state {all, wX, u1, u3} of 16 cells x 256 threads (packed words) + one flag
+size_t fast_long_slab_state_bytes(int lb, int lc)
+{
+    using C = fast::Long2Cfg<1>;
+    const long long tasks = (long long)((lb + C::BJ - 1) / C::BJ) * ((lc + C::KSPAN - 1) / C::KSPAN);
+    return (size_t)tasks * 4 * 16 * C::NT * sizeof(uint32_t);
+}
+size_t fast_long_slab_flag_bytes(int lb, int lc)
+{
+    using C = fast::Long2Cfg<1>;
+    const long long tasks = (long long)((lb + C::BJ - 1) / C::BJ) * ((lc + C::KSPAN - 1) / C::KSPAN);
+    return (size_t)tasks * sizeof(int);
+}
+
 size_t fast_long2_col_face_bytes(int la, int lb)
 {
     using C = fast::Long2Cfg<1>;

@@ -1,6 +1,6 @@
 // fast_long.cuh -- K2L: block-sweep kernel for ONE long triple (BASELINE configs 3 and 5), second generation.
 //
-// Same decomposition as fast_sweep.cuh's LONG mode -- the RTL's slicing method (src/TriAlign_1cyc.v:127-140,289-335):
+// The RTL's slicing method (src/TriAlign_1cyc.v:127-140,289-335):
 // the (j,k) plane is cut into blocks, every block is swept over all of A, block faces stream CTA -> CTA through
 // HBM/L2 gated by per-task progress counters; the two 16-bit halves of a word are two k-ADJACENT 64x64 blocks, the
 // high half running PLAG planes behind the low half (thread (tj,tk)'s high half is the logical thread (tj,tk+16) of a
@@ -13,7 +13,7 @@
 //     left-edge threads merge "previous pair's high block" with "this pair's low block" (hi_lo);
 //   * a symbols of both halves pre-combined into one code per step;
 //   * tile patches dealt to the warps so that every scheduler carries the same edge duty (see stream_thread_pos).
-// Task descriptors, claim order, face rings, slab hand-over layout: shared with fast_sweep.cuh (SweepArgs, SweepTask).
+// Task descriptors, face rings, slab hand-over layout: sweep_common.cuh (SweepArgs, SweepTask).
 #pragma once
 
 #include "fast_stream.cuh"
@@ -400,7 +400,7 @@ TA_HD void long2_thread_step(const Long2Regs<C> &R, Long2Regs<C> &Rn, const Long
         }
     }
 
-    // Run-time wrap check (used when wrap-freedom at score_bits cannot be proved a priori), see fast_sweep.cuh: `all`
+    // Run-time wrap check (used when wrap-freedom at score_bits cannot be proved a priori): `all`
     // moves by at most +3 / -4 per plane, so sampling every 16th plane of a cell with 45 / 60 margins bounds every
     // plane.  Sampled on every 16th STEP: warp-uniform (sampling by plane index made 11 of 16 steps of a warp diverge
     // into this block, its lanes having 11 different skews).

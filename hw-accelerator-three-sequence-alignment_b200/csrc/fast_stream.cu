@@ -120,7 +120,7 @@ long long stream_face_bytes(int len, long long grid)
 
 bool fast_stream_supports(int len)
 {
-    return len >= Cfg::LEN_MIN && len <= Cfg::LEN_MAX && fast_sweep_supports(len, len, len);
+    return len >= Cfg::LEN_MIN && len <= Cfg::LEN_MAX && fast_long_supports(len, len, len);
 }
 
 int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,

@@ -6,7 +6,7 @@
 //     thread (tj,tk) owns a 4x4 tile for all i and runs plane i of task t at global step
 //         s = t*len + (i-1) + LAG*(tj+tk)
 //     -- the tasks of a CTA (all blocks of its pairs, j-blocks fastest) stream through the array BACK TO BACK, so the
-//     LAG*(TJ+TK-2)-step fill/drain is paid once per CTA, not once per block (fast_sweep.cuh's BATCH mode pays it per
+//     LAG*(TJ+TK-2)-step fill/drain is paid once per CTA, not once per block (a per-block kernel pays it per
 //     block: 287 steps for 256 planes), and there is no per-task set-up phase: the next task's descriptor, (b,c)
 //     symbols and score tables are staged into a third buffer while two tasks are in flight;
 //   * K1's lagged barrier (LAG 2): tile edges are consumed two steps after publication, so a warp only waits for
@@ -20,7 +20,7 @@
 // Exactness domain and potentials: fast_core.cuh (block-local j,k; absolute i; faces re-based when written).
 #pragma once
 
-#include "fast_sweep.cuh"  // cp.async / 128-bit store helpers shared with K2
+#include "sweep_common.cuh"  // task descriptor, cp.async / 128-bit store helpers
 
 namespace trialign {
 namespace fast {
@@ -433,8 +433,9 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
         }
     }
 
-    uint32_t viol = R.viol;
+    uint32_t viol = 0;
     if (CHECK) {
+        viol = R.viol;
         if ((s & (kStreamCheckEvery - 1)) == 0) {
             uint32_t mx = n_all[0][0], mn = n_all[0][0];
 #pragma unroll
@@ -490,7 +491,7 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
             Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
             Rn.cBC[r][c] = R.cBC[r][c];
         }
-    Rn.viol = viol;
+    if (CHECK) Rn.viol = viol;
 }
 
 // global steps a CTA runs for P pairs: steps 0 .. this value

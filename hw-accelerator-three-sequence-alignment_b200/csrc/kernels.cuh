@@ -22,9 +22,9 @@ bool fast_batch_supports(int len);
 int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                    int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr);
 
-// K2: block-sweep kernels for long triples (fast_sweep.cu); same exactness condition as K1 plus the 16-bit envelope
-// checked by fast_sweep_supports().
-bool fast_sweep_supports(int la, int lb, int lc);
+// K2L: block-sweep kernel for ONE long triple (fast_long.cu); same exactness condition as K1 plus the 16-bit envelope
+// checked by fast_long_supports().
+bool fast_long_supports(int la, int lb, int lc);
 // 16-bit range of a launch over `planes` planes of a triple of la_total x lb x lc (i-slab pipeline: planes < la_total)
 bool fast_long_range_ok(int planes, int la_total, int lb, int lc);
 // i-slab pipeline of one long triple over several GPUs: a launch computes planes (i_begin, i_begin+la] and hands the
@@ -38,13 +38,9 @@ struct SlabLink {
     void *out_state;       // nullptr for the last slab
     void *out_flags;
 };
-size_t fast_sweep_slab_state_bytes(int lb, int lc);
-size_t fast_sweep_slab_flag_bytes(int lb, int lc);
-int fast_sweep_long_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, const uint8_t *d_b, int lb,
-                        const uint8_t *d_c, int lc, int32_t *d_score, int32_t *d_states, int check_bits, int *d_viol,
-                        const SlabLink *slab = nullptr);
-// K2L (fast_long.cu): the same decomposition on the K1 / K2S step engine (split-phase or lagged mbarrier, block halos
-// prefetched by the edge threads); the default for one long triple.  Same arguments, same hand-over layout.
+size_t fast_long_slab_state_bytes(int lb, int lc);
+size_t fast_long_slab_flag_bytes(int lb, int lc);
+// K2L runs on the K1 / K2S step engine (split-phase or lagged mbarrier, block halos prefetched by the edge threads).
 // column pipeline of one long triple over several GPUs: a launch sweeps ALL planes of a contiguous range of block-column
 // pairs; the K faces crossing the range's edges stream to / from the neighbour GPUs through peer memory, gated by
 // epoch-tagged progress words at system scope.  in_* live on this GPU, out_* are peer pointers.
@@ -64,8 +60,6 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
                    const SlabLink *slab = nullptr, const ColLink *col = nullptr);
 // check_bits > 0 selects the range-checked kernel: *d_viol (zeroed by the caller) becomes non-zero if some value came
 // close enough to the score_bits = check_bits limits that a wrap cannot be excluded.
-int fast_sweep_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                         int64_t n, int len, int32_t *d_scores);
 
 // K2S: streaming block-sweep kernel for batches of equal-length triples longer than 64 (fast_stream.cu): all blocks of
 // a CTA's pairs stream through the systolic array back to back.  Same exactness condition as K1 / K2.

@@ -113,227 +113,6 @@ extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// K2 (fast_sweep.cuh): block sweep with faces in "global" memory.  LONG mode runs several emulated CTAs round-robin,
-// one wavefront step per turn; a CTA whose dependencies are not ready simply skips its turn (the kernel spins).
-// ---------------------------------------------------------------------------------------------------------------
-#include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_sweep.cuh"
-
-namespace {
-
-template <class C>
-struct EmuCta {
-    std::unique_ptr<SweepSmem<C>> S{new SweepSmem<C>};
-    std::vector<SweepRegs<C>> R = std::vector<SweepRegs<C>>(C::NT);
-    std::vector<SweepConsts<C>> K = std::vector<SweepConsts<C>>(C::NT);
-    bool has_task = false, prologue_done = false;
-    int s = 0, cert = -2;
-    void setup(const SweepArgs &A)
-    {
-        for (int tid = 0; tid < C::NT; ++tid) sweep_load_bc<C>(*S, A, tid);
-        for (int tid = 0; tid < C::NT; ++tid) sweep_build_tables<C>(*S, tid);
-        for (int tid = 0; tid < C::NT; ++tid) {
-            int tj, tk;
-            sweep_thread_pos<C>(tid, tj, tk);
-            sweep_init_thread<C>(R[tid], *S, tj, tk);
-        }
-        prologue_done = false;
-        s = 0;
-        cert = -2;
-    }
-    void fetch(const SweepArgs &A, int step)
-    {
-        for (int tid = 0; tid < C::NT; ++tid) {
-            int tj, tk;
-            sweep_thread_pos<C>(tid, tj, tk);
-            sweep_edge_fetch<C>(*S, A, tj, tk, step);
-        }
-    }
-    uint32_t viol() const
-    {
-        uint32_t v = 0;
-        for (const auto &r : R) v |= r.viol;
-        return v;
-    }
-    void step(const SweepArgs &A, int step)
-    {
-        for (int tid = 0; tid < C::NT; ++tid) {
-            int tj, tk;
-            sweep_thread_pos<C>(tid, tj, tk);
-            sweep_thread_step<C, true>(R[tid], K[tid], *S, A, tj, tk, step, tid);
-            sweep_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, step + 1, tid);
-        }
-    }
-    void prepare0(const SweepArgs &A)
-    {
-        for (int tid = 0; tid < C::NT; ++tid) {
-            int tj, tk;
-            sweep_thread_pos<C>(tid, tj, tk);
-            sweep_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, 0, tid);
-        }
-    }
-};
-
-}  // namespace
-
-static int g_emu_gate = 4;
-extern "C" void emu_set_gate(int gate) { g_emu_gate = gate; }  // gate interval of the emulated LONG-mode runs
-
-namespace {
-// one (slab of a) long triple on n_ctas emulated CTAs; iface_* may be null
-int run_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int base, int n_ctas,
-             int want_states, int32_t *out8, int check_bits, int *viol_out, const uint32_t *iface_in, uint32_t *iface_out,
-             int last_slab)
-{
-    using C = SweepCfg<true>;
-    if (la < 1 || lb < 1 || lc < 1 || la > C::LA_MAX || n_ctas < 1) return -1;
-    SweepArgs A{};
-    A.a = a; A.b = b; A.c = c; A.n = 1; A.la = la; A.lb = lb; A.lc = lc;
-    A.nbj = (lb + C::BJ - 1) / C::BJ;
-    A.nbkp = (lc + C::KSPAN - 1) / C::KSPAN;
-    A.tasks_total = (long long)A.nbj * A.nbkp;
-    A.gate = g_emu_gate;
-    A.fj_slot_words = (long long)(la + C::LAG + 2) * C::FJ_ROW_WORDS;
-    A.fk_slot_words = (long long)(la + C::LAG + 2) * C::FK_ROW_WORDS;
-    A.fj_ring = (int)A.tasks_total;  // the emulation keeps every face (ring re-use is a launcher concern)
-    A.fk_ring = (int)A.tasks_total;
-    std::vector<uint32_t> fj((size_t)A.fj_ring * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
-    std::vector<int> prog((size_t)A.tasks_total, 0);
-    unsigned long long counter = 0;
-    // claim order exactly as the launcher builds it
-    std::vector<int> order((size_t)A.tasks_total), pos_of((size_t)A.tasks_total);
-    for (int t = 0; t < (int)A.tasks_total; ++t) order[t] = t;
-    const int nbj = A.nbj;
-    std::stable_sort(order.begin(), order.end(), [nbj](int x, int y) {
-        return sweep_order_key(x % nbj, x / nbj) < sweep_order_key(y % nbj, y / nbj);
-    });
-    for (int p = 0; p < (int)A.tasks_total; ++p) pos_of[order[p]] = p;
-    A.order = order.data(); A.pos_of = pos_of.data();
-    A.face_j = fj.data(); A.face_k = fk.data(); A.progress = prog.data(); A.counter = &counter;
-    A.out = out8; A.out_states = want_states ? out8 + 1 : nullptr; A.base = base;
-    A.iface_in = iface_in; A.iface_out = iface_out; A.last_slab = last_slab;
-    int viol = 0;
-    A.viol_flag = &viol;
-    const int lim = 1 << ((check_bits > 0 ? check_bits : 16) - 1);
-    A.check_hi = lim - 1 - 3 - 45;
-    A.check_lo = -lim + 8 + 60;
-    std::vector<EmuCta<C>> ctas(n_ctas);
-    for (auto &cta : ctas) {
-        std::memset(cta.S.get(), 0xA5, sizeof(SweepSmem<C>));
-        for (int tid = 0; tid < C::NT; ++tid) sweep_load_a<C>(*cta.S, A, tid, 0);
-    }
-    const int steps = sweep_task_steps<C>(A);
-    long long finished = 0, idle_rounds = 0;
-    while (finished < A.tasks_total) {
-        bool progressed = false;
-        for (auto &cta : ctas) {
-            if (!cta.has_task) {
-                if ((long long)counter >= A.tasks_total) continue;
-                sweep_describe_long<C>(A, (long long)counter++, cta.S->task);
-                cta.has_task = true;
-                cta.setup(A);
-                progressed = true;
-                continue;
-            }
-            const SweepTask &T = cta.S->task;
-            const int tp = T.top_task >= 0 ? prog[T.top_task] : 0, lp = T.left_task >= 0 ? prog[T.left_task] : 0;
-            if (!cta.prologue_done) {
-                cta.cert = sweep_certified<C>(A, T, tp, lp);
-                if (cta.cert < -1) continue;
-                cta.fetch(A, -1);
-                cta.prepare0(A);
-                cta.prologue_done = true;
-                progressed = true;
-                continue;
-            }
-            // the fetch of step s must have been certified before the barrier that ended step s-1 (the kernel samples
-            // the counters only when it has to)
-            if (cta.cert < cta.s) {
-                cta.cert = sweep_certified<C>(A, T, tp, lp);
-                if (cta.cert < cta.s) continue;
-            }
-            cta.fetch(A, cta.s);
-            cta.step(A, cta.s);
-            if (sweep_publish_now<C>(A, cta.s)) prog[T.self_task] = cta.s + 1;
-            progressed = true;
-            if (++cta.s > steps) {
-                if (cta.viol()) viol = 1;
-                prog[T.self_task] = kProgressDone;
-                cta.has_task = false;
-                ++finished;
-            }
-        }
-        if (!progressed && ++idle_rounds > 4) return -2;  // deadlock
-    }
-    if (viol_out) *viol_out = viol;
-    return 0;
-}
-}  // namespace
-
-extern "C" int emu_fast_sweep_long(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
-                                   int base, int n_ctas, int want_states, int32_t *out8, int check_bits, int *viol_out)
-{
-    return run_long(a, la, b, lb, c, lc, base, n_ctas, want_states, out8, check_bits, viol_out, nullptr, nullptr, 1);
-}
-
-// the i-slab pipeline, slabs run one after the other (what n_slabs GPUs do concurrently, task by task)
-extern "C" int emu_fast_sweep_slabs(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc,
-                                    int base, int n_ctas, int n_slabs, int32_t *out8)
-{
-    using C = SweepCfg<true>;
-    const long long tasks = (long long)((lb + C::BJ - 1) / C::BJ) * ((lc + C::KSPAN - 1) / C::KSPAN);
-    std::vector<uint32_t> st[2];
-    st[0].assign((size_t)tasks * 4 * 16 * C::NT, 0xDEADBEEFu);
-    st[1] = st[0];
-    for (int g = 0; g < n_slabs; ++g) {
-        const int i0 = (int)((long long)la * g / n_slabs), i1 = (int)((long long)la * (g + 1) / n_slabs);
-        if (i1 <= i0) return -3;
-        const int rc = run_long(a + i0, i1 - i0, b, lb, c, lc, base, n_ctas, 1, out8, 0, nullptr,
-                                g > 0 ? st[(g - 1) & 1].data() : nullptr, g + 1 < n_slabs ? st[g & 1].data() : nullptr,
-                                g + 1 == n_slabs);
-        if (rc) return rc;
-    }
-    return 0;
-}
-
-extern "C" int emu_fast_sweep_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
-                                    int n_ctas, int32_t *scores)
-{
-    using C = SweepCfg<false>;
-    if (len < 1 || len > C::LA_MAX || n < 0 || n_ctas < 1) return -1;
-    SweepArgs A{};
-    A.a = a; A.b = b; A.c = c; A.n = n; A.la = A.lb = A.lc = len;
-    A.nbj = (len + C::BJ - 1) / C::BJ;
-    A.nbkp = (len + C::KSPAN - 1) / C::KSPAN;
-    A.pairs_total = (n + 1) / 2;
-    A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
-    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
-    A.fj_ring = 2;
-    A.fk_ring = A.nbj + 1;
-    std::vector<uint32_t> fj((size_t)n_ctas * A.fj_ring * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)n_ctas * A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
-    A.face_j = fj.data(); A.face_k = fk.data();
-    A.out = scores; A.base = base;
-    EmuCta<C> cta;
-    const int steps = sweep_task_steps<C>(A);
-    for (int cid = 0; cid < n_ctas; ++cid) {
-        std::memset(cta.S.get(), 0xA5, sizeof(SweepSmem<C>));
-        for (long long pair = cid; pair < A.pairs_total; pair += n_ctas) {
-            for (int tid = 0; tid < C::NT; ++tid) sweep_load_a<C>(*cta.S, A, tid, pair);
-            for (int q = 0; q < A.nbj * A.nbkp; ++q) {
-                sweep_describe_batch<C>(A, cid, pair, q, cta.S->task);
-                cta.setup(A);
-                cta.fetch(A, -1);
-                cta.prepare0(A);
-                for (int s = 0; s <= steps; ++s) {
-                    cta.fetch(A, s);
-                    cta.step(A, s);
-                }
-            }
-        }
-    }
-    return 0;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
 // K2S (fast_stream.cuh): all blocks of a CTA's pairs streamed back to back, lagged barrier, faces in "global" memory.
 // Warps advance in a pseudo-random order (schedule_seed != 0: with bursts), at most two steps apart, exactly what the
 // kernel's mbarrier protocol allows.  Every emulated CTA gets poisoned shared memory and poisoned face rings.

@@ -55,103 +55,6 @@ def test_batch_kernel_extremes(emu, ob):
     assert _run(emu, z, o, t, 1).tolist() == ob.score_batch(z, o, t, 16).tolist()  # all-mismatch: most negative
 
 
-# ---- K2: block sweep with faces in global memory (fast_sweep.cuh) ----
-@pytest.fixture(scope="module")
-def emu_sweep(emu):
-    emu.emu_fast_sweep_long.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p, C.c_int,
-                                        C.POINTER(C.c_int)]
-    emu.emu_fast_sweep_batch.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, i32p]
-    return emu
-
-
-def _long(L, a, b, c, n_ctas, check_bits=0, gate=None):
-    """One long triple on n_ctas emulated CTAs.  Without an explicit gate interval both of the launcher's settings
-    (4 and 16 steps between progress releases) are run and must agree."""
-    if gate is None:
-        r4, r16 = _long(L, a, b, c, n_ctas, check_bits, 4), _long(L, a, b, c, n_ctas, check_bits, 16)
-        assert r4 == r16
-        return r4
-    L.emu_set_gate(gate)
-    a, b, c = (np.ascontiguousarray(x, dtype=np.uint8) for x in (a, b, c))
-    out = np.zeros(8, np.int32)
-    viol = C.c_int(0)
-    base = 2 * min(len(a), len(b), len(c)) + 64
-    rc = L.emu_fast_sweep_long(a.ctypes.data_as(u8p), len(a), b.ctypes.data_as(u8p), len(b), c.ctypes.data_as(u8p),
-                               len(c), base, n_ctas, 1, out.ctypes.data_as(i32p), check_bits, C.byref(viol))
-    assert rc == 0, "emulated CTAs deadlocked" if rc == -2 else rc
-    if check_bits:
-        return int(out[0]), out[1:].tolist(), int(viol.value)
-    return int(out[0]), out[1:].tolist()
-
-
-def test_sweep_range_check_is_sound_and_not_trigger_happy(emu_sweep, ob):
-    """The run-time wrap check must fire whenever the oracle's value range leaves the safe band of score_bits, and
-    must stay quiet for ordinary inputs."""
-    rng = np.random.default_rng(77)
-    a, b, c = ob.mutated_triple(rng, 150, rate=0.02)        # nearly identical: all grows to ~3*150 = 450
-    _, _, (lo, hi) = ob.score(a, b, c, 32, want_range=True)
-    for w in (9, 10, 11, 12):
-        lim = 1 << (w - 1)
-        _, _, viol = _long(emu_sweep, a, b, c, 2, check_bits=w)
-        wraps_possible = hi + 3 > lim - 1 or lo - 4 < -lim
-        if wraps_possible:
-            assert viol, (w, lo, hi)                       # soundness: never miss a possible wrap
-        if hi + 3 + 45 + 12 <= lim - 1 and lo - 8 - 60 - 12 >= -lim:
-            assert not viol, (w, lo, hi)                   # and no false alarm when far from the limits
-    x, y, z = (rng.integers(0, 4, 150, dtype=np.uint8) for _ in range(3))
-    assert _long(emu_sweep, x, y, z, 2, check_bits=10)[2] == 0
-
-
-@pytest.mark.parametrize("shape,n_ctas", [((5, 5, 5), 1), ((1, 5, 1), 1), ((20, 64, 64), 1), ((30, 64, 128), 1),
-                                          ((40, 70, 130), 2), ((33, 130, 200), 3), ((100, 200, 300), 4),
-                                          ((50, 129, 257), 5), ((10, 1, 1), 1), ((17, 260, 70), 2)])
-def test_sweep_long_choreography(emu_sweep, ob, shape, n_ctas):
-    la, lb, lc = shape
-    rng = np.random.default_rng(la * 7 + lb * 3 + lc)
-    for mutated in (True, False):
-        if mutated:
-            a, b, c = ob.mutated_triple(rng, max(shape))
-            a, b, c = a[:la], b[:lb], c[:lc]
-        else:
-            a, b, c = (rng.integers(0, 4, n, dtype=np.uint8) for n in shape)
-        s, fin = _long(emu_sweep, a, b, c, n_ctas)
-        es, efin = ob.score(a, b, c, 16)
-        assert s == es and fin == efin.tolist()
-
-
-@pytest.mark.parametrize("ln,n,n_ctas", [(10, 3, 1), (64, 2, 1), (65, 4, 2), (130, 3, 2), (200, 5, 3)])
-def test_sweep_batch_choreography(emu_sweep, ob, ln, n, n_ctas):
-    rng = np.random.default_rng(ln + n)
-    a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
-    b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
-    c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
-    for t in range(0, n, 2):
-        a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
-    out = np.full(n, -99999, np.int32)
-    rc = emu_sweep.emu_fast_sweep_batch(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln,
-                                        2 * ln + 64, n_ctas, out.ctypes.data_as(i32p))
-    assert rc == 0
-    assert out.tolist() == ob.score_batch(a, b, c, 16).tolist()
-
-
-@pytest.mark.parametrize("shape,n_slabs,n_ctas", [((40, 70, 130), 2, 2), ((64, 64, 64), 4, 1), ((100, 129, 257), 3, 3),
-                                                  ((37, 200, 140), 8, 2)])
-def test_sweep_i_slab_pipeline(emu_sweep, ob, shape, n_slabs, n_ctas):
-    """Planes split into slabs, each slab continuing from the hand-over state of the previous one (the multi-GPU
-    path of SURVEY.md 8(e)(2)), must give the single-pass result."""
-    emu_sweep.emu_fast_sweep_slabs.argtypes = [u8p, C.c_int, u8p, C.c_int, u8p, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
-    la, lb, lc = shape
-    rng = np.random.default_rng(sum(shape) + n_slabs)
-    a, b, c = ob.mutated_triple(rng, max(shape))
-    a, b, c = (np.ascontiguousarray(x) for x in (a[:la], b[:lb], c[:lc]))
-    out = np.zeros(8, np.int32)
-    rc = emu_sweep.emu_fast_sweep_slabs(a.ctypes.data_as(u8p), la, b.ctypes.data_as(u8p), lb, c.ctypes.data_as(u8p), lc,
-                                        2 * min(shape) + 64, n_ctas, n_slabs, out.ctypes.data_as(i32p))
-    assert rc == 0
-    es, efin = ob.score(a, b, c, 16)
-    assert int(out[0]) == es and out[1:].tolist() == efin.tolist()
-
-
 # ---- K2S: streaming block sweep for batches of triples longer than 64 (fast_stream.cuh) ----
 @pytest.mark.parametrize("ln,n,ppc", [(61, 9, 5), (64, 7, 4), (65, 3, 2), (100, 5, 2), (128, 4, 1), (130, 7, 4), (200, 5, 3), (256, 2, 1)])
 def test_stream_kernel_choreography(emu, ob, ln, n, ppc):

@@ -159,9 +159,8 @@ def test_fast_long_kernel_shapes(gpu_ta, ob, shape):
 
 @pytest.mark.parametrize("ln,n", [(65, 7), (100, 12), (130, 5), (256, 6), (200, 601), (321, 3)])
 def test_fast_long_batch_kernels(gpu_ta, ob, ln, n):
-    """Batches of triples longer than 64: the streaming block-sweep kernel K2S (default) and the per-block kernel
-    (option k2=sweep, also the fallback for very long batches) against the oracle.  n = 601 gives every CTA several
-    pairs, so tasks of different pairs follow each other inside the array."""
+    """Batches of triples longer than 64: the streaming block-sweep kernel K2S against the oracle.  n = 601 gives
+    every CTA several pairs, so tasks of different pairs follow each other inside the array."""
     rng = np.random.default_rng(ln * 31 + n)
     a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
     b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
@@ -173,13 +172,23 @@ def test_fast_long_batch_kernels(gpu_ta, ob, ln, n):
         got = gpu_ta.TriAlign(w).align_batch(a, b, c)
         assert gpu_ta.last_path() == "fast_stream"
         assert got.tolist() == want[w], (ln, n, w)
-    gpu_ta.set_option("k2", "sweep")
-    try:
-        got = gpu_ta.TriAlign(16).align_batch(a, b, c)
-        assert gpu_ta.last_path() == "fast_long"
-    finally:
-        gpu_ta.set_option("k2", None)
-    assert got.tolist() == want[16], (ln, n)
+
+
+def test_batch_of_very_long_triples_runs_one_k2l_launch_each(gpu_ta, ob):
+    """Beyond K2S's 2,048 every triple of a batch is a job of its own for K2L (one launch per triple)."""
+    rng = np.random.default_rng(77)
+    n, ln = 2, 2100
+    a, b, c = (rng.integers(0, 4, (n, ln), dtype=np.uint8) for _ in range(3))
+    b[0], c[0] = a[0], a[0]  # identical sequences score 3L; the other triple against the single-triple entry point
+    before = gpu_ta.launch_count()
+    got = gpu_ta.TriAlign(16).align_batch(a, b, c)
+    assert gpu_ta.last_path() == "fast_long" and gpu_ta.launch_count() - before == n
+    assert got.tolist() == [3 * ln, gpu_ta.TriAlign(16).align(a[1], b[1], c[1])]
+    # the oracle on a prefix of the same data through the same path (uniform batches of length 2,060)
+    m = 2060
+    got = gpu_ta.TriAlign(16).align_batch(a[1:, :m], a[1:, :m][:, ::-1].copy(), c[1:, :m])
+    x, y, z = a[1, :m], a[1, :m][::-1].copy(), c[1, :m]
+    assert got.tolist() == [gpu_ta.TriAlign(16).align(x, y, z)]
 
 
 def test_stream_kernel_extremes_and_repeats(gpu_ta, ob):
