@@ -47,15 +47,23 @@ WORKLOADS = {
 }
 
 
-def csrc_hash():
-    """Hash of the kernel sources; profiles/ncu_kernel_stats.json records the one its captures were taken from."""
+KERNEL_SOURCES = {  # the files a workload's dominant kernel is compiled from
+    "batch64": ("fast_core.cuh", "fast_batch.cuh", "fast_batch.cu"),
+    "batch256": ("fast_core.cuh", "sweep_common.cuh", "fast_stream.cuh", "fast_stream.cu"),
+    "long1024": ("fast_core.cuh", "sweep_common.cuh", "fast_stream.cuh", "fast_long.cuh", "fast_long.cu"),
+    "long8192": ("fast_core.cuh", "sweep_common.cuh", "fast_stream.cuh", "fast_long.cuh", "fast_long.cu"),
+}
+
+
+def csrc_hash(workload):
+    """Hash of the sources of a workload's kernel; profiles/ncu_kernel_stats.json records the one its capture was
+    taken from, so a kernel that changed after its capture shows up as `stale`."""
     d = os.path.join(ROOT, "hw-accelerator-three-sequence-alignment_b200", "csrc")
     h = hashlib.sha256()
-    for name in sorted(os.listdir(d)):
-        if name.endswith((".cu", ".cuh")):
-            h.update(name.encode())
-            with open(os.path.join(d, name), "rb") as f:
-                h.update(f.read())
+    for name in KERNEL_SOURCES[workload]:
+        h.update(name.encode())
+        with open(os.path.join(d, name), "rb") as f:
+            h.update(f.read())
     return h.hexdigest()[:16]
 
 
@@ -68,7 +76,7 @@ def kernel_stats(workload):
         ks = doc.get(workload)
         if ks is not None:
             ks = dict(ks)
-            ks["stale"] = ks.get("csrc_hash", doc.get("csrc_hash")) != csrc_hash()
+            ks["stale"] = ks.get("csrc_hash") != csrc_hash(workload)
         return ks
     except Exception:
         return None

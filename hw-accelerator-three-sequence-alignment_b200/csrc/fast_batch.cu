@@ -41,8 +41,8 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
 
 // MINB = CTAs per SM the register budget is set for: 2 (<= 128 registers, a few words spilled) lets two CTAs cover each
 // other's barrier waits and fixed-latency stalls (4 warps per scheduler instead of 2).
-template <class Cfg, bool SPLIT, int MINB = 1, bool CHECK = false>
-__global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchArgs A)
+template <class Cfg, bool SPLIT, int MINB, bool CHECK>
+__device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const fast::BatchCheck *chk)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchAr
     __syncthreads();
 
     fast::BatchRegs<Cfg> R;
-    R.viol = 0;
+    uint32_t viol = 0;  // CHECK kernels only
     fast::BatchConsts<Cfg> K;
     fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, 0);
     const int steps = fast::batch_total_steps<Cfg>(P);
@@ -85,12 +85,11 @@ __global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchAr
         // a loop unrolled by two, so the loop-carried plane state needs no register moves; an odd extra step at the
         // end runs on drained threads only.
         fast::BatchRegs<Cfg> R2;
-        R2.viol = 0;
 #define TA_BATCH_STEP(RIN, ROUT, S_)                                                        \
     do {                                                                                   \
         const int s_ = (S_);                                                               \
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                     \
-        fast::batch_thread_step<Cfg, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, P, pair_base); \
+        fast::batch_thread_step<Cfg, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, P, pair_base, &viol, chk); \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                \
         fast::batch_uniform_actions<Cfg>(S, A, tid, s_, P, pair_base);                     \
         fast::batch_thread_prepare<Cfg>(ROUT, K, S, A, tj, tk, s_ + 1);                    \
@@ -104,7 +103,7 @@ __global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchAr
     } else {
 #pragma unroll 1
         for (int s = 0; s <= steps; ++s) {
-            fast::batch_thread_step<Cfg, CHECK>(R, R, K, S, A, tj, tk, s, P, pair_base);
+            fast::batch_thread_step<Cfg, CHECK>(R, R, K, S, A, tj, tk, s, P, pair_base, &viol, chk);
             if (SPLIT) bar_arrive_warp(&step_bar[0]);
             fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
             fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, s + 1);
@@ -114,6 +113,17 @@ __global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchAr
     }
 }
 
+template <class Cfg, bool SPLIT, int MINB = 1>
+__global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchArgs A)
+{
+    fast_batch_body<Cfg, SPLIT, MINB, false>(A, nullptr);
+}
+template <class Cfg, bool SPLIT>
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel_checked(fast::BatchArgs A, fast::BatchCheck chk)
+{
+    fast_batch_body<Cfg, SPLIT, 1, true>(A, &chk);
+}
+
 }  // namespace
 
 bool fast_batch_supports(int len) { return len >= 1 && len <= 64; }
@@ -121,11 +131,13 @@ bool fast_batch_supports(int len) { return len >= 1 && len <= 64; }
 namespace {
 
 template <class Cfg, bool SPLIT, int MINB = 1, bool CHECK = false>
-int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant)
+int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant, fast::BatchCheck chk = {})
 {
     static_assert(MINB * (sizeof(fast::BatchSmem<Cfg>) + 1024 + 64) <= 228 * 1024, "shared memory budget");
     const size_t smem = sizeof(fast::BatchSmem<Cfg>);
-    auto kernel = fast_batch_kernel<Cfg, SPLIT, MINB, CHECK>;
+    const void *kernel;
+    if constexpr (CHECK) kernel = (const void *)fast_batch_kernel_checked<Cfg, SPLIT>;
+    else kernel = (const void *)fast_batch_kernel<Cfg, SPLIT, MINB>;
     static bool attr_set[kMaxDevices] = {};
     if (!attr_set[ctx->device]) {
         TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -146,7 +158,8 @@ int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant
         std::fprintf(stderr, "[trialign] K1: variant=%d threads=%d grid=%lld pairs/cta=%lld smem=%zu ctas/sm=%d\n", variant,
                      Cfg::NT, grid, ppc, smem, occ);
     }
-    kernel<<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
+    if constexpr (CHECK) fast_batch_kernel_checked<Cfg, SPLIT><<<(unsigned)grid, Cfg::NT, smem, st>>>(A, chk);
+    else fast_batch_kernel<Cfg, SPLIT, MINB><<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TRIALIGN_OK;
@@ -177,16 +190,15 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     A.pairs_total = (n + 1) / 2;
     A.pairs_per_cta = 1;
     A.base = 2 * 64 + 32;  // >= 2*min(len)+8 plus the "-1" headroom of the reductions (common.cuh envelope)
-    A.check_lo = A.check_hi = 0;
-    A.pair_flags = nullptr;
     if (check_bits > 0) {
         // candidates reach all+3 and (min all)-8; the margins cover the unsampled planes between two samples
         // (`all` moves by at most +3 / -4 per plane)
         const int lim = 1 << (check_bits - 1), gap = fast::kBatchCheckEvery - 1;
-        A.check_hi = lim - 1 - 3 - 3 * gap;
-        A.check_lo = -lim + 8 + 4 * gap;
-        A.pair_flags = d_pair_flags;
-        return launch_batch<Cfg256L, true, 1, true>(ctx, st, A, 100);
+        fast::BatchCheck chk;
+        chk.check_hi = lim - 1 - 3 - 3 * gap;
+        chk.check_lo = -lim + 8 + 4 * gap;
+        chk.pair_flags = d_pair_flags;
+        return launch_batch<Cfg256L, true, 1, true>(ctx, st, A, 100, chk);
     }
     switch (variant) {
     case 1: return launch_batch<Cfg256, true>(ctx, st, A, variant);

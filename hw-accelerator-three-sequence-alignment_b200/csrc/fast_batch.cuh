@@ -66,9 +66,13 @@ struct BatchArgs {
     long long pairs_total;     // ceil(n/2)
     int pairs_per_cta;         // contiguous chunk per CTA
     int base;                  // potential base (common.cuh envelope), < 2^15
-    // range-checked variant (CHECK kernels, used when wrap-freedom at score_bits cannot be proved from the length):
-    // every sampled `all` must lie in [check_lo, check_hi]; pair_flags[pair] gets bit 0 / bit 1 set when the low / high
-    // triple of the pair came too close to the score_bits limits (the dispatcher re-runs those on the literal kernel)
+};
+
+// Range-checked variant (CHECK kernels, used when wrap-freedom at score_bits cannot be proved from the length): every
+// sampled `all` must lie in [check_lo, check_hi]; pair_flags[pair] gets bit 0 / bit 1 set when the low / high triple of
+// the pair came too close to the score_bits limits (the dispatcher re-runs those on the literal kernel).  A separate
+// kernel parameter, so that the unchecked kernels' parameter block (and ptxas's allocation) stays as it was.
+struct BatchCheck {
     int check_lo, check_hi;
     int *pair_flags;
 };
@@ -92,7 +96,6 @@ template <class C>
 struct BatchRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
     uint32_t cBC[C::RJ][C::RK];                                                        // per-cell constant
-    uint32_t viol;                                                                     // CHECK: range violations of the current pair
 };
 
 // Constants of the step a thread is about to run (a_i against the tile's rows / columns), fetched one step ahead in
@@ -182,7 +185,6 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
                 const uint32_t nbc = neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]);
                 R.cBC[r][c] = pair_const(nbc);
             }
-        R.viol = 0;
     }
 
     const int code = S.acode[buf][i - 1];
@@ -203,9 +205,12 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
 // R = plane i-1 state (input), Rn = plane i state (output; may be R itself): the lagged-barrier kernel alternates two
 // register sets in a step loop unrolled by two, so that the loop-carried state needs no register moves.
 // CHECK: the run-time range check (see BatchArgs), sampled every kBatchCheckEvery-th step (warp-uniform).
+// `viol` (CHECK only) accumulates the violations of the pair this thread is working on; it lives outside BatchRegs so
+// that the unchecked kernels compile exactly as without the check.
 template <class C, bool CHECK = false>
 TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
-                             const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base)
+                             const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base, uint32_t *viol_io = nullptr,
+                             const BatchCheck *chk = nullptr)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int u = s - C::LAG * (tj + tk);
@@ -315,9 +320,8 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
         S.col[ws][1][tk][j0 + r] = n_u2[r][RK - 1];
     }
 
-    uint32_t viol = 0;
     if (CHECK) {
-        viol = R.viol;
+        uint32_t viol = i == 1 ? 0u : *viol_io;  // a new pair enters this thread
         if ((s & (kBatchCheckEvery - 1)) == 0 && i <= A.len) {
             // only cells of the real triple count: padding (j or k beyond len) decays without bound of its own
             uint32_t mx = 0u, mn = 0xFFFFFFFFu;
@@ -331,7 +335,7 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
                     }
             // true value = stored - phi(cell); phi grows by 2 per row / column inside the tile
             const int ph = A.base + 2 * (i + j0 + 1 + k0 + 1), slack = 2 * (RJ + RK - 2);
-            const int h = ph + A.check_hi, l = ph + A.check_lo + slack;
+            const int h = ph + chk->check_hi, l = ph + chk->check_lo + slack;
             const uint32_t hi_lim = rep((uint32_t)(h > 0xFFFF ? 0xFFFF : h)), lo_lim = rep((uint32_t)(l < 0 ? 0 : l));
             viol |= (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
         }
@@ -339,11 +343,12 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
         if (i == C::L && viol != 0 && u >= 0 && p < P) {
             const int bits = ((viol & 0xFFFFu) ? 1 : 0) | ((viol >> 16) ? 2 : 0);
 #if defined(__CUDA_ARCH__)
-            atomicOr(A.pair_flags + (pair_base + p), bits);
+            atomicOr(chk->pair_flags + (pair_base + p), bits);
 #else
-            A.pair_flags[pair_base + p] |= bits;
+            chk->pair_flags[pair_base + p] |= bits;
 #endif
         }
+        *viol_io = viol;
     }
 
     // Score = max of the 7 states of cell (len,len,len) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
@@ -368,7 +373,6 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
             Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
             Rn.cBC[r][c] = R.cBC[r][c];
         }
-    if (CHECK) Rn.viol = viol;
 }
 
 // Steps a CTA needs for P pairs, and the CTA-uniform actions of global step s.

@@ -402,7 +402,7 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
     // fill) and at L = 8,192 (943 vs 860).  Long sweeps release their progress less often (a release is a MEMBAR.GPU).
     // Options k2_lag / k2_gate (trialign_set_option) override for experiments.
     int lag = 1;
-    A.gate = la >= 4096 ? 16 : 4;
+    A.gate = la >= 4096 ? 32 : 4;  // measured at L = 8,192: gate 8 1,101, 16 1,115, 32 1,126 GCUPS; at L = 1,024: 2 435, 4 461, 8 457
     {
         const int v = opt_int("k2_lag", 0);
         if (v == 1 || v == 2) lag = v;

@@ -39,7 +39,7 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
 }
 
 template <bool CHECK>
-__global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArgs A)
+__device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, const fast::RangeCheck *chk)
 {
     using C = Cfg;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArg
     __syncthreads();
 
     fast::StreamRegs<C> R, R2;
-    R.viol = R2.viol = 0;
+    uint32_t viol = 0;  // CHECK kernel only
     fast::StreamConsts<C> K;
     fast::StreamPos pos = fast::stream_start_pos<C>(A, tj, tk);
     if (tj == 0 || tk == 0) fast::stream_edge_fetch<C>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1));
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArg
         const int s_ = (S_);                                                                      \
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                            \
         fast::ta_copy_wait_prev();                                                                \
-        fast::stream_thread_step<C, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, pos);                  \
+        fast::stream_thread_step<C, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, pos, &viol, chk);      \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                       \
         if (g_t < tasks) fast::stream_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off); \
         fast::stream_thread_prepare<C>(ROUT, K, S, A, tj, tk, pos, s_ + 1, true);                 \
@@ -97,6 +97,13 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArg
         TA_STREAM_STEP(R2, R, s + 1);
     }
 #undef TA_STREAM_STEP
+}
+
+// Two plain kernels around the one body (the unchecked one is the default path; the checked one adds the range test).
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArgs A) { fast_stream_body<false>(A, nullptr); }
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel_checked(fast::StreamArgs A, fast::RangeCheck chk)
+{
+    fast_stream_body<true>(A, &chk);
 }
 
 // contiguous chunks of pairs, one persistent CTA per SM (fill/drain once per CTA); the step counter stays below 2^30
@@ -132,11 +139,11 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
     const size_t smem = sizeof(fast::StreamSmem<C>);
     static bool attr_set[kMaxDevices] = {};
     if (!attr_set[ctx->device]) {
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_checked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_checked, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
         attr_set[ctx->device] = true;
     }
@@ -166,12 +173,13 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
                      len, A.nbj, A.nbk, grid, ppc, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
     if (check_bits > 0) {
         const int lim = 1 << (check_bits - 1), gap = fast::kStreamCheckEvery - 1;
-        A.check_hi = lim - 1 - 3 - 3 * gap;
-        A.check_lo = -lim + 8 + 4 * gap;
-        A.pair_flags = d_pair_flags;
-        fast_stream_kernel<true><<<(unsigned)grid, C::NT, smem, st>>>(A);
+        fast::RangeCheck chk;
+        chk.check_hi = lim - 1 - 3 - 3 * gap;
+        chk.check_lo = -lim + 8 + 4 * gap;
+        chk.pair_flags = d_pair_flags;
+        fast_stream_kernel_checked<<<(unsigned)grid, C::NT, smem, st>>>(A, chk);
     } else {
-        fast_stream_kernel<false><<<(unsigned)grid, C::NT, smem, st>>>(A);
+        fast_stream_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
     }
     count_launch();
     TA_CUDA(cudaGetLastError());

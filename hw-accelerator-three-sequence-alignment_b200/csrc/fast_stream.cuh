@@ -72,8 +72,13 @@ struct StreamArgs {
     int fk_ring;                  // nbj + 1
     int32_t *scores;              // [n]
     int base;                     // potential base
-    // range-checked variant (CHECK kernels), as in fast_batch.cuh: sampled `all` in [check_lo, check_hi], else
-    // pair_flags[pair] gets bit 0 / 1 set for the low / high triple
+};
+
+// Range-checked variant (CHECK kernels), as in fast_batch.cuh: sampled `all` in [check_lo, check_hi], else
+// pair_flags[pair] gets bit 0 / 1 set for the low / high triple.  A separate kernel parameter: the unchecked kernel's
+// parameter block -- and with it ptxas's register allocation (223 registers; 194 and 3 % slower with three more words
+// in StreamArgs) -- stays exactly as it was.
+struct RangeCheck {
     int check_lo, check_hi;
     int *pair_flags;
 };
@@ -97,7 +102,6 @@ template <class C>
 struct StreamRegs {
     uint32_t all[C::RJ][C::RK], wX[C::RJ][C::RK], u1[C::RJ][C::RK], u3[C::RJ][C::RK];  // plane i-1
     uint32_t cBC[C::RJ][C::RK];                                                        // per-cell (b,c) constant
-    uint32_t viol;                                                                     // CHECK: violations of the current task
 };
 
 template <class C>
@@ -298,7 +302,6 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
                 R.all[r][c] = z; R.wX[r][c] = z; R.u1[r][c] = z; R.u3[r][c] = z;
                 R.cBC[r][c] = pair_const(neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]));
             }
-        R.viol = 0;
     }
     const int code = S.acode[S.task[buf].abuf][p.i - 1];
     TA_CHECK(code >= 0 && code < 16);
@@ -325,9 +328,12 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
 // R = plane i-1 state (input), Rn = plane i state (output; may be R itself).  The kernel alternates two register sets
 // (R -> Rn, Rn -> R) in a step loop unrolled by two, so that the loop-carried state needs no register moves.
 // CHECK: the run-time range check (see StreamArgs), sampled every kStreamCheckEvery-th step (warp-uniform).
+// `viol` (CHECK only) accumulates the violations of the task this thread is working on; it lives outside StreamRegs so
+// that the unchecked kernel compiles exactly as without the check.
 template <class C, bool CHECK = false>
 TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const StreamConsts<C> &K, StreamSmem<C> &S,
-                              const StreamArgs &A, int tj, int tk, int s, const StreamPos &p)
+                              const StreamArgs &A, int tj, int tk, int s, const StreamPos &p, uint32_t *viol_io = nullptr,
+                              const RangeCheck *chk = nullptr)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int j0 = tj * RJ, k0 = tk * RK;
@@ -433,9 +439,8 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
         }
     }
 
-    uint32_t viol = 0;
     if (CHECK) {
-        viol = R.viol;
+        uint32_t viol = p.i == 1 ? 0u : *viol_io;  // a new task enters this thread
         if ((s & (kStreamCheckEvery - 1)) == 0) {
             uint32_t mx = n_all[0][0], mn = n_all[0][0];
 #pragma unroll
@@ -446,7 +451,7 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
                     mn = vmin3(mn, n_all[r][c], n_all[r][c + 1]);
                 }
             const int ph = A.base + 2 * (p.i + j0 + 1 + k0 + 1), slack = 2 * (RJ + RK - 2);
-            const int h = ph + A.check_hi, l = ph + A.check_lo + slack;
+            const int h = ph + chk->check_hi, l = ph + chk->check_lo + slack;
             const uint32_t hi_lim = rep((uint32_t)(h > 0xFFFF ? 0xFFFF : h)), lo_lim = rep((uint32_t)(l < 0 ? 0 : l));
             viol |= (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
         }
@@ -455,12 +460,13 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
             if (T.valid) {
                 const int bits = ((viol & 0xFFFFu) ? 1 : 0) | ((viol >> 16) ? 2 : 0);
 #if defined(__CUDA_ARCH__)
-                atomicOr(A.pair_flags + T.pair, bits);
+                atomicOr(chk->pair_flags + T.pair, bits);
 #else
-                A.pair_flags[T.pair] |= bits;
+                chk->pair_flags[T.pair] |= bits;
 #endif
             }
         }
+        *viol_io = viol;
     }
 
     // Score = max of the 7 states of cell (len,len,len) (src/TriAlign_1cyc.v:141-142) = `all` of that cell
@@ -491,7 +497,6 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
             Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
             Rn.cBC[r][c] = R.cBC[r][c];
         }
-    if (CHECK) Rn.viol = viol;
 }
 
 // global steps a CTA runs for P pairs: steps 0 .. this value
