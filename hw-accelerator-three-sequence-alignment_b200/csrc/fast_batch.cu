@@ -69,7 +69,7 @@ __device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const 
         }
         for (int e = tid; e < 3 * 2 * 64; e += Cfg::NT) (&S.seq[fill][0][0][0])[e] = 0;
     }
-    fast::load_pair_sequences<Cfg>(S, A, tid, pair_base, 0);
+    fast::load_pair_sequences<Cfg, CHECK>(S, A, tid, pair_base, 0);
     __syncthreads();
     fast::build_pair_tables<Cfg>(S, tid, 0);
     __syncthreads();
@@ -91,7 +91,7 @@ __device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const 
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                     \
         fast::batch_thread_step<Cfg, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, P, pair_base, &viol, chk); \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                \
-        fast::batch_uniform_actions<Cfg>(S, A, tid, s_, P, pair_base);                     \
+        fast::batch_uniform_actions<Cfg, CHECK>(S, A, tid, s_, P, pair_base);                    \
         fast::batch_thread_prepare<Cfg>(ROUT, K, S, A, tj, tk, s_ + 1);                    \
     } while (0)
 #pragma unroll 1
@@ -105,7 +105,7 @@ __device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const 
         for (int s = 0; s <= steps; ++s) {
             fast::batch_thread_step<Cfg, CHECK>(R, R, K, S, A, tj, tk, s, P, pair_base, &viol, chk);
             if (SPLIT) bar_arrive_warp(&step_bar[0]);
-            fast::batch_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
+            fast::batch_uniform_actions<Cfg, CHECK>(S, A, tid, s, P, pair_base);
             fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, s + 1);
             if (SPLIT) bar_wait(&step_bar[0], s & 1);
             else __syncthreads();

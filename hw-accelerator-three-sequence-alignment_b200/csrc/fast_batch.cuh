@@ -123,7 +123,8 @@ TA_HD void thread_pos(int tid, int &tj, int &tk)
 TA_HD uint32_t phi(const BatchArgs &A, int i, int jl, int kl) { return rep((uint32_t)(A.base + 2 * (i + jl + kl))); }
 
 // ---- CTA-uniform actions, executed by every thread at fixed global steps ----
-template <class C>
+// PAD (the range-checked kernels): positions beyond len get codes that match nothing, see below.
+template <class C, bool PAD = false>
 TA_HD void load_pair_sequences(BatchSmem<C> &S, const BatchArgs &A, int tid, long long pair, int buf)
 {
     for (int e = tid; e < 3 * 2 * 64; e += C::NT) {
@@ -133,7 +134,7 @@ TA_HD void load_pair_sequences(BatchSmem<C> &S, const BatchArgs &A, int tid, lon
         // positions beyond len are padding: b gets code 4, c code 5 -- they match nothing, not even each other, so
         // padded cells decay instead of growing like a run of matches (keeps the range check free of false alarms;
         // real cells never depend on padded ones)
-        uint8_t v = which == 0 ? 0 : (uint8_t)(3 + which);
+        uint8_t v = (!PAD || which == 0) ? 0 : (uint8_t)(3 + which);
         if (t < A.n && pos < A.len) v = src[t * A.len + pos] & 3;  // PE keeps bits [1:0] (src/PE_1cyc.v:63-66)
         S.seq[buf][which][half][pos] = v;
     }
@@ -379,12 +380,12 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
 template <class C>
 TA_HD int batch_total_steps(int P) { return P * C::L + C::SKEW; }
 
-template <class C>
+template <class C, bool PAD = false>
 TA_HD void batch_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, int s, int P, long long pair_base)
 {
     const int q = (s >> 6) + 1;  // pair that starts entering the array at step 64*q
     if (q < P) {
-        if ((s & 63) == C::LOAD_AT) load_pair_sequences<C>(S, A, tid, pair_base + q, q % C::NBUF);
+        if ((s & 63) == C::LOAD_AT) load_pair_sequences<C, PAD>(S, A, tid, pair_base + q, q % C::NBUF);
         if ((s & 63) == C::BUILD_AT) build_pair_tables<C>(S, tid, q % C::NBUF);
     }
 }
