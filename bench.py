@@ -355,7 +355,8 @@ def roofline(workload, cells_per_s_per_gpu, clocks, world=1, slab=False, n=None)
     return out
 
 
-def run_batch(R, ta, name, steps, warmup, n_per_rank, first, golden_scores, want_cpu, parity, total_strong=None):
+def run_batch(R, ta, name, steps, warmup, n_per_rank, first, golden_scores, want_cpu, parity, total_strong=None,
+              oracle_check=0):
     """Batch workload on this rank's GPU: device-resident timing + host-pointer e2e + golden comparison."""
     import ctypes as C
 
@@ -383,6 +384,14 @@ def run_batch(R, ta, name, steps, warmup, n_per_rank, first, golden_scores, want
     u8p, i32p = C.POINTER(C.c_uint8), C.POINTER(C.c_int32)
     ha, hb, hc = (x.cpu().pin_memory() for x in (da, db, dc))
     hout = torch.empty(n_per_rank, dtype=torch.int32).pin_memory()
+    if R.rank == 0 and oracle_check:
+        # the oracle itself on the first triples of the timed batch (beyond the few frozen in golden.json)
+        import oracle_bindings as ob
+
+        k = min(oracle_check, n_per_rank, len(head))
+        want = ob.score_batch(ha[:k].numpy(), hb[:k].numpy(), hc[:k].numpy(), w, host_threads())
+        parity.append({"workload": name, "against": "oracle O1 on the first triples of the timed batch", "checked": int(k),
+                       "ok": want.tolist() == head[:k]})
 
     def e2e_step():
         rc = L.trialign_score_batch(C.cast(ha.data_ptr(), u8p), C.cast(hb.data_ptr(), u8p), C.cast(hc.data_ptr(), u8p),
@@ -525,11 +534,12 @@ def run_ours(args, rank, world, local_rank):
             lsteps = 100  # long1024 takes 2.3 ms per step: enough steps for the clock sampler to see the load
             if world == 1:
                 secondary.append(run_long(R, ta, "long1024", lsteps, 3, parity, multi=False))
-                secondary.append(run_batch(R, ta, "batch256", 2, 3, 1 << 18, 0, gs[4]["scores"], False, parity))
+                secondary.append(run_batch(R, ta, "batch256", 2, 3, 1 << 18, 0, gs[4]["scores"], False, parity, oracle_check=48))
                 secondary.append(run_long(R, ta, "long8192", min(ssteps, 3), 3, parity, multi=False))
             else:
                 n = (1 << 18) // world  # config 4 as written: 262,144 triples in total, contiguous split
-                secondary.append(run_batch(R, ta, "batch256", 2, 3, n, rank * n, gs[4]["scores"], False, parity, total_strong=True))
+                secondary.append(run_batch(R, ta, "batch256", 2, 3, n, rank * n, gs[4]["scores"], False, parity, total_strong=True,
+                                           oracle_check=48))
                 one = run_long(R, ta, "long8192", 2, 3, parity, multi=False)   # rank 0 alone: the efficiency's denominator
                 many = run_long(R, ta, "long8192", min(ssteps, 3), 3, parity, multi=True)
                 if rank == 0:

@@ -30,6 +30,7 @@ from .trialign import (  # noqa: F401
     launch_count,
     library,
     library_path,
+    pack_batch_ram128,
     pack_seq_ram128,
     read_scores,
     read_seq_dat,

@@ -285,9 +285,11 @@ int first_device(unsigned devices)
 }
 
 // host-pointer batch on ONE device: stage in, run, stage out; kernel time measured with events on the stream
+// packed: a/b/c are batches in the testbench's 128-bit RAM format ([n][ceil(len/32)][16] bytes, la = lb = lc = len); they
+// are uploaded as they are and expanded on the device.
 int run_host_batch_on_device(int device, const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int la,
                              int lb, int lc, int score_bits, int backend, int32_t *scores, int32_t *finals,
-                             double *seconds)
+                             double *seconds, bool packed = false)
 {
     DeviceGuard guard;
     DeviceCtx *ctx = nullptr;
@@ -297,7 +299,8 @@ int run_host_batch_on_device(int device, const uint8_t *a, const uint8_t *b, con
     cudaStream_t st = ctx->stream;
     const size_t na = (size_t)n * la, nb = (size_t)n * lb, nc = (size_t)n * lc;
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
-    if ((rc = ctx->seq.reserve(up(na) + up(nb) + up(nc) + 256))) return rc;
+    const size_t ram = packed ? up((size_t)n * ((la + 31) / 32) * 16) : 0;  // one packed array
+    if ((rc = ctx->seq.reserve(up(na) + up(nb) + up(nc) + 3 * ram + 256))) return rc;
     const size_t n_pad = ((size_t)n + 63) & ~(size_t)63;  // finals start on a 256-byte boundary
     if ((rc = ctx->out.reserve(n_pad * sizeof(int32_t) + (finals ? (size_t)n * 7 * sizeof(int32_t) : 0)))) return rc;
     uint8_t *d_a = (uint8_t *)ctx->seq.ptr, *d_b = d_a + up(na), *d_c = d_b + up(nb);
@@ -306,9 +309,20 @@ int run_host_batch_on_device(int device, const uint8_t *a, const uint8_t *b, con
     ScratchLease lease(ctx, st);
     {
         NvtxRange r("trialign:h2d");
-        TA_CUDA(cudaMemcpyAsync(d_a, a, na, cudaMemcpyHostToDevice, st));
-        TA_CUDA(cudaMemcpyAsync(d_b, b, nb, cudaMemcpyHostToDevice, st));
-        TA_CUDA(cudaMemcpyAsync(d_c, c, nc, cudaMemcpyHostToDevice, st));
+        if (packed) {
+            uint8_t *r_a = d_c + up(nc), *r_b = r_a + ram, *r_c = r_b + ram;
+            const size_t bytes = (size_t)n * ((la + 31) / 32) * 16;
+            TA_CUDA(cudaMemcpyAsync(r_a, a, bytes, cudaMemcpyHostToDevice, st));
+            TA_CUDA(cudaMemcpyAsync(r_b, b, bytes, cudaMemcpyHostToDevice, st));
+            TA_CUDA(cudaMemcpyAsync(r_c, c, bytes, cudaMemcpyHostToDevice, st));
+            if ((rc = unpack_ram128_run(st, r_a, n, la, d_a)) || (rc = unpack_ram128_run(st, r_b, n, la, d_b)) ||
+                (rc = unpack_ram128_run(st, r_c, n, la, d_c)))
+                return rc;
+        } else {
+            TA_CUDA(cudaMemcpyAsync(d_a, a, na, cudaMemcpyHostToDevice, st));
+            TA_CUDA(cudaMemcpyAsync(d_b, b, nb, cudaMemcpyHostToDevice, st));
+            TA_CUDA(cudaMemcpyAsync(d_c, c, nc, cudaMemcpyHostToDevice, st));
+        }
     }
     TA_CUDA(cudaEventRecord(ctx->ev0, st));
     {
@@ -853,9 +867,10 @@ int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     return TRIALIGN_OK;
 }
 
-int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len, int score_bits,
-                         int backend, unsigned devices, int32_t *scores)
+static int score_batch_impl(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len, int score_bits,
+                            int backend, unsigned devices, int32_t *scores, bool packed)
 {
+    const size_t stride = packed ? (size_t)((len + 31) / 32) * 16 : (size_t)len;  // host bytes per sequence
     if (n < 0 || len < 0 || score_bits < 2 || score_bits > 32) return TRIALIGN_EINVAL;
     if (n > 0 && !scores) return TRIALIGN_EINVAL;
     if (n > 0 && len > 0 && (!a || !b || !c)) return TRIALIGN_EINVAL;
@@ -881,7 +896,8 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
     ts.last_devices = (int)devs.size();
     if (devs.size() == 1) {
         double sec = -1.0;
-        rc = run_host_batch_on_device(devs[0], a, b, c, n, len, len, len, score_bits, backend, scores, nullptr, &sec);
+        rc = run_host_batch_on_device(devs[0], a, b, c, n, len, len, len, score_bits, backend, scores, nullptr, &sec,
+                                      packed);
         ts.last_seconds = sec;
         return rc;
     }
@@ -898,9 +914,9 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
             tls().scoring_active = ts.scoring_active;  // the *_ex scoring of the calling thread
             tls().scoring = ts.scoring;
             if (t1 > t0)
-                rcs[g] = run_host_batch_on_device(devs[g], a + (size_t)t0 * len, b + (size_t)t0 * len,
-                                                  c + (size_t)t0 * len, t1 - t0, len, len, len, score_bits,
-                                                  backend, scores + t0, nullptr, &secs[g]);
+                rcs[g] = run_host_batch_on_device(devs[g], a + (size_t)t0 * stride, b + (size_t)t0 * stride,
+                                                  c + (size_t)t0 * stride, t1 - t0, len, len, len, score_bits,
+                                                  backend, scores + t0, nullptr, &secs[g], packed);
             paths[g] = tls().last_path;
             errs[g] = tls().cuda_error;
             flagged[g] = tls().last_flagged;
@@ -919,6 +935,33 @@ int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, i
     }
     ts.last_seconds = worst;
     return TRIALIGN_OK;
+}
+
+int trialign_score_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, int64_t n, int len, int score_bits,
+                         int backend, unsigned devices, int32_t *scores)
+{
+    return score_batch_impl(a, b, c, n, len, score_bits, backend, devices, scores, false);
+}
+
+// ---- the testbench's packed sequence RAMs as a direct input (src/TriAlign_tb.sv:94-96,150-169) ----
+int trialign_score_batch_ram128(const uint8_t *ram_a, const uint8_t *ram_b, const uint8_t *ram_c, int64_t n, int len,
+                                int score_bits, int backend, unsigned devices, int32_t *scores)
+{
+    return score_batch_impl(ram_a, ram_b, ram_c, n, len, score_bits, backend, devices, scores, true);
+}
+
+int trialign_score_ram128(const uint8_t *ram_a, int la, const uint8_t *ram_b, int lb, const uint8_t *ram_c, int lc,
+                          int score_bits, int backend, unsigned devices, int32_t *score, int32_t final_states[7])
+{
+    if (la < 0 || lb < 0 || lc < 0) return TRIALIGN_EINVAL;
+    if ((la && !ram_a) || (lb && !ram_b) || (lc && !ram_c)) return TRIALIGN_EINVAL;
+    // one triple: the three sequences are expanded on the host (a few KB) and take the ordinary path, multi-GPU included
+    std::vector<uint8_t> a((size_t)la), b((size_t)lb), c((size_t)lc);
+    int rc;
+    if ((rc = trialign_unpack_seq_ram128(ram_a, la, a.data(), la)) || (rc = trialign_unpack_seq_ram128(ram_b, lb, b.data(), lb)) ||
+        (rc = trialign_unpack_seq_ram128(ram_c, lc, c.data(), lc)))
+        return rc;
+    return trialign_score(a.data(), la, b.data(), lb, c.data(), lc, score_bits, backend, devices, score, final_states);
 }
 
 // ---- explicit scoring parameters ----

@@ -87,6 +87,10 @@ long long all_triples_count(int nseq);
 int all_triples_gather(cudaStream_t st, const uint8_t *d_seqs, int nseq, int len, long long first, long long count,
                        uint8_t *d_a, uint8_t *d_b, uint8_t *d_c);
 
+// the testbench's packed 128-bit sequence RAM format, expanded on the device (seq_formats.cu): d_ram is
+// [n][ceil(len/32)][16] bytes, d_out [n][len] symbol bytes
+int unpack_ram128_run(cudaStream_t st, const uint8_t *d_ram, int64_t n, int len, uint8_t *d_out);
+
 // synthetic generator on the device (synth_kernel.cu)
 int synth_run(cudaStream_t st, uint64_t seed, int64_t first, int64_t n, int len, uint8_t *d_a, uint8_t *d_b,
               uint8_t *d_c);

@@ -162,6 +162,11 @@ def library() -> C.CDLL:
     L.trialign_last_path.restype = C.c_int
     L.trialign_last_devices.restype = C.c_int
     L.trialign_last_flagged.restype = C.c_int64
+    L.trialign_score_ram128.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p,
+                                        _i32p]
+    L.trialign_score_ram128.restype = C.c_int
+    L.trialign_score_batch_ram128.argtypes = [_u8p, _u8p, _u8p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p]
+    L.trialign_score_batch_ram128.restype = C.c_int
     L.trialign_multi_plan.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     L.trialign_multi_plan.restype = C.c_int
     L.trialign_set_option.argtypes = [C.c_char_p, C.c_char_p]
@@ -282,6 +287,28 @@ class TriAlign:
                                       _p(fin, _i32p))
         _check(rc, "trialign_score")
         return (int(s.value), fin) if return_states else int(s.value)
+
+    def align_ram128(self, ram_a, la: int, ram_b, lb: int, ram_c, lc: int, return_states: bool = False):
+        """One triple given as testbench RAM images (pack_seq_ram128): 128-bit words of 4-bit symbols."""
+        ra, rb, rc_ = (np.ascontiguousarray(np.asarray(x, np.uint8)).reshape(-1) for x in (ram_a, ram_b, ram_c))
+        s = C.c_int32(0)
+        fin = np.zeros(7, np.int32)
+        rc = library().trialign_score_ram128(_p(ra, _u8p), la, _p(rb, _u8p), lb, _p(rc_, _u8p), lc, self.score_bits,
+                                             self.backend, _devmask(self.devices), C.byref(s), _p(fin, _i32p))
+        _check(rc, "trialign_score_ram128")
+        return (int(s.value), fin) if return_states else int(s.value)
+
+    def align_batch_ram128(self, ram_a, ram_b, ram_c, n: int, length: int) -> np.ndarray:
+        """A uniform batch as RAM images: three uint8 arrays [n][ceil(length/32)][16] (pack_batch_ram128)."""
+        ra, rb, rc_ = (np.ascontiguousarray(np.asarray(x, np.uint8)).reshape(-1) for x in (ram_a, ram_b, ram_c))
+        need = n * ((length + 31) // 32) * 16
+        if ra.size < need or rb.size < need or rc_.size < need:
+            raise ValueError("RAM images are smaller than n x ceil(length/32) words")
+        out = np.zeros(n, np.int32)
+        rc = library().trialign_score_batch_ram128(_p(ra, _u8p), _p(rb, _u8p), _p(rc_, _u8p), n, length, self.score_bits,
+                                                   self.backend, _devmask(self.devices), _p(out, _i32p))
+        _check(rc, "trialign_score_batch_ram128")
+        return out
 
     def traceback(self, A, B, C_):
         """Optimal alignment of one triple -> (score, start cell (i0,j0,k0), moves uint8[columns]).  moves are in
@@ -415,6 +442,16 @@ def pack_seq_ram128(seq) -> np.ndarray:
     ram = np.zeros((words, 16), np.uint8)
     _check(library().trialign_pack_seq_ram128(_p(s, _u8p), s.size, _p(ram, _u8p), words), "trialign_pack_seq_ram128")
     return ram
+
+
+def pack_batch_ram128(seqs) -> np.ndarray:
+    """[n][len] symbols -> [n][ceil(len/32)][16] RAM images (vectorised pack_seq_ram128, one image per row)."""
+    s = np.ascontiguousarray(np.asarray(seqs, dtype=np.uint8))
+    n, ln = s.shape
+    words = (ln + 31) // 32
+    pad = np.zeros((n, words * 32), np.uint8)
+    pad[:, :ln] = s & 15
+    return (pad[:, 0::2] | (pad[:, 1::2] << 4)).reshape(n, words, 16)
 
 
 def unpack_seq_ram128(ram, n: int) -> np.ndarray:

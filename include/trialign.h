@@ -231,6 +231,14 @@ int trialign_read_scores(const char *path, int32_t *s, int64_t cap, int64_t *n);
  * points apply that truncation themselves).  cap_words / cap count 128-bit words / symbols; ECAPACITY if too small. */
 int trialign_pack_seq_ram128(const uint8_t *sym, int n, uint8_t *ram, int cap_words);
 int trialign_unpack_seq_ram128(const uint8_t *ram, int n, uint8_t *sym, int cap);
+/* The same RAM images as a direct compute input (the FPGA-side format of the testbench): a sequence of
+ * n symbols occupies ceil(n/32) words of 16 bytes; a batch is [n][ceil(len/32)][16] bytes per sequence array.  The batch
+ * is uploaded packed (half the bytes of the one-symbol-per-byte layout) and expanded on the GPU; everything else --
+ * kernels, device mask, results -- is trialign_score / trialign_score_batch. */
+int trialign_score_ram128(const uint8_t *ram_a, int la, const uint8_t *ram_b, int lb, const uint8_t *ram_c, int lc,
+                          int score_bits, int backend, unsigned devices, int32_t *score, int32_t final_states[7]);
+int trialign_score_batch_ram128(const uint8_t *ram_a, const uint8_t *ram_b, const uint8_t *ram_c, int64_t n, int len,
+                                int score_bits, int backend, unsigned devices, int32_t *scores);
 /* Stimulus for the reference testbench: the `seqA_ram[w][hi:lo] <= SYM;` lines of its initial block
  * (src/TriAlign_tb.sv:423-1959), one per symbol position for A, then B, then C, each padded with `A` up to total_len
  * positions (the testbench ships total_len = 512).  A maintainer pastes / `include`s the file in place of that block

@@ -498,3 +498,23 @@ def test_explicit_scoring_fixture(gpu_ta):
         s, fin = eng.align(np.array(case["a"], np.uint8), np.array(case["b"], np.uint8), np.array(case["c"], np.uint8),
                            return_states=True)
         assert s == case["score"] and fin.tolist() == case["final_states"], (case["name"], case["scoring"])
+
+
+def test_packed_ram128_input_formats(gpu_ta, ob, golden):
+    """The testbench's 128-bit sequence RAM words as a direct compute input (src/TriAlign_tb.sv:94-96,150-169): one
+    triple and a batch, packed on the host, expanded on the GPU; code N = 4 aliases to A like in the RTL."""
+    d = golden["dat"]
+    eng = gpu_ta.TriAlign(score_bits=12)
+    rams = [gpu_ta.pack_seq_ram128(d[k]) for k in "ABC"]
+    assert eng.align_ram128(rams[0], 64, rams[1], 64, rams[2], 64) == 1
+    x = np.array([4, 0, 1, 2, 3, 4, 4, 1, 2], np.uint8)
+    s, fin = eng.align_ram128(gpu_ta.pack_seq_ram128(x), 9, gpu_ta.pack_seq_ram128(x[::-1].copy()), 9,
+                              gpu_ta.pack_seq_ram128(x), 9, return_states=True)
+    es, efin = ob.score(x, x[::-1].copy(), x, 12)
+    assert s == es and fin.tolist() == efin.tolist()
+    rng = np.random.default_rng(128)
+    for n, ln in ((33, 64), (7, 45), (5, 130)):
+        A, B, Cc = (rng.integers(0, 5, (n, ln), dtype=np.uint8) for _ in range(3))
+        got = eng.align_batch_ram128(gpu_ta.pack_batch_ram128(A), gpu_ta.pack_batch_ram128(B), gpu_ta.pack_batch_ram128(Cc), n, ln)
+        assert got.tolist() == ob.score_batch(A, B, Cc, 12).tolist(), (n, ln)
+        assert gpu_ta.pack_batch_ram128(A)[0].tolist() == gpu_ta.pack_seq_ram128(A[0]).tolist()
