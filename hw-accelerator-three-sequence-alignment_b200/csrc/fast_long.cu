@@ -36,6 +36,25 @@ __device__ __forceinline__ void st_release_sys(int *p, int v)
     asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// Polling without ordering: a relaxed load does not hold back the memory operations that follow it, so the gate warp
+// runs its step while the value is in flight (an acquire load is an LDG plus an L1 invalidate that waits for it: the
+// gate warp -- and with it the CTA's next barrier -- stood still for an L2 round trip at every poll: 9.8 % of the
+// stall samples of the 8192^3 sweep).  The acquire fence follows once, when a new value is actually relied upon.
+__device__ __forceinline__ int ld_relaxed(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ int ld_relaxed_sys(const int *p)
+{
+    int v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+
 // split-phase CTA barrier, one arrival per warp (as in fast_batch.cu)
 __device__ __forceinline__ void bar_init(uint64_t *bar, int count)
 {
@@ -145,6 +164,16 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             if (COLS && left_remote) return col_decode(ld_acquire_sys(left_p), A.epoch);
             return ld_acquire(left_p);
         };
+        // the step loop polls relaxed and fences once per certification it relies on (see ld_relaxed)
+        auto poll_top = [&]() { return ld_relaxed(top_p); };
+        auto poll_left = [&]() {
+            if (COLS && left_remote) return col_decode(ld_relaxed_sys(left_p), A.epoch);
+            return ld_relaxed(left_p);
+        };
+        auto certify_fence = [&]() {
+            if (COLS && left_remote) fence_acquire_sys();
+            else fence_acquire_gpu();
+        };
         // publication of this task's progress: locally, and to the right neighbour GPU for the last local column
         // The remote word is released at system scope -- a MEMBAR.SYS that waits for the acknowledgements of the face
         // rows stored into the neighbour's memory over NVLink, several microseconds with the CTA held at its next
@@ -182,8 +211,8 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
         const bool need = tid == kGateTid && cert < want;                                                               \
         int tp = 0, lp = 0;                                                                                             \
         if (need) {                                                                                                     \
-            tp = top_p ? ld_acquire(top_p) : 0;                                                                         \
-            lp = left_p ? load_left() : 0;                                                                              \
+            tp = top_p ? poll_top() : 0;                                                                                \
+            lp = left_p ? poll_left() : 0;                                                                              \
         }                                                                                                               \
         if (LAG == 2) {                                                                                                 \
             if (g >= 2) bar_wait(&step_bar[g & 1], ((g - 2) >> 1) & 1); /* everybody has finished step s-2 */           \
@@ -197,8 +226,9 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             cert = fast::long2_certified<C>(A, T, tp, lp);                                                              \
             while (cert < want) {                                                                                       \
                 __nanosleep(40);                                                                                        \
-                cert = fast::long2_certified<C>(A, T, top_p ? ld_acquire(top_p) : 0, left_p ? load_left() : 0);         \
+                cert = fast::long2_certified<C>(A, T, top_p ? poll_top() : 0, left_p ? poll_left() : 0);                \
             }                                                                                                           \
+            certify_fence(); /* the rows certified by the values just read are ordered after them */                    \
         }                                                                                                               \
         bar_arrive_warp(&step_bar[LAG == 2 ? (g & 1) : 0]);                                                             \
         fast::long2_thread_prepare<C, RARE>(ROUT, K, S, A, tj, tk, s_ + 1, tid);                                        \
