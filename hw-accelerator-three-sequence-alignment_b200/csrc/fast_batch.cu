@@ -118,6 +118,48 @@ __global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchAr
 {
     fast_batch_body<Cfg, SPLIT, MINB, false>(A, nullptr);
 }
+
+// Two planes per step (fast_batch.cuh, "P2"): the lagged-barrier layout's four edge slots and three pair buffers, one
+// split-phase barrier per TWO planes.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2_kernel(fast::BatchArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
+    __shared__ __align__(8) uint64_t step_bar[1];
+    const int tid = threadIdx.x;
+    const long long pair_base = (long long)blockIdx.x * A.pairs_per_cta;
+    long long left = A.pairs_total - pair_base;
+    if (left <= 0) return;
+    const int P = left < A.pairs_per_cta ? (int)left : A.pairs_per_cta;
+    int tj, tk;
+    fast::thread_pos<Cfg>(tid, tj, tk);
+    if (tid == 0) bar_init(&step_bar[0], Cfg::NT / 32);
+    for (int fill = 1; fill < Cfg::NBUF; ++fill) {
+        for (int e = tid; e < 64; e += Cfg::NT) {
+            S.acode[fill][e] = 0;
+            S.bpk[fill][e] = 0;
+            S.cpk[fill][e] = 0;
+        }
+        for (int e = tid; e < 3 * 2 * 64; e += Cfg::NT) (&S.seq[fill][0][0][0])[e] = 0;
+    }
+    fast::load_pair_sequences<Cfg>(S, A, tid, pair_base, 0);
+    __syncthreads();
+    fast::build_pair_tables<Cfg>(S, tid, 0);
+    __syncthreads();
+    fast::BatchRegs<Cfg> R, R2;
+    fast::BatchConsts<Cfg> K0, K1;
+    fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, 0);
+    const int steps = fast::batch2_total_steps<Cfg>(P);
+#pragma unroll 1
+    for (int s = 0; s <= steps; ++s) {
+        fast::batch2_thread_step<Cfg>(R, R2, K0, K1, S, A, tj, tk, s, P, pair_base);
+        bar_arrive_warp(&step_bar[0]);
+        fast::batch2_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
+        fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, s + 1);
+        bar_wait(&step_bar[0], s & 1);  // everybody has finished step s
+    }
+}
 template <class Cfg, bool SPLIT>
 __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel_checked(fast::BatchArgs A, fast::BatchCheck chk)
 {
@@ -165,6 +207,30 @@ int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant
     return TRIALIGN_OK;
 }
 
+int launch_batch2(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A)
+{
+    using Cfg = Cfg256L;  // its shared-memory layout: four edge slots, three pair buffers
+    const size_t smem = sizeof(fast::BatchSmem<Cfg>);
+    static bool attr_set[kMaxDevices] = {};
+    if (!attr_set[ctx->device]) {
+        TA_CUDA(cudaFuncSetAttribute(fast_batch2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_batch2_kernel<Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        attr_set[ctx->device] = true;
+    }
+    long long ppc = (A.pairs_total + ctx->sm_count - 1) / ctx->sm_count;
+    if (ppc < 1) ppc = 1;
+    if (ppc > (1 << 20)) ppc = 1 << 20;
+    A.pairs_per_cta = (int)ppc;
+    const long long grid = (A.pairs_total + ppc - 1) / ppc;
+    if (opt_debug())
+        std::fprintf(stderr, "[trialign] K1 P2: grid=%lld pairs/cta=%lld smem=%zu\n", grid, ppc, smem);
+    fast_batch2_kernel<Cfg><<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
 }  // namespace
 
 int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
@@ -172,8 +238,9 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
 {
     if (n <= 0) return TRIALIGN_OK;
     // option k1 selects a variant for comparison: "256" / "512" threads per CTA; suffix "m" = split-phase mbarrier
-    // instead of __syncthreads, suffix "l" = lagged barrier (LAG 2), e.g. k1=512m.  Default: 256l (measured fastest).
-    int variant = 4;
+    // instead of __syncthreads, "l" = lagged barrier (LAG 2), "m2" = two CTAs per SM, "p2" = two planes per step, e.g.
+    // k1=512m.  Default: 256p2 (1,506 GCUPS on 1M x 64^3; 256l 1,472, 256m 1,357, 256m2 1,359).
+    int variant = 16;
     {
         char e[8] = {0};
         if (trialign_get_option("k1", e, sizeof e) == TRIALIGN_OK && e[0] && std::strcmp(e, "stream") != 0) {
@@ -182,6 +249,7 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
             if (e[1] && e[2] && e[3] == 'm') variant |= 1;
             if (e[1] && e[2] && e[3] == 'l') variant |= 4;
             if (e[1] && e[2] && e[3] == 'm' && e[4] == '2') variant = 8;  // 256m2: two CTAs per SM
+            if (e[1] && e[2] && e[3] == 'p' && e[4] == '2') variant = 16; // 256p2: two planes per step
         }
     }
     fast::BatchArgs A;
@@ -200,6 +268,7 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         chk.pair_flags = d_pair_flags;
         return launch_batch<Cfg256L, true, 1, true>(ctx, st, A, 100, chk);
     }
+    if (variant == 16) return launch_batch2(ctx, st, A);
     switch (variant) {
     case 1: return launch_batch<Cfg256, true>(ctx, st, A, variant);
     case 2: return launch_batch<Cfg512, false>(ctx, st, A, variant);

@@ -162,18 +162,16 @@ TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf)
 }
 
 // ---- the part of step s that does not depend on the neighbours' step s-1 (runs between arrive and wait) ----
-template <class C>
-TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
-                                int tk, int s)
+// Core: pair p (CTA-local, -1 while the pipeline fills), plane i.  RESET = false: only the constants of plane i.
+template <class C, bool RESET = true>
+TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
+                                   int tk, int p, int i)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
-    const int u = s - C::LAG * (tj + tk);
-    const int p = u >> 6;          // pair index within this CTA's chunk (-1 while the pipeline fills)
-    const int i = (u & 63) + 1;    // plane 1..64
     const int buf = (p + C::NBUF) % C::NBUF;
     const int j0 = tj * RJ, k0 = tk * RK;  // block-local index of the cell left/above the tile
 
-    if (i == 1) {
+    if (RESET && i == 1) {
         // new pair enters this thread: plane 0 is the all-zero border (src/PE_1cyc.v:164-178 override), and the
         // tile's (b,c) constants change
         const uint32_t zb = phi(A, 0, j0 + 1, k0 + 1);
@@ -202,22 +200,33 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchS
     }
 }
 
+template <class C>
+TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
+                                int tk, int s)
+{
+    const int u = s - C::LAG * (tj + tk);
+    batch_thread_prepare_at<C>(R, K, S, A, tj, tk, u >> 6, (u & 63) + 1);  // pair u / 64, plane 1..64
+}
+
 // ---- one wavefront step of one thread: halos published at step s-1 -> tile -> publish for step s+1 ----
 // R = plane i-1 state (input), Rn = plane i state (output; may be R itself): the lagged-barrier kernel alternates two
 // register sets in a step loop unrolled by two, so that the loop-carried state needs no register moves.
 // CHECK: the run-time range check (see BatchArgs), sampled every kBatchCheckEvery-th step (warp-uniform).
 // `viol` (CHECK only) accumulates the violations of the pair this thread is working on; it lives outside BatchRegs so
 // that the unchecked kernels compile exactly as without the check.
-template <class C, bool CHECK = false>
-TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
-                             const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base, uint32_t *viol_io = nullptr,
-                             const BatchCheck *chk = nullptr)
+// The halos of one plane of a thread's tile (see batch_load_halos).
+template <class C>
+struct BatchHalo {
+    uint32_t T_wY[C::RK], T_u1[C::RK], T_u2[C::RK + 1], T_all[C::RK + 1], L_wZ[C::RJ], L_u3[C::RJ], L_u2[C::RJ], L_all[C::RJ];
+};
+
+template <class C>
+TA_HD void batch_load_halos(BatchHalo<C> &H, const BatchSmem<C> &S, const BatchArgs &A, int tj, int tk, int rs, int i)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
-    const int u = s - C::LAG * (tj + tk);
-    const int p = u >> 6;
-    const int i = (u & 63) + 1;
     const int j0 = tj * RJ, k0 = tk * RK;
+    uint32_t (&T_wY)[RK] = H.T_wY, (&T_u1)[RK] = H.T_u1, (&T_u2)[RK + 1] = H.T_u2, (&T_all)[RK + 1] = H.T_all;
+    uint32_t (&L_wZ)[RJ] = H.L_wZ, (&L_u3)[RJ] = H.L_u3, (&L_u2)[RJ] = H.L_u2, (&L_all)[RJ] = H.L_all;
 
     // halos: top = bottom row of thread (tj-1,tk), left = right column of (tj,tk-1), both published at step s-1.
     // T_u2/T_all[c] belong to column k0+c (c = 0 is the corner cell, c = RK the cell above-right of the tile);
@@ -225,8 +234,7 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
     // so its value is relayed by the left neighbour (which read it one step ago as its own T_*[RK]).
     // "old" = plane i-1 values, which the neighbours publish one step late (the RTL's _d1/_d2 delay registers,
     // src/PE_1cyc.v:80-109): they are known at the START of the publishing step, so those stores leave early.
-    const int rs = (s - C::LAG) & (C::NSLOT - 1), ws = s & (C::NSLOT - 1);
-    uint32_t T_wY[RK], T_u1[RK], T_u2[RK + 1], T_all[RK + 1], L_wZ[RJ], L_u3[RJ], L_u2[RJ], L_all[RJ];
+    // rs: the edge slot read (written by the neighbours LAG steps ago)
     if (tj > 0) {
 #pragma unroll
         for (int c = 0; c < RK; ++c) {
@@ -276,6 +284,18 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
     }
     L_u2[0] = T_u2[0];
     L_all[0] = T_all[0];
+}
+
+// Halos in hand: relay the corner, publish the old half of the own edges, update the tile, publish the new half (slot ws).
+template <class C, bool CHECK = false>
+TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, const BatchHalo<C> &H,
+                                  BatchSmem<C> &S, const BatchArgs &A, int tj, int tk, int ws, int u, int p, int i, int s,
+                                  int P, long long pair_base, uint32_t *viol_io = nullptr, const BatchCheck *chk = nullptr)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    const int j0 = tj * RJ, k0 = tk * RK;
+    const uint32_t (&T_wY)[RK] = H.T_wY, (&T_u1)[RK] = H.T_u1, (&T_u2)[RK + 1] = H.T_u2, (&T_all)[RK + 1] = H.T_all;
+    const uint32_t (&L_wZ)[RJ] = H.L_wZ, (&L_u3)[RJ] = H.L_u3, (&L_u2)[RJ] = H.L_u2, (&L_all)[RJ] = H.L_all;
     S.corner[ws][0][tj][tk] = T_u2[RK];
     S.corner[ws][1][tj][tk] = T_all[RK];
     // the plane i-1 half of this thread's own edges is already known
@@ -374,6 +394,75 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
             Rn.all[r][c] = n_all[r][c]; Rn.wX[r][c] = n_wX[r][c]; Rn.u1[r][c] = n_u1[r][c]; Rn.u3[r][c] = n_u3[r][c];
             Rn.cBC[r][c] = R.cBC[r][c];
         }
+}
+
+// rs / ws: the edge slot read (written by the neighbours LAG steps ago) and the one written now
+template <class C, bool CHECK = false>
+TA_HD void batch_thread_step_at(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
+                                const BatchArgs &A, int tj, int tk, int rs, int ws, int u, int p, int i, int s, int P,
+                                long long pair_base, uint32_t *viol_io = nullptr, const BatchCheck *chk = nullptr)
+{
+    BatchHalo<C> H;
+    batch_load_halos<C>(H, S, A, tj, tk, rs, i);
+    batch_thread_step_halo<C, CHECK>(R, Rn, K, H, S, A, tj, tk, ws, u, p, i, s, P, pair_base, viol_io, chk);
+}
+
+template <class C, bool CHECK = false>
+TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
+                             const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base, uint32_t *viol_io = nullptr,
+                             const BatchCheck *chk = nullptr)
+{
+    const int u = s - C::LAG * (tj + tk);
+    batch_thread_step_at<C, CHECK>(R, Rn, K, S, A, tj, tk, (s - C::LAG) & (C::NSLOT - 1), s & (C::NSLOT - 1), u, u >> 6,
+                                   (u & 63) + 1, s, P, pair_base, viol_io, chk);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two planes per step (K1 "P2").  Thread (tj,tk) runs planes 2u+1 and 2u+2 of pair u / 32 at global step s, u = s - (tj+tk):
+// one barrier, one spin, one round of index arithmetic and staging checks per 32 cells instead of per 16.  The four
+// edge slots of the lagged-barrier layout hold {even step, odd step} x {first, second plane}: edges are consumed ONE step
+// after publication (the barrier is waited for every step, but there are half as many), plane by plane, so the step is
+// two plane updates back to back (R -> R2 -> R: the register sets alternate as in the unrolled single-plane loop).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kBatch2Steps = 32;   // steps per pair: 64 planes, two per step
+constexpr int kBatch2LoadAt = 8, kBatch2BuildAt = 12;
+
+template <class C>
+TA_HD int batch2_total_steps(int P) { return P * kBatch2Steps + (C::TJ + C::TK - 2); }
+
+template <class C>
+TA_HD void batch2_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K0, BatchConsts<C> &K1, const BatchSmem<C> &S,
+                                 const BatchArgs &A, int tj, int tk, int s)
+{
+    const int u = s - (tj + tk), p = u >> 5, i0 = 2 * (u & 31) + 1;
+    batch_thread_prepare_at<C, true>(R, K0, S, A, tj, tk, p, i0);
+    batch_thread_prepare_at<C, false>(R, K1, S, A, tj, tk, p, i0 + 1);
+}
+
+template <class C>
+TA_HD void batch2_thread_step(BatchRegs<C> &R, BatchRegs<C> &R2, const BatchConsts<C> &K0, const BatchConsts<C> &K1,
+                              BatchSmem<C> &S, const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base)
+{
+    static_assert(C::NSLOT == 4, "two step parities x two planes");
+    const int u = s - (tj + tk), p = u >> 5, i0 = 2 * (u & 31) + 1;
+    const int rs = ((s - 1) & 1) << 1, ws = (s & 1) << 1;
+    // both planes' halos first: they were published a step ago, and loading the second plane's only after the first
+    // plane's stores would put a shared-memory round trip into the middle of the step
+    BatchHalo<C> H0, H1;
+    batch_load_halos<C>(H0, S, A, tj, tk, rs, i0);
+    batch_load_halos<C>(H1, S, A, tj, tk, rs + 1, i0 + 1);
+    batch_thread_step_halo<C, false>(R, R2, K0, H0, S, A, tj, tk, ws, u, p, i0, s, P, pair_base);
+    batch_thread_step_halo<C, false>(R2, R, K1, H1, S, A, tj, tk, ws + 1, u, p, i0 + 1, s, P, pair_base);
+}
+
+template <class C>
+TA_HD void batch2_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, int s, int P, long long pair_base)
+{
+    const int q = s / kBatch2Steps + 1;  // pair that starts entering the array at step 32*q
+    if (q < P) {
+        if (s % kBatch2Steps == kBatch2LoadAt) load_pair_sequences<C>(S, A, tid, pair_base + q, q % C::NBUF);
+        if (s % kBatch2Steps == kBatch2BuildAt) build_pair_tables<C>(S, tid, q % C::NBUF);
+    }
 }
 
 // Steps a CTA needs for P pairs, and the CTA-uniform actions of global step s.

@@ -100,6 +100,60 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
     return 0;
 }
 
+// K1 "P2": two planes per step on the lagged-barrier layout (fast_batch2_kernel).  Schedule of the kernel: step s |
+// arrive | uniform actions, prepare s+1 | wait for everybody's step s.  Threads run their step in forward and reverse
+// order on alternate steps: nothing a step reads may have been written in the same step.
+extern "C" int emu_fast_batch2(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                               int pairs_per_cta, int32_t *scores)
+{
+    using C = BatchCfg<4, 4, 16, 16, 2>;
+    if (len < 1 || len > 64 || n < 0) return -1;
+    BatchArgs A;
+    A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
+    A.pairs_total = (n + 1) / 2;
+    A.pairs_per_cta = pairs_per_cta;
+    A.base = base;
+    auto S = std::make_unique<BatchSmem<C>>();
+    std::vector<BatchRegs<C>> R(C::NT), R2(C::NT);
+    std::vector<BatchConsts<C>> K0(C::NT), K1(C::NT);
+    for (long long pair_base = 0; pair_base < A.pairs_total; pair_base += pairs_per_cta) {
+        const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
+        std::memset(S.get(), 0xA5, sizeof(BatchSmem<C>));
+        std::memset(R.data(), 0x5A, R.size() * sizeof(BatchRegs<C>));
+        std::memset(R2.data(), 0x5A, R2.size() * sizeof(BatchRegs<C>));
+        for (int fill = 1; fill < C::NBUF; ++fill) {
+            std::memset(S->acode[fill], 0, sizeof S->acode[fill]);
+            std::memset(S->seq[fill], 0, sizeof S->seq[fill]);
+            std::memset(S->bpk[fill], 0, sizeof S->bpk[fill]);
+            std::memset(S->cpk[fill], 0, sizeof S->cpk[fill]);
+        }
+        for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
+        for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            thread_pos<C>(tid, tj, tk);
+            batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, 0);
+        }
+        const int steps = batch2_total_steps<C>(P);
+        for (int s = 0; s <= steps; ++s) {
+            for (int x = 0; x < C::NT; ++x) {
+                const int tid = (s & 1) ? C::NT - 1 - x : x;
+                int tj, tk;
+                thread_pos<C>(tid, tj, tk);
+                batch2_thread_step<C>(R[tid], R2[tid], K0[tid], K1[tid], *S, A, tj, tk, s, P, pair_base);
+            }
+            for (int x = 0; x < C::NT; ++x) {
+                const int tid = (s & 1) ? x : C::NT - 1 - x;
+                int tj, tk;
+                thread_pos<C>(tid, tj, tk);
+                batch2_uniform_actions<C>(*S, A, tid, s, P, pair_base);
+                batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, s + 1);
+            }
+        }
+    }
+    return 0;
+}
+
 // threads = 256: 16x16 threads x 4x4 cells; threads = 512: 16x32 threads x 4x2 cells; lag = 1 / 2 (see BatchCfg);
 // schedule_seed != 0 (lag 2 only): warps advance in a pseudo-random order with bursts
 extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,

@@ -32,6 +32,13 @@ def _run(L, a, b, c, pairs_per_cta):
                               pairs_per_cta, th, lag, seed, out.ctypes.data_as(i32p))
         assert rc == 0
         outs.append(out)
+    # K1 "P2": two planes per step (fast_batch2_kernel)
+    out = np.full(n, -99999, np.int32)
+    L.emu_fast_batch2.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, i32p]
+    rc = L.emu_fast_batch2(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, 2 * 64 + 32,
+                           pairs_per_cta, out.ctypes.data_as(i32p))
+    assert rc == 0
+    outs.append(out)
     assert all(o.tolist() == outs[0].tolist() for o in outs)
     return outs[0]
 
