@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256, 1) long2_kernel(fast::SweepArgs A)
             int s = 0;
             const int mid_begin = fast::long2_mid_begin<C>(A);
             int mid_end = fast::long2_mid_end<C>(A);
-            // Experiment (TRIALIGN_K2_PP=1, unchecked kernel only): the middle loop unrolled by two over two alternating
+            // Experiment (option k2_pp=1, unchecked kernel only): the middle loop unrolled by two over two alternating
             // register sets, which removes the register moves of the loop-carried state (+4.5 % in K1 / K2S).  Here it
             // gains nothing at L = 8,192 (1,131 vs 1,124 GCUPS) and loses a lot whenever tasks run in lock-step with
             // their producers (1,024^3: 392 vs 492; 4,096 x 1,024^2: 536 vs 763), so it stays off.

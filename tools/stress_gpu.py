@@ -42,9 +42,9 @@ while time.time() < t_end:
         a, b, c = mutated(n, ln, float(rng.choice([0.02, 0.15, 0.75])))
         fast = ta.TriAlign(w).align_batch(a, b, c)
         path = ta.last_path()
+        counts["flagged"] += ta.last_flagged()
         lit = ta.TriAlign(w, backend=ta.BACKEND_GPU_LITERAL).align_batch(a, b, c)
         assert fast.tolist() == lit.tolist(), ("batch", ln, n, w, path)
-        counts["flagged"] += ta.last_flagged() if path == "fast_then_literal" else 0
         if n * ln ** 3 <= ORACLE_CELLS:
             assert fast.tolist() == ob.score_batch(a, b, c, w).tolist(), ("batch vs oracle", ln, n, w, path)
             counts["oracle_checked"] += 1
@@ -65,13 +65,12 @@ while time.time() < t_end:
         a, b, c = mutated(n, ln, float(rng.choice([0.02, 0.15, 0.75])))
         fast = ta.TriAlign(w).align_batch(a, b, c)
         path = ta.last_path()
+        counts["flagged"] += ta.last_flagged()
         lit = ta.TriAlign(w, backend=ta.BACKEND_GPU_LITERAL).align_batch(a, b, c)
         assert fast.tolist() == lit.tolist(), ("short batch", ln, n, w, path)
         if n * ln ** 3 <= ORACLE_CELLS:
             assert fast.tolist() == ob.score_batch(a, b, c, w).tolist(), ("short batch vs oracle", ln, n, w, path)
             counts["oracle_checked"] += 1
     counts[path] = counts.get(path, 0) + 1
-    if path == "fast_then_literal" and kind == 2:
-        counts["flagged"] += ta.last_flagged()
     rounds += 1
 print("stress ok:", rounds, "rounds", counts, flush=True)

@@ -1,5 +1,6 @@
 """Kernel-only time of single long triples of various block-grid shapes (how the step time and the block-to-block
-pipeline fill of K2L add up).  usage (GPU box): python tools/time_long_shapes.py"""
+pipeline fill of K2L add up).  usage (GPU box): python tools/time_long_shapes.py [name=value ...]   (library options,
+e.g. k2_gate=8; SHAPES=short in the environment selects the short shape list)"""
 import json
 import os
 import sys
@@ -10,7 +11,8 @@ import numpy as np
 
 import trialign_b200 as ta
 
-TAG = " ".join(f"{k[9:]}={v}" for k, v in sorted(os.environ.items()) if k.startswith("TRIALIGN_K2"))
+ta.apply_option_args(sys.argv[1:])
+TAG = " ".join(sys.argv[1:])
 SHAPES = [(1024, 64, 128), (1024, 128, 128), (1024, 256, 128), (1024, 1024, 128), (1024, 64, 256), (1024, 64, 1024),
           (1024, 1024, 1024), (4096, 64, 128), (4096, 1024, 1024), (2048, 2048, 2048)]
 if os.environ.get("SHAPES") == "short":
