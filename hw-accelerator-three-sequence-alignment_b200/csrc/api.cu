@@ -391,6 +391,7 @@ struct MultiPipe {
     std::vector<size_t> state_bytes, flag_bytes;
     int epoch = 0;
     bool peers_ready = false;
+    int la = 0, lb = 0, lc = 0;         // shape of the last run: another shape maps tasks to other flag words
 };
 std::mutex g_multi_mu;
 std::map<unsigned, std::unique_ptr<MultiPipe>> g_multi;
@@ -457,6 +458,15 @@ int run_host_triple_multi(const std::vector<int> &devs, unsigned mask, bool cols
     }
     for (size_t g = 1; g < G; ++g)
         if ((rc = multi_reserve(mp, g, sbytes, fbytes))) return rc;
+    if (la != mp.la || lb != mp.lb || lc != mp.lc) {
+        // Flags are compared with the epoch and never cleared; with another shape a word may still hold what a run
+        // 2,047 epochs ago left there.  Nothing is in flight (every run ends synchronised): clear them.
+        for (size_t g = 1; g < G; ++g) {
+            TA_CUDA(cudaSetDevice(devs[g]));
+            TA_CUDA(cudaMemset(mp.flags[g], 0, mp.flag_bytes[g]));
+        }
+        mp.la = la; mp.lb = lb; mp.lc = lc;
+    }
     mp.epoch = mp.epoch % 2047 + 1;  // 1..2047: the column pipeline tags its progress words with 11 bits
     auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
     const int pairs = (lc + 127) / 128;
