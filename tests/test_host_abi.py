@@ -259,3 +259,24 @@ def test_last_devices_before_any_call(ta):
     assert ta.last_devices() >= 0
     assert ta.library().trialign_slab_score_dev(0, None, 1, None, 1, None, 1, 0, 1, None, None, None, None, 0, 16, None,
                                                 None) == -1
+
+
+def test_c_host_example_links_against_the_c_abi(ta, tmp_path):
+    """The C host of INTEGRATION.md section 2(a) (plus the device-mask, options and explicit-scoring calls) compiles with
+    plain gcc against include/trialign.h, links to lib/libtrialign.so and -- on a box without a GPU -- fails loudly with
+    the library's own error text instead of computing anything on the CPU."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no gcc")
+    src = os.path.join(ROOT, "tests", "examples", "host_example.c")
+    exe = str(tmp_path / "host_example")
+    libdir = os.path.dirname(ta.library_path())
+    subprocess.run([gcc, "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", libdir, "-ltrialign", "-o", exe],
+                   check=True, capture_output=True)
+    env = dict(os.environ, LD_LIBRARY_PATH=libdir + ":" + os.environ.get("LD_LIBRARY_PATH", ""))
+    proc = subprocess.run([exe], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    if ta.device_count() == 0:
+        assert proc.returncode == 1 and "no usable CUDA device" in proc.stderr
