@@ -81,9 +81,13 @@ constexpr int kBatchCheckEvery = 8;  // steps between two range samples: `all` m
 
 template <class C>
 struct BatchSmem {
-    uint32_t row[C::NSLOT][4][C::TJ][C::ROW_STRIDE];  // [slot][wY,u2,u1(old),all(old)][tj][k]   bottom rows
-    uint32_t col[C::NSLOT][4][C::TK][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk][j]   right columns
-    uint32_t corner[C::NSLOT][2][C::TJ][C::CORNER_STRIDE];  // [slot][u2,all(old)][tj][tk]  relay of the cell above-right of a tile
+    // Index 0 of the tj / tk dimension is the zero BORDER plane (src/TriAlign_1cyc.v:156-181: all 7 states are 0, i.e.
+    // every reduced value equals the potential): thread (0,tk) / (tj,0) writes it for itself, one plane ahead
+    // (batch_write_borders), so that every thread loads its halos with the same instructions -- no border branches, no
+    // per-lane register shuffling in the step (5 of 8 warps used to run the border code on top of the common path).
+    uint32_t row[C::NSLOT][4][C::TJ + 1][C::ROW_STRIDE];  // [slot][wY,u2,u1(old),all(old)][tj+1][k]   bottom rows
+    uint32_t col[C::NSLOT][4][C::TK + 1][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk+1][j]   right columns
+    uint32_t corner[C::NSLOT][2][C::TJ][C::CORNER_STRIDE];  // [slot][u2,all(old)][tj][tk+1]  relay of the cell above-right of a tile
     uint32_t tabAB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  pair constant {4,2}
     uint32_t tabMB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  triple row constant {9,3}
     uint32_t tabK[C::NBUF][16][C::TABK_STRIDE];      // [buf][a code][tabk_index]  pair constant {4,2} and triple column constant {9,6}
@@ -162,6 +166,40 @@ TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf)
 }
 
 // ---- the part of step s that does not depend on the neighbours' step s-1 (runs between arrive and wait) ----
+// Zero-border halos of plane i into edge slot `slot` (the slot the step of plane i reads): index 0 of the tj / tk
+// dimension, written and read by thread (0,tk) / (tj,0) only, so no barrier is involved.
+template <class C>
+TA_HD void batch_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tj, int tk, int slot, int i)
+{
+    constexpr int RJ = C::RJ, RK = C::RK;
+    if (tj == 0) {  // j = 0 border plane (src/TriAlign_1cyc.v:156-165)
+        const int k0 = tk * RK;
+        const uint32_t e = phi(A, i, 0, k0 + 1);
+#pragma unroll
+        for (int c = 0; c < RK; ++c) {
+            const uint32_t now = e + (uint32_t)c * 0x00020002u, old = now - 0x00020002u;
+            S.row[slot][0][0][k0 + c] = now;
+            S.row[slot][1][0][k0 + c] = now;
+            S.row[slot][2][0][k0 + c] = old;
+            S.row[slot][3][0][k0 + c] = old;
+        }
+    }
+    if (tk == 0) {  // k = 0 border plane (src/TriAlign_1cyc.v:166-174); the corner cell (j0, 0) lies on it too
+        const int j0 = tj * RJ;
+        const uint32_t e = phi(A, i, j0, 0);
+        S.corner[slot][0][tj][0] = e;
+        S.corner[slot][1][tj][0] = e - 0x00020002u;
+#pragma unroll
+        for (int r = 0; r < RJ; ++r) {
+            const uint32_t now = e + (uint32_t)(r + 1) * 0x00020002u, old = now - 0x00020002u;
+            S.col[slot][0][0][j0 + r] = now;
+            S.col[slot][1][0][j0 + r] = now;
+            S.col[slot][2][0][j0 + r] = old;
+            S.col[slot][3][0][j0 + r] = old;
+        }
+    }
+}
+
 // Core: pair p (CTA-local, -1 while the pipeline fills), plane i.  RESET = false: only the constants of plane i.
 template <class C, bool RESET = true>
 TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
@@ -201,11 +239,12 @@ TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const Bat
 }
 
 template <class C>
-TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
+TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, BatchSmem<C> &S, const BatchArgs &A, int tj,
                                 int tk, int s)
 {
     const int u = s - C::LAG * (tj + tk);
     batch_thread_prepare_at<C>(R, K, S, A, tj, tk, u >> 6, (u & 63) + 1);  // pair u / 64, plane 1..64
+    if (tj == 0 || tk == 0) batch_write_borders<C>(S, A, tj, tk, (s - C::LAG) & (C::NSLOT - 1), (u & 63) + 1);
 }
 
 // ---- one wavefront step of one thread: halos published at step s-1 -> tile -> publish for step s+1 ----
@@ -234,53 +273,27 @@ TA_HD void batch_load_halos(BatchHalo<C> &H, const BatchSmem<C> &S, const BatchA
     // so its value is relayed by the left neighbour (which read it one step ago as its own T_*[RK]).
     // "old" = plane i-1 values, which the neighbours publish one step late (the RTL's _d1/_d2 delay registers,
     // src/PE_1cyc.v:80-109): they are known at the START of the publishing step, so those stores leave early.
-    // rs: the edge slot read (written by the neighbours LAG steps ago)
-    if (tj > 0) {
+    // rs: the edge slot read (written by the neighbours LAG steps ago; index 0 = border, written by this thread itself)
+    (void)A;
+    (void)i;
 #pragma unroll
-        for (int c = 0; c < RK; ++c) {
-            T_wY[c] = S.row[rs][0][tj - 1][k0 + c];
-            T_u1[c] = S.row[rs][2][tj - 1][k0 + c];
-            T_u2[c + 1] = S.row[rs][1][tj - 1][k0 + c];
-            T_all[c + 1] = S.row[rs][3][tj - 1][k0 + c];
-        }
-        if (tk > 0) {
-            T_u2[0] = S.corner[rs][0][tj][tk - 1];
-            T_all[0] = S.corner[rs][1][tj][tk - 1];
-        } else {  // corner lies on the k = 0 border plane
-            T_u2[0] = phi(A, i, j0, 0);
-            T_all[0] = phi(A, i - 1, j0, 0);
-        }
-    } else {  // j = 0 border plane (src/TriAlign_1cyc.v:156-165: all 7 states are 0 -> every reduced value is phi)
-#pragma unroll
-        for (int c = 0; c < RK; ++c) {
-            T_wY[c] = phi(A, i, 0, k0 + c + 1);
-            T_u1[c] = phi(A, i - 1, 0, k0 + c + 1);
-        }
-#pragma unroll
-        for (int c = 0; c <= RK; ++c) {
-            T_u2[c] = phi(A, i, 0, k0 + c);
-            T_all[c] = phi(A, i - 1, 0, k0 + c);
-        }
+    for (int c = 0; c < RK; ++c) {
+        T_wY[c] = S.row[rs][0][tj][k0 + c];
+        T_u1[c] = S.row[rs][2][tj][k0 + c];
+        T_u2[c + 1] = S.row[rs][1][tj][k0 + c];
+        T_all[c + 1] = S.row[rs][3][tj][k0 + c];
     }
-    if (tk > 0) {
+    T_u2[0] = S.corner[rs][0][tj][tk];
+    T_all[0] = S.corner[rs][1][tj][tk];
 #pragma unroll
-        for (int r = 0; r < RJ; ++r) {
-            L_wZ[r] = S.col[rs][0][tk - 1][j0 + r];
-            L_u3[r] = S.col[rs][2][tk - 1][j0 + r];
-        }
+    for (int r = 0; r < RJ; ++r) {
+        L_wZ[r] = S.col[rs][0][tk][j0 + r];
+        L_u3[r] = S.col[rs][2][tk][j0 + r];
+    }
 #pragma unroll
-        for (int r = 1; r < RJ; ++r) {
-            L_u2[r] = S.col[rs][1][tk - 1][j0 + r - 1];
-            L_all[r] = S.col[rs][3][tk - 1][j0 + r - 1];
-        }
-    } else {  // k = 0 border plane (src/TriAlign_1cyc.v:166-174)
-#pragma unroll
-        for (int r = 0; r < RJ; ++r) {
-            L_wZ[r] = phi(A, i, j0 + r + 1, 0);
-            L_u3[r] = phi(A, i - 1, j0 + r + 1, 0);
-            L_u2[r] = phi(A, i, j0 + r, 0);
-            L_all[r] = phi(A, i - 1, j0 + r, 0);
-        }
+    for (int r = 1; r < RJ; ++r) {
+        L_u2[r] = S.col[rs][1][tk][j0 + r - 1];
+        L_all[r] = S.col[rs][3][tk][j0 + r - 1];
     }
     L_u2[0] = T_u2[0];
     L_all[0] = T_all[0];
@@ -296,18 +309,18 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
     const int j0 = tj * RJ, k0 = tk * RK;
     const uint32_t (&T_wY)[RK] = H.T_wY, (&T_u1)[RK] = H.T_u1, (&T_u2)[RK + 1] = H.T_u2, (&T_all)[RK + 1] = H.T_all;
     const uint32_t (&L_wZ)[RJ] = H.L_wZ, (&L_u3)[RJ] = H.L_u3, (&L_u2)[RJ] = H.L_u2, (&L_all)[RJ] = H.L_all;
-    S.corner[ws][0][tj][tk] = T_u2[RK];
-    S.corner[ws][1][tj][tk] = T_all[RK];
+    S.corner[ws][0][tj][tk + 1] = T_u2[RK];
+    S.corner[ws][1][tj][tk + 1] = T_all[RK];
     // the plane i-1 half of this thread's own edges is already known
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
-        S.row[ws][2][tj][k0 + c] = R.u1[RJ - 1][c];
-        S.row[ws][3][tj][k0 + c] = R.all[RJ - 1][c];
+        S.row[ws][2][tj + 1][k0 + c] = R.u1[RJ - 1][c];
+        S.row[ws][3][tj + 1][k0 + c] = R.all[RJ - 1][c];
     }
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
-        S.col[ws][2][tk][j0 + r] = R.u3[r][RK - 1];
-        S.col[ws][3][tk][j0 + r] = R.all[r][RK - 1];
+        S.col[ws][2][tk + 1][j0 + r] = R.u3[r][RK - 1];
+        S.col[ws][3][tk + 1][j0 + r] = R.all[r][RK - 1];
     }
 
     // the tile, row-major (within a plane a cell needs its j-1, k-1 and (j-1,k-1) neighbours)
@@ -332,13 +345,13 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
     // publish the plane-i half of the tile's bottom row and right column for the neighbours' step s+1
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
-        S.row[ws][0][tj][k0 + c] = n_wY[RJ - 1][c];
-        S.row[ws][1][tj][k0 + c] = n_u2[RJ - 1][c];
+        S.row[ws][0][tj + 1][k0 + c] = n_wY[RJ - 1][c];
+        S.row[ws][1][tj + 1][k0 + c] = n_u2[RJ - 1][c];
     }
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
-        S.col[ws][0][tk][j0 + r] = n_wZ[r][RK - 1];
-        S.col[ws][1][tk][j0 + r] = n_u2[r][RK - 1];
+        S.col[ws][0][tk + 1][j0 + r] = n_wZ[r][RK - 1];
+        S.col[ws][1][tk + 1][j0 + r] = n_u2[r][RK - 1];
     }
 
     if (CHECK) {
@@ -431,12 +444,17 @@ template <class C>
 TA_HD int batch2_total_steps(int P) { return P * kBatch2Steps + (C::TJ + C::TK - 2); }
 
 template <class C>
-TA_HD void batch2_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K0, BatchConsts<C> &K1, const BatchSmem<C> &S,
+TA_HD void batch2_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K0, BatchConsts<C> &K1, BatchSmem<C> &S,
                                  const BatchArgs &A, int tj, int tk, int s)
 {
     const int u = s - (tj + tk), p = u >> 5, i0 = 2 * (u & 31) + 1;
     batch_thread_prepare_at<C, true>(R, K0, S, A, tj, tk, p, i0);
     batch_thread_prepare_at<C, false>(R, K1, S, A, tj, tk, p, i0 + 1);
+    if (tj == 0 || tk == 0) {
+        const int rs = ((s - 1) & 1) << 1;
+        batch_write_borders<C>(S, A, tj, tk, rs, i0);
+        batch_write_borders<C>(S, A, tj, tk, rs + 1, i0 + 1);
+    }
 }
 
 template <class C>
