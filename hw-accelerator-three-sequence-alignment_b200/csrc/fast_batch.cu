@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2_kernel(fast::BatchArgs
     fast::load_pair_sequences<Cfg>(S, A, tid, pair_base, 0);
     __syncthreads();
     fast::build_pair_tables<Cfg>(S, tid, 0);
+    fast::batch2_write_borders<Cfg>(S, A, tid, 0);
     __syncthreads();
     fast::BatchRegs<Cfg> R, R2;
     fast::BatchConsts<Cfg> K0, K1;
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2_kernel(fast::BatchArgs
     const int steps = fast::batch2_total_steps<Cfg>(P);
 #pragma unroll 1
     for (int s = 0; s <= steps; ++s) {
+        fast::batch2_write_borders<Cfg>(S, A, tid, s + 1);  // everybody has finished step s-1, the slots' last reader
         fast::batch2_thread_step<Cfg>(R, R2, K0, K1, S, A, tj, tk, s, P, pair_base);
         bar_arrive_warp(&step_bar[0]);
         fast::batch2_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);

@@ -450,10 +450,35 @@ TA_HD void batch2_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K0, BatchConst
     const int u = s - (tj + tk), p = u >> 5, i0 = 2 * (u & 31) + 1;
     batch_thread_prepare_at<C, true>(R, K0, S, A, tj, tk, p, i0);
     batch_thread_prepare_at<C, false>(R, K1, S, A, tj, tk, p, i0 + 1);
-    if (tj == 0 || tk == 0) {
-        const int rs = ((s - 1) & 1) << 1;
-        batch_write_borders<C>(S, A, tj, tk, rs, i0);
-        batch_write_borders<C>(S, A, tj, tk, rs + 1, i0 + 1);
+}
+
+// Zero-border halos (index 0 of the edge slots' tj / tk dimension, see BatchSmem) of the two planes that step st reads,
+// written by ALL threads of the CTA -- one 128-bit group each, the first 64 threads one corner word on top -- instead of
+// by the edge threads for themselves: the edge threads sit in 5 of the 8 warps, every step ends at a CTA barrier and the
+// warp with the most duties paces it.  Called at the top of step st-1 (any time between "everybody finished step st-2",
+// the last reader of these slots, and the caller's arrival at the barrier of step st-1).
+// A reader (0,tk) / (tj,0) at step st is at planes 2((st-t)&31)+1 and +2 (t = tk / tj); the potential of its halo cells
+// is the same expression of t for the row and the column: 2(i + 4t + 1 + c) [- 2 for the plane i-1 ("old") arrays].
+template <class C>
+TA_HD void batch2_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tid, int st)
+{
+    static_assert(C::NT == 256 && C::RJ == 4 && C::RK == 4 && C::TJ == 16 && C::TK == 16, "one 128-bit group per thread");
+    const int rs = ((st - 1) & 1) << 1;
+    {
+        const int t = tid & 15, arr = (tid >> 4) & 3, pl = (tid >> 6) & 1, col = tid >> 7;
+        const int i = 2 * ((st - t) & 31) + 1 + pl;
+        const uint32_t e = rep((uint32_t)(A.base + 2 * (i + 4 * t + 1 - (arr >> 1))));
+        uint32_t *dst = col ? &S.col[rs + pl][arr][0][4 * t] : &S.row[rs + pl][arr][0][4 * t];
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(e, e + 0x00020002u, e + 0x00040004u, e + 0x00060006u);
+#else
+        for (int c = 0; c < 4; ++c) dst[c] = e + (uint32_t)c * 0x00020002u;
+#endif
+    }
+    if (tid < 64) {  // the corner cell (j0, 0) of the k = 0 border plane
+        const int t = tid & 15, arr = (tid >> 4) & 1, pl = tid >> 5;
+        const int i = 2 * ((st - t) & 31) + 1 + pl;
+        S.corner[rs + pl][arr][t][0] = rep((uint32_t)(A.base + 2 * (i + 4 * t - arr)));
     }
 }
 

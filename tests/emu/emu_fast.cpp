@@ -129,6 +129,7 @@ extern "C" int emu_fast_batch2(const uint8_t *a, const uint8_t *b, const uint8_t
         }
         for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
         for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) batch2_write_borders<C>(*S, A, tid, 0);
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             thread_pos<C>(tid, tj, tk);
@@ -140,6 +141,7 @@ extern "C" int emu_fast_batch2(const uint8_t *a, const uint8_t *b, const uint8_t
                 const int tid = (s & 1) ? C::NT - 1 - x : x;
                 int tj, tk;
                 thread_pos<C>(tid, tj, tk);
+                batch2_write_borders<C>(*S, A, tid, s + 1);  // next step's border halos: not read by anybody's step s
                 batch2_thread_step<C>(R[tid], R2[tid], K0[tid], K1[tid], *S, A, tj, tk, s, P, pair_base);
             }
             for (int x = 0; x < C::NT; ++x) {
