@@ -23,6 +23,7 @@ from .trialign import (  # noqa: F401
     get_option,
     last_devices,
     last_flagged,
+    last_segments,
     multi_plan,
     set_option,
     last_path,

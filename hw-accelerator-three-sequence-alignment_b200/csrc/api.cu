@@ -76,10 +76,12 @@ NvtxRange::~NvtxRange() { nvtxRangePop(); }
 // Every experiment switch of the kernels is an explicit option of the library; nothing is read from the environment.
 static const char *const kOptionNames[] = {
     "debug",       // 1: launch geometry of the fast kernels on stderr
-    "k1",          // K1 variant for A/B runs: 256 | 256m | 256m2 | 512 | 512m | 256l | 256p2 (default) | stream (K2S on len <= 64)
+    "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l | 256p2 (default) | stream (K2S on len <= 64)
     "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate", "k2_rgate", "k2_cols_order",  // K2L experiment parameters (fast_long.cu)
     "multi",       // one long triple on several GPUs: "slab" (i-slab pipeline) | "cols" (column pipeline); default: auto
     "multi_min",   // smallest la (slab) / lc (cols) per GPU for which the multi-GPU pipeline is used (default 64 / 128)
+    "kt_seg",      // traceback: anti-diagonal planes per segment of the checkpointed form (default: whole cube if it fits)
+    "kt_budget_mb",  // traceback: memory budget for direction words + checkpoints (default: 85 % of the free device memory)
 };
 static std::mutex g_opt_mu;
 static std::map<std::string, std::string> g_opts;
@@ -857,6 +859,7 @@ int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
     TA_CUDA(cudaMemcpyAsync(d_c, c, lc, cudaMemcpyHostToDevice, st));
     TA_CUDA(cudaEventRecord(ctx->ev0, st));
     ts.last_path = TRIALIGN_PATH_TRACEBACK;
+    ts.last_segments = 0;
     rc = traceback_run(ctx, st, d_a, la, d_b, lb, d_c, lc, score_bits, d_out, d_moves);
     if (rc) {
         cudaStreamSynchronize(st);
@@ -1212,6 +1215,8 @@ int trialign_last_path(void) { return tls().last_path; }
 int trialign_last_devices(void) { return tls().last_devices; }
 
 int64_t trialign_last_flagged(void) { return tls().last_flagged; }
+
+int trialign_last_segments(void) { return tls().last_segments; }
 
 int64_t trialign_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -21,6 +21,7 @@ struct ThreadState {
     int last_path = TRIALIGN_PATH_NONE;
     int last_devices = 0;         // GPUs that served the last compute call of this thread
     int64_t last_flagged = 0;     // triples the range-checked batch path re-scored on the literal kernel (last call)
+    int last_segments = 0;        // segments of the last traceback (1 = whole direction cube in memory)
     bool scoring_active = false;  // a *_ex entry point with non-RTL scoring is in progress on this thread
     trialign_scoring scoring{};
 };
@@ -77,7 +78,8 @@ struct DeviceCtx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int sm_count = 0;
     Scratch seq, out, planes, faces, misc;
-    Scratch dirs;        // direction cube of the traceback path
+    Scratch dirs;        // direction cube (or one segment of it) of the traceback path
+    Scratch ckpt;        // checkpointed traceback: the rolling planes parked at the segment boundaries
     Scratch viol;        // range-check flag of the checked fast path (never reallocated by the kernels)
     Scratch flagged;     // per-triple range-check flags + compaction buffers of the checked batch path
     // Stream ordering of the shared scratch buffers: every enqueue that touches them records scratch_ev on its stream;

@@ -240,8 +240,8 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
 {
     if (n <= 0) return TRIALIGN_OK;
     // option k1 selects a variant for comparison: "256" / "512" threads per CTA; suffix "m" = split-phase mbarrier
-    // instead of __syncthreads, "l" = lagged barrier (LAG 2), "m2" = two CTAs per SM, "p2" = two planes per step, e.g.
-    // k1=512m.  Default: 256p2 (1,506 GCUPS on 1M x 64^3; 256l 1,472, 256m 1,357, 256m2 1,359).
+    // instead of __syncthreads, "l" = lagged barrier (LAG 2), "p2" = two planes per step, e.g. k1=512m.  Default: 256p2.
+    // (A two-CTAs-per-SM build, 128 registers, ran at exactly the speed of its one-CTA form in round 2 and is gone.)
     int variant = 16;
     {
         char e[8] = {0};
@@ -250,7 +250,6 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
             if (e[0] == '5') variant = 2;
             if (e[1] && e[2] && e[3] == 'm') variant |= 1;
             if (e[1] && e[2] && e[3] == 'l') variant |= 4;
-            if (e[1] && e[2] && e[3] == 'm' && e[4] == '2') variant = 8;  // 256m2: two CTAs per SM
             if (e[1] && e[2] && e[3] == 'p' && e[4] == '2') variant = 16; // 256p2: two planes per step
         }
     }
@@ -276,7 +275,6 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     case 2: return launch_batch<Cfg512, false>(ctx, st, A, variant);
     case 3: return launch_batch<Cfg512, true>(ctx, st, A, variant);
     case 4: return launch_batch<Cfg256L, true>(ctx, st, A, variant);
-    case 8: return launch_batch<Cfg256, true, 2>(ctx, st, A, variant);
     default: return launch_batch<Cfg256, false>(ctx, st, A, variant);
     }
 }

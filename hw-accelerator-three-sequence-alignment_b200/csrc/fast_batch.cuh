@@ -33,10 +33,11 @@ struct BatchCfg {
     static constexpr int NBUF = LAG + 1;         // per-pair sequence / table buffers
     static constexpr int BJ = RJ * TJ, BK = RK * TK, NT = TJ * TK;
     static constexpr int L = 64;                 // planes per pair (sequences are padded to 64)
-    // shared-memory strides (32-bit words), chosen so that the 8 / 16 lanes of one access wavefront (8 consecutive tk
-    // of one tj per quarter-warp, see thread_pos) fall into distinct banks
+    // shared-memory strides (32-bit words), chosen so that the 8 / 16 lanes of one access wavefront (see thread_pos)
+    // fall into distinct banks
     static constexpr int ROW_STRIDE = RK == 4 ? BK : BK + 16;   // 64-bit row accesses: two tj per wavefront
-    static constexpr int COL_STRIDE = BJ + 4;                   // 128-bit column accesses: lanes differ in tk
+    static constexpr bool DIAG = TJ == 16 && TK == 16;          // lanes of an access group along an anti-diagonal, see thread_pos
+    static constexpr int COL_STRIDE = DIAG ? BJ + 8 : BJ + 4;   // 128-bit column accesses: lanes differ in tk (and tj: DIAG)
     static constexpr int CORNER_STRIDE = TK + 8;                // 32-bit accesses: a warp spans 4 tj x 8 tk
     static constexpr int TABJ_STRIDE = 68;                      // j-indexed tables: lanes of a wavefront differ in code only
     static constexpr int TABK_STRIDE = 128;                     // k-indexed tables: {cAC, tC} per code, see tabk_index
@@ -109,19 +110,27 @@ struct BatchConsts {
     uint32_t cAB[C::RJ], tB[C::RJ], cAC[C::RK], tC[C::RK];
 };
 
-// thread id -> position in the TJ x TK thread grid.  A quarter-warp holds 8 consecutive tk of one tj
-// (conflict-free shared-memory accesses, see BatchCfg); a warp spans 4 tj x 8 tk (11 distinct skews).
-// Warps whose tiles touch the j = 0 / k = 0 border planes execute the border code on top of the common path; hardware
-// warp w issues from scheduler w % 4, so the 4x8-tile patches are dealt to the warps such that every scheduler gets
-// about the same amount of border work (256 threads: patches {both borders, none}, {top, left}, {left, none} x 2).
+// thread id -> position in the TJ x TK thread grid.
+// 256 threads (DIAG): eight consecutive lanes (the unit of a 128-bit shared-memory access) hold eight consecutive tj of
+// one WRAPPED anti-diagonal (tj + tk) mod 16 = dd; a warp holds the wrapped diagonals 2w and 2w+1.  Lanes on one
+// diagonal are on the same plane, so a warp sees at most 4 distinct skews instead of the 11 of a 4x8 patch: the
+// per-pair reset (117 instructions, executed by the whole warp whenever one lane enters a new pair) runs 4 instead
+// of 11 times per pair, and the a-code / score-table look-ups of an access group mostly hit one address.  Bank
+// groups: rows 64 tj + 4 tk -> tk mod 8, columns 72 tk + 4 tj -> (2 tk + tj) mod 8 = (2 dd - tj) mod 8, k-indexed
+// tables -> tk mod 8, j-indexed tables -> (code + tj) mod 8: all distinct within the eight lanes.
+// 512 threads: a quarter-warp holds 8 consecutive tk of one tj, a warp spans 4 tj x 8 tk.
 template <class C>
 TA_HD void thread_pos(int tid, int &tj, int &tk)
 {
-    const int lane = tid & 31;
-    int warp = tid >> 5;
-    if (C::NT == 256) warp = (0x75632410u >> (4 * warp)) & 7;  // warps 0..7 -> patches 0,1,4,2,3,6,5,7
-    tk = (lane & 7) + 8 * (warp % (C::TK / 8));
-    tj = (lane >> 3) + 4 * (warp / (C::TK / 8));
+    if (C::DIAG) {
+        const int oct = tid >> 3, dd = oct >> 1;
+        tj = 8 * (oct & 1) + (tid & 7);
+        tk = (dd - tj) & 15;
+    } else {
+        const int lane = tid & 31, warp = tid >> 5;
+        tk = (lane & 7) + 8 * (warp % (C::TK / 8));
+        tj = (lane >> 3) + 4 * (warp / (C::TK / 8));
+    }
 }
 
 TA_HD uint32_t phi(const BatchArgs &A, int i, int jl, int kl) { return rep((uint32_t)(A.base + 2 * (i + jl + kl))); }

@@ -162,6 +162,7 @@ def library() -> C.CDLL:
     L.trialign_last_path.restype = C.c_int
     L.trialign_last_devices.restype = C.c_int
     L.trialign_last_flagged.restype = C.c_int64
+    L.trialign_last_segments.restype = C.c_int
     L.trialign_score_ram128.argtypes = [_u8p, C.c_int, _u8p, C.c_int, _u8p, C.c_int, C.c_int, C.c_int, C.c_uint, _i32p,
                                         _i32p]
     L.trialign_score_ram128.restype = C.c_int
@@ -223,6 +224,11 @@ def multi_plan(la: int, lb: int, lc: int, score_bits: int, n_devices: int) -> st
 def last_flagged() -> int:
     """Triples of the last batch call that the range check handed to the literal kernel."""
     return int(library().trialign_last_flagged())
+
+
+def last_segments() -> int:
+    """Segments of the last align() call (1 = whole direction cube kept, > 1 = checkpointed recomputation)."""
+    return int(library().trialign_last_segments())
 
 
 def set_option(name: str, value=None) -> None:

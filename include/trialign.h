@@ -155,8 +155,12 @@ int trialign_score_dev(int device, const uint8_t *d_a, int la, const uint8_t *d_
  * The traceback runs on ONE GPU: the first of the `devices` mask (the direction cube is not partitioned).
  * moves[0..*n_moves): one byte per alignment column, first column first: bit0 = A advances, bit1 = B, bit2 = C
  * (7 = three symbols aligned / state M, 1 = Ix, 2 = Iy, 4 = Iz, 3 = Ixy, 6 = Iyz, 5 = Ixz).  *score equals
- * trialign_score()'s.  cap < *n_moves gives ECAPACITY (cap = la+lb+lc always suffices); the direction cube needs
- * la*lb*lc*4 bytes of device memory (ENOMEM beyond that).  Any score_bits in [2,32]. */
+ * trialign_score()'s.  cap < *n_moves gives ECAPACITY (cap = la+lb+lc always suffices).  Any score_bits in [2,32].
+ * Memory: the direction cube takes la*lb*lc*4 bytes; when that exceeds the budget (option kt_budget_mb, default 85 %
+ * of the free device memory) the sweep is cut into segments of D anti-diagonal planes with the rolling planes
+ * checkpointed at the boundaries, and every segment but the last is swept a second time when the walk reaches it:
+ * D*lb*lc*4 + ((la+lb+lc)/D - 2) * 28*(lb+1)*(lc+1)*sizeof(score) bytes, D ~ sqrt(7*(la+lb+lc)*sizeof(score)) (option
+ * kt_seg forces D).  ENOMEM only when even that does not fit.  trialign_last_segments() tells which form ran. */
 int trialign_align(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                    unsigned devices, int32_t *score, int32_t start[3], uint8_t *moves, int cap, int *n_moves);
 
@@ -258,6 +262,8 @@ int trialign_last_path(void);                             /* enum trialign_path 
 int trialign_last_devices(void);                          /* GPUs that served the last call (0 before any call) */
 int64_t trialign_last_flagged(void);                      /* triples of the last batch call that the range check sent to
                                                              the literal kernel (path FAST_THEN_LITERAL) */
+int trialign_last_segments(void);                         /* segments of the last trialign_align (1 = the whole direction
+                                                             cube was kept; > 1 = checkpointed recomputation) */
 int64_t trialign_launch_count(void);                      /* kernels launched by this process so far */
 
 #ifdef __cplusplus

@@ -388,6 +388,47 @@ def test_traceback_long_triple_path_is_worth_the_fast_kernels_score(gpu_ta, ob, 
     assert ob.rescore_path(a, b, c, start, moves) == s
 
 
+@pytest.mark.parametrize("seg", [1, 5, 37, 100])
+def test_traceback_checkpointed_recomputation_walks_the_same_path(gpu_ta, ob, seg):
+    """Checkpointed form (segments of `kt_seg` anti-diagonal planes, every segment but the last re-swept from its
+    checkpoint when the walk reaches it): the path must equal the oracle's move for move, also under wrap."""
+    try:
+        for shape, w in (((40, 17, 33), 12), ((64, 64, 64), 12), ((30, 30, 30), 6), ((96, 80, 100), 16), ((3, 1, 2), 12)):
+            rng = np.random.default_rng(sum(shape) + seg)
+            a, b, c = ob.mutated_triple(rng, max(shape), rate=0.15)
+            a, b, c = a[: shape[0]], b[: shape[1]], c[: shape[2]]
+            gpu_ta.set_option("kt_seg", seg)
+            s, start, moves = gpu_ta.TriAlign(score_bits=w).traceback(a, b, c)
+            nseg = gpu_ta.last_segments()
+            assert nseg == max(1, -(-(sum(shape) - 2) // seg)), (shape, seg, nseg)
+            es, estart, emoves = ob.align(a, b, c, w)
+            assert (s, start) == (es, estart) and moves.tolist() == emoves.tolist(), (shape, w, seg)
+    finally:
+        gpu_ta.set_option("kt_seg", None)
+
+
+def test_traceback_switches_to_checkpoints_when_the_cube_exceeds_the_budget(gpu_ta, ob):
+    """256^3 at 16 bits: the direction cube takes 67 MB; with a 60 MB budget the path must come out of the segmented
+    form (8 segments of 104 planes, 49 MB) and equal the whole-cube one; 20 MB cannot hold even that: ENOMEM."""
+    rng = np.random.default_rng(256)
+    a, b, c = ob.mutated_triple(rng, 256, rate=0.2)
+    eng = gpu_ta.TriAlign(score_bits=16)
+    whole = eng.traceback(a, b, c)
+    assert gpu_ta.last_segments() == 1
+    try:
+        gpu_ta.set_option("kt_budget_mb", 60)
+        seg = eng.traceback(a, b, c)
+        assert gpu_ta.last_segments() == 8
+        assert seg[0] == whole[0] and seg[1] == whole[1] and seg[2].tolist() == whole[2].tolist()
+        assert ob.rescore_path(a, b, c, seg[1], seg[2]) == seg[0] == eng.align(a, b, c)
+        gpu_ta.set_option("kt_budget_mb", 20)
+        with pytest.raises(Exception) as e:
+            eng.traceback(a, b, c)
+        assert "memory" in str(e.value).lower()
+    finally:
+        gpu_ta.set_option("kt_budget_mb", None)
+
+
 def test_traceback_golden_paths(gpu_ta, golden):
     """Every golden case (dat/ triple, prefixes, role permutations, wrap cases, ragged lengths): the GPU traceback
     must reproduce the frozen path, start cell and score."""
