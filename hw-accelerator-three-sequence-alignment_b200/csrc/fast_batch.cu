@@ -72,6 +72,10 @@ __device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const 
     fast::load_pair_sequences<Cfg, CHECK>(S, A, tid, pair_base, 0);
     __syncthreads();
     fast::build_pair_tables<Cfg>(S, tid, 0);
+    if constexpr (Cfg::LAG == 2 && Cfg::DIAG) {
+        fast::batch_write_borders_all<Cfg>(S, A, tid, 0);
+        fast::batch_write_borders_all<Cfg>(S, A, tid, 1);
+    }
     __syncthreads();
 
     fast::BatchRegs<Cfg> R;
@@ -89,6 +93,7 @@ __device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const 
     do {                                                                                   \
         const int s_ = (S_);                                                               \
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                     \
+        if constexpr (Cfg::LAG == 2 && Cfg::DIAG) fast::batch_write_borders_all<Cfg>(S, A, tid, s_ + 2); \
         fast::batch_thread_step<Cfg, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, P, pair_base, &viol, chk); \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                \
         fast::batch_uniform_actions<Cfg, CHECK>(S, A, tid, s_, P, pair_base);                    \

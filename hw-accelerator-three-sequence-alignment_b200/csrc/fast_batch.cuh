@@ -253,7 +253,36 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, BatchSmem<C>
 {
     const int u = s - C::LAG * (tj + tk);
     batch_thread_prepare_at<C>(R, K, S, A, tj, tk, u >> 6, (u & 63) + 1);  // pair u / 64, plane 1..64
-    if (tj == 0 || tk == 0) batch_write_borders<C>(S, A, tj, tk, (s - C::LAG) & (C::NSLOT - 1), (u & 63) + 1);
+    // the lagged-barrier 256-thread kernel spreads the border halos over all threads (batch_write_borders_all)
+    if (!(C::LAG == 2 && C::DIAG) && (tj == 0 || tk == 0))
+        batch_write_borders<C>(S, A, tj, tk, (s - C::LAG) & (C::NSLOT - 1), (u & 63) + 1);
+}
+
+// Lagged-barrier kernel (LAG 2, 256 threads): the zero-border halos that step st reads (edge slot (st-2) & 3, last read at
+// step st-4), written by the first 160 threads -- one 128-bit group or one corner word each -- at the top of step st-2:
+// the writer has seen everybody finish step st-4, and the readers start step st only after everybody's arrival for
+// step st-2.  (With the anti-diagonal thread layout every warp holds edge threads; written by the edge threads for
+// themselves, as in the LAG 1 kernels, every warp would run the border code with one or two lanes.)
+// A reader (0,tk) / (tj,0) is at plane ((st - 2t) & 63) + 1 at step st (t = tk / tj).
+template <class C>
+TA_HD void batch_write_borders_all(BatchSmem<C> &S, const BatchArgs &A, int tid, int st)
+{
+    static_assert(C::LAG == 2 && C::DIAG && C::RJ == 4 && C::RK == 4, "one 128-bit group per thread");
+    const int slot = (st - 2) & (C::NSLOT - 1), t = tid & 15;
+    const int i = ((st - 2 * t) & 63) + 1;
+    if (tid < 128) {
+        const int arr = (tid >> 4) & 3, col = tid >> 6;
+        const uint32_t e = rep((uint32_t)(A.base + 2 * (i + 4 * t + 1 - (arr >> 1))));
+        uint32_t *dst = col ? &S.col[slot][arr][0][4 * t] : &S.row[slot][arr][0][4 * t];
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(e, e + 0x00020002u, e + 0x00040004u, e + 0x00060006u);
+#else
+        for (int c = 0; c < 4; ++c) dst[c] = e + (uint32_t)c * 0x00020002u;
+#endif
+    } else if (tid < 160) {  // the corner cell (j0, 0) of the k = 0 border plane
+        const int arr = (tid >> 4) & 1;
+        S.corner[slot][arr][t][0] = rep((uint32_t)(A.base + 2 * (i + 4 * t - arr)));
+    }
 }
 
 // ---- one wavefront step of one thread: halos published at step s-1 -> tile -> publish for step s+1 ----

@@ -37,6 +37,11 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
         }
         for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
         for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
+        if constexpr (C::LAG == 2 && C::DIAG)
+            for (int tid = 0; tid < C::NT; ++tid) {
+                batch_write_borders_all<C>(*S, A, tid, 0);
+                batch_write_borders_all<C>(*S, A, tid, 1);
+            }
         const int steps = batch_total_steps<C>(P);
         std::vector<BatchConsts<C>> K(C::NT);
         for (int tid = 0; tid < C::NT; ++tid) {
@@ -78,6 +83,8 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
                     if (s > steps) break;
                     const int mn = *std::min_element(done.begin(), done.end());
                     if (mn < s - 2) break;  // bar_wait(step s-2) would block
+                    if constexpr (C::LAG == 2 && C::DIAG)
+                        for (int lane = 0; lane < 32; ++lane) batch_write_borders_all<C>(*S, A, w * 32 + lane, s + 2);
                     for (int lane = 0; lane < 32; ++lane) {
                         const int tid = w * 32 + lane;
                         int tj, tk;
