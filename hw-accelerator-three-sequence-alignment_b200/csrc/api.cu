@@ -178,14 +178,20 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
                    int32_t *d_finals)
 {
     ThreadState &ts = tls();
-    if (ts.scoring_active) {  // non-RTL scoring parameters (*_ex entry points): the literal kernel evaluates them as given
+    const bool want_fast = backend != TRIALIGN_BACKEND_GPU_LITERAL;
+    // non-RTL scoring parameters (*_ex entry points): batches of short triples inside score_fast_domain() run the
+    // range-checked K1 with the constants as a kernel argument (below); everything else goes to the literal kernel,
+    // which evaluates the parameters as given
+    const trialign_scoring *scoring = ts.scoring_active ? &ts.scoring : nullptr;
+    const bool scored_fast = scoring && want_fast && !d_finals && la == lb && lb == lc && fast_batch_supports(la) &&
+                             score_fast_domain(*scoring, score_bits);
+    if (scoring && !scored_fast) {
         if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
         ts.last_path = TRIALIGN_PATH_LITERAL;
-        return literal_run(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals, &ts.scoring);
+        return literal_run(ctx, st, d_a, d_b, d_c, n, la, lb, lc, score_bits, d_scores, d_finals, scoring);
     }
-    const bool want_fast = backend != TRIALIGN_BACKEND_GPU_LITERAL;
     // fast paths are used only where they are provably bit-exact: no candidate can wrap at score_bits
-    if (want_fast && provably_wrap_free(la, lb, lc, score_bits)) {
+    if (want_fast && !scoring && provably_wrap_free(la, lb, lc, score_bits)) {
         if (!d_finals && la == lb && lb == lc && la <= 64 && fast_stream_supports(la) && opt_is("k1", "stream")) {
             ts.last_path = TRIALIGN_PATH_FAST_STREAM;  // experiment: K2S on a single block per pair (len 61..64)
             return fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores);
@@ -216,7 +222,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     }
     // One long triple whose wrap-freedom cannot be proved from the lengths: run the fast kernel with its run-time
     // range check, and fall back to the literal kernel only if some value came near the score_bits limits.
-    if (want_fast && n == 1 && score_bits >= 10 && score_bits <= 16 && fast_long_supports(la, lb, lc)) {
+    if (want_fast && !scoring && n == 1 && score_bits >= 10 && score_bits <= 16 && fast_long_supports(la, lb, lc)) {
         int rc = ctx->viol.reserve(256);
         if (rc) return rc;
         int *d_viol = (int *)ctx->viol.ptr;
@@ -236,8 +242,9 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     }
     // A batch whose wrap-freedom cannot be proved from the length: the range-checked batch kernels flag, per triple,
     // values that came near the score_bits limits; only the flagged triples are re-scored by the literal kernel.
-    if (want_fast && !d_finals && la == lb && lb == lc && score_bits >= 6 && score_bits <= 16 &&
-        (fast_batch_supports(la) || (fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count)))) {
+    if (scored_fast ||
+        (want_fast && !d_finals && la == lb && lb == lc && score_bits >= 6 && score_bits <= 16 &&
+         (fast_batch_supports(la) || (fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count))))) {
         const int64_t pairs = (n + 1) / 2;
         const size_t flag_bytes = (((size_t)pairs * sizeof(int)) + 255) & ~(size_t)255;
         const size_t list_bytes = (((size_t)n * sizeof(int)) + 255) & ~(size_t)255;
@@ -248,7 +255,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         int *d_list = (int *)((char *)ctx->flagged.ptr + 256 + flag_bytes);
         TA_CUDA(cudaMemsetAsync(d_flags, 0, flag_bytes, st));
         const bool k1 = fast_batch_supports(la);
-        rc = k1 ? fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags)
+        rc = k1 ? fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags, scoring)
                 : fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags);
         if (rc) return rc;
         if ((rc = fixup_compact(st, d_flags, n, d_list, d_count))) return rc;
@@ -268,7 +275,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         uint8_t *g_a = (uint8_t *)ctx->misc.ptr, *g_b = g_a + arr, *g_c = g_b + arr;
         int32_t *g_scores = (int32_t *)(g_c + arr);
         if ((rc = fixup_gather(st, d_a, d_b, d_c, la, d_list, count, g_a, g_b, g_c))) return rc;
-        if ((rc = literal_run(ctx, st, g_a, g_b, g_c, count, la, la, la, score_bits, g_scores, nullptr))) return rc;
+        if ((rc = literal_run(ctx, st, g_a, g_b, g_c, count, la, la, la, score_bits, g_scores, nullptr, scoring))) return rc;
         if ((rc = fixup_scatter(st, g_scores, d_list, count, d_scores))) return rc;
         ts.last_path = TRIALIGN_PATH_FAST_THEN_LITERAL;
         return TRIALIGN_OK;

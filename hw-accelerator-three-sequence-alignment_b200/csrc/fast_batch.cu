@@ -1,4 +1,5 @@
 // fast_batch.cu -- K1 launcher: CTA-wide systolic kernel for batches of short triples (see fast_batch.cuh).
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -41,8 +42,8 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
 
 // MINB = CTAs per SM the register budget is set for: 2 (<= 128 registers, a few words spilled) lets two CTAs cover each
 // other's barrier waits and fixed-latency stalls (4 warps per scheduler instead of 2).
-template <class Cfg, bool SPLIT, int MINB, bool CHECK>
-__device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const fast::BatchCheck *chk)
+template <class Cfg, bool SPLIT, int MINB, bool CHECK, class SC = fast::ScoreRtl>
+__device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const fast::BatchCheck *chk, const SC &sc = SC())
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
@@ -71,17 +72,17 @@ __device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const 
     }
     fast::load_pair_sequences<Cfg, CHECK>(S, A, tid, pair_base, 0);
     __syncthreads();
-    fast::build_pair_tables<Cfg>(S, tid, 0);
+    fast::build_pair_tables<Cfg, SC>(S, tid, 0, sc);
     if constexpr (Cfg::LAG == 2 && Cfg::DIAG) {
-        fast::batch_write_borders_all<Cfg>(S, A, tid, 0);
-        fast::batch_write_borders_all<Cfg>(S, A, tid, 1);
+        fast::batch_write_borders_all<Cfg, SC>(S, A, tid, 0, sc);
+        fast::batch_write_borders_all<Cfg, SC>(S, A, tid, 1, sc);
     }
     __syncthreads();
 
     fast::BatchRegs<Cfg> R;
     uint32_t viol = 0;  // CHECK kernels only
     fast::BatchConsts<Cfg> K;
-    fast::batch_thread_prepare<Cfg>(R, K, S, A, tj, tk, 0);
+    fast::batch_thread_prepare<Cfg, SC>(R, K, S, A, tj, tk, 0, sc);
     const int steps = fast::batch_total_steps<Cfg>(P);
     if (Cfg::LAG == 2) {
         // Lagged barrier: everybody has finished step s-2 (even and odd steps use separate barriers, so the one waited
@@ -93,11 +94,11 @@ __device__ __forceinline__ void fast_batch_body(const fast::BatchArgs &A, const 
     do {                                                                                   \
         const int s_ = (S_);                                                               \
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                     \
-        if constexpr (Cfg::LAG == 2 && Cfg::DIAG) fast::batch_write_borders_all<Cfg>(S, A, tid, s_ + 2); \
-        fast::batch_thread_step<Cfg, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, P, pair_base, &viol, chk); \
+        if constexpr (Cfg::LAG == 2 && Cfg::DIAG) fast::batch_write_borders_all<Cfg, SC>(S, A, tid, s_ + 2, sc); \
+        fast::batch_thread_step<Cfg, CHECK, SC>(RIN, ROUT, K, S, A, tj, tk, s_, P, pair_base, &viol, chk, sc); \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                \
-        fast::batch_uniform_actions<Cfg, CHECK>(S, A, tid, s_, P, pair_base);                    \
-        fast::batch_thread_prepare<Cfg>(ROUT, K, S, A, tj, tk, s_ + 1);                    \
+        fast::batch_uniform_actions<Cfg, CHECK, SC>(S, A, tid, s_, P, pair_base, sc);      \
+        fast::batch_thread_prepare<Cfg, SC>(ROUT, K, S, A, tj, tk, s_ + 1, sc);            \
     } while (0)
 #pragma unroll 1
         for (int s = 0; s <= steps; s += 2) {
@@ -172,6 +173,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel_checked(fast::Ba
 {
     fast_batch_body<Cfg, SPLIT, 1, true>(A, &chk);
 }
+// Run-time scoring parameters (trialign_score_batch_ex): the range-checked lagged-barrier kernel with
+// the constants of fast::ScoreGen as a third kernel parameter.  SOP: sum-of-pairs triple score.
+template <class Cfg, bool SOP>
+__global__ void __launch_bounds__(Cfg::NT, 1)
+fast_batch_kernel_scored(fast::BatchArgs A, fast::BatchCheck chk, fast::ScoreGen<SOP> sc)
+{
+    fast_batch_body<Cfg, true, 1, true, fast::ScoreGen<SOP>>(A, &chk, sc);
+}
 
 }  // namespace
 
@@ -240,10 +249,59 @@ int launch_batch2(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A)
 
 }  // namespace
 
+bool score_fast_domain(const trialign_scoring &sc, int score_bits)
+{
+    const int M = sc.match, X = sc.mismatch, GO = sc.gap_open, GE = sc.gap_extend;
+    if (GE < 0 || GE > 4 || GO < GE || GO > 8 || M > 8 || X < -8 || X > M) return false;
+    if (X + 3 * GE < 0 || 3 * X + 6 * GE < 0) return false;  // pair / triple constants in potential form
+    if (sc.triple_rule == TRIALIGN_TRIPLE_RTL) {
+        // temp_ABC = min(row constant, column constant) needs 3X <= 2(M+X) <= 3M; all three + 6 GE non-negative
+        if (!(3 * X <= 2 * (M + X) && 2 * (M + X) <= 3 * M) || 2 * (M + X) + 6 * GE < 0) return false;
+    }
+    if (score_bits < 6) return false;
+    if (score_bits <= 16) {  // the window the range check accepts must not be empty
+        const fast::ScoreMargins m = fast::score_margins(M, X);
+        const int lim = 1 << (score_bits - 1);
+        if (lim - 1 - m.add_max < 8 || -lim + 2 * (2 * GO - m.add_min) > -8) return false;
+    }
+    return true;
+}
+
 int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                   int64_t n, int len, int32_t *d_scores, int check_bits, int *d_pair_flags)
+                   int64_t n, int len, int32_t *d_scores, int check_bits, int *d_pair_flags, const trialign_scoring *scoring)
 {
     if (n <= 0) return TRIALIGN_OK;
+    if (scoring) {
+        if (check_bits <= 0 || !d_pair_flags || !score_fast_domain(*scoring, check_bits)) return TRIALIGN_EINVAL;
+        fast::BatchArgs A;
+        A.a = d_a; A.b = d_b; A.c = d_c;
+        A.n = n; A.len = len; A.scores = d_scores;
+        A.pairs_total = (n + 1) / 2;
+        A.pairs_per_cta = 1;
+        const int M = scoring->match, X = scoring->mismatch, GO = scoring->gap_open, GE = scoring->gap_extend;
+        A.base = fast::score_base(X, GO, GE);
+        const fast::BatchCheck chk = fast::score_check(M, X, GO, check_bits, d_pair_flags);
+        using Cfg = Cfg256L;
+        const size_t smem = sizeof(fast::BatchSmem<Cfg>);
+        const bool sop = scoring->triple_rule == TRIALIGN_TRIPLE_SUM_OF_PAIRS;
+        const void *kernel = sop ? (const void *)fast_batch_kernel_scored<Cfg, true> : (const void *)fast_batch_kernel_scored<Cfg, false>;
+        static bool attr_set[kMaxDevices][2] = {};
+        if (!attr_set[ctx->device][sop]) {
+            TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+            attr_set[ctx->device][sop] = true;
+        }
+        long long ppc = (A.pairs_total + ctx->sm_count - 1) / ctx->sm_count;
+        if (ppc < 1) ppc = 1;
+        if (ppc > (1 << 20)) ppc = 1 << 20;
+        A.pairs_per_cta = (int)ppc;
+        const unsigned grid = (unsigned)((A.pairs_total + ppc - 1) / ppc);
+        if (sop) fast_batch_kernel_scored<Cfg, true><<<grid, Cfg::NT, smem, st>>>(A, chk, fast::make_score_gen<true>(M, X, GO, GE));
+        else fast_batch_kernel_scored<Cfg, false><<<grid, Cfg::NT, smem, st>>>(A, chk, fast::make_score_gen<false>(M, X, GO, GE));
+        count_launch();
+        TA_CUDA(cudaGetLastError());
+        return TRIALIGN_OK;
+    }
     // option k1 selects a variant for comparison: "256" / "512" threads per CTA; suffix "m" = split-phase mbarrier
     // instead of __syncthreads, "l" = lagged barrier (LAG 2), "p2" = two planes per step, e.g. k1=512m.  Default: 256p2.
     // (A two-CTAs-per-SM build, 128 registers, ran at exactly the speed of its one-CTA form in round 2 and is gone.)

@@ -78,6 +78,53 @@ struct BatchCheck {
     int *pair_flags;
 };
 
+// ---- run-time scoring parameters on the host side (fast_core.cuh: ScoreGen) ----
+template <bool SOP>
+inline ScoreGen<SOP> make_score_gen(int M, int X, int GO, int GE)
+{
+    ScoreGen<SOP> g;
+    g.pi_ = (uint32_t)(2 * GE);
+    g.pi2_ = rep((uint32_t)(2 * GE));
+    g.dec_ = 0u - rep((uint32_t)(GO - GE));
+    g.dech_ = rep((uint32_t)(0x10000 - (GO - GE)));
+    g.pair_eq = rep((uint32_t)(M + 3 * GE));
+    g.pair_d = rep((uint32_t)(M - X));
+    g.row_eq = rep((uint32_t)(3 * M + 6 * GE));
+    g.row_d = rep((uint32_t)(3 * M - 3 * X));
+    g.col_eq = rep((uint32_t)(3 * M + 6 * GE));
+    g.col_d = rep((uint32_t)(3 * M - 2 * (M + X)));
+    g.sop_sub = rep((uint32_t)(3 * GE));
+    return g;
+}
+// margins of the range check in true score units: a candidate exceeds the largest `all` of its predecessors by at most
+// add_max and undercuts the smallest by at most 2 * (2 GO - add_min) (a state is at least all(pred) - 2 GO + add_min)
+struct ScoreMargins {
+    int add_max, add_min;
+};
+inline ScoreMargins score_margins(int M, int X)
+{
+    const int v[7] = {3 * M, 2 * (M + X), 3 * X, M + 2 * X, M, X, 0};
+    ScoreMargins m{0, 0};
+    for (int x : v) {
+        m.add_max = x > m.add_max ? x : m.add_max;
+        m.add_min = x < m.add_min ? x : m.add_min;
+    }
+    return m;
+}
+// potential base: every state is at least -(2 GO + 2 GE m) + 3 min(X, 0) (a gap chain from the zero border)
+inline int score_base(int X, int GO, int GE) { return 2 * GE * 64 + 8 * GO + 16 + 6 * (X < 0 ? -X : 0); }
+// every step is sampled; score_bits > 16 cannot wrap at these lengths and parameter sizes: limits out of reach
+inline BatchCheck score_check(int M, int X, int GO, int check_bits, int *pair_flags)
+{
+    const ScoreMargins m = score_margins(M, X);
+    const long long lim = check_bits <= 16 ? (1ll << (check_bits - 1)) : (1ll << 20);
+    BatchCheck chk;
+    chk.check_hi = (int)(lim - 1 - m.add_max);
+    chk.check_lo = (int)(-lim + 2 * (2 * GO - m.add_min));
+    chk.pair_flags = pair_flags;
+    return chk;
+}
+
 constexpr int kBatchCheckEvery = 8;  // steps between two range samples: `all` moves by at most +3 / -4 per plane
 
 template <class C>
@@ -134,6 +181,11 @@ TA_HD void thread_pos(int tid, int &tj, int &tk)
 }
 
 TA_HD uint32_t phi(const BatchArgs &A, int i, int jl, int kl) { return rep((uint32_t)(A.base + 2 * (i + jl + kl))); }
+template <class SC>
+TA_HD uint32_t phi(const BatchArgs &A, int i, int jl, int kl, const SC &sc)
+{
+    return rep((uint32_t)(A.base + (int)sc.pi() * (i + jl + kl)));
+}
 
 // ---- CTA-uniform actions, executed by every thread at fixed global steps ----
 // PAD (the range-checked kernels): positions beyond len get codes that match nothing, see below.
@@ -153,8 +205,8 @@ TA_HD void load_pair_sequences(BatchSmem<C> &S, const BatchArgs &A, int tid, lon
     }
 }
 
-template <class C>
-TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf)
+template <class C, class SC = ScoreRtl>
+TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf, const SC &sc = SC())
 {
     for (int e = tid; e < 16 * 64; e += C::NT) {
         const int code = e >> 6, p = e & 63;
@@ -162,10 +214,10 @@ TA_HD void build_pair_tables(BatchSmem<C> &S, int tid, int buf)
         const uint32_t bp = (uint32_t)S.seq[buf][1][0][p] | ((uint32_t)S.seq[buf][1][1][p] << 16);
         const uint32_t cp = (uint32_t)S.seq[buf][2][0][p] | ((uint32_t)S.seq[buf][2][1][p] << 16);
         const uint32_t nab = neq_flag(ap, bp), nac = neq_flag(ap, cp);
-        S.tabAB[buf][code][p] = pair_const(nab);
-        S.tabMB[buf][code][p] = triple_row_const(nab);
-        S.tabK[buf][code][tabk_index<C>(0, p)] = pair_const(nac);
-        S.tabK[buf][code][tabk_index<C>(1, p)] = triple_col_const(nac);
+        S.tabAB[buf][code][p] = pair_const(nab, sc);
+        S.tabMB[buf][code][p] = triple_row_const(nab, sc);
+        S.tabK[buf][code][tabk_index<C>(0, p)] = pair_const(nac, sc);
+        S.tabK[buf][code][tabk_index<C>(1, p)] = triple_col_const(nac, sc);
         if (code == 0) {
             S.bpk[buf][p] = bp;
             S.cpk[buf][p] = cp;
@@ -210,9 +262,9 @@ TA_HD void batch_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tj, int 
 }
 
 // Core: pair p (CTA-local, -1 while the pipeline fills), plane i.  RESET = false: only the constants of plane i.
-template <class C, bool RESET = true>
+template <class C, bool RESET = true, class SC = ScoreRtl>
 TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
-                                   int tk, int p, int i)
+                                   int tk, int p, int i, const SC &sc = SC())
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int buf = (p + C::NBUF) % C::NBUF;
@@ -221,15 +273,15 @@ TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const Bat
     if (RESET && i == 1) {
         // new pair enters this thread: plane 0 is the all-zero border (src/PE_1cyc.v:164-178 override), and the
         // tile's (b,c) constants change
-        const uint32_t zb = phi(A, 0, j0 + 1, k0 + 1);
+        const uint32_t zb = phi(A, 0, j0 + 1, k0 + 1, sc);
 #pragma unroll
         for (int r = 0; r < RJ; ++r)
 #pragma unroll
             for (int c = 0; c < RK; ++c) {
-                const uint32_t z = zb + (uint32_t)(r + c) * 0x00020002u;
+                const uint32_t z = zb + (uint32_t)(r + c) * sc.pi2();
                 R.all[r][c] = z; R.wX[r][c] = z; R.u1[r][c] = z; R.u3[r][c] = z;
                 const uint32_t nbc = neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]);
-                R.cBC[r][c] = pair_const(nbc);
+                R.cBC[r][c] = pair_const(nbc, sc);
             }
     }
 
@@ -247,12 +299,13 @@ TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const Bat
     }
 }
 
-template <class C>
+template <class C, class SC = ScoreRtl>
 TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, BatchSmem<C> &S, const BatchArgs &A, int tj,
-                                int tk, int s)
+                                int tk, int s, const SC &sc = SC())
 {
+    static_assert(SC::kRtl || (C::LAG == 2 && C::DIAG), "run-time scoring: lagged-barrier 256-thread kernel only");
     const int u = s - C::LAG * (tj + tk);
-    batch_thread_prepare_at<C>(R, K, S, A, tj, tk, u >> 6, (u & 63) + 1);  // pair u / 64, plane 1..64
+    batch_thread_prepare_at<C, true, SC>(R, K, S, A, tj, tk, u >> 6, (u & 63) + 1, sc);  // pair u / 64, plane 1..64
     // the lagged-barrier 256-thread kernel spreads the border halos over all threads (batch_write_borders_all)
     if (!(C::LAG == 2 && C::DIAG) && (tj == 0 || tk == 0))
         batch_write_borders<C>(S, A, tj, tk, (s - C::LAG) & (C::NSLOT - 1), (u & 63) + 1);
@@ -264,24 +317,24 @@ TA_HD void batch_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K, BatchSmem<C>
 // step st-2.  (With the anti-diagonal thread layout every warp holds edge threads; written by the edge threads for
 // themselves, as in the LAG 1 kernels, every warp would run the border code with one or two lanes.)
 // A reader (0,tk) / (tj,0) is at plane ((st - 2t) & 63) + 1 at step st (t = tk / tj).
-template <class C>
-TA_HD void batch_write_borders_all(BatchSmem<C> &S, const BatchArgs &A, int tid, int st)
+template <class C, class SC = ScoreRtl>
+TA_HD void batch_write_borders_all(BatchSmem<C> &S, const BatchArgs &A, int tid, int st, const SC &sc = SC())
 {
     static_assert(C::LAG == 2 && C::DIAG && C::RJ == 4 && C::RK == 4, "one 128-bit group per thread");
     const int slot = (st - 2) & (C::NSLOT - 1), t = tid & 15;
     const int i = ((st - 2 * t) & 63) + 1;
     if (tid < 128) {
         const int arr = (tid >> 4) & 3, col = tid >> 6;
-        const uint32_t e = rep((uint32_t)(A.base + 2 * (i + 4 * t + 1 - (arr >> 1))));
+        const uint32_t e = rep((uint32_t)(A.base + (int)sc.pi() * (i + 4 * t + 1 - (arr >> 1)))), d = sc.pi2();
         uint32_t *dst = col ? &S.col[slot][arr][0][4 * t] : &S.row[slot][arr][0][4 * t];
 #if defined(__CUDA_ARCH__)
-        *reinterpret_cast<uint4 *>(dst) = make_uint4(e, e + 0x00020002u, e + 0x00040004u, e + 0x00060006u);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(e, e + d, e + 2 * d, e + 3 * d);
 #else
-        for (int c = 0; c < 4; ++c) dst[c] = e + (uint32_t)c * 0x00020002u;
+        for (int c = 0; c < 4; ++c) dst[c] = e + (uint32_t)c * d;
 #endif
     } else if (tid < 160) {  // the corner cell (j0, 0) of the k = 0 border plane
         const int arr = (tid >> 4) & 1;
-        S.corner[slot][arr][t][0] = rep((uint32_t)(A.base + 2 * (i + 4 * t - arr)));
+        S.corner[slot][arr][t][0] = rep((uint32_t)(A.base + (int)sc.pi() * (i + 4 * t - arr)));
     }
 }
 
@@ -338,10 +391,11 @@ TA_HD void batch_load_halos(BatchHalo<C> &H, const BatchSmem<C> &S, const BatchA
 }
 
 // Halos in hand: relay the corner, publish the old half of the own edges, update the tile, publish the new half (slot ws).
-template <class C, bool CHECK = false>
+template <class C, bool CHECK = false, class SC = ScoreRtl>
 TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, const BatchHalo<C> &H,
                                   BatchSmem<C> &S, const BatchArgs &A, int tj, int tk, int ws, int u, int p, int i, int s,
-                                  int P, long long pair_base, uint32_t *viol_io = nullptr, const BatchCheck *chk = nullptr)
+                                  int P, long long pair_base, uint32_t *viol_io = nullptr, const BatchCheck *chk = nullptr,
+                                  const SC &sc = SC())
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int j0 = tj * RJ, k0 = tk * RK;
@@ -373,9 +427,9 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
             const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
             const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
             const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
-            const uint32_t cM = triple_const(K.tB[r], K.tC[c]);
-            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
-                                                 R.cBC[r][c], K.cAC[c], nullptr);
+            const uint32_t cM = triple_const_of(K.tB[r], K.tC[c], K.cAB[r], R.cBC[r][c], K.cAC[c], sc);
+            const CellOut o = cell_update<false, SC>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
+                                                     R.cBC[r][c], K.cAC[c], nullptr, sc);
             n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
             n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
         }
@@ -394,7 +448,8 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
 
     if (CHECK) {
         uint32_t viol = i == 1 ? 0u : *viol_io;  // a new pair enters this thread
-        if ((s & (kBatchCheckEvery - 1)) == 0 && i <= A.len) {
+        // run-time scoring: every step is sampled (the +3 / -4 per plane bound belongs to the RTL's constants)
+        if ((SC::kRtl ? (s & (kBatchCheckEvery - 1)) == 0 : true) && i <= A.len) {
             // only cells of the real triple count: padding (j or k beyond len) decays without bound of its own
             uint32_t mx = 0u, mn = 0xFFFFFFFFu;
 #pragma unroll
@@ -402,11 +457,14 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
 #pragma unroll
                 for (int c = 0; c < RK; ++c)
                     if (j0 + r < A.len && k0 + c < A.len) {
-                        mx = vmax2(mx, n_all[r][c]);
-                        mn = vmin2(mn, n_all[r][c]);
+                        // run-time scoring: pi can be large against a narrow score_bits, so the cell's own share of
+                        // the potential is taken off first (FMA pipe) and the limits below are exact per cell
+                        const uint32_t v = SC::kRtl ? n_all[r][c] : fadd(n_all[r][c], 0u - (uint32_t)(r + c) * sc.pi2());
+                        mx = vmax2(mx, v);
+                        mn = vmin2(mn, v);
                     }
             // true value = stored - phi(cell); phi grows by 2 per row / column inside the tile
-            const int ph = A.base + 2 * (i + j0 + 1 + k0 + 1), slack = 2 * (RJ + RK - 2);
+            const int ph = A.base + (int)sc.pi() * (i + j0 + 1 + k0 + 1), slack = SC::kRtl ? 2 * (RJ + RK - 2) : 0;
             const int h = ph + chk->check_hi, l = ph + chk->check_lo + slack;
             const uint32_t hi_lim = rep((uint32_t)(h > 0xFFFF ? 0xFFFF : h)), lo_lim = rep((uint32_t)(l < 0 ? 0 : l));
             viol |= (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
@@ -432,7 +490,7 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
 #pragma unroll
             for (int c = 0; c < RK; ++c)
                 if (r == rf && c == cf) v = n_all[r][c];
-        const int off = A.base + 2 * (3 * A.len);
+        const int off = A.base + (int)sc.pi() * (3 * A.len);
         const long long t0 = 2 * (pair_base + p);
         if (t0 < A.n) A.scores[t0] = (int32_t)(v & 0xFFFFu) - off;
         if (t0 + 1 < A.n) A.scores[t0 + 1] = (int32_t)(v >> 16) - off;
@@ -448,24 +506,25 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
 }
 
 // rs / ws: the edge slot read (written by the neighbours LAG steps ago) and the one written now
-template <class C, bool CHECK = false>
+template <class C, bool CHECK = false, class SC = ScoreRtl>
 TA_HD void batch_thread_step_at(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
                                 const BatchArgs &A, int tj, int tk, int rs, int ws, int u, int p, int i, int s, int P,
-                                long long pair_base, uint32_t *viol_io = nullptr, const BatchCheck *chk = nullptr)
+                                long long pair_base, uint32_t *viol_io = nullptr, const BatchCheck *chk = nullptr,
+                                const SC &sc = SC())
 {
     BatchHalo<C> H;
     batch_load_halos<C>(H, S, A, tj, tk, rs, i);
-    batch_thread_step_halo<C, CHECK>(R, Rn, K, H, S, A, tj, tk, ws, u, p, i, s, P, pair_base, viol_io, chk);
+    batch_thread_step_halo<C, CHECK, SC>(R, Rn, K, H, S, A, tj, tk, ws, u, p, i, s, P, pair_base, viol_io, chk, sc);
 }
 
-template <class C, bool CHECK = false>
+template <class C, bool CHECK = false, class SC = ScoreRtl>
 TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const BatchConsts<C> &K, BatchSmem<C> &S,
                              const BatchArgs &A, int tj, int tk, int s, int P, long long pair_base, uint32_t *viol_io = nullptr,
-                             const BatchCheck *chk = nullptr)
+                             const BatchCheck *chk = nullptr, const SC &sc = SC())
 {
     const int u = s - C::LAG * (tj + tk);
-    batch_thread_step_at<C, CHECK>(R, Rn, K, S, A, tj, tk, (s - C::LAG) & (C::NSLOT - 1), s & (C::NSLOT - 1), u, u >> 6,
-                                   (u & 63) + 1, s, P, pair_base, viol_io, chk);
+    batch_thread_step_at<C, CHECK, SC>(R, Rn, K, S, A, tj, tk, (s - C::LAG) & (C::NSLOT - 1), s & (C::NSLOT - 1), u, u >> 6,
+                                       (u & 63) + 1, s, P, pair_base, viol_io, chk, sc);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -550,13 +609,14 @@ TA_HD void batch2_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, 
 template <class C>
 TA_HD int batch_total_steps(int P) { return P * C::L + C::SKEW; }
 
-template <class C, bool PAD = false>
-TA_HD void batch_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, int s, int P, long long pair_base)
+template <class C, bool PAD = false, class SC = ScoreRtl>
+TA_HD void batch_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, int s, int P, long long pair_base,
+                                 const SC &sc = SC())
 {
     const int q = (s >> 6) + 1;  // pair that starts entering the array at step 64*q
     if (q < P) {
         if ((s & 63) == C::LOAD_AT) load_pair_sequences<C, PAD>(S, A, tid, pair_base + q, q % C::NBUF);
-        if ((s & 63) == C::BUILD_AT) build_pair_tables<C>(S, tid, q % C::NBUF);
+        if ((s & 63) == C::BUILD_AT) build_pair_tables<C, SC>(S, tid, q % C::NBUF, sc);
     }
 }
 

@@ -96,6 +96,37 @@ TA_HD uint32_t vaddmax(uint32_t a, uint32_t b, uint32_t c)
 }
 #endif
 
+// ---- scoring parameters (the testbench's commented-out match / mismatch / gap ports) ----
+// The factoring holds for any MATCH, MISMATCH, GO, GE with GO2 = 2 GO, GE2 = 2 GE, GOGE = GO + GE (src/PE_1cyc.v:57-59):
+// the cost table keeps the form GO*|G(m)| - (GO-GE)*|G(m) & G(q)|.  With delta = GO - GE,
+//     u. = max(all - delta, h.)      w. = max(max(u,u') - delta, I.)
+// and the potential grows by pi = 2 GE per unit of i+j+k, so that a one-symbol gap move (two gapped sequences, 2 GE)
+// still needs no add, a pair move adds s + 3 GE and the M move adds S3 + 6 GE -- all >= 0 inside the domain
+// score_fast_domain() accepts, hence carry-free 32-bit adds.
+// ScoreRtl: the RTL's localparams (src/PE_1cyc.v:53-56) as compile-time constants -- the default of every template
+// below, so that the kernels of the RTL's scoring compile exactly as before.  ScoreGen: run-time values (a separate
+// kernel parameter of the *_scored kernels).  SOP: the paper's sum-of-pairs rule instead of the RTL's temp_ABC.
+struct ScoreRtl {
+    static constexpr bool kRtl = true, kSop = false;
+    TA_HD uint32_t pi() const { return 2; }
+    TA_HD uint32_t pi2() const { return 0x00020002u; }  // pi in both halves
+    TA_HD uint32_t dec() const { return 0u - kOnes; }   // -delta as ONE 32-bit addend: x + dec() = x - delta in both halves
+    TA_HD uint32_t dech() const { return 0xFFFFFFFFu; } // -delta as a per-half addend (VIADDMNMX.U16x2 adds half by half)
+};
+template <bool SOP>
+struct ScoreGen {
+    static constexpr bool kRtl = false, kSop = SOP;
+    uint32_t pi_, pi2_, dec_, dech_;  // 2 GE; the same in both halves; 0 - delta * 0x00010001; (-delta & 0xFFFF) in both halves
+    uint32_t pair_eq, pair_d;       // pair constant: pair_eq - pair_d * [x != y]   (s + 3 GE, both halves)
+    uint32_t row_eq, row_d;         // RTL rule: tB = row_eq - row_d * [a != b]    (3 MATCH + 6 GE  /  3 MISMATCH + 6 GE)
+    uint32_t col_eq, col_d;         // RTL rule: tC = col_eq - col_d * [a != c]    (3 MATCH + 6 GE  /  2 (MATCH+MISMATCH) + 6 GE)
+    uint32_t sop_sub;               // sum of pairs: cM = cAB + cBC + cAC - 3 GE (both halves)
+    TA_HD uint32_t pi() const { return pi_; }
+    TA_HD uint32_t pi2() const { return pi2_; }
+    TA_HD uint32_t dec() const { return dec_; }
+    TA_HD uint32_t dech() const { return dech_; }
+};
+
 // Reduced outputs of one cell, all in the cell's own potential.
 struct CellOut {
     uint32_t all, u1, u2, u3, wX, wY, wZ;
@@ -113,9 +144,10 @@ struct CellOut {
 // Those are lane-exact as long as the LOW lane is >= 1, which holds for every live value (potentials are >= base -
 // envelope > 0, common.cuh); a dead low lane can only disturb a dead high lane (the halves of a word start and stop
 // together in BATCH mode, and in LONG mode the low half stays live -- clamped a index -- until the high half ends).
-template <bool WANT_STATES>
+template <bool WANT_STATES, class SC = ScoreRtl>
 TA_HD CellOut cell_update(uint32_t p_all, uint32_t p_wX, uint32_t p_wY, uint32_t p_wZ, uint32_t p_u1, uint32_t p_u2,
-                          uint32_t p_u3, uint32_t cM, uint32_t cAB, uint32_t cBC, uint32_t cAC, uint32_t *st)
+                          uint32_t p_u3, uint32_t cM, uint32_t cAB, uint32_t cBC, uint32_t cAC, uint32_t *st,
+                          const SC &sc = SC())
 {
     const uint32_t X = p_wX, Y = p_wY, Z = p_wZ;
     const uint32_t XY = fadd(p_u1, cAB);
@@ -129,10 +161,16 @@ TA_HD CellOut cell_update(uint32_t p_all, uint32_t p_wX, uint32_t p_wY, uint32_t
     const uint32_t hA = vmax3(Y, Z, YZ);
     const uint32_t hB = vmax3(X, Z, XZ);
     o.all = vaddmax(p_all, cM, vmax3(hC, hA, hB));
-    o.u1 = vdecmax(o.all, hC);
-    o.u2 = vdecmax(o.all, hA);
-    o.u3 = vdecmax(o.all, hB);
-    const uint32_t d1 = fadd(o.u1, 0u - kOnes), d2 = fadd(o.u2, 0u - kOnes), d3 = fadd(o.u3, 0u - kOnes);
+    if (SC::kRtl) {
+        o.u1 = vdecmax(o.all, hC);
+        o.u2 = vdecmax(o.all, hA);
+        o.u3 = vdecmax(o.all, hB);
+    } else {
+        o.u1 = vaddmax(o.all, sc.dech(), hC);
+        o.u2 = vaddmax(o.all, sc.dech(), hA);
+        o.u3 = vaddmax(o.all, sc.dech(), hB);
+    }
+    const uint32_t d1 = fadd(o.u1, sc.dec()), d2 = fadd(o.u2, sc.dec()), d3 = fadd(o.u3, sc.dec());
     o.wX = vmax3(d3, d1, X);
     o.wY = vmax3(d2, d1, Y);
     o.wZ = vmax3(d2, d3, Z);
@@ -148,6 +186,24 @@ TA_HD uint32_t pair_const(uint32_t neq) { return 0x00040004u - 2u * neq; }      
 TA_HD uint32_t triple_row_const(uint32_t neq_ab) { return 0x00090009u - 6u * neq_ab; }
 TA_HD uint32_t triple_col_const(uint32_t neq_ac) { return 0x00090009u - 3u * neq_ac; }
 TA_HD uint32_t triple_const(uint32_t tB, uint32_t tC) { return vmin2(tB, tC); }
+
+// the same from run-time parameters (neq has 0 / 1 per half, so the products stay inside their halves)
+TA_HD uint32_t pair_const(uint32_t neq, const ScoreRtl &) { return pair_const(neq); }
+TA_HD uint32_t triple_row_const(uint32_t neq, const ScoreRtl &) { return triple_row_const(neq); }
+TA_HD uint32_t triple_col_const(uint32_t neq, const ScoreRtl &) { return triple_col_const(neq); }
+template <bool SOP>
+TA_HD uint32_t pair_const(uint32_t neq, const ScoreGen<SOP> &sc) { return sc.pair_eq - (sc.pair_d & 0xFFFFu) * neq; }
+template <bool SOP>
+TA_HD uint32_t triple_row_const(uint32_t neq, const ScoreGen<SOP> &sc) { return sc.row_eq - (sc.row_d & 0xFFFFu) * neq; }
+template <bool SOP>
+TA_HD uint32_t triple_col_const(uint32_t neq, const ScoreGen<SOP> &sc) { return sc.col_eq - (sc.col_d & 0xFFFFu) * neq; }
+// cM of one cell: RTL rule min(tB, tC); sum of pairs cAB + cBC + cAC - 3 GE (three adds on the FMA pipe)
+template <class SC>
+TA_HD uint32_t triple_const_of(uint32_t tB, uint32_t tC, uint32_t cAB, uint32_t cBC, uint32_t cAC, const SC &sc)
+{
+    if constexpr (SC::kSop) return fadd(fadd(fadd(cAB, cAC), cBC), 0u - sc.sop_sub);
+    else return triple_const(tB, tC);
+}
 
 }  // namespace fast
 }  // namespace trialign

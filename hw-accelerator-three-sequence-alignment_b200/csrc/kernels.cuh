@@ -19,8 +19,14 @@ int literal_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8
 bool fast_batch_supports(int len);
 // check_bits > 0: the range-checked variant; d_pair_flags[(n+1)/2] (zeroed by the caller) gets bit 0 / 1 set for the
 // low / high triple of a pair whose values came too close to the score_bits = check_bits limits.
+// scoring != nullptr (always with check_bits > 0): run-time scoring parameters inside score_fast_domain().
 int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                   int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr);
+                   int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr,
+                   const trialign_scoring *scoring = nullptr);
+// Non-RTL scoring parameters the factored kernels can evaluate (fast_core.cuh): small non-negative gap costs with
+// GE <= GO, MISMATCH <= MATCH, every potential-form constant (s + 3 GE, S3 + 6 GE) non-negative, the RTL triple rule
+// factorisable as min(row, column) constant, and a score_bits whose limits leave room for the range check's margins.
+bool score_fast_domain(const trialign_scoring &sc, int score_bits);
 
 // K2L: block-sweep kernel for ONE long triple (fast_long.cu); same exactness condition as K1 plus the 16-bit envelope
 // checked by fast_long_supports().

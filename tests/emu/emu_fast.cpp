@@ -13,10 +13,15 @@
 
 using namespace trialign::fast;
 
-template <class C>
+// SC = ScoreRtl: the unchecked kernel.  SC = ScoreGen<..>: run-time scoring parameters on the range-checked kernel
+// (PAD sequences, per-pair flags), as fast_batch_kernel_scored runs it.
+template <class C, class SC = ScoreRtl>
 static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
-                              int pairs_per_cta, int schedule_seed, int32_t *scores)
+                              int pairs_per_cta, int schedule_seed, int32_t *scores, const SC &sc = SC(),
+                              const BatchCheck *chk = nullptr)
 {
+    constexpr bool CHECK = !SC::kRtl;
+    std::vector<uint32_t> viol(C::NT, 0);
     if (len < 1 || len > 64 || n < 0) return -1;
     BatchArgs A;
     A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
@@ -35,19 +40,19 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
             std::memset(S->bpk[fill], 0, sizeof S->bpk[fill]);
             std::memset(S->cpk[fill], 0, sizeof S->cpk[fill]);
         }
-        for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
-        for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C, CHECK>(*S, A, tid, pair_base, 0);
+        for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C, SC>(*S, tid, 0, sc);
         if constexpr (C::LAG == 2 && C::DIAG)
             for (int tid = 0; tid < C::NT; ++tid) {
-                batch_write_borders_all<C>(*S, A, tid, 0);
-                batch_write_borders_all<C>(*S, A, tid, 1);
+                batch_write_borders_all<C, SC>(*S, A, tid, 0, sc);
+                batch_write_borders_all<C, SC>(*S, A, tid, 1, sc);
             }
         const int steps = batch_total_steps<C>(P);
         std::vector<BatchConsts<C>> K(C::NT);
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             thread_pos<C>(tid, tj, tk);
-            batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, 0);
+            batch_thread_prepare<C, SC>(R[tid], K[tid], *S, A, tj, tk, 0, sc);
         }
         if (C::LAG == 1) {
             // the kernel's schedule: step s | arrive | uniform actions, prepare s+1 | wait.  Two passes per step: nothing
@@ -56,13 +61,13 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
                 for (int tid = 0; tid < C::NT; ++tid) {
                     int tj, tk;
                     thread_pos<C>(tid, tj, tk);
-                    batch_thread_step<C>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+                    batch_thread_step<C, CHECK, SC>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, P, pair_base, &viol[tid], chk, sc);
                 }
                 for (int tid = C::NT - 1; tid >= 0; --tid) {
                     int tj, tk;
                     thread_pos<C>(tid, tj, tk);
-                    batch_uniform_actions<C>(*S, A, tid, s, P, pair_base);
-                    batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, s + 1);
+                    batch_uniform_actions<C, CHECK, SC>(*S, A, tid, s, P, pair_base, sc);
+                    batch_thread_prepare<C, SC>(R[tid], K[tid], *S, A, tj, tk, s + 1, sc);
                 }
             }
         } else {
@@ -84,19 +89,19 @@ static int emu_fast_batch_cfg(const uint8_t *a, const uint8_t *b, const uint8_t 
                     const int mn = *std::min_element(done.begin(), done.end());
                     if (mn < s - 2) break;  // bar_wait(step s-2) would block
                     if constexpr (C::LAG == 2 && C::DIAG)
-                        for (int lane = 0; lane < 32; ++lane) batch_write_borders_all<C>(*S, A, w * 32 + lane, s + 2);
+                        for (int lane = 0; lane < 32; ++lane) batch_write_borders_all<C, SC>(*S, A, w * 32 + lane, s + 2, sc);
                     for (int lane = 0; lane < 32; ++lane) {
                         const int tid = w * 32 + lane;
                         int tj, tk;
                         thread_pos<C>(tid, tj, tk);
-                        batch_thread_step<C>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, P, pair_base);
+                        batch_thread_step<C, CHECK, SC>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, P, pair_base, &viol[tid], chk, sc);
                     }
                     for (int lane = 0; lane < 32; ++lane) {
                         const int tid = w * 32 + lane;
                         int tj, tk;
                         thread_pos<C>(tid, tj, tk);
-                        batch_uniform_actions<C>(*S, A, tid, s, P, pair_base);
-                        batch_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, s + 1);
+                        batch_uniform_actions<C, CHECK, SC>(*S, A, tid, s, P, pair_base, sc);
+                        batch_thread_prepare<C, SC>(R[tid], K[tid], *S, A, tj, tk, s + 1, sc);
                     }
                     done[w] = s;
                     if (s == steps) ++finished;
@@ -161,6 +166,19 @@ extern "C" int emu_fast_batch2(const uint8_t *a, const uint8_t *b, const uint8_t
         }
     }
     return 0;
+}
+
+// Run-time scoring parameters (fast_batch_kernel_scored): lagged-barrier 256-thread kernel, range-checked at check_bits;
+// flags[(n+1)/2] gets bit 0 / 1 for the low / high triple of a pair the check did not clear.
+extern "C" int emu_fast_batch_ex(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int pairs_per_cta,
+                                 int schedule_seed, int M, int X, int GO, int GE, int sop, int check_bits, int32_t *scores,
+                                 int *flags)
+{
+    using C = BatchCfg<4, 4, 16, 16, 2>;
+    const BatchCheck chk = score_check(M, X, GO, check_bits, flags);
+    const int base = score_base(X, GO, GE);
+    if (sop) return emu_fast_batch_cfg<C, ScoreGen<true>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, make_score_gen<true>(M, X, GO, GE), &chk);
+    return emu_fast_batch_cfg<C, ScoreGen<false>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, make_score_gen<false>(M, X, GO, GE), &chk);
 }
 
 // threads = 256: 16x16 threads x 4x4 cells; threads = 512: 16x32 threads x 4x2 cells; lag = 1 / 2 (see BatchCfg);

@@ -62,6 +62,42 @@ def test_batch_kernel_extremes(emu, ob):
     assert _run(emu, z, o, t, 1).tolist() == ob.score_batch(z, o, t, 16).tolist()  # all-mismatch: most negative
 
 
+# ---- K1 with run-time scoring parameters (fast_batch_kernel_scored) ----
+SCORINGS = [(1, -1, 2, 1, 0), (2, -1, 2, 1, 0), (2, -1, 2, 1, 1), (1, -1, 2, 1, 1), (3, -2, 3, 1, 0), (2, 0, 0, 0, 0),
+            (4, -4, 8, 2, 1), (8, -8, 8, 4, 0), (1, -2, 4, 2, 1), (3, 1, 1, 1, 0), (0, 0, 1, 0, 1)]
+
+
+@pytest.mark.parametrize("sc", SCORINGS)
+def test_batch_kernel_with_runtime_scoring(emu, ob, sc):
+    """The factored update with MATCH / MISMATCH / GO / GE (and the triple rule) as run-time values, on the range-checked
+    lagged-barrier kernel with warps drifting: every triple the check clears must carry the oracle's score; at 16 bits
+    nothing may be flagged, at a narrow width the flagged ones are exactly allowed to differ."""
+    emu.emu_fast_batch_ex.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_int, i32p, C.POINTER(C.c_int)]
+    M, X, GO, GE, rule = sc
+    rng = np.random.default_rng(sum(abs(v) for v in sc) * 7 + rule)
+    for ln, n, ppc in [(64, 6, 2), (37, 5, 3), (8, 3, 1)]:
+        a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        for t in range(0, n, 2):
+            a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+        for w, seed in [(16, 0), (16, 9), (9, 3)]:
+            out = np.full(n, -99999, np.int32)
+            flags = np.zeros((n + 1) // 2, np.int32)
+            rc = emu.emu_fast_batch_ex(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, ppc, seed,
+                                       M, X, GO, GE, rule, w, out.ctypes.data_as(i32p),
+                                       flags.ctypes.data_as(C.POINTER(C.c_int)))
+            assert rc == 0
+            want = [ob.score_ex(a[t], b[t], c[t], w, sc)[0] for t in range(n)]
+            flagged = [bool(flags[t // 2] >> (t & 1) & 1) for t in range(n)]
+            if w == 16:
+                assert not any(flagged), (sc, ln, flags)
+            for t in range(n):
+                if not flagged[t]:
+                    assert out[t] == want[t], (sc, ln, w, t, out.tolist(), want)
+
+
 # ---- K2S: streaming block sweep for batches of triples longer than 64 (fast_stream.cuh) ----
 @pytest.mark.parametrize("ln,n,ppc", [(61, 9, 5), (64, 7, 4), (65, 3, 2), (100, 5, 2), (128, 4, 1), (130, 7, 4), (200, 5, 3), (256, 2, 1)])
 def test_stream_kernel_choreography(emu, ob, ln, n, ppc):

@@ -496,6 +496,31 @@ def test_explicit_scoring_matches_the_oracle(gpu_ta, ob, sc):
     assert got.tolist() == [ob.score_ex(A[t], B[t], Cc[t], 12, sc)[0] for t in range(n)]
 
 
+@pytest.mark.parametrize("sc", [(2, -1, 2, 1, 0), (2, -1, 2, 1, 1), (1, -1, 2, 1, 1), (3, -2, 3, 1, 0), (2, 0, 0, 0, 0),
+                                (4, -4, 8, 2, 1), (8, -8, 8, 4, 0), (3, 1, 1, 1, 0)])
+def test_explicit_scoring_batches_run_the_factored_kernel(gpu_ta, ob, sc):
+    """Batches of short triples with scoring parameters inside the fast domain: the range-checked K1 with the constants
+    as a kernel argument, flagged triples re-scored by the literal kernel with the same parameters; every score against
+    the independent table-driven oracle, at a width where nothing wraps and at widths where some triples do."""
+    rng = np.random.default_rng(sum(abs(v) for v in sc) + 1000 * sc[4])
+    scoring = gpu_ta.Scoring(*sc)
+    for n, ln in ((61, 64), (16, 33), (5, 1)):
+        A = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        B = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        Cc = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        for t in range(0, n, 3):
+            A[t], B[t], Cc[t] = ob.mutated_triple(rng, ln, rate=0.1)
+        for w in (16, 20, 9, 7):
+            got = gpu_ta.TriAlign(w, scoring=scoring).align_batch(A, B, Cc)
+            path, flagged = gpu_ta.last_path(), gpu_ta.last_flagged()
+            want = [ob.score_ex(A[t], B[t], Cc[t], w, sc)[0] for t in range(n)]
+            assert got.tolist() == want, (sc, n, ln, w, path)
+            if w >= 16:
+                assert path == "fast_batch" and flagged == 0, (sc, w, path, flagged)
+            else:
+                assert path in ("fast_batch", "fast_then_literal", "literal"), path
+
+
 def test_rtl_scoring_through_the_ex_entry_points_uses_the_fast_kernels(gpu_ta, ob):
     a, b, c = gpu_ta.synth_batch(0x5EED0002, 0, 64, 64)
     got = gpu_ta.TriAlign(12, scoring=gpu_ta.Scoring()).align_batch(a, b, c)

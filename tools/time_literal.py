@@ -46,6 +46,17 @@ def single(ln, w, backend, label):
                       "gcups": round(ln ** 3 / ms / 1e6, 1)}), flush=True)
 
 
+def batch_ex(n, ln, w, sc, label):
+    """Explicit scoring parameters (host-pointer entry point; device time of the kernels from trialign_last_timing)."""
+    a, b, c = ta.synth_batch(0x5EED0002, 0, n, ln)
+    eng = ta.TriAlign(score_bits=w, scoring=ta.Scoring(*sc))
+    eng.align_batch(a, b, c)
+    eng.align_batch(a, b, c)
+    dev, cells = ta.last_timing()
+    print(json.dumps({"case": label, "scoring": list(sc), "triples": n, "len": ln, "score_bits": w, "path": ta.last_path(),
+                      "flagged": ta.last_flagged(), "ms": round(dev * 1e3, 3), "gcups": round(cells / dev / 1e9, 1)}), flush=True)
+
+
 batch(1 << 16, 64, 12, ta.BACKEND_GPU_LITERAL, "KL literal batch")
 batch(1 << 12, 256, 12, ta.BACKEND_GPU_LITERAL, "KL literal batch")
 single(512, 12, ta.BACKEND_GPU_LITERAL, "KL literal single")
@@ -55,3 +66,6 @@ batch(1 << 20, 64, 8, ta.BACKEND_AUTO, "K1 range-checked (W=8), nothing flagged"
 batch(1 << 20, 64, 8, ta.BACKEND_AUTO, "K1 range-checked (W=8), 1/1024 flagged -> literal", hot=1024)
 batch(1 << 14, 256, 10, ta.BACKEND_AUTO, "K2S range-checked (W=10), nothing flagged")
 batch(1 << 14, 256, 12, ta.BACKEND_AUTO, "K2S unchecked (W=12)")
+batch_ex(1 << 18, 64, 12, (2, -1, 2, 1, 0), "K1 run-time scoring, the testbench's MATCH=2 / MISMATCH=-1 / GO=2 / GE=1")
+batch_ex(1 << 18, 64, 12, (1, -1, 2, 1, 1), "K1 run-time scoring, sum of pairs")
+batch_ex(1 << 14, 64, 12, (5, -4, 10, 1, 1), "outside the fast domain (GO = 10): literal kernel")
