@@ -183,8 +183,10 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
     // range-checked K1 with the constants as a kernel argument (below); everything else goes to the literal kernel,
     // which evaluates the parameters as given
     const trialign_scoring *scoring = ts.scoring_active ? &ts.scoring : nullptr;
-    const bool scored_fast = scoring && want_fast && !d_finals && la == lb && lb == lc && fast_batch_supports(la) &&
-                             score_fast_domain(*scoring, score_bits);
+    const bool scored_fast =
+        scoring && want_fast && !d_finals && la == lb && lb == lc &&
+        ((fast_batch_supports(la) && score_fast_domain(*scoring, score_bits)) ||
+         (fast_stream_supports(la) && fast_stream_fits(la, n, ctx->sm_count) && fast_stream_score_ok(*scoring, la, score_bits)));
     if (scoring && !scored_fast) {
         if (backend == TRIALIGN_BACKEND_GPU_FAST) return TRIALIGN_EINEXACT;
         ts.last_path = TRIALIGN_PATH_LITERAL;
@@ -256,7 +258,7 @@ int dispatch_batch(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         TA_CUDA(cudaMemsetAsync(d_flags, 0, flag_bytes, st));
         const bool k1 = fast_batch_supports(la);
         rc = k1 ? fast_batch_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags, scoring)
-                : fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags);
+                : fast_stream_run(ctx, st, d_a, d_b, d_c, n, la, d_scores, score_bits, d_flags, scoring);
         if (rc) return rc;
         if ((rc = fixup_compact(st, d_flags, n, d_list, d_count))) return rc;
         int count = 0;

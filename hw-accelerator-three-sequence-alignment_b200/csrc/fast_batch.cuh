@@ -112,7 +112,8 @@ inline ScoreMargins score_margins(int M, int X)
     return m;
 }
 // potential base: every state is at least -(2 GO + 2 GE m) + 3 min(X, 0) (a gap chain from the zero border)
-inline int score_base(int X, int GO, int GE) { return 2 * GE * 64 + 8 * GO + 16 + 6 * (X < 0 ? -X : 0); }
+inline int score_base_len(int X, int GO, int GE, int len) { return 2 * GE * len + 8 * GO + 16 + 6 * (X < 0 ? -X : 0); }
+inline int score_base(int X, int GO, int GE) { return score_base_len(X, GO, GE, 64); }
 // every step is sampled; score_bits > 16 cannot wrap at these lengths and parameter sizes: limits out of reach
 inline BatchCheck score_check(int M, int X, int GO, int check_bits, int *pair_flags)
 {

@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 
+#include "fast_batch.cuh"  // host helpers of the run-time scoring parameters
 #include "fast_stream.cuh"
 #include "kernels.cuh"
 
@@ -38,8 +39,8 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-template <bool CHECK>
-__device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, const fast::RangeCheck *chk)
+template <bool CHECK, class SC = fast::ScoreRtl>
+__device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, const fast::RangeCheck *chk, const SC &sc = SC())
 {
     using C = Cfg;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -61,17 +62,17 @@ __device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, cons
     fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, -1);  // filler the pipeline fill runs on
     fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, 0);
     __syncthreads();
-    fast::stream_stage_build<C>(S, tid, -1);
-    fast::stream_stage_build<C>(S, tid, 0);
+    fast::stream_stage_build<C, SC>(S, tid, -1, sc);
+    fast::stream_stage_build<C, SC>(S, tid, 0, sc);
     __syncthreads();
 
     fast::StreamRegs<C> R, R2;
     uint32_t viol = 0;  // CHECK kernel only
     fast::StreamConsts<C> K;
     fast::StreamPos pos = fast::stream_start_pos<C>(A, tj, tk);
-    if (tj == 0 || tk == 0) fast::stream_edge_fetch<C>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1));
+    if (tj == 0 || tk == 0) fast::stream_edge_fetch<C, SC>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1), sc);
     fast::ta_copy_commit();
-    fast::stream_thread_prepare<C>(R, K, S, A, tj, tk, pos, 0, false);
+    fast::stream_thread_prepare<C, SC>(R, K, S, A, tj, tk, pos, 0, false, sc);
     const int steps = (int)fast::stream_total_steps<C>(A, P) | 1;  // an even number of steps: the loop runs two per turn
     int g_t = 0, g_off = 0;
     // one step: wait until everybody has finished step s-2 (even and odd steps use separate barriers) and this thread's
@@ -81,10 +82,10 @@ __device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, cons
         const int s_ = (S_);                                                                      \
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                            \
         fast::ta_copy_wait_prev();                                                                \
-        fast::stream_thread_step<C, CHECK>(RIN, ROUT, K, S, A, tj, tk, s_, pos, &viol, chk);      \
+        fast::stream_thread_step<C, CHECK, SC>(RIN, ROUT, K, S, A, tj, tk, s_, pos, &viol, chk, sc); \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                       \
-        if (g_t < tasks) fast::stream_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off); \
-        fast::stream_thread_prepare<C>(ROUT, K, S, A, tj, tk, pos, s_ + 1, true);                 \
+        if (g_t < tasks) fast::stream_uniform_actions<C, SC>(S, A, tid, cta, P, pair_base, g_t, g_off, sc); \
+        fast::stream_thread_prepare<C, SC>(ROUT, K, S, A, tj, tk, pos, s_ + 1, true, sc);         \
         if (++g_off == A.len) {                                                                   \
             g_off = 0;                                                                            \
             ++g_t;                                                                                \
@@ -104,6 +105,14 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArg
 __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel_checked(fast::StreamArgs A, fast::RangeCheck chk)
 {
     fast_stream_body<true>(A, &chk);
+}
+// Run-time scoring parameters (trialign_score_batch_ex): the range-checked kernel with the constants
+// of fast::ScoreGen as a third kernel parameter.  SOP: sum-of-pairs triple score.
+template <bool SOP>
+__global__ void __launch_bounds__(Cfg::NT, 1)
+fast_stream_kernel_scored(fast::StreamArgs A, fast::RangeCheck chk, fast::ScoreGen<SOP> sc)
+{
+    fast_stream_body<true, fast::ScoreGen<SOP>>(A, &chk, sc);
 }
 
 // contiguous chunks of pairs, one persistent CTA per SM (fill/drain once per CTA); the step counter stays below 2^30
@@ -130,8 +139,19 @@ bool fast_stream_supports(int len)
     return len >= Cfg::LEN_MIN && len <= Cfg::LEN_MAX && fast_long_supports(len, len, len);
 }
 
+// 16-bit lane range with run-time parameters: the potential base, pi per unit of (absolute i + block-local j, k) and the
+// largest value a cell can hold (three-way matches all along) must stay below 2^16
+bool fast_stream_score_ok(const trialign_scoring &sc, int len, int score_bits)
+{
+    if (!score_fast_domain(sc, score_bits) || len < Cfg::LEN_MIN || len > Cfg::LEN_MAX) return false;
+    const long long pi = 2 * sc.gap_extend;
+    const long long top = fast::score_base_len(sc.mismatch, sc.gap_open, sc.gap_extend, len) + pi * (len + Cfg::BJ + Cfg::BK) +
+                          3ll * std::max(sc.match, 0) * len + 64;
+    return top < 65536;
+}
+
 int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                    int64_t n, int len, int32_t *d_scores, int check_bits, int *d_pair_flags)
+                    int64_t n, int len, int32_t *d_scores, int check_bits, int *d_pair_flags, const trialign_scoring *scoring)
 {
     using C = Cfg;
     if (n <= 0) return TRIALIGN_OK;
@@ -144,6 +164,12 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
                                      (int)cudaSharedmemCarveoutMaxShared));
         TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_checked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_checked, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
         attr_set[ctx->device] = true;
     }
@@ -171,7 +197,18 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
     if (opt_debug())
         std::fprintf(stderr, "[trialign] K2S stream: len=%d blocks %dx%d grid=%lld pairs/cta=%lld faces=%.1f MB smem=%zu base=%d\n",
                      len, A.nbj, A.nbk, grid, ppc, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
-    if (check_bits > 0) {
+    if (scoring) {
+        if (check_bits <= 0 || !d_pair_flags || !fast_stream_score_ok(*scoring, len, check_bits)) return TRIALIGN_EINVAL;
+        const int M = scoring->match, X = scoring->mismatch, GO = scoring->gap_open, GE = scoring->gap_extend;
+        A.base = fast::score_base_len(X, GO, GE, len);
+        const fast::BatchCheck bc = fast::score_check(M, X, GO, check_bits, d_pair_flags);
+        fast::RangeCheck chk;
+        chk.check_hi = bc.check_hi; chk.check_lo = bc.check_lo; chk.pair_flags = d_pair_flags;
+        if (scoring->triple_rule == TRIALIGN_TRIPLE_SUM_OF_PAIRS)
+            fast_stream_kernel_scored<true><<<(unsigned)grid, C::NT, smem, st>>>(A, chk, fast::make_score_gen<true>(M, X, GO, GE));
+        else
+            fast_stream_kernel_scored<false><<<(unsigned)grid, C::NT, smem, st>>>(A, chk, fast::make_score_gen<false>(M, X, GO, GE));
+    } else if (check_bits > 0) {
         const int lim = 1 << (check_bits - 1), gap = fast::kStreamCheckEvery - 1;
         fast::RangeCheck chk;
         chk.check_hi = lim - 1 - 3 - 3 * gap;

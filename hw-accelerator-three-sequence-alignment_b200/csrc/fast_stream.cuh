@@ -129,7 +129,11 @@ TA_HD void stream_thread_pos(int tid, int &tj, int &tk)
     tj = (lane >> 3) + 4 * (patch >> 1);
 }
 
-TA_HD uint32_t stream_phi(const StreamArgs &A, int i, int jl, int kl) { return rep((uint32_t)(A.base + 2 * (i + jl + kl))); }
+template <class SC = ScoreRtl>
+TA_HD uint32_t stream_phi(const StreamArgs &A, int i, int jl, int kl, const SC &sc = SC())
+{
+    return rep((uint32_t)(A.base + (int)sc.pi() * (i + jl + kl)));
+}
 
 TA_HD void stream_advance(const StreamArgs &A, StreamPos &p, int nbuf)
 {
@@ -201,34 +205,35 @@ TA_HD void stream_stage_load(StreamSmem<C> &S, const StreamArgs &A, int tid, int
     }
 }
 
-template <class C>
-TA_HD void stream_stage_build(StreamSmem<C> &S, int tid, int t)
+template <class C, class SC = ScoreRtl>
+TA_HD void stream_stage_build(StreamSmem<C> &S, int tid, int t, const SC &sc = SC())
 {
     const int buf = (t + C::NBUF) % C::NBUF;
     for (int e = tid; e < 16 * 64; e += C::NT) {
         const int code = e >> 6, p = e & 63;
         const uint32_t ap = (uint32_t)(code & 3) | ((uint32_t)(code >> 2) << 16);
         const uint32_t nab = neq_flag(ap, S.bpk[buf][p]), nac = neq_flag(ap, S.cpk[buf][p]);
-        S.tabAB[buf][code][p] = pair_const(nab);
-        S.tabMB[buf][code][p] = triple_row_const(nab);
-        S.tabK[buf][code][p] = pair_const(nac);
-        S.tabK[buf][code][64 + p] = triple_col_const(nac);
+        S.tabAB[buf][code][p] = pair_const(nab, sc);
+        S.tabMB[buf][code][p] = triple_row_const(nab, sc);
+        S.tabK[buf][code][p] = pair_const(nac, sc);
+        S.tabK[buf][code][64 + p] = triple_col_const(nac, sc);
     }
 }
 
 // CTA-uniform actions of global step s = g_t*len + g_off (every thread tracks g_t / g_off in registers)
-template <class C>
+template <class C, class SC = ScoreRtl>
 TA_HD void stream_uniform_actions(StreamSmem<C> &S, const StreamArgs &A, int tid, int cta, int P, long long pair_base,
-                                  int g_t, int g_off)
+                                  int g_t, int g_off, const SC &sc = SC())
 {
     if (g_off == C::LOAD_AT) stream_stage_load<C>(S, A, tid, cta, P, pair_base, g_t + 1);
-    if (g_off == C::BUILD_AT) stream_stage_build<C>(S, tid, g_t + 1);
+    if (g_off == C::BUILD_AT) stream_stage_build<C, SC>(S, tid, g_t + 1, sc);
 }
 
 // ---- block-edge halos of the step that runs plane p.i of task p.t, into edge slot `slot` (the slot that step reads).
 // Only thread (0,tk) / (tj,0) writes and reads these entries, so no barrier is involved: cp.async + wait_group. ----
-template <class C>
-TA_HD void stream_edge_fetch(StreamSmem<C> &S, const StreamArgs &A, int tj, int tk, const StreamPos &p, int slot)
+template <class C, class SC = ScoreRtl>
+TA_HD void stream_edge_fetch(StreamSmem<C> &S, const StreamArgs &A, int tj, int tk, const StreamPos &p, int slot,
+                             const SC &sc = SC())
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const StreamTask &T = S.task[p.buf];
@@ -241,10 +246,10 @@ TA_HD void stream_edge_fetch(StreamSmem<C> &S, const StreamArgs &A, int tj, int 
 #pragma unroll
             for (int v = 0; v < 4; ++v) ta_copy16(&S.row[slot][v][0][k0], src + v * C::ROW_STRIDE);
         } else {  // j = 0 border plane: all 7 states are 0 (src/TriAlign_1cyc.v:156-165), reduced values = phi
-            const uint32_t e = stream_phi(A, i, 0, k0 + 1);
+            const uint32_t e = stream_phi(A, i, 0, k0 + 1, sc);
 #pragma unroll
             for (int c = 0; c < RK; ++c) {
-                const uint32_t now = e + (uint32_t)c * 0x00020002u, old = now - 0x00020002u;
+                const uint32_t now = e + (uint32_t)c * sc.pi2(), old = now - sc.pi2();
                 S.row[slot][0][0][k0 + c] = now;
                 S.row[slot][1][0][k0 + c] = now;
                 S.row[slot][2][0][k0 + c] = old;
@@ -265,12 +270,12 @@ TA_HD void stream_edge_fetch(StreamSmem<C> &S, const StreamArgs &A, int tj, int 
             ta_copy4(&S.corner[slot][0][tj][0], fk + (long long)i * C::FK_ROW_WORDS + 1 * C::COL_STRIDE + cidx);
             ta_copy4(&S.corner[slot][1][tj][0], fk + (long long)i * C::FK_ROW_WORDS + 3 * C::COL_STRIDE + cidx);
         } else {  // k = 0 border plane (src/TriAlign_1cyc.v:166-174); the corner cell (j0, 0) lies on it too
-            const uint32_t e = stream_phi(A, i, j0, 0);
+            const uint32_t e = stream_phi(A, i, j0, 0, sc);
             S.corner[slot][0][tj][0] = e;
-            S.corner[slot][1][tj][0] = e - 0x00020002u;
+            S.corner[slot][1][tj][0] = e - sc.pi2();
 #pragma unroll
             for (int r = 0; r < RJ; ++r) {
-                const uint32_t now = e + (uint32_t)(r + 1) * 0x00020002u, old = now - 0x00020002u;
+                const uint32_t now = e + (uint32_t)(r + 1) * sc.pi2(), old = now - sc.pi2();
                 S.col[slot][0][0][j0 + r] = now;
                 S.col[slot][1][0][j0 + r] = now;
                 S.col[slot][2][0][j0 + r] = old;
@@ -282,9 +287,9 @@ TA_HD void stream_edge_fetch(StreamSmem<C> &S, const StreamArgs &A, int tj, int 
 
 // ---- the part of a step that does not depend on the neighbours: move on to the next plane, per-task reset, the
 // step's constants, and the halo fetch of the step after it.  s1 = the global step being prepared. ----
-template <class C>
+template <class C, class SC = ScoreRtl>
 TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSmem<C> &S, const StreamArgs &A, int tj,
-                                 int tk, StreamPos &p, int s1, bool advance)
+                                 int tk, StreamPos &p, int s1, bool advance, const SC &sc = SC())
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     if (advance) stream_advance(A, p, C::NBUF);
@@ -293,14 +298,14 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
     if (p.i == 1) {
         // a new task enters this thread: plane 0 is the all-zero border (src/PE_1cyc.v:164-178 override), and the
         // tile's (b,c) constants change
-        const uint32_t zb = stream_phi(A, 0, j0 + 1, k0 + 1);
+        const uint32_t zb = stream_phi(A, 0, j0 + 1, k0 + 1, sc);
 #pragma unroll
         for (int r = 0; r < RJ; ++r)
 #pragma unroll
             for (int c = 0; c < RK; ++c) {
-                const uint32_t z = zb + (uint32_t)(r + c) * 0x00020002u;
+                const uint32_t z = zb + (uint32_t)(r + c) * sc.pi2();
                 R.all[r][c] = z; R.wX[r][c] = z; R.u1[r][c] = z; R.u3[r][c] = z;
-                R.cBC[r][c] = pair_const(neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]));
+                R.cBC[r][c] = pair_const(neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]), sc);
             }
     }
     const int code = S.acode[S.task[buf].abuf][p.i - 1];
@@ -319,7 +324,7 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
     if (tj == 0 || tk == 0) {
         StreamPos q = p;
         stream_advance(A, q, C::NBUF);
-        stream_edge_fetch<C>(S, A, tj, tk, q, (s1 + 1 + C::LAG) & (C::NSLOT - 1));
+        stream_edge_fetch<C, SC>(S, A, tj, tk, q, (s1 + 1 + C::LAG) & (C::NSLOT - 1), sc);
     }
     ta_copy_commit();
 }
@@ -330,10 +335,10 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
 // CHECK: the run-time range check (see StreamArgs), sampled every kStreamCheckEvery-th step (warp-uniform).
 // `viol` (CHECK only) accumulates the violations of the task this thread is working on; it lives outside StreamRegs so
 // that the unchecked kernel compiles exactly as without the check.
-template <class C, bool CHECK = false>
+template <class C, bool CHECK = false, class SC = ScoreRtl>
 TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const StreamConsts<C> &K, StreamSmem<C> &S,
                               const StreamArgs &A, int tj, int tk, int s, const StreamPos &p, uint32_t *viol_io = nullptr,
-                              const RangeCheck *chk = nullptr)
+                              const RangeCheck *chk = nullptr, const SC &sc = SC())
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int j0 = tj * RJ, k0 = tk * RK;
@@ -388,9 +393,9 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
             const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : T_u1[c];
             const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? T_u2[c] : L_u2[r]);
             const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : L_u3[r];
-            const uint32_t cM = triple_const(K.tB[r], K.tC[c]);
-            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
-                                                 R.cBC[r][c], K.cAC[c], nullptr);
+            const uint32_t cM = triple_const_of(K.tB[r], K.tC[c], K.cAB[r], R.cBC[r][c], K.cAC[c], sc);
+            const CellOut o = cell_update<false, SC>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
+                                                     R.cBC[r][c], K.cAC[c], nullptr, sc);
             n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
             n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
         }
@@ -413,7 +418,7 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
         if (tj == C::TJ - 1) {
             uint32_t *fj = T.fj_w;
             if (fj) {
-                const uint32_t adj = rep(2 * C::BJ);
+                const uint32_t adj = rep(sc.pi() * C::BJ);
                 uint32_t *dst = fj + (long long)p.i * C::FJ_ROW_WORDS + k0;
                 ta_store4(dst + 0 * C::ROW_STRIDE, n_wY[RJ - 1][0] - adj, n_wY[RJ - 1][1] - adj, n_wY[RJ - 1][2] - adj, n_wY[RJ - 1][3] - adj);
                 ta_store4(dst + 1 * C::ROW_STRIDE, n_u2[RJ - 1][0] - adj, n_u2[RJ - 1][1] - adj, n_u2[RJ - 1][2] - adj, n_u2[RJ - 1][3] - adj);
@@ -424,7 +429,7 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
         if (tk == C::TK - 1) {
             uint32_t *fk = T.fk_w;
             if (fk) {
-                const uint32_t adj = rep(2 * C::BK);
+                const uint32_t adj = rep(sc.pi() * C::BK);
                 uint32_t *dst = fk + (long long)p.i * C::FK_ROW_WORDS + j0;
                 ta_store4(dst + 0 * C::COL_STRIDE, n_wZ[0][RK - 1] - adj, n_wZ[1][RK - 1] - adj, n_wZ[2][RK - 1] - adj, n_wZ[3][RK - 1] - adj);
                 ta_store4(dst + 1 * C::COL_STRIDE, n_u2[0][RK - 1] - adj, n_u2[1][RK - 1] - adj, n_u2[2][RK - 1] - adj, n_u2[3][RK - 1] - adj);
@@ -441,16 +446,20 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
 
     if (CHECK) {
         uint32_t viol = p.i == 1 ? 0u : *viol_io;  // a new task enters this thread
-        if ((s & (kStreamCheckEvery - 1)) == 0) {
+        // run-time scoring: every step is sampled (the +3 / -4 per plane bound belongs to the RTL's constants) and the
+        // cell's own share of the potential is taken off first, so that the limits are exact per cell
+        if (SC::kRtl ? (s & (kStreamCheckEvery - 1)) == 0 : true) {
             uint32_t mx = n_all[0][0], mn = n_all[0][0];
 #pragma unroll
             for (int r = 0; r < RJ; ++r)
 #pragma unroll
                 for (int c = 0; c < RK; c += 2) {
-                    mx = vmax3(mx, n_all[r][c], n_all[r][c + 1]);
-                    mn = vmin3(mn, n_all[r][c], n_all[r][c + 1]);
+                    const uint32_t v0 = SC::kRtl ? n_all[r][c] : fadd(n_all[r][c], 0u - (uint32_t)(r + c) * sc.pi2());
+                    const uint32_t v1 = SC::kRtl ? n_all[r][c + 1] : fadd(n_all[r][c + 1], 0u - (uint32_t)(r + c + 1) * sc.pi2());
+                    mx = vmax3(mx, v0, v1);
+                    mn = vmin3(mn, v0, v1);
                 }
-            const int ph = A.base + 2 * (p.i + j0 + 1 + k0 + 1), slack = 2 * (RJ + RK - 2);
+            const int ph = A.base + (int)sc.pi() * (p.i + j0 + 1 + k0 + 1), slack = SC::kRtl ? 2 * (RJ + RK - 2) : 0;
             const int h = ph + chk->check_hi, l = ph + chk->check_lo + slack;
             const uint32_t hi_lim = rep((uint32_t)(h > 0xFFFF ? 0xFFFF : h)), lo_lim = rep((uint32_t)(l < 0 ? 0 : l));
             viol |= (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
@@ -482,7 +491,7 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
 #pragma unroll
                     for (int c = 0; c < RK; ++c)
                         if (r == rf && c == cf) v = n_all[r][c];
-                const int off = A.base + 2 * (A.len + jl + kl);
+                const int off = A.base + (int)sc.pi() * (A.len + jl + kl);
                 const long long t0 = 2 * T.pair;
                 if (t0 < A.n) A.scores[t0] = (int32_t)(v & 0xFFFFu) - off;
                 if (t0 + 1 < A.n) A.scores[t0 + 1] = (int32_t)(v >> 16) - off;

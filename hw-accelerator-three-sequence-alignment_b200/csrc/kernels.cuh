@@ -72,7 +72,10 @@ int fast_long2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la, 
 bool fast_stream_supports(int len);
 bool fast_stream_fits(int len, int64_t n, int sm_count);  // CTA-private face rings within the memory budget
 int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                    int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr);
+                    int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr,
+                    const trialign_scoring *scoring = nullptr);
+// run-time scoring parameters on K2S: score_fast_domain() plus the 16-bit lane range at this length
+bool fast_stream_score_ok(const trialign_scoring &sc, int len, int score_bits);
 
 // flagged-triple plumbing of the checked batch path (batch_fixup.cu): compaction of the per-pair flags into a list of
 // triple indices, gather of those triples into contiguous arrays, scatter of their re-computed scores

@@ -200,10 +200,13 @@ extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t 
 // ---------------------------------------------------------------------------------------------------------------
 #include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_stream.cuh"
 
-extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
-                               int pairs_per_cta, int schedule_seed, int32_t *scores)
+template <class SC>
+static int emu_fast_stream_sc(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                              int pairs_per_cta, int schedule_seed, int32_t *scores, const SC &sc, const RangeCheck *chk)
 {
     using C = StreamCfg;
+    constexpr bool CHECK = !SC::kRtl;
+    std::vector<uint32_t> viol(C::NT, 0);
     if (len < C::LEN_MIN || len > C::LEN_MAX || n < 0 || pairs_per_cta < 1) return -1;
     StreamArgs A{};
     A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
@@ -230,14 +233,14 @@ extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t
         std::memset(R.data(), 0x5A, R.size() * sizeof(StreamRegs<C>));
         for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, -1);
         for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, 0);
-        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, -1);
-        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C, SC>(*S, tid, -1, sc);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C, SC>(*S, tid, 0, sc);
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             stream_thread_pos<C>(tid, tj, tk);
             pos[tid] = stream_start_pos<C>(A, tj, tk);
-            if (tj == 0 || tk == 0) stream_edge_fetch<C>(*S, A, tj, tk, pos[tid], C::LAG & (C::NSLOT - 1));
-            stream_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, pos[tid], 0, false);
+            if (tj == 0 || tk == 0) stream_edge_fetch<C, SC>(*S, A, tj, tk, pos[tid], C::LAG & (C::NSLOT - 1), sc);
+            stream_thread_prepare<C, SC>(R[tid], K[tid], *S, A, tj, tk, pos[tid], 0, false, sc);
         }
         const int steps = (int)stream_total_steps<C>(A, P);
         constexpr int NW = C::NT / 32;
@@ -257,14 +260,14 @@ extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t
                     const int tid = w * 32 + lane;
                     int tj, tk;
                     stream_thread_pos<C>(tid, tj, tk);
-                    stream_thread_step<C>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, pos[tid]);
+                    stream_thread_step<C, CHECK, SC>(R[tid], R[tid], K[tid], *S, A, tj, tk, s, pos[tid], &viol[tid], chk, sc);
                 }
                 for (int lane = 0; lane < 32; ++lane) {
                     const int tid = w * 32 + lane;
                     int tj, tk;
                     stream_thread_pos<C>(tid, tj, tk);
-                    if (g_t < tasks) stream_uniform_actions<C>(*S, A, tid, cta, P, pair_base, g_t, g_off);
-                    stream_thread_prepare<C>(R[tid], K[tid], *S, A, tj, tk, pos[tid], s + 1, true);
+                    if (g_t < tasks) stream_uniform_actions<C, SC>(*S, A, tid, cta, P, pair_base, g_t, g_off, sc);
+                    stream_thread_prepare<C, SC>(R[tid], K[tid], *S, A, tj, tk, pos[tid], s + 1, true, sc);
                 }
                 done[w] = s;
                 if (s == steps) ++finished;
@@ -272,6 +275,25 @@ extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t
         }
     }
     return 0;
+}
+
+extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                               int pairs_per_cta, int schedule_seed, int32_t *scores)
+{
+    return emu_fast_stream_sc<ScoreRtl>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, ScoreRtl(), nullptr);
+}
+
+// run-time scoring parameters on the range-checked kernel (fast_stream_kernel_scored)
+extern "C" int emu_fast_stream_ex(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int pairs_per_cta,
+                                  int schedule_seed, int M, int X, int GO, int GE, int sop, int check_bits, int32_t *scores,
+                                  int *flags)
+{
+    const BatchCheck bc = score_check(M, X, GO, check_bits, flags);
+    RangeCheck chk;
+    chk.check_hi = bc.check_hi; chk.check_lo = bc.check_lo; chk.pair_flags = flags;
+    const int base = score_base_len(X, GO, GE, len);
+    if (sop) return emu_fast_stream_sc<ScoreGen<true>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, make_score_gen<true>(M, X, GO, GE), &chk);
+    return emu_fast_stream_sc<ScoreGen<false>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, make_score_gen<false>(M, X, GO, GE), &chk);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -98,6 +98,34 @@ def test_batch_kernel_with_runtime_scoring(emu, ob, sc):
                     assert out[t] == want[t], (sc, ln, w, t, out.tolist(), want)
 
 
+@pytest.mark.parametrize("sc", [(2, -1, 2, 1, 0), (1, -1, 2, 1, 1), (3, -2, 3, 1, 0), (2, 0, 0, 0, 0), (4, -4, 8, 2, 1)])
+def test_stream_kernel_with_runtime_scoring(emu, ob, sc):
+    """K2S with run-time scoring parameters: faces re-based with pi = 2 GE per block, zero borders, range check."""
+    emu.emu_fast_stream_ex.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_int, i32p, C.POINTER(C.c_int)]
+    M, X, GO, GE, rule = sc
+    rng = np.random.default_rng(sum(abs(v) for v in sc) * 5 + rule)
+    for ln, n, ppc in [(130, 4, 2), (70, 3, 1)]:
+        a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        a[0], b[0], c[0] = ob.mutated_triple(rng, ln)
+        for w, seed in [(16, 4), (10, 0)]:
+            out = np.full(n, -99999, np.int32)
+            flags = np.zeros((n + 1) // 2, np.int32)
+            rc = emu.emu_fast_stream_ex(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, ppc, seed,
+                                        M, X, GO, GE, rule, w, out.ctypes.data_as(i32p),
+                                        flags.ctypes.data_as(C.POINTER(C.c_int)))
+            assert rc == 0
+            want = [ob.score_ex(a[t], b[t], c[t], w, sc)[0] for t in range(n)]
+            flagged = [bool(flags[t // 2] >> (t & 1) & 1) for t in range(n)]
+            if w == 16:
+                assert not any(flagged), (sc, ln, flags)
+            for t in range(n):
+                if not flagged[t]:
+                    assert out[t] == want[t], (sc, ln, w, t, out.tolist(), want)
+
+
 # ---- K2S: streaming block sweep for batches of triples longer than 64 (fast_stream.cuh) ----
 @pytest.mark.parametrize("ln,n,ppc", [(61, 9, 5), (64, 7, 4), (65, 3, 2), (100, 5, 2), (128, 4, 1), (130, 7, 4), (200, 5, 3), (256, 2, 1)])
 def test_stream_kernel_choreography(emu, ob, ln, n, ppc):

@@ -521,6 +521,24 @@ def test_explicit_scoring_batches_run_the_factored_kernel(gpu_ta, ob, sc):
                 assert path in ("fast_batch", "fast_then_literal", "literal"), path
 
 
+@pytest.mark.parametrize("sc", [(2, -1, 2, 1, 0), (1, -1, 2, 1, 1), (3, -2, 3, 1, 0), (4, -4, 8, 2, 1)])
+def test_explicit_scoring_batches_longer_than_64_run_the_streaming_kernel(gpu_ta, ob, sc):
+    """K2S with run-time scoring parameters (len 65..2048 inside the 16-bit lane range), against the oracle."""
+    rng = np.random.default_rng(sum(abs(v) for v in sc) + 77)
+    scoring = gpu_ta.Scoring(*sc)
+    for n, ln, w in ((7, 130, 16), (5, 200, 12), (4, 96, 9)):
+        A = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        B = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        Cc = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        for t in range(0, n, 2):
+            A[t], B[t], Cc[t] = ob.mutated_triple(rng, ln, rate=0.1)
+        got = gpu_ta.TriAlign(w, scoring=scoring).align_batch(A, B, Cc)
+        path = gpu_ta.last_path()
+        assert got.tolist() == [ob.score_ex(A[t], B[t], Cc[t], w, sc)[0] for t in range(n)], (sc, n, ln, w, path)
+        if w == 16:
+            assert path == "fast_stream", path
+
+
 def test_rtl_scoring_through_the_ex_entry_points_uses_the_fast_kernels(gpu_ta, ob):
     a, b, c = gpu_ta.synth_batch(0x5EED0002, 0, 64, 64)
     got = gpu_ta.TriAlign(12, scoring=gpu_ta.Scoring()).align_batch(a, b, c)

@@ -68,4 +68,5 @@ batch(1 << 14, 256, 10, ta.BACKEND_AUTO, "K2S range-checked (W=10), nothing flag
 batch(1 << 14, 256, 12, ta.BACKEND_AUTO, "K2S unchecked (W=12)")
 batch_ex(1 << 18, 64, 12, (2, -1, 2, 1, 0), "K1 run-time scoring, the testbench's MATCH=2 / MISMATCH=-1 / GO=2 / GE=1")
 batch_ex(1 << 18, 64, 12, (1, -1, 2, 1, 1), "K1 run-time scoring, sum of pairs")
+batch_ex(1 << 13, 256, 12, (2, -1, 2, 1, 0), "K2S run-time scoring, MATCH=2 / MISMATCH=-1 / GO=2 / GE=1")
 batch_ex(1 << 14, 64, 12, (5, -4, 10, 1, 1), "outside the fast domain (GO = 10): literal kernel")
