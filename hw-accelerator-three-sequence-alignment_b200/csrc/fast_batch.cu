@@ -156,7 +156,8 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2_kernel(fast::BatchArgs
     __syncthreads();
     fast::BatchRegs<Cfg> R, R2;
     fast::BatchConsts<Cfg> K0, K1;
-    fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, 0);
+    uint32_t codes = fast::batch2_fetch_codes<Cfg>(S, tj, tk, 0);
+    fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, 0, codes);
     const int steps = fast::batch2_total_steps<Cfg>(P);
 #pragma unroll 1
     for (int s = 0; s <= steps; ++s) {
@@ -164,7 +165,7 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2_kernel(fast::BatchArgs
         fast::batch2_thread_step<Cfg>(R, R2, K0, K1, S, A, tj, tk, s, P, pair_base);
         bar_arrive_warp(&step_bar[0]);
         fast::batch2_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
-        fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, s + 1);
+        fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, s + 1, codes);
         bar_wait(&step_bar[0], s & 1);  // everybody has finished step s
     }
 }

@@ -38,7 +38,11 @@ struct BatchCfg {
     static constexpr int ROW_STRIDE = RK == 4 ? BK : BK + 16;   // 64-bit row accesses: two tj per wavefront
     static constexpr bool DIAG = TJ == 16 && TK == 16;          // lanes of an access group along an anti-diagonal, see thread_pos
     static constexpr int COL_STRIDE = DIAG ? BJ + 8 : BJ + 4;   // 128-bit column accesses: lanes differ in tk (and tj: DIAG)
-    static constexpr int CORNER_STRIDE = TK + 8;                // 32-bit accesses: a warp spans 4 tj x 8 tk
+    // corner relay, 32-bit accesses by whole warps.  DIAG: [tk+1][tj] with stride 48 -- the 32 lanes of a warp (two
+    // wrapped anti-diagonals) and the border writers (consecutive tj of row 0) all hit distinct banks; otherwise
+    // [tj][tk+1] (a warp spans 4 tj x 8 tk)
+    static constexpr int CORNER_ROWS = DIAG ? TK + 1 : TJ;
+    static constexpr int CORNER_STRIDE = DIAG ? 48 : TK + 8;
     static constexpr int TABJ_STRIDE = 68;                      // j-indexed tables: lanes of a wavefront differ in code only
     static constexpr int TABK_STRIDE = 128;                     // k-indexed tables: {cAC, tC} per code, see tabk_index
     static constexpr int SKEW = LAG * (TJ + TK - 2);
@@ -136,7 +140,7 @@ struct BatchSmem {
     // per-lane register shuffling in the step (5 of 8 warps used to run the border code on top of the common path).
     uint32_t row[C::NSLOT][4][C::TJ + 1][C::ROW_STRIDE];  // [slot][wY,u2,u1(old),all(old)][tj+1][k]   bottom rows
     uint32_t col[C::NSLOT][4][C::TK + 1][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk+1][j]   right columns
-    uint32_t corner[C::NSLOT][2][C::TJ][C::CORNER_STRIDE];  // [slot][u2,all(old)][tj][tk+1]  relay of the cell above-right of a tile
+    uint32_t corner[C::NSLOT][2][C::CORNER_ROWS][C::CORNER_STRIDE];  // [slot][u2,all(old)] x (tj, tk+1), see corner_at: relay of the cell above-right of a tile
     uint32_t tabAB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  pair constant {4,2}
     uint32_t tabMB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  triple row constant {9,3}
     uint32_t tabK[C::NBUF][16][C::TABK_STRIDE];      // [buf][a code][tabk_index]  pair constant {4,2} and triple column constant {9,6}
@@ -144,6 +148,18 @@ struct BatchSmem {
     uint8_t seq[C::NBUF][3][2][64];                  // [buf][A,B,C][half][pos]
     uint8_t acode[C::NBUF][64];                      // a_lo | a_hi << 2
 };
+
+// corner relay entry of tile row tj, column index x (0 = the k = 0 border plane, tk + 1 = written by thread (tj,tk))
+template <class C>
+TA_HD uint32_t &corner_at(BatchSmem<C> &S, int slot, int arr, int tj, int x)
+{
+    return C::DIAG ? S.corner[slot][arr][x][tj] : S.corner[slot][arr][tj][x];
+}
+template <class C>
+TA_HD const uint32_t &corner_at(const BatchSmem<C> &S, int slot, int arr, int tj, int x)
+{
+    return C::DIAG ? S.corner[slot][arr][x][tj] : S.corner[slot][arr][tj][x];
+}
 
 template <class C>
 struct BatchRegs {
@@ -249,8 +265,8 @@ TA_HD void batch_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tj, int 
     if (tk == 0) {  // k = 0 border plane (src/TriAlign_1cyc.v:166-174); the corner cell (j0, 0) lies on it too
         const int j0 = tj * RJ;
         const uint32_t e = phi(A, i, j0, 0);
-        S.corner[slot][0][tj][0] = e;
-        S.corner[slot][1][tj][0] = e - 0x00020002u;
+        corner_at<C>(S, slot, 0, tj, 0) = e;
+        corner_at<C>(S, slot, 1, tj, 0) = e - 0x00020002u;
 #pragma unroll
         for (int r = 0; r < RJ; ++r) {
             const uint32_t now = e + (uint32_t)(r + 1) * 0x00020002u, old = now - 0x00020002u;
@@ -263,9 +279,10 @@ TA_HD void batch_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tj, int 
 }
 
 // Core: pair p (CTA-local, -1 while the pipeline fills), plane i.  RESET = false: only the constants of plane i.
+// code_in >= 0: the a code of plane i, fetched a step ahead by the caller (two-plane kernel).
 template <class C, bool RESET = true, class SC = ScoreRtl>
 TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const BatchSmem<C> &S, const BatchArgs &A, int tj,
-                                   int tk, int p, int i, const SC &sc = SC())
+                                   int tk, int p, int i, const SC &sc = SC(), int code_in = -1)
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int buf = (p + C::NBUF) % C::NBUF;
@@ -286,8 +303,8 @@ TA_HD void batch_thread_prepare_at(BatchRegs<C> &R, BatchConsts<C> &K, const Bat
             }
     }
 
-    const int code = S.acode[buf][i - 1];
-    TA_CHECK(code >= 0 && code < 16);
+    const int code = code_in >= 0 ? code_in : S.acode[buf][i - 1];
+    TA_CHECK(code >= 0 && code < 16 && code == S.acode[buf][i - 1]);
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
         K.cAB[r] = S.tabAB[buf][code][j0 + r];
@@ -335,7 +352,7 @@ TA_HD void batch_write_borders_all(BatchSmem<C> &S, const BatchArgs &A, int tid,
 #endif
     } else if (tid < 160) {  // the corner cell (j0, 0) of the k = 0 border plane
         const int arr = (tid >> 4) & 1;
-        S.corner[slot][arr][t][0] = rep((uint32_t)(A.base + (int)sc.pi() * (i + 4 * t - arr)));
+        corner_at<C>(S, slot, arr, t, 0) = rep((uint32_t)(A.base + (int)sc.pi() * (i + 4 * t - arr)));
     }
 }
 
@@ -375,8 +392,8 @@ TA_HD void batch_load_halos(BatchHalo<C> &H, const BatchSmem<C> &S, const BatchA
         T_u2[c + 1] = S.row[rs][1][tj][k0 + c];
         T_all[c + 1] = S.row[rs][3][tj][k0 + c];
     }
-    T_u2[0] = S.corner[rs][0][tj][tk];
-    T_all[0] = S.corner[rs][1][tj][tk];
+    T_u2[0] = corner_at<C>(S, rs, 0, tj, tk);
+    T_all[0] = corner_at<C>(S, rs, 1, tj, tk);
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
         L_wZ[r] = S.col[rs][0][tk][j0 + r];
@@ -402,8 +419,8 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
     const int j0 = tj * RJ, k0 = tk * RK;
     const uint32_t (&T_wY)[RK] = H.T_wY, (&T_u1)[RK] = H.T_u1, (&T_u2)[RK + 1] = H.T_u2, (&T_all)[RK + 1] = H.T_all;
     const uint32_t (&L_wZ)[RJ] = H.L_wZ, (&L_u3)[RJ] = H.L_u3, (&L_u2)[RJ] = H.L_u2, (&L_all)[RJ] = H.L_all;
-    S.corner[ws][0][tj][tk + 1] = T_u2[RK];
-    S.corner[ws][1][tj][tk + 1] = T_all[RK];
+    corner_at<C>(S, ws, 0, tj, tk + 1) = T_u2[RK];
+    corner_at<C>(S, ws, 1, tj, tk + 1) = T_all[RK];
     // the plane i-1 half of this thread's own edges is already known
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
@@ -536,18 +553,32 @@ TA_HD void batch_thread_step(const BatchRegs<C> &R, BatchRegs<C> &Rn, const Batc
 // two plane updates back to back (R -> R2 -> R: the register sets alternate as in the unrolled single-plane loop).
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBatch2Steps = 32;   // steps per pair: 64 planes, two per step
-constexpr int kBatch2LoadAt = 8, kBatch2BuildAt = 12;
+constexpr int kBatch2PrefetchAt = 2, kBatch2LoadAt = 8, kBatch2BuildAt = 12;
 
 template <class C>
 TA_HD int batch2_total_steps(int P) { return P * kBatch2Steps + (C::TJ + C::TK - 2); }
 
+// the a codes of the two planes thread (tj,tk) runs at step s, as one 16-bit load (plane 2x+1 sits at an even offset)
+template <class C>
+TA_HD uint32_t batch2_fetch_codes(const BatchSmem<C> &S, int tj, int tk, int s)
+{
+    const int u = s - (tj + tk), p = u >> 5, x = u & 31;
+    const uint8_t *src = &S.acode[(p + C::NBUF) % C::NBUF][2 * x];
+    return (uint32_t)src[0] | ((uint32_t)src[1] << 8);
+}
+
+// codes: batch2_fetch_codes(s), fetched one step ahead (the pair's codes are staged long before its first plane enters
+// thread (0,0)), so that the table look-ups below do not wait for a shared-memory round trip; on return it holds the
+// codes of step s + 1.
 template <class C>
 TA_HD void batch2_thread_prepare(BatchRegs<C> &R, BatchConsts<C> &K0, BatchConsts<C> &K1, BatchSmem<C> &S,
-                                 const BatchArgs &A, int tj, int tk, int s)
+                                 const BatchArgs &A, int tj, int tk, int s, uint32_t &codes)
 {
     const int u = s - (tj + tk), p = u >> 5, i0 = 2 * (u & 31) + 1;
-    batch_thread_prepare_at<C, true>(R, K0, S, A, tj, tk, p, i0);
-    batch_thread_prepare_at<C, false>(R, K1, S, A, tj, tk, p, i0 + 1);
+    const uint32_t now = codes;
+    codes = batch2_fetch_codes<C>(S, tj, tk, s + 1);
+    batch_thread_prepare_at<C, true>(R, K0, S, A, tj, tk, p, i0, ScoreRtl(), (int)(now & 0xFFu));
+    batch_thread_prepare_at<C, false>(R, K1, S, A, tj, tk, p, i0 + 1, ScoreRtl(), (int)(now >> 8));
 }
 
 // Zero-border halos (index 0 of the edge slots' tj / tk dimension, see BatchSmem) of the two planes that step st reads,
@@ -576,7 +607,7 @@ TA_HD void batch2_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tid, in
     if (tid < 64) {  // the corner cell (j0, 0) of the k = 0 border plane
         const int t = tid & 15, arr = (tid >> 4) & 1, pl = tid >> 5;
         const int i = 2 * ((st - t) & 31) + 1 + pl;
-        S.corner[rs + pl][arr][t][0] = rep((uint32_t)(A.base + 2 * (i + 4 * t - arr)));
+        corner_at<C>(S, rs + pl, arr, t, 0) = rep((uint32_t)(A.base + 2 * (i + 4 * t - arr)));
     }
 }
 
@@ -596,11 +627,31 @@ TA_HD void batch2_thread_step(BatchRegs<C> &R, BatchRegs<C> &R2, const BatchCons
     batch_thread_step_halo<C, false>(R2, R, K1, H1, S, A, tj, tk, ws + 1, u, p, i0 + 1, s, P, pair_base);
 }
 
+// the six 64-byte sequences of a pair are read with byte loads a few steps later: pull their lines in now, so that the
+// loads (and the stores that wait for them) do not stall on HBM in the middle of a step
+template <class C>
+TA_HD void prefetch_pair_sequences(const BatchArgs &A, int tid, long long pair)
+{
+#if defined(__CUDA_ARCH__)
+    if (tid < 12) {
+        const int which = tid >> 2, half = (tid >> 1) & 1, end = tid & 1;
+        const long long t = 2 * pair + half;
+        if (t < A.n) {
+            const uint8_t *src = (which == 0 ? A.a : (which == 1 ? A.b : A.c)) + t * A.len + (end ? A.len - 1 : 0);
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(src));
+        }
+    }
+#else
+    (void)A; (void)tid; (void)pair;
+#endif
+}
+
 template <class C>
 TA_HD void batch2_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, int s, int P, long long pair_base)
 {
     const int q = s / kBatch2Steps + 1;  // pair that starts entering the array at step 32*q
     if (q < P) {
+        if (s % kBatch2Steps == kBatch2PrefetchAt) prefetch_pair_sequences<C>(A, tid, pair_base + q);
         if (s % kBatch2Steps == kBatch2LoadAt) load_pair_sequences<C>(S, A, tid, pair_base + q, q % C::NBUF);
         if (s % kBatch2Steps == kBatch2BuildAt) build_pair_tables<C>(S, tid, q % C::NBUF);
     }

@@ -128,6 +128,7 @@ extern "C" int emu_fast_batch2(const uint8_t *a, const uint8_t *b, const uint8_t
     auto S = std::make_unique<BatchSmem<C>>();
     std::vector<BatchRegs<C>> R(C::NT), R2(C::NT);
     std::vector<BatchConsts<C>> K0(C::NT), K1(C::NT);
+    std::vector<uint32_t> codes(C::NT);
     for (long long pair_base = 0; pair_base < A.pairs_total; pair_base += pairs_per_cta) {
         const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
         std::memset(S.get(), 0xA5, sizeof(BatchSmem<C>));
@@ -145,7 +146,8 @@ extern "C" int emu_fast_batch2(const uint8_t *a, const uint8_t *b, const uint8_t
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             thread_pos<C>(tid, tj, tk);
-            batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, 0);
+            codes[tid] = batch2_fetch_codes<C>(*S, tj, tk, 0);
+            batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, 0, codes[tid]);
         }
         const int steps = batch2_total_steps<C>(P);
         for (int s = 0; s <= steps; ++s) {
@@ -161,7 +163,7 @@ extern "C" int emu_fast_batch2(const uint8_t *a, const uint8_t *b, const uint8_t
                 int tj, tk;
                 thread_pos<C>(tid, tj, tk);
                 batch2_uniform_actions<C>(*S, A, tid, s, P, pair_base);
-                batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, s + 1);
+                batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, s + 1, codes[tid]);
             }
         }
     }
