@@ -102,7 +102,7 @@ int trialign_device_count(void);            /* 0 when no driver / no device; nev
 /* Run-time options: the experiment switches of the kernels (A/B variants, gate intervals, multi-GPU decomposition).
  * Nothing in the library reads the environment; a caller that wants a non-default kernel says so explicitly.
  * Names: debug, k1, k2_lag, k2_pp, k2_gatetid, k2_early, k2_gate, k2_rgate, k2_cols_order, multi ("slab" | "cols";
- * default: chosen by trialign_multi_plan), multi_min.
+ * default: chosen by trialign_multi_plan), multi_min, kt_seg, kt_budget_mb (traceback, see trialign_align).
  * value NULL or "" restores the default.  Unknown names give TRIALIGN_EINVAL.  Process-wide, thread-safe. */
 int trialign_set_option(const char *name, const char *value);
 int trialign_get_option(const char *name, char *buf, int cap); /* "" when unset */
@@ -121,9 +121,12 @@ int trialign_score(const uint8_t *a, int la, const uint8_t *b, int lb, const uin
                    int backend, unsigned devices, int32_t *score, int32_t final_states[7]);
 
 /* The same with explicit scoring parameters.  trialign_scoring_rtl() fills in the RTL's constants; with exactly those
- * the call is identical to trialign_score / trialign_score_batch (all kernels).  Any other setting runs the literal
- * kernel (every candidate wrapped to score_bits before the signed max, as the RTL's datapath would with other
- * localparams); |match|, |mismatch|, gap_open, gap_extend <= 1024, gap costs >= 0, else TRIALIGN_EINVAL. */
+ * the call is identical to trialign_score / trialign_score_batch (all kernels).  With other values a BATCH of triples of
+ * up to 2,048 symbols runs the factored kernels with the constants as a kernel argument, range-checked on every step
+ * and with the flagged triples re-scored literally, provided 0 <= GE <= 4, GE <= GO <= 8, -8 <= MISMATCH <= MATCH <= 8,
+ * MISMATCH >= -2 GE and score_bits >= 6; single triples and everything else run the literal kernel (every candidate
+ * wrapped to score_bits before the signed max, as the RTL's datapath would with other localparams).  The result does
+ * not depend on the kernel.  |match|, |mismatch|, gap_open, gap_extend <= 1024, gap costs >= 0, else TRIALIGN_EINVAL. */
 void trialign_scoring_rtl(trialign_scoring *sc);
 int trialign_score_ex(const uint8_t *a, int la, const uint8_t *b, int lb, const uint8_t *c, int lc, int score_bits,
                       const trialign_scoring *scoring, unsigned devices, int32_t *score, int32_t final_states[7]);
