@@ -23,6 +23,7 @@ namespace fast {
 
 template <int LAG_>
 struct Long2Cfg {
+    static constexpr bool DIST = false;  // block-edge duties stay with the edge threads (stream_thread_pos)
     static constexpr int RJ = 4, RK = 4, TJ = 16, TK = 16, LAG = LAG_;
     static constexpr int NSLOT = 2 * LAG;
     static constexpr int BJ = RJ * TJ, BK = RK * TK, NT = TJ * TK;

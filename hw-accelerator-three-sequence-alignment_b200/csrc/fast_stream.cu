@@ -39,10 +39,9 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-template <bool CHECK, class SC = fast::ScoreRtl>
+template <class C, bool CHECK, class SC = fast::ScoreRtl>
 __device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, const fast::RangeCheck *chk, const SC &sc = SC())
 {
-    using C = Cfg;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     fast::StreamSmem<C> &S = *reinterpret_cast<fast::StreamSmem<C> *>(smem_raw);
     __shared__ __align__(8) uint64_t step_bar[2];
@@ -70,8 +69,23 @@ __device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, cons
     uint32_t viol = 0;  // CHECK kernel only
     fast::StreamConsts<C> K;
     fast::StreamPos pos = fast::stream_start_pos<C>(A, tj, tk);
-    if (tj == 0 || tk == 0) fast::stream_edge_fetch<C, SC>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1), sc);
-    fast::ta_copy_commit();
+    // DIST: the edge thread this thread serves every step -- fetch (threads 0..127): its position two steps ahead,
+    // store (threads 128..255): two steps back, starting with step 0 at the top of step 2
+    fast::StreamPos duty = fast::stream_pos_at<C>(A, C::LAG * (tid < 128 ? (tid & 15) : C::TJ - 1 + (tid & 15)), 0);
+    if constexpr (C::DIST) {
+        if (tid < 128) {
+            fast::stream_duty_fetch<C, SC>(S, A, tid, duty, 0, sc);
+            fast::stream_advance(A, duty, C::NBUF);
+            fast::stream_duty_fetch<C, SC>(S, A, tid, duty, 1, sc);
+            fast::stream_advance(A, duty, C::NBUF);
+        }
+        fast::ta_copy_commit();
+        fast::ta_copy_wait();
+        __syncthreads();
+    } else {
+        if (tj == 0 || tk == 0) fast::stream_edge_fetch<C, SC>(S, A, tj, tk, pos, (0 + C::LAG) & (C::NSLOT - 1), sc);
+        fast::ta_copy_commit();
+    }
     fast::stream_thread_prepare<C, SC>(R, K, S, A, tj, tk, pos, 0, false, sc);
     const int steps = (int)fast::stream_total_steps<C>(A, P) | 1;  // an even number of steps: the loop runs two per turn
     int g_t = 0, g_off = 0;
@@ -81,8 +95,20 @@ __device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, cons
     do {                                                                                          \
         const int s_ = (S_);                                                                      \
         if (s_ >= 2) bar_wait(&step_bar[s_ & 1], ((s_ - 2) >> 1) & 1);                            \
-        fast::ta_copy_wait_prev();                                                                \
+        if constexpr (C::DIST) {                                                                  \
+            if (tid < 128) {                                                                      \
+                fast::stream_duty_fetch<C, SC>(S, A, tid, duty, s_ + 2, sc);                      \
+                fast::stream_advance(A, duty, C::NBUF);                                           \
+            } else if (s_ >= 2) {                                                                 \
+                fast::stream_duty_store<C, SC>(S, A, tid, duty, s_ - 2, sc);                      \
+                fast::stream_advance(A, duty, C::NBUF);                                           \
+            }                                                                                     \
+            fast::ta_copy_commit();                                                               \
+        } else {                                                                                  \
+            fast::ta_copy_wait_prev();                                                            \
+        }                                                                                         \
         fast::stream_thread_step<C, CHECK, SC>(RIN, ROUT, K, S, A, tj, tk, s_, pos, &viol, chk, sc); \
+        if constexpr (C::DIST) fast::ta_copy_wait();                                              \
         bar_arrive_warp(&step_bar[s_ & 1]);                                                       \
         if (g_t < tasks) fast::stream_uniform_actions<C, SC>(S, A, tid, cta, P, pair_base, g_t, g_off, sc); \
         fast::stream_thread_prepare<C, SC>(ROUT, K, S, A, tj, tk, pos, s_ + 1, true, sc);         \
@@ -101,10 +127,15 @@ __device__ __forceinline__ void fast_stream_body(const fast::StreamArgs &A, cons
 }
 
 // Two plain kernels around the one body (the unchecked one is the default path; the checked one adds the range test).
-__global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArgs A) { fast_stream_body<false>(A, nullptr); }
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel(fast::StreamArgs A) { fast_stream_body<Cfg, false>(A, nullptr); }
 __global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel_checked(fast::StreamArgs A, fast::RangeCheck chk)
 {
-    fast_stream_body<true>(A, &chk);
+    fast_stream_body<Cfg, true>(A, &chk);
+}
+// the block-edge duties dealt to all threads (fast_stream.cuh: StreamCfgT<true>)
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_stream_kernel_dist(fast::StreamArgs A)
+{
+    fast_stream_body<fast::StreamCfgD, false>(A, nullptr);
 }
 // Run-time scoring parameters (trialign_score_batch_ex): the range-checked kernel with the constants
 // of fast::ScoreGen as a third kernel parameter.  SOP: sum-of-pairs triple score.
@@ -112,7 +143,7 @@ template <bool SOP>
 __global__ void __launch_bounds__(Cfg::NT, 1)
 fast_stream_kernel_scored(fast::StreamArgs A, fast::RangeCheck chk, fast::ScoreGen<SOP> sc)
 {
-    fast_stream_body<true, fast::ScoreGen<SOP>>(A, &chk, sc);
+    fast_stream_body<Cfg, true, fast::ScoreGen<SOP>>(A, &chk, sc);
 }
 
 // contiguous chunks of pairs, one persistent CTA per SM (fill/drain once per CTA); the step counter stays below 2^30
@@ -128,7 +159,7 @@ void stream_plan(int len, int64_t n, int sm_count, long long &ppc, long long &gr
 long long stream_face_bytes(int len, long long grid)
 {
     const int nbj = (len + Cfg::BJ - 1) / Cfg::BJ;
-    const long long fj = (long long)(len + 2) * Cfg::FJ_ROW_WORDS, fk = (long long)(len + 2) * Cfg::FK_ROW_WORDS;
+    const long long fj = (long long)(len + 2) * Cfg::FJ_ROW_WORDS, fk = (long long)(len + 2) * fast::StreamCfgD::FK_ROW_WORDS;
     return grid * (2 * fj + (nbj + 1) * fk) * 4 + 1024;
 }
 
@@ -156,19 +187,27 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
     using C = Cfg;
     if (n <= 0) return TRIALIGN_OK;
     static_assert(sizeof(fast::StreamSmem<C>) + 64 <= 227 * 1024, "shared memory budget");
-    const size_t smem = sizeof(fast::StreamSmem<C>);
+    static_assert(sizeof(fast::StreamSmem<fast::StreamCfgD>) + 64 <= 227 * 1024, "shared memory budget");
+    // option k2s=dist: the block-edge duties dealt to all threads (A/B form of the unchecked kernel; measured 2 % slower
+    // than the edge-thread form, 1,268 vs 1,296 GCUPS on 32,768 x 256^3, so it is not the default)
+    const bool dist = !scoring && check_bits <= 0 && opt_is("k2s", "dist");
+    const size_t smem = dist ? sizeof(fast::StreamSmem<fast::StreamCfgD>) : sizeof(fast::StreamSmem<C>);
     static bool attr_set[kMaxDevices] = {};
     if (!attr_set[ctx->device]) {
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fast::StreamSmem<C>)));
         TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_checked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_dist, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(fast::StreamSmem<fast::StreamCfgD>)));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_dist, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_checked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fast::StreamSmem<C>)));
         TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_checked, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fast::StreamSmem<C>)));
         TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(fast::StreamSmem<C>)));
         TA_CUDA(cudaFuncSetAttribute(fast_stream_kernel_scored<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
         attr_set[ctx->device] = true;
@@ -184,7 +223,7 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
     A.pairs_per_cta = (int)ppc;
     // face rings are private to a CTA; CTAs beyond one wave reuse nothing, so the rings are sized by the grid
     A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
-    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
+    A.fk_slot_words = (long long)(len + 2) * (dist ? fast::StreamCfgD::FK_ROW_WORDS : C::FK_ROW_WORDS);
     A.fk_ring = A.nbj + 1;
     const size_t fj_bytes = (size_t)grid * 2 * A.fj_slot_words * 4;
     const size_t fk_bytes = (size_t)grid * A.fk_ring * A.fk_slot_words * 4;
@@ -216,7 +255,8 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
         chk.pair_flags = d_pair_flags;
         fast_stream_kernel_checked<<<(unsigned)grid, C::NT, smem, st>>>(A, chk);
     } else {
-        fast_stream_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
+        if (dist) fast_stream_kernel_dist<<<(unsigned)grid, C::NT, smem, st>>>(A);
+        else fast_stream_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
     }
     count_launch();
     TA_CUDA(cudaGetLastError());

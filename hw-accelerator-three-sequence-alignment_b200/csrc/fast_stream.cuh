@@ -34,12 +34,23 @@ TA_HD void ta_copy_commit() {}
 TA_HD void ta_copy_wait_prev() {}
 #endif
 
-struct StreamCfg {
+// DIST = false (default): the block-edge duties (face fetch / border halos, face stores) belong to the edge threads, a
+// warp is a 4x8 patch of tiles.
+// DIST = true (option k2s=dist, A/B form: what made K1 16 % faster makes K2S 2 % slower -- its step never had border
+// branches, and the duty bookkeeping now runs in every warp): the duties are dealt to ALL threads by thread id -- one 128-bit group per thread and step: warps 0-3 move
+// the halos of the step two ahead into the edge slots (face rows with cp.async, or the zero-border potential), warps
+// 4-7 copy the bottom rows / right columns published two steps ago from the edge slots to the face rings -- so the step
+// itself has no edge code at all and every warp runs the same instruction stream (the step ends at a CTA barrier: the
+// warp with the most duties paced all eight); with that the lanes of a warp can lie along anti-diagonals as in K1
+// (fast_batch.cuh: thread_pos), which needs the column stride 72.
+template <bool DIST_>
+struct StreamCfgT {
+    static constexpr bool DIST = DIST_;
     static constexpr int RJ = 4, RK = 4, TJ = 16, TK = 16, LAG = 2;
     static constexpr int NSLOT = 2 * LAG;   // edge buffers: written at step s, read at step s+LAG
     static constexpr int NBUF = 3;          // task buffers: two tasks in flight + one being staged
     static constexpr int BJ = RJ * TJ, BK = RK * TK, NT = TJ * TK;
-    static constexpr int ROW_STRIDE = BK, COL_STRIDE = BJ + 4, CORNER_STRIDE = TK + 8;
+    static constexpr int ROW_STRIDE = BK, COL_STRIDE = DIST ? BJ + 8 : BJ + 4, CORNER_STRIDE = TK + 8;
     static constexpr int TABJ_STRIDE = 68, TABK_STRIDE = 128;
     static constexpr int SKEW = LAG * (TJ + TK - 2);
     static constexpr int LEN_MIN = SKEW + 1;   // at most two tasks in flight; staging fits inside a task
@@ -49,6 +60,8 @@ struct StreamCfg {
     static constexpr int FK_ROW_WORDS = 4 * COL_STRIDE;  // one plane of a K face: the same of 64 rows + relay entry
     static_assert(BUILD_AT + 8 < LEN_MIN, "staging schedule");
 };
+using StreamCfg = StreamCfgT<false>;
+using StreamCfgD = StreamCfgT<true>;
 
 struct StreamTask {
     int valid;                    // 0: filler (pipeline fill / drain): border halos, no faces, no score
@@ -123,6 +136,12 @@ struct StreamPos {
 template <class C>
 TA_HD void stream_thread_pos(int tid, int &tj, int &tk)
 {
+    if (C::DIST) {  // eight consecutive lanes = eight consecutive tj of one wrapped anti-diagonal (see fast_batch.cuh)
+        const int oct = tid >> 3, dd = oct >> 1;
+        tj = 8 * (oct & 1) + (tid & 7);
+        tk = (dd - tj) & 15;
+        return;
+    }
     const int lane = tid & 31;
     const int patch = (0x45237610u >> (4 * (tid >> 5))) & 7;  // warps 0..7 -> patches 0,1,6,7,3,2,5,4
     tk = (lane & 7) + 8 * (patch & 1);
@@ -321,12 +340,71 @@ TA_HD void stream_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K, StreamSme
         K.tC[c] = S.tabK[buf][code][64 + k0 + c];
     }
     // block-edge halos of step s1 + 1 (two steps ahead of the step that has just run)
-    if (tj == 0 || tk == 0) {
-        StreamPos q = p;
-        stream_advance(A, q, C::NBUF);
-        stream_edge_fetch<C, SC>(S, A, tj, tk, q, (s1 + 1 + C::LAG) & (C::NSLOT - 1), sc);
+    if (!C::DIST) {
+        if (tj == 0 || tk == 0) {
+            StreamPos q = p;
+            stream_advance(A, q, C::NBUF);
+            stream_edge_fetch<C, SC>(S, A, tj, tk, q, (s1 + 1 + C::LAG) & (C::NSLOT - 1), sc);
+        }
+        ta_copy_commit();
     }
-    ta_copy_commit();
+}
+
+// ---- DIST: the block-edge duties by thread id ----
+// position of a thread with skew `back` (= LAG * (tj + tk)) at global step x >= back - len
+template <class C>
+TA_HD StreamPos stream_pos_at(const StreamArgs &A, int back, int x)
+{
+    StreamPos p;
+    const int u = x - back;
+    p.t = u >= 0 ? u / A.len : -1;
+    p.i = u - p.t * A.len + 1;
+    p.buf = (p.t + C::NBUF) % C::NBUF;
+    return p;
+}
+
+// Threads 0..127: the halos that the edge thread (0,t) [rows, tid < 64] / (t,0) [columns] reads at step r -- array
+// arr = (tid >> 4) & 3, its four words -- into index 0 of edge slot (r - LAG); p = that edge thread's position at step r.
+// The column threads of the u2 / all(old) arrays bring the corner word along.  Called at the top of step r - 2: the
+// slot's last readers (step r - 4) are known to be done, and the caller's copies land (cp.async wait) before it
+// arrives for step r - 2, which every reader of step r waits for.
+template <class C, class SC = ScoreRtl>
+TA_HD void stream_duty_fetch(StreamSmem<C> &S, const StreamArgs &A, int tid, const StreamPos &p, int r, const SC &sc = SC())
+{
+    const int t = tid & 15, arr = (tid >> 4) & 3, col = tid >> 6, slot = (r - C::LAG) & (C::NSLOT - 1);
+    const StreamTask &T = S.task[p.buf];
+    const uint32_t *face = col ? T.fk_r : T.fj_r;
+    uint32_t *dst = col ? &S.col[slot][arr][0][4 * t] : &S.row[slot][arr][0][4 * t];
+    if (face) {
+        const uint32_t *row = face + (long long)p.i * (col ? C::FK_ROW_WORDS : C::FJ_ROW_WORDS) + arr * (col ? C::COL_STRIDE : C::ROW_STRIDE);
+        ta_copy16(dst, row + 4 * t);
+        // corner cell (row above the tile, last column of the block to the left): face entry j0-1, or the relay entry
+        // for the block's first tile row
+        if (col && (arr & 1)) ta_copy4(&S.corner[slot][arr >> 1][t][0], row + (t > 0 ? 4 * t - 1 : C::BJ));
+    } else {  // zero border plane (src/TriAlign_1cyc.v:156-181): all 7 states are 0, reduced values = the potential
+        const uint32_t e = rep((uint32_t)(A.base + (int)sc.pi() * (p.i + 4 * t + 1 - (arr >> 1)))), d = sc.pi2();
+        ta_store4(dst, e, e + d, e + 2 * d, e + 3 * d);
+        if (col && (arr & 1)) S.corner[slot][arr >> 1][t][0] = e - d;  // cell (j0, 0): one column before the tile's first
+    }
+}
+
+// Threads 128..255: the bottom row of thread (15,t) [tid < 192] / right column of (t,15), array arr, published at step
+// q into index 16 of edge slot q & 3, to the face ring of the task that thread was in (p = its position at step q),
+// re-based to the consumer's frame.  Called at the top of step q + 2 (everybody has finished step q; the slot is
+// written again at step q + 4).  The u2 / all(old) column threads of tile row 0 copy the relay entry along.
+template <class C, class SC = ScoreRtl>
+TA_HD void stream_duty_store(StreamSmem<C> &S, const StreamArgs &A, int tid, const StreamPos &p, int q, const SC &sc = SC())
+{
+    (void)A;
+    const int t = tid & 15, arr = (tid >> 4) & 3, col = (tid >> 6) & 1, slot = q & (C::NSLOT - 1);
+    const StreamTask &T = S.task[p.buf];
+    uint32_t *face = col ? T.fk_w : T.fj_w;
+    if (!face) return;
+    const uint32_t adj = rep(sc.pi() * (col ? C::BK : C::BJ));
+    const uint32_t *src = col ? &S.col[slot][arr][C::TK][4 * t] : &S.row[slot][arr][C::TJ][4 * t];
+    uint32_t *row = face + (long long)p.i * (col ? C::FK_ROW_WORDS : C::FJ_ROW_WORDS) + arr * (col ? C::COL_STRIDE : C::ROW_STRIDE);
+    ta_store4(row + 4 * t, src[0] - adj, src[1] - adj, src[2] - adj, src[3] - adj);
+    if (col && t == 0 && (arr & 1)) row[C::BJ] = S.corner[slot][arr >> 1][0][C::TK] - adj;
 }
 
 // ---- one wavefront step of one thread: halos published at step s-LAG -> tile -> publish for step s+LAG ----
@@ -413,7 +491,7 @@ TA_HD void stream_thread_step(const StreamRegs<C> &R, StreamRegs<C> &Rn, const S
     }
 
     // block faces to global memory, re-based to the consumer's frame (its halo row / column has local index 0)
-    if (tj == C::TJ - 1 || tk == C::TK - 1) {
+    if (!C::DIST && (tj == C::TJ - 1 || tk == C::TK - 1)) {
         const StreamTask &T = S.task[p.buf];
         if (tj == C::TJ - 1) {
             uint32_t *fj = T.fj_w;

@@ -202,11 +202,10 @@ extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t 
 // ---------------------------------------------------------------------------------------------------------------
 #include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_stream.cuh"
 
-template <class SC>
+template <class SC, class C = StreamCfg>
 static int emu_fast_stream_sc(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
                               int pairs_per_cta, int schedule_seed, int32_t *scores, const SC &sc, const RangeCheck *chk)
 {
-    using C = StreamCfg;
     constexpr bool CHECK = !SC::kRtl;
     std::vector<uint32_t> viol(C::NT, 0);
     if (len < C::LEN_MIN || len > C::LEN_MAX || n < 0 || pairs_per_cta < 1) return -1;
@@ -226,7 +225,7 @@ static int emu_fast_stream_sc(const uint8_t *a, const uint8_t *b, const uint8_t 
     auto S = std::make_unique<StreamSmem<C>>();
     std::vector<StreamRegs<C>> R(C::NT);
     std::vector<StreamConsts<C>> K(C::NT);
-    std::vector<StreamPos> pos(C::NT);
+    std::vector<StreamPos> pos(C::NT), duty(C::NT);
     for (int cta = 0; cta < n_ctas; ++cta) {
         const long long pair_base = (long long)cta * pairs_per_cta;
         const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
@@ -241,7 +240,15 @@ static int emu_fast_stream_sc(const uint8_t *a, const uint8_t *b, const uint8_t 
             int tj, tk;
             stream_thread_pos<C>(tid, tj, tk);
             pos[tid] = stream_start_pos<C>(A, tj, tk);
-            if (tj == 0 || tk == 0) stream_edge_fetch<C, SC>(*S, A, tj, tk, pos[tid], C::LAG & (C::NSLOT - 1), sc);
+            duty[tid] = stream_pos_at<C>(A, C::LAG * (tid < 128 ? (tid & 15) : C::TJ - 1 + (tid & 15)), 0);
+            if (C::DIST) {
+                if (tid < 128) {
+                    stream_duty_fetch<C, SC>(*S, A, tid, duty[tid], 0, sc);
+                    stream_advance(A, duty[tid], C::NBUF);
+                    stream_duty_fetch<C, SC>(*S, A, tid, duty[tid], 1, sc);
+                    stream_advance(A, duty[tid], C::NBUF);
+                }
+            } else if (tj == 0 || tk == 0) stream_edge_fetch<C, SC>(*S, A, tj, tk, pos[tid], C::LAG & (C::NSLOT - 1), sc);
             stream_thread_prepare<C, SC>(R[tid], K[tid], *S, A, tj, tk, pos[tid], 0, false, sc);
         }
         const int steps = (int)stream_total_steps<C>(A, P);
@@ -258,6 +265,17 @@ static int emu_fast_stream_sc(const uint8_t *a, const uint8_t *b, const uint8_t 
                 if (s > steps) break;
                 if (*std::min_element(done.begin(), done.end()) < s - 2) break;  // bar_wait(step s-2) would block
                 const int g_t = s / len, g_off = s % len;
+                if (C::DIST)  // the duties at the top of the step: halos of step s+2 in, faces of step s-2 out
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int tid = w * 32 + lane;
+                        if (tid < 128) {
+                            stream_duty_fetch<C, SC>(*S, A, tid, duty[tid], s + 2, sc);
+                            stream_advance(A, duty[tid], C::NBUF);
+                        } else if (s >= 2) {
+                            stream_duty_store<C, SC>(*S, A, tid, duty[tid], s - 2, sc);
+                            stream_advance(A, duty[tid], C::NBUF);
+                        }
+                    }
                 for (int lane = 0; lane < 32; ++lane) {
                     const int tid = w * 32 + lane;
                     int tj, tk;
@@ -283,6 +301,13 @@ extern "C" int emu_fast_stream(const uint8_t *a, const uint8_t *b, const uint8_t
                                int pairs_per_cta, int schedule_seed, int32_t *scores)
 {
     return emu_fast_stream_sc<ScoreRtl>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, ScoreRtl(), nullptr);
+}
+
+// the block-edge duties dealt to all threads (fast_stream_kernel_dist)
+extern "C" int emu_fast_stream_dist(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                                    int pairs_per_cta, int schedule_seed, int32_t *scores)
+{
+    return emu_fast_stream_sc<ScoreRtl, StreamCfgD>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, ScoreRtl(), nullptr);
 }
 
 // run-time scoring parameters on the range-checked kernel (fast_stream_kernel_scored)

@@ -139,12 +139,15 @@ def test_stream_kernel_choreography(emu, ob, ln, n, ppc):
     for t in range(0, n, 2):  # mutated copies exercise large positive values
         a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
     want = ob.score_batch(a, b, c, 16).tolist()
-    for seed in (0, 5, 12):
-        out = np.full(n, -99999, np.int32)
-        rc = emu.emu_fast_stream(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln,
-                                 2 * ln + 8 + 32, ppc, seed, out.ctypes.data_as(i32p))
-        assert rc == 0
-        assert out.tolist() == want, seed
+    emu.emu_fast_stream_dist.argtypes = emu.emu_fast_stream.argtypes
+    # both forms of the kernel: block-edge duties on the edge threads / dealt to all threads by thread id
+    for fn in (emu.emu_fast_stream, emu.emu_fast_stream_dist):
+        for seed in (0, 5, 12):
+            out = np.full(n, -99999, np.int32)
+            rc = fn(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln,
+                    2 * ln + 8 + 32, ppc, seed, out.ctypes.data_as(i32p))
+            assert rc == 0
+            assert out.tolist() == want, (seed, fn is emu.emu_fast_stream_dist)
 
 
 # ---- K2L: one long triple on the K1/K2S step engine (fast_long.cuh) ----

@@ -330,6 +330,24 @@ def test_fast_kernels_agree_with_literal_kernel_beyond_oracle_sizes(gpu_ta):
     assert gpu_ta.TriAlign(16).align(x, x, x) == 3 * 4096
 
 
+def test_stream_kernel_with_duties_dealt_to_all_threads(gpu_ta, ob):
+    """Option k2s=dist (A/B form of K2S: face fetches, border halos and face stores by thread id) against the oracle."""
+    rng = np.random.default_rng(2718)
+    try:
+        gpu_ta.set_option("k2s", "dist")
+        for n, ln in ((9, 130), (4, 256), (301, 70)):
+            a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+            b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+            c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+            for t in range(0, n, 2):
+                a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+            got = gpu_ta.TriAlign(16).align_batch(a, b, c)
+            assert gpu_ta.last_path() == "fast_stream"
+            assert got.tolist() == ob.score_batch(a, b, c, 16).tolist(), (n, ln)
+    finally:
+        gpu_ta.set_option("k2s", None)
+
+
 # ---- traceback (trialign_align; SURVEY.md 8(f).2) ----
 @pytest.mark.parametrize("shape,w", [((1, 1, 1), 12), ((5, 7, 3), 12), ((24, 24, 24), 7), ((40, 17, 33), 12),
                                      ((64, 64, 64), 12), ((30, 30, 30), 6), ((96, 80, 100), 16), ((128, 128, 128), 12)])
