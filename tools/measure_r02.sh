@@ -10,10 +10,13 @@ if [ "$N" = 1 ]; then
   python __graft_entry__.py smoke 2>&1 | tail -1
   python bench.py --steps 20 --warmup 3 > gpurun_out/r02_bench_1gpu.json 2> gpurun_out/r02_bench_1gpu.err; echo "bench rc=$?"
   python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_bench_reference.json 2> /dev/null
-  python tools/time_literal.py > gpurun_out/r02_fallbacks.jsonl 2>&1
-  python tools/time_slabs.py > gpurun_out/r02_time_slabs.jsonl 2>&1
-  python tools/time_cols.py > gpurun_out/r02_time_cols.jsonl 2>&1
-  python tools/stress_gpu.py 60 2>&1 | tail -1
+  if [ "${FULL:-0}" = 1 ]; then   # the slower side measurements (kept in profiles/ from earlier calls of the round)
+    python tools/time_literal.py > gpurun_out/r02_fallbacks.jsonl 2>&1
+    python tools/time_traceback.py 256 512 1024 > gpurun_out/r02_traceback.jsonl 2>&1
+    python tools/time_slabs.py > gpurun_out/r02_time_slabs.jsonl 2>&1
+    python tools/time_cols.py > gpurun_out/r02_time_cols.jsonl 2>&1
+  fi
+  python tools/stress_gpu.py ${STRESS:-30} 2>&1 | tail -1
 else
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29500"
   python -m pytest tests/test_gpu_long.py -m gpu -q -k "multi or mask or split or pipelines" 2>&1 | tail -3

@@ -8,7 +8,7 @@ set -x
 $B --steps 2 --warmup 3 > gpurun_out/r02_plain_k1.log 2>&1 || exit 1
 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r02_plain_full.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r02_ncu_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:fast_batch_kernel -s 3 -c 1 -o gpurun_out/r02_k1 -f $B --steps 1 --warmup 3 > gpurun_out/r02_ncu_k1.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fast_batch -s 3 -c 1 -o gpurun_out/r02_k1 -f $B --steps 1 --warmup 3 > gpurun_out/r02_ncu_k1.log 2>&1
 $B --steps 1 --warmup 3 --workload batch256 --triples 4096 > gpurun_out/r02_plain_k2s.log 2>&1 || exit 1
 ncu --set full --clock-control none --import-source on -k regex:fast_stream_kernel -s 3 -c 1 -o gpurun_out/r02_k2s -f $B --steps 1 --warmup 3 --workload batch256 --triples 4096 > gpurun_out/r02_ncu_k2s.log 2>&1
 $B --steps 1 --warmup 3 --workload long1024 > gpurun_out/r02_plain_k2l1024.log 2>&1 || exit 1
