@@ -78,7 +78,8 @@ static const char *const kOptionNames[] = {
     "debug",       // 1: launch geometry of the fast kernels on stderr
     "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l | 256p2 (default) | stream (K2S on len <= 64)
     "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate", "k2_rgate", "k2_cols_order",  // K2L experiment parameters (fast_long.cu)
-    "k2s",         // K2S variant for A/B runs: "dist" = block-edge duties dealt to all threads (default: on the edge threads)
+    "k2s",         // K2S variant for A/B runs: "p1" = one plane per step, duties on the edge threads; "dist" = one plane
+                   // per step, duties dealt to all threads (default: two planes per step, fast_stream2.cu)
     "multi",       // one long triple on several GPUs: "slab" (i-slab pipeline) | "cols" (column pipeline); default: auto
     "multi_min",   // smallest la (slab) / lc (cols) per GPU for which the multi-GPU pipeline is used (default 64 / 128)
     "kt_seg",      // traceback: anti-diagonal planes per segment of the checkpointed form (default: whole cube if it fits)

@@ -221,6 +221,8 @@ TA_HD void stream_stage_load(StreamSmem<C> &S, const StreamArgs &A, int tid, int
             const uint32_t a1 = (t1 < A.n) ? (A.a[t1 * A.len + e] & 3) : 0;
             S.acode[p % C::NBUF][e] = (uint8_t)(a0 | (a1 << 2));
         }
+        // the two-planes-per-step kernel (fast_stream2.cuh) runs one padding plane behind an odd len
+        if (tid == 0 && A.len < C::LEN_MAX) S.acode[p % C::NBUF][A.len] = 0;
     }
 }
 

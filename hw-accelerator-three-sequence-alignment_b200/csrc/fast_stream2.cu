@@ -1,0 +1,150 @@
+// fast_stream2.cu -- launcher of K2S "P2": two planes per step (see fast_stream2.cuh).  One persistent CTA per SM sweeps
+// all blocks of its contiguous chunk of pairs back to back.
+#include <algorithm>
+#include <cstdio>
+
+#include "fast_stream2.cuh"
+#include "kernels.cuh"
+
+namespace trialign {
+
+namespace {
+
+using C2 = fast::Stream2Cfg;
+
+// split-phase CTA barrier, one arrival per warp (as in fast_batch.cu)
+__device__ __forceinline__ void bar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_warp(uint64_t *bar)
+{
+    __syncwarp();  // orders the other lanes' shared-memory / global stores before lane 0's release
+    if ((threadIdx.x & 31) == 0)
+        asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+
+__global__ void __launch_bounds__(C2::NT, 1) fast_stream2_kernel(fast::StreamArgs A)
+{
+    using C = C2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::StreamSmem<C> &S = *reinterpret_cast<fast::StreamSmem<C> *>(smem_raw);
+    __shared__ __align__(8) uint64_t step_bar[1];
+    const int tid = threadIdx.x, cta = blockIdx.x;
+    const long long pair_base = (long long)cta * A.pairs_per_cta;
+    const long long left = A.pairs_total - pair_base;
+    if (left <= 0) return;
+    const int P = left < A.pairs_per_cta ? (int)left : A.pairs_per_cta;
+    const int tasks = P * A.nbj * A.nbk, L2 = fast::stream2_steps_per_task(A);
+    int tj, tk;
+    fast::stream_thread_pos<C>(tid, tj, tk);
+
+    if (tid == 0) bar_init(&step_bar[0], C::NT / 32);
+    fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, -1);  // filler the pipeline fill runs on
+    fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, 0);
+    __syncthreads();
+    fast::stream_stage_build<C>(S, tid, -1);
+    fast::stream_stage_build<C>(S, tid, 0);
+    __syncthreads();
+
+    fast::StreamRegs<C> R, R2;
+    fast::StreamConsts<C> K0, K1;
+    fast::Stream2Pos pos = fast::stream2_pos_at<C>(A, tj + tk, 0);
+    // the edge threads this thread serves: IN -> (0,t) / (t,0), skew t, one step ahead; OUT -> (15,t) / (t,15), skew
+    // 15 + t, one step back (starting with step 0 at the top of step 1)
+    fast::Stream2Pos pin = fast::stream2_pos_at<C>(A, tid & 15, 0), pout = fast::stream2_pos_at<C>(A, C::TJ - 1 + (tid & 15), 0);
+    fast::stream2_duty_in<C>(S, A, tid, pin, 0);
+    fast::stream2_advance<C>(A, pin);
+    fast::ta_copy_commit();
+    fast::ta_copy_wait();
+    __syncthreads();
+    fast::stream2_thread_prepare<C>(R, K0, K1, S, A, tj, tk, pos);
+    const int steps = (int)fast::stream2_total_steps<C>(A, P);
+    int g_t = 0, g_off = 0;
+#pragma unroll 1
+    for (int s = 0; s <= steps; ++s) {
+        // everybody has finished step s-1: halos of step s+1 in, faces of step s-1 out
+        fast::stream2_duty_in<C>(S, A, tid, pin, s + 1);
+        fast::stream2_advance<C>(A, pin);
+        if (s >= 1) {
+            fast::stream2_duty_out<C>(S, tid, pout, s - 1);
+            fast::stream2_advance<C>(A, pout);
+        }
+        fast::ta_copy_commit();
+        fast::stream2_thread_step<C>(R, R2, K0, K1, S, A, tj, tk, s, pos);
+        fast::ta_copy_wait();
+        bar_arrive_warp(&step_bar[0]);
+        if (g_t < tasks) fast::stream2_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off);
+        if (++g_off == L2) {
+            g_off = 0;
+            ++g_t;
+        }
+        fast::stream2_advance<C>(A, pos);
+        fast::stream2_thread_prepare<C>(R, K0, K1, S, A, tj, tk, pos);
+        bar_wait(&step_bar[0], s & 1);  // everybody has finished step s
+    }
+}
+
+}  // namespace
+
+bool fast_stream2_supports(int len) { return len >= C2::LEN_MIN && len <= C2::LEN_MAX && fast_long_supports(len + 1, len, len); }
+
+// pairs per CTA / grid as for the one-plane kernel (the step counter stays far below 2^30)
+int fast_stream2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
+                     int64_t n, int len, int32_t *d_scores)
+{
+    using C = C2;
+    if (n <= 0) return TRIALIGN_OK;
+    static_assert(sizeof(fast::StreamSmem<C>) + 64 <= 227 * 1024, "shared memory budget");
+    const size_t smem = sizeof(fast::StreamSmem<C>);
+    static bool attr_set[kMaxDevices] = {};
+    if (!attr_set[ctx->device]) {
+        TA_CUDA(cudaFuncSetAttribute(fast_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_stream2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
+        attr_set[ctx->device] = true;
+    }
+    fast::StreamArgs A{};
+    A.a = d_a; A.b = d_b; A.c = d_c;
+    A.n = n; A.len = len; A.scores = d_scores;
+    A.nbj = (len + C::BJ - 1) / C::BJ;
+    A.nbk = (len + C::BK - 1) / C::BK;
+    A.pairs_total = (n + 1) / 2;
+    const long long nb = A.nbj, steps_per_pair = nb * nb * ((len + 1) / 2);
+    long long ppc = (A.pairs_total + ctx->sm_count - 1) / ctx->sm_count;
+    ppc = std::max<long long>(1, std::min<long long>(ppc, (1ll << 30) / steps_per_pair));
+    const long long grid = (A.pairs_total + ppc - 1) / ppc;
+    A.pairs_per_cta = (int)ppc;
+    // face rings are private to a CTA; rows 0 .. len+1 (an odd len runs one padding plane)
+    A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
+    A.fk_ring = A.nbj + 1;
+    const size_t fj_bytes = (size_t)grid * 2 * A.fj_slot_words * 4;
+    const size_t fk_bytes = (size_t)grid * A.fk_ring * A.fk_slot_words * 4;
+    int rc = ctx->faces.reserve(fj_bytes + fk_bytes + 1024);
+    if (rc) return rc;
+    A.face_j = (uint32_t *)ctx->faces.ptr;
+    A.face_k = (uint32_t *)((char *)ctx->faces.ptr + ((fj_bytes + 255) & ~(size_t)255));
+    A.base = (int)(-envelope_lo((long long)len + 1) + 32);
+    if (opt_debug())
+        std::fprintf(stderr, "[trialign] K2S P2: len=%d blocks %dx%d grid=%lld pairs/cta=%lld faces=%.1f MB smem=%zu base=%d\n",
+                     len, A.nbj, A.nbk, grid, ppc, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
+    fast_stream2_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TRIALIGN_OK;
+}
+
+}  // namespace trialign

@@ -324,6 +324,94 @@ extern "C" int emu_fast_stream_ex(const uint8_t *a, const uint8_t *b, const uint
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// K2S "P2" (fast_stream2.cuh): two planes per step, block-edge duties by thread id.  Schedule of the kernel: duties
+// (halos of step s+1 in, faces of step s-1 out) | step s | arrive | uniform actions, prepare s+1 | wait for everybody's
+// step s.  Threads run forward and in reverse on alternate steps (schedule_seed: a rotated start), so nothing a step
+// reads may have been written in the same step.  Poisoned shared memory and face rings.
+// ---------------------------------------------------------------------------------------------------------------
+#include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_stream2.cuh"
+
+extern "C" int emu_fast_stream2(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                                int pairs_per_cta, int schedule_seed, int32_t *scores)
+{
+    using C = Stream2Cfg;
+    if (len < C::LEN_MIN || len > C::LEN_MAX || n < 0 || pairs_per_cta < 1) return -1;
+    StreamArgs A{};
+    A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
+    A.nbj = (len + C::BJ - 1) / C::BJ;
+    A.nbk = (len + C::BK - 1) / C::BK;
+    A.pairs_total = (n + 1) / 2;
+    A.pairs_per_cta = pairs_per_cta;
+    A.fj_slot_words = (long long)(len + 2) * C::FJ_ROW_WORDS;
+    A.fk_slot_words = (long long)(len + 2) * C::FK_ROW_WORDS;
+    A.fk_ring = A.nbj + 1;
+    A.base = base;
+    const int n_ctas = (int)((A.pairs_total + pairs_per_cta - 1) / pairs_per_cta), L2 = stream2_steps_per_task(A);
+    std::vector<uint32_t> fj((size_t)n_ctas * 2 * A.fj_slot_words, 0xDEADBEEFu), fk((size_t)n_ctas * A.fk_ring * A.fk_slot_words, 0xDEADBEEFu);
+    A.face_j = fj.data(); A.face_k = fk.data();
+    auto S = std::make_unique<StreamSmem<C>>();
+    std::vector<StreamRegs<C>> R(C::NT), R2(C::NT);
+    std::vector<StreamConsts<C>> K0(C::NT), K1(C::NT);
+    std::vector<Stream2Pos> pos(C::NT), pin(C::NT), pout(C::NT);
+    for (int cta = 0; cta < n_ctas; ++cta) {
+        const long long pair_base = (long long)cta * pairs_per_cta;
+        const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
+        const int tasks = P * A.nbj * A.nbk;
+        std::memset(S.get(), 0xA5, sizeof(StreamSmem<C>));
+        std::memset(R.data(), 0x5A, R.size() * sizeof(StreamRegs<C>));
+        std::memset(R2.data(), 0x5A, R2.size() * sizeof(StreamRegs<C>));
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, -1);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, 0);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, -1);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            stream_thread_pos<C>(tid, tj, tk);
+            pos[tid] = stream2_pos_at<C>(A, tj + tk, 0);
+            pin[tid] = stream2_pos_at<C>(A, tid & 15, 0);
+            pout[tid] = stream2_pos_at<C>(A, C::TJ - 1 + (tid & 15), 0);
+            stream2_duty_in<C>(*S, A, tid, pin[tid], 0);
+            stream2_advance<C>(A, pin[tid]);
+        }
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            stream_thread_pos<C>(tid, tj, tk);
+            stream2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, pos[tid]);
+        }
+        const int steps = (int)stream2_total_steps<C>(A, P);
+        int g_t = 0, g_off = 0;
+        for (int s = 0; s <= steps; ++s) {
+            const int rot = schedule_seed ? (int)(((unsigned)s * 2654435761u + (unsigned)schedule_seed * 40503u) >> 8) % C::NT : 0;
+            for (int x = 0; x < C::NT; ++x) {
+                const int tid = (((s & 1) ? C::NT - 1 - x : x) + rot) % C::NT;
+                int tj, tk;
+                stream_thread_pos<C>(tid, tj, tk);
+                stream2_duty_in<C>(*S, A, tid, pin[tid], s + 1);
+                stream2_advance<C>(A, pin[tid]);
+                if (s >= 1) {
+                    stream2_duty_out<C>(*S, tid, pout[tid], s - 1);
+                    stream2_advance<C>(A, pout[tid]);
+                }
+                stream2_thread_step<C>(R[tid], R2[tid], K0[tid], K1[tid], *S, A, tj, tk, s, pos[tid]);
+            }
+            for (int x = 0; x < C::NT; ++x) {
+                const int tid = (((s & 1) ? x : C::NT - 1 - x) + rot) % C::NT;
+                int tj, tk;
+                stream_thread_pos<C>(tid, tj, tk);
+                if (g_t < tasks) stream2_uniform_actions<C>(*S, A, tid, cta, P, pair_base, g_t, g_off);
+                stream2_advance<C>(A, pos[tid]);
+                stream2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, pos[tid]);
+            }
+            if (++g_off == L2) {
+                g_off = 0;
+                ++g_t;
+            }
+        }
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // K2L (fast_long.cuh): one long triple on several emulated CTAs.  Every CTA runs the kernel's own protocol: the warps of
 // a CTA drift (a warp may run step s once every warp has finished step s-LAG), the gate warp cannot finish a step
 // before the producers' progress certifies the halo fetches AHEAD steps later, progress is published with the

@@ -150,6 +150,27 @@ def test_stream_kernel_choreography(emu, ob, ln, n, ppc):
             assert out.tolist() == want, (seed, fn is emu.emu_fast_stream_dist)
 
 
+@pytest.mark.parametrize("ln,n,ppc", [(65, 3, 2), (66, 5, 3), (100, 5, 2), (127, 4, 4), (128, 4, 1), (129, 3, 2), (131, 7, 4),
+                                      (200, 5, 3), (255, 2, 1), (256, 2, 1)])
+def test_stream2_kernel_choreography(emu, ob, ln, n, ppc):
+    """K2S with two planes per step (fast_stream2.cuh): odd lengths run a padding plane, the block-edge duties are dealt
+    to all threads by thread id (halos in one step ahead, faces out one step later)."""
+    emu.emu_fast_stream2.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    rng = np.random.default_rng(ln * 17 + n)
+    a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+    for t in range(0, n, 2):  # mutated copies exercise large positive values
+        a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+    want = ob.score_batch(a, b, c, 16).tolist()
+    for seed in (0, 5, 12):
+        out = np.full(n, -99999, np.int32)
+        rc = emu.emu_fast_stream2(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln,
+                                  2 * (ln + 1) + 8 + 32, ppc, seed, out.ctypes.data_as(i32p))
+        assert rc == 0
+        assert out.tolist() == want, seed
+
+
 # ---- K2L: one long triple on the K1/K2S step engine (fast_long.cuh) ----
 @pytest.fixture(scope="module")
 def emu_long2(emu):
