@@ -186,9 +186,10 @@ int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const u
 {
     using C = Cfg;
     if (n <= 0) return TRIALIGN_OK;
-    // the unchecked default: two planes per step (fast_stream2.cu); options k2s=p1 / k2s=dist keep the one-plane forms
-    if (!scoring && check_bits <= 0 && fast_stream2_supports(len) && !opt_is("k2s", "p1") && !opt_is("k2s", "dist"))
-        return fast_stream2_run(ctx, st, d_a, d_b, d_c, n, len, d_scores);
+    // the default: two planes per step (fast_stream2.cu); options k2s=p1 / k2s=dist keep the one-plane forms
+    if (fast_stream2_supports(len) && !opt_is("k2s", "p1") && !opt_is("k2s", "dist") &&
+        (!scoring || fast_stream_score_ok(*scoring, len + 1 <= C::LEN_MAX ? len + 1 : len, check_bits)))
+        return fast_stream2_run(ctx, st, d_a, d_b, d_c, n, len, d_scores, check_bits, d_pair_flags, scoring);
     static_assert(sizeof(fast::StreamSmem<C>) + 64 <= 227 * 1024, "shared memory budget");
     static_assert(sizeof(fast::StreamSmem<fast::StreamCfgD>) + 64 <= 227 * 1024, "shared memory budget");
     // option k2s=dist: the block-edge duties dealt to all threads (A/B form of the unchecked kernel; measured 2 % slower

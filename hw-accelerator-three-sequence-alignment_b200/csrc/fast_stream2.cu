@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdio>
 
+#include "fast_batch.cuh"  // host helpers of the run-time scoring parameters
 #include "fast_stream2.cuh"
 #include "kernels.cuh"
 
@@ -36,7 +37,8 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
-__global__ void __launch_bounds__(C2::NT, 1) fast_stream2_kernel(fast::StreamArgs A)
+template <bool CHECK, class SC = fast::ScoreRtl>
+__device__ __forceinline__ void fast_stream2_body(const fast::StreamArgs &A, const fast::RangeCheck *chk, const SC &sc = SC())
 {
     using C = C2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -55,46 +57,68 @@ __global__ void __launch_bounds__(C2::NT, 1) fast_stream2_kernel(fast::StreamArg
     fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, -1);  // filler the pipeline fill runs on
     fast::stream_stage_load<C>(S, A, tid, cta, P, pair_base, 0);
     __syncthreads();
-    fast::stream_stage_build<C>(S, tid, -1);
-    fast::stream_stage_build<C>(S, tid, 0);
+    fast::stream_stage_build<C, SC>(S, tid, -1, sc);
+    fast::stream_stage_build<C, SC>(S, tid, 0, sc);
     __syncthreads();
 
     fast::StreamRegs<C> R, R2;
+    uint32_t viol = 0;  // CHECK kernels only
     fast::StreamConsts<C> K0, K1;
     fast::Stream2Pos pos = fast::stream2_pos_at<C>(A, tj + tk, 0);
     // the edge threads this thread serves: IN -> (0,t) / (t,0), skew t, one step ahead; OUT -> (15,t) / (t,15), skew
     // 15 + t, one step back (starting with step 0 at the top of step 1)
     fast::Stream2Pos pin = fast::stream2_pos_at<C>(A, tid & 15, 0), pout = fast::stream2_pos_at<C>(A, C::TJ - 1 + (tid & 15), 0);
-    fast::stream2_duty_in<C>(S, A, tid, pin, 0);
+    fast::stream2_duty_in<C, SC>(S, A, tid, pin, 0, sc);
     fast::stream2_advance<C>(A, pin);
     fast::ta_copy_commit();
     fast::ta_copy_wait();
     __syncthreads();
-    fast::stream2_thread_prepare<C>(R, K0, K1, S, A, tj, tk, pos);
+    fast::stream2_thread_prepare<C, SC>(R, K0, K1, S, A, tj, tk, pos, sc);
     const int steps = (int)fast::stream2_total_steps<C>(A, P);
     int g_t = 0, g_off = 0;
 #pragma unroll 1
     for (int s = 0; s <= steps; ++s) {
         // everybody has finished step s-1: halos of step s+1 in, faces of step s-1 out
-        fast::stream2_duty_in<C>(S, A, tid, pin, s + 1);
+        fast::stream2_duty_in<C, SC>(S, A, tid, pin, s + 1, sc);
         fast::stream2_advance<C>(A, pin);
         if (s >= 1) {
-            fast::stream2_duty_out<C>(S, tid, pout, s - 1);
+            fast::stream2_duty_out<C, SC>(S, tid, pout, s - 1, sc);
             fast::stream2_advance<C>(A, pout);
         }
         fast::ta_copy_commit();
-        fast::stream2_thread_step<C>(R, R2, K0, K1, S, A, tj, tk, s, pos);
+        fast::stream2_thread_step<C, CHECK, SC>(R, R2, K0, K1, S, A, tj, tk, s, pos, &viol, chk, sc);
         fast::ta_copy_wait();
         bar_arrive_warp(&step_bar[0]);
-        if (g_t < tasks) fast::stream2_uniform_actions<C>(S, A, tid, cta, P, pair_base, g_t, g_off);
+        if (g_t < tasks) fast::stream2_uniform_actions<C, SC>(S, A, tid, cta, P, pair_base, g_t, g_off, sc);
         if (++g_off == L2) {
             g_off = 0;
             ++g_t;
         }
         fast::stream2_advance<C>(A, pos);
-        fast::stream2_thread_prepare<C>(R, K0, K1, S, A, tj, tk, pos);
+        fast::stream2_thread_prepare<C, SC>(R, K0, K1, S, A, tj, tk, pos, sc);
         bar_wait(&step_bar[0], s & 1);  // everybody has finished step s
     }
+}
+
+__global__ void __launch_bounds__(C2::NT, 1) fast_stream2_kernel(fast::StreamArgs A) { fast_stream2_body<false>(A, nullptr); }
+__global__ void __launch_bounds__(C2::NT, 1) fast_stream2_kernel_checked(fast::StreamArgs A, fast::RangeCheck chk)
+{
+    fast_stream2_body<true>(A, &chk);
+}
+// run-time scoring parameters (trialign_score_batch_ex): range-checked on every plane, constants as a kernel argument
+template <bool SOP>
+__global__ void __launch_bounds__(C2::NT, 1)
+fast_stream2_kernel_scored(fast::StreamArgs A, fast::RangeCheck chk, fast::ScoreGen<SOP> sc)
+{
+    fast_stream2_body<true, fast::ScoreGen<SOP>>(A, &chk, sc);
+}
+
+template <class K>
+int set_smem_attr(K kernel, size_t smem)
+{
+    TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TA_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
+    return TRIALIGN_OK;
 }
 
 }  // namespace
@@ -103,7 +127,7 @@ bool fast_stream2_supports(int len) { return len >= C2::LEN_MIN && len <= C2::LE
 
 // pairs per CTA / grid as for the one-plane kernel (the step counter stays far below 2^30)
 int fast_stream2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                     int64_t n, int len, int32_t *d_scores)
+                     int64_t n, int len, int32_t *d_scores, int check_bits, int *d_pair_flags, const trialign_scoring *scoring)
 {
     using C = C2;
     if (n <= 0) return TRIALIGN_OK;
@@ -111,9 +135,11 @@ int fast_stream2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const 
     const size_t smem = sizeof(fast::StreamSmem<C>);
     static bool attr_set[kMaxDevices] = {};
     if (!attr_set[ctx->device]) {
-        TA_CUDA(cudaFuncSetAttribute(fast_stream2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TA_CUDA(cudaFuncSetAttribute(fast_stream2_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     (int)cudaSharedmemCarveoutMaxShared));
+        int rc0;
+        if ((rc0 = set_smem_attr(fast_stream2_kernel, smem))) return rc0;
+        if ((rc0 = set_smem_attr(fast_stream2_kernel_checked, smem))) return rc0;
+        if ((rc0 = set_smem_attr(fast_stream2_kernel_scored<false>, smem))) return rc0;
+        if ((rc0 = set_smem_attr(fast_stream2_kernel_scored<true>, smem))) return rc0;
         attr_set[ctx->device] = true;
     }
     fast::StreamArgs A{};
@@ -141,7 +167,29 @@ int fast_stream2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const 
     if (opt_debug())
         std::fprintf(stderr, "[trialign] K2S P2: len=%d blocks %dx%d grid=%lld pairs/cta=%lld faces=%.1f MB smem=%zu base=%d\n",
                      len, A.nbj, A.nbk, grid, ppc, (fj_bytes + fk_bytes) / 1e6, smem, A.base);
-    fast_stream2_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
+    if (scoring) {
+        if (check_bits <= 0 || !d_pair_flags || !fast_stream_score_ok(*scoring, len + 1 <= C::LEN_MAX ? len + 1 : len, check_bits))
+            return TRIALIGN_EINVAL;
+        const int M = scoring->match, X = scoring->mismatch, GO = scoring->gap_open, GE = scoring->gap_extend;
+        A.base = fast::score_base_len(X, GO, GE, len + 1);
+        const fast::BatchCheck bc = fast::score_check(M, X, GO, check_bits, d_pair_flags);
+        fast::RangeCheck chk;
+        chk.check_hi = bc.check_hi; chk.check_lo = bc.check_lo; chk.pair_flags = d_pair_flags;
+        if (scoring->triple_rule == TRIALIGN_TRIPLE_SUM_OF_PAIRS)
+            fast_stream2_kernel_scored<true><<<(unsigned)grid, C::NT, smem, st>>>(A, chk, fast::make_score_gen<true>(M, X, GO, GE));
+        else
+            fast_stream2_kernel_scored<false><<<(unsigned)grid, C::NT, smem, st>>>(A, chk, fast::make_score_gen<false>(M, X, GO, GE));
+    } else if (check_bits > 0) {
+        // every 8th plane is sampled; the margins cover the planes in between (`all` moves by at most +3 / -4 per plane)
+        const int lim = 1 << (check_bits - 1), gap = 7;
+        fast::RangeCheck chk;
+        chk.check_hi = lim - 1 - 3 - 3 * gap;
+        chk.check_lo = -lim + 8 + 4 * gap;
+        chk.pair_flags = d_pair_flags;
+        fast_stream2_kernel_checked<<<(unsigned)grid, C::NT, smem, st>>>(A, chk);
+    } else {
+        fast_stream2_kernel<<<(unsigned)grid, C::NT, smem, st>>>(A);
+    }
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TRIALIGN_OK;

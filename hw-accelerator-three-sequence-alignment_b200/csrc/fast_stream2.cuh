@@ -15,7 +15,7 @@
 //     at the top of step s a thread brings in the halos that an edge thread reads at step s+1 (cp.async from the face
 //     rings, or the zero-border potential) and copies out what an edge thread published at step s-1 (index 16 of the
 //     edge slots) -- the step itself has no edge code, and the lanes of a warp lie along anti-diagonals as in K1.
-// Unchecked kernel only: the range-checked and run-time-scoring forms stay on fast_stream.cuh.
+// CHECK / SC template parameters: the range-checked and run-time-scoring forms (see fast_stream.cuh, fast_core.cuh).
 #pragma once
 
 #include "fast_stream.cuh"
@@ -76,8 +76,8 @@ TA_HD Stream2Pos stream2_pos_at(const StreamArgs &A, int back, int s)
 // words -- into index 0 of edge slot rs(st) + pl; p = that edge thread's position at step st.  The column threads of the
 // u2 / all(old) arrays bring the corner word along.  Called at the top of step st - 1 (the slot's last readers, step
 // st - 2, are done); the copies land (cp.async wait) before the caller arrives for step st - 1.
-template <class C>
-TA_HD void stream2_duty_in(StreamSmem<C> &S, const StreamArgs &A, int tid, const Stream2Pos &p, int st)
+template <class C, class SC = ScoreRtl>
+TA_HD void stream2_duty_in(StreamSmem<C> &S, const StreamArgs &A, int tid, const Stream2Pos &p, int st, const SC &sc = SC())
 {
     const int t = tid & 15, arr = (tid >> 4) & 3, pl = (tid >> 6) & 1, col = tid >> 7;
     const int slot = (((st - 1) & 1) << 1) + pl, i = 2 * p.x + 1 + pl;
@@ -91,9 +91,9 @@ TA_HD void stream2_duty_in(StreamSmem<C> &S, const StreamArgs &A, int tid, const
         // for the block's first tile row
         if (col && (arr & 1)) ta_copy4(&S.corner[slot][arr >> 1][t][0], row + (t > 0 ? 4 * t - 1 : C::BJ));
     } else {  // zero border plane (src/TriAlign_1cyc.v:156-181): all 7 states are 0, reduced values = the potential
-        const uint32_t e = rep((uint32_t)(A.base + 2 * (i + 4 * t + 1 - (arr >> 1))));
-        ta_store4(dst, e, e + 0x00020002u, e + 0x00040004u, e + 0x00060006u);
-        if (col && (arr & 1)) S.corner[slot][arr >> 1][t][0] = e - 0x00020002u;  // cell (j0, 0)
+        const uint32_t e = rep((uint32_t)(A.base + (int)sc.pi() * (i + 4 * t + 1 - (arr >> 1)))), d = sc.pi2();
+        ta_store4(dst, e, e + d, e + 2 * d, e + 3 * d);
+        if (col && (arr & 1)) S.corner[slot][arr >> 1][t][0] = e - d;  // cell (j0, 0)
     }
 }
 
@@ -101,15 +101,15 @@ TA_HD void stream2_duty_in(StreamSmem<C> &S, const StreamArgs &A, int tid, const
 // index 16 of edge slot ws(ss) + pl -- to the face ring of the task that thread was in (p = its position at step ss),
 // re-based to the consumer's frame.  Called at the top of step ss + 1 (everybody has finished step ss; the slot is
 // written again at step ss + 2).  The u2 / all(old) column threads of tile row 0 copy the relay entry along.
-template <class C>
-TA_HD void stream2_duty_out(StreamSmem<C> &S, int tid, const Stream2Pos &p, int ss)
+template <class C, class SC = ScoreRtl>
+TA_HD void stream2_duty_out(StreamSmem<C> &S, int tid, const Stream2Pos &p, int ss, const SC &sc = SC())
 {
     const int t = tid & 15, arr = (tid >> 4) & 3, pl = (tid >> 6) & 1, col = tid >> 7;
     const int slot = ((ss & 1) << 1) + pl, i = 2 * p.x + 1 + pl;
     const StreamTask &T = S.task[p.buf];
     uint32_t *face = col ? T.fk_w : T.fj_w;
     if (!face) return;
-    const uint32_t adj = rep(2 * (col ? C::BK : C::BJ));
+    const uint32_t adj = rep(sc.pi() * (col ? C::BK : C::BJ));
     const uint32_t *src = col ? &S.col[slot][arr][C::TK][4 * t] : &S.row[slot][arr][C::TJ][4 * t];
     uint32_t *row = face + (long long)i * (col ? C::FK_ROW_WORDS : C::FJ_ROW_WORDS) + arr * (col ? C::COL_STRIDE : C::ROW_STRIDE);
     ta_store4(row + 4 * t, src[0] - adj, src[1] - adj, src[2] - adj, src[3] - adj);
@@ -117,23 +117,23 @@ TA_HD void stream2_duty_out(StreamSmem<C> &S, int tid, const Stream2Pos &p, int 
 }
 
 // ---- the part of a step that does not depend on the neighbours: per-task reset and the constants of both planes ----
-template <class C>
+template <class C, class SC = ScoreRtl>
 TA_HD void stream2_thread_prepare(StreamRegs<C> &R, StreamConsts<C> &K0, StreamConsts<C> &K1, const StreamSmem<C> &S,
-                                  const StreamArgs &A, int tj, int tk, const Stream2Pos &p)
+                                  const StreamArgs &A, int tj, int tk, const Stream2Pos &p, const SC &sc = SC())
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int j0 = tj * RJ, k0 = tk * RK, buf = p.buf;
     if (p.x == 0) {
         // a new task enters this thread: plane 0 is the all-zero border (src/PE_1cyc.v:164-178 override), and the
         // tile's (b,c) constants change
-        const uint32_t zb = stream_phi(A, 0, j0 + 1, k0 + 1);
+        const uint32_t zb = stream_phi(A, 0, j0 + 1, k0 + 1, sc);
 #pragma unroll
         for (int r = 0; r < RJ; ++r)
 #pragma unroll
             for (int c = 0; c < RK; ++c) {
-                const uint32_t z = zb + (uint32_t)(r + c) * 0x00020002u;
+                const uint32_t z = zb + (uint32_t)(r + c) * sc.pi2();
                 R.all[r][c] = z; R.wX[r][c] = z; R.u1[r][c] = z; R.u3[r][c] = z;
-                R.cBC[r][c] = pair_const(neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]));
+                R.cBC[r][c] = pair_const(neq_flag(S.bpk[buf][j0 + r], S.cpk[buf][k0 + c]), sc);
             }
     }
     const uint8_t *codes = &S.acode[S.task[buf].abuf][2 * p.x];  // planes 2x+1, 2x+2 (a padding plane reads code 0)
@@ -192,9 +192,12 @@ TA_HD void stream2_load_halos(Stream2Halo<C> &H, const StreamSmem<C> &S, int tj,
 
 // one plane of one thread: relay the corner, publish the old half of the own edges, update the tile, publish the new
 // half (edge slot ws).  R = plane i-1 state, Rn = plane i state.
-template <class C>
+// CHECK: the run-time range check of every plane that belongs to the triple (i <= len: the padding plane of an odd len
+// is not part of it); `viol` accumulates the violations of the task this thread is working on.
+template <class C, bool CHECK = false, class SC = ScoreRtl>
 TA_HD void stream2_thread_plane(const StreamRegs<C> &R, StreamRegs<C> &Rn, const StreamConsts<C> &K, const Stream2Halo<C> &H,
-                                StreamSmem<C> &S, const StreamArgs &A, int tj, int tk, int ws, int buf, int i)
+                                StreamSmem<C> &S, const StreamArgs &A, int tj, int tk, int ws, int buf, int i,
+                                uint32_t *viol_io = nullptr, const RangeCheck *chk = nullptr, const SC &sc = SC())
 {
     constexpr int RJ = C::RJ, RK = C::RK;
     const int j0 = tj * RJ, k0 = tk * RK;
@@ -222,9 +225,9 @@ TA_HD void stream2_thread_plane(const StreamRegs<C> &R, StreamRegs<C> &Rn, const
             const uint32_t p_u1 = r > 0 ? R.u1[r - 1][c] : H.T_u1[c];
             const uint32_t p_u2 = (r > 0 && c > 0) ? n_u2[r - 1][c - 1] : (r == 0 ? H.T_u2[c] : H.L_u2[r]);
             const uint32_t p_u3 = c > 0 ? R.u3[r][c - 1] : H.L_u3[r];
-            const uint32_t cM = triple_const(K.tB[r], K.tC[c]);
-            const CellOut o = cell_update<false>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
-                                                 R.cBC[r][c], K.cAC[c], nullptr);
+            const uint32_t cM = triple_const_of(K.tB[r], K.tC[c], K.cAB[r], R.cBC[r][c], K.cAC[c], sc);
+            const CellOut o = cell_update<false, SC>(p_all, R.wX[r][c], p_wY, p_wZ, p_u1, p_u2, p_u3, cM, K.cAB[r],
+                                                     R.cBC[r][c], K.cAC[c], nullptr, sc);
             n_all[r][c] = o.all; n_wX[r][c] = o.wX; n_u1[r][c] = o.u1; n_u3[r][c] = o.u3;
             n_wY[r][c] = o.wY; n_wZ[r][c] = o.wZ; n_u2[r][c] = o.u2;
         }
@@ -253,12 +256,46 @@ TA_HD void stream2_thread_plane(const StreamRegs<C> &R, StreamRegs<C> &Rn, const
 #pragma unroll
                     for (int c = 0; c < RK; ++c)
                         if (r == rf && c == cf) v = n_all[r][c];
-                const int off = A.base + 2 * (A.len + jl + kl);
+                const int off = A.base + (int)sc.pi() * (A.len + jl + kl);
                 const long long t0 = 2 * T.pair;
                 if (t0 < A.n) A.scores[t0] = (int32_t)(v & 0xFFFFu) - off;
                 if (t0 + 1 < A.n) A.scores[t0 + 1] = (int32_t)(v >> 16) - off;
             }
         }
+    }
+
+    if (CHECK) {
+        // RTL constants: every 8th plane is sampled (`all` moves by at most +3 / -4 per plane; the margins of the limits
+        // cover the planes in between); run-time scoring: every plane, limits exact per cell
+        uint32_t viol = i == 1 ? 0u : *viol_io;  // a new task enters this thread
+        if ((SC::kRtl ? (i & 7) == 0 : true) && i <= A.len) {
+            uint32_t mx = n_all[0][0], mn = n_all[0][0];
+#pragma unroll
+            for (int r = 0; r < RJ; ++r)
+#pragma unroll
+                for (int c = 0; c < RK; c += 2) {
+                    const uint32_t v0 = SC::kRtl ? n_all[r][c] : fadd(n_all[r][c], 0u - (uint32_t)(r + c) * sc.pi2());
+                    const uint32_t v1 = SC::kRtl ? n_all[r][c + 1] : fadd(n_all[r][c + 1], 0u - (uint32_t)(r + c + 1) * sc.pi2());
+                    mx = vmax3(mx, v0, v1);
+                    mn = vmin3(mn, v0, v1);
+                }
+            const int ph = A.base + (int)sc.pi() * (i + j0 + 1 + k0 + 1), slack = SC::kRtl ? 2 * (RJ + RK - 2) : 0;
+            const int h = ph + chk->check_hi, l = ph + chk->check_lo + slack;
+            const uint32_t hi_lim = rep((uint32_t)(h > 0xFFFF ? 0xFFFF : h)), lo_lim = rep((uint32_t)(l < 0 ? 0 : l));
+            viol |= (vmax2(mx, hi_lim) ^ hi_lim) | (vmin2(mn, lo_lim) ^ lo_lim);
+        }
+        if (i == A.len && viol != 0) {  // the task's last real plane leaves this thread: report
+            const StreamTask &T = S.task[buf];
+            if (T.valid) {
+                const int bits = ((viol & 0xFFFFu) ? 1 : 0) | ((viol >> 16) ? 2 : 0);
+#if defined(__CUDA_ARCH__)
+                atomicOr(chk->pair_flags + T.pair, bits);
+#else
+                chk->pair_flags[T.pair] |= bits;
+#endif
+            }
+        }
+        *viol_io = viol;
     }
 
 #pragma unroll
@@ -272,25 +309,26 @@ TA_HD void stream2_thread_plane(const StreamRegs<C> &R, StreamRegs<C> &Rn, const
 
 // one step of one thread: both planes' halos first (published a step ago), then the two plane updates back to back,
 // R -> R2 -> R
-template <class C>
+template <class C, bool CHECK = false, class SC = ScoreRtl>
 TA_HD void stream2_thread_step(StreamRegs<C> &R, StreamRegs<C> &R2, const StreamConsts<C> &K0, const StreamConsts<C> &K1,
-                               StreamSmem<C> &S, const StreamArgs &A, int tj, int tk, int s, const Stream2Pos &p)
+                               StreamSmem<C> &S, const StreamArgs &A, int tj, int tk, int s, const Stream2Pos &p,
+                               uint32_t *viol_io = nullptr, const RangeCheck *chk = nullptr, const SC &sc = SC())
 {
     const int rs = ((s - 1) & 1) << 1, ws = (s & 1) << 1, i0 = 2 * p.x + 1;
     Stream2Halo<C> H0, H1;
     stream2_load_halos<C>(H0, S, tj, tk, rs);
     stream2_load_halos<C>(H1, S, tj, tk, rs + 1);
-    stream2_thread_plane<C>(R, R2, K0, H0, S, A, tj, tk, ws, p.buf, i0);
-    stream2_thread_plane<C>(R2, R, K1, H1, S, A, tj, tk, ws + 1, p.buf, i0 + 1);
+    stream2_thread_plane<C, CHECK, SC>(R, R2, K0, H0, S, A, tj, tk, ws, p.buf, i0, viol_io, chk, sc);
+    stream2_thread_plane<C, CHECK, SC>(R2, R, K1, H1, S, A, tj, tk, ws + 1, p.buf, i0 + 1, viol_io, chk, sc);
 }
 
 // CTA-uniform actions of the global step that is step g_off of task g_t for thread (0,0): stage task g_t + 1
-template <class C>
+template <class C, class SC = ScoreRtl>
 TA_HD void stream2_uniform_actions(StreamSmem<C> &S, const StreamArgs &A, int tid, int cta, int P, long long pair_base,
-                                   int g_t, int g_off)
+                                   int g_t, int g_off, const SC &sc = SC())
 {
     if (g_off == C::LOAD_AT) stream_stage_load<C>(S, A, tid, cta, P, pair_base, g_t + 1);
-    if (g_off == C::BUILD_AT) stream_stage_build<C>(S, tid, g_t + 1);
+    if (g_off == C::BUILD_AT) stream_stage_build<C, SC>(S, tid, g_t + 1, sc);
 }
 
 // global steps a CTA runs for P pairs: steps 0 .. this value

@@ -74,11 +74,12 @@ bool fast_stream_fits(int len, int64_t n, int sm_count);  // CTA-private face ri
 int fast_stream_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
                     int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr,
                     const trialign_scoring *scoring = nullptr);
-// K2S "P2" (fast_stream2.cu): two planes per step, block-edge duties by thread id; the unchecked default for len >= 65
-// (option k2s=p1 keeps the one-plane kernel)
+// K2S "P2" (fast_stream2.cu): two planes per step, block-edge duties by thread id; the default for len >= 65, also
+// range-checked and with run-time scoring parameters (option k2s=p1 keeps the one-plane kernels)
 bool fast_stream2_supports(int len);
 int fast_stream2_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const uint8_t *d_b, const uint8_t *d_c,
-                     int64_t n, int len, int32_t *d_scores);
+                     int64_t n, int len, int32_t *d_scores, int check_bits = 0, int *d_pair_flags = nullptr,
+                     const trialign_scoring *scoring = nullptr);
 // run-time scoring parameters on K2S: score_fast_domain() plus the 16-bit lane range at this length
 bool fast_stream_score_ok(const trialign_scoring &sc, int len, int score_bits);
 

@@ -331,10 +331,12 @@ extern "C" int emu_fast_stream_ex(const uint8_t *a, const uint8_t *b, const uint
 // ---------------------------------------------------------------------------------------------------------------
 #include "../../hw-accelerator-three-sequence-alignment_b200/csrc/fast_stream2.cuh"
 
-extern "C" int emu_fast_stream2(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
-                                int pairs_per_cta, int schedule_seed, int32_t *scores)
+template <bool CHECK, class SC>
+static int emu_fast_stream2_sc(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                               int pairs_per_cta, int schedule_seed, int32_t *scores, const SC &sc, const RangeCheck *chk)
 {
     using C = Stream2Cfg;
+    std::vector<uint32_t> viol(C::NT, 0);
     if (len < C::LEN_MIN || len > C::LEN_MAX || n < 0 || pairs_per_cta < 1) return -1;
     StreamArgs A{};
     A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
@@ -362,21 +364,21 @@ extern "C" int emu_fast_stream2(const uint8_t *a, const uint8_t *b, const uint8_
         std::memset(R2.data(), 0x5A, R2.size() * sizeof(StreamRegs<C>));
         for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, -1);
         for (int tid = 0; tid < C::NT; ++tid) stream_stage_load<C>(*S, A, tid, cta, P, pair_base, 0);
-        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, -1);
-        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C, SC>(*S, tid, -1, sc);
+        for (int tid = 0; tid < C::NT; ++tid) stream_stage_build<C, SC>(*S, tid, 0, sc);
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             stream_thread_pos<C>(tid, tj, tk);
             pos[tid] = stream2_pos_at<C>(A, tj + tk, 0);
             pin[tid] = stream2_pos_at<C>(A, tid & 15, 0);
             pout[tid] = stream2_pos_at<C>(A, C::TJ - 1 + (tid & 15), 0);
-            stream2_duty_in<C>(*S, A, tid, pin[tid], 0);
+            stream2_duty_in<C, SC>(*S, A, tid, pin[tid], 0, sc);
             stream2_advance<C>(A, pin[tid]);
         }
         for (int tid = 0; tid < C::NT; ++tid) {
             int tj, tk;
             stream_thread_pos<C>(tid, tj, tk);
-            stream2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, pos[tid]);
+            stream2_thread_prepare<C, SC>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, pos[tid], sc);
         }
         const int steps = (int)stream2_total_steps<C>(A, P);
         int g_t = 0, g_off = 0;
@@ -386,21 +388,21 @@ extern "C" int emu_fast_stream2(const uint8_t *a, const uint8_t *b, const uint8_
                 const int tid = (((s & 1) ? C::NT - 1 - x : x) + rot) % C::NT;
                 int tj, tk;
                 stream_thread_pos<C>(tid, tj, tk);
-                stream2_duty_in<C>(*S, A, tid, pin[tid], s + 1);
+                stream2_duty_in<C, SC>(*S, A, tid, pin[tid], s + 1, sc);
                 stream2_advance<C>(A, pin[tid]);
                 if (s >= 1) {
-                    stream2_duty_out<C>(*S, tid, pout[tid], s - 1);
+                    stream2_duty_out<C, SC>(*S, tid, pout[tid], s - 1, sc);
                     stream2_advance<C>(A, pout[tid]);
                 }
-                stream2_thread_step<C>(R[tid], R2[tid], K0[tid], K1[tid], *S, A, tj, tk, s, pos[tid]);
+                stream2_thread_step<C, CHECK, SC>(R[tid], R2[tid], K0[tid], K1[tid], *S, A, tj, tk, s, pos[tid], &viol[tid], chk, sc);
             }
             for (int x = 0; x < C::NT; ++x) {
                 const int tid = (((s & 1) ? x : C::NT - 1 - x) + rot) % C::NT;
                 int tj, tk;
                 stream_thread_pos<C>(tid, tj, tk);
-                if (g_t < tasks) stream2_uniform_actions<C>(*S, A, tid, cta, P, pair_base, g_t, g_off);
+                if (g_t < tasks) stream2_uniform_actions<C, SC>(*S, A, tid, cta, P, pair_base, g_t, g_off, sc);
                 stream2_advance<C>(A, pos[tid]);
-                stream2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, pos[tid]);
+                stream2_thread_prepare<C, SC>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, pos[tid], sc);
             }
             if (++g_off == L2) {
                 g_off = 0;
@@ -409,6 +411,32 @@ extern "C" int emu_fast_stream2(const uint8_t *a, const uint8_t *b, const uint8_
         }
     }
     return 0;
+}
+
+extern "C" int emu_fast_stream2(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                                int pairs_per_cta, int schedule_seed, int32_t *scores)
+{
+    return emu_fast_stream2_sc<false, ScoreRtl>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, ScoreRtl(), nullptr);
+}
+
+// sop < 0: the RTL's constants, range-checked at check_bits (every 8th plane); sop = 0 / 1: run-time scoring parameters
+extern "C" int emu_fast_stream2_ex(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int pairs_per_cta,
+                                   int schedule_seed, int M, int X, int GO, int GE, int sop, int check_bits, int32_t *scores,
+                                   int *flags)
+{
+    RangeCheck chk;
+    chk.pair_flags = flags;
+    if (sop < 0) {
+        const int lim = 1 << (check_bits - 1), gap = 7;
+        chk.check_hi = lim - 1 - 3 - 3 * gap;
+        chk.check_lo = -lim + 8 + 4 * gap;
+        return emu_fast_stream2_sc<true, ScoreRtl>(a, b, c, n, len, 2 * (len + 1) + 8 + 32, pairs_per_cta, schedule_seed, scores, ScoreRtl(), &chk);
+    }
+    const BatchCheck bc = score_check(M, X, GO, check_bits, flags);
+    chk.check_hi = bc.check_hi; chk.check_lo = bc.check_lo;
+    const int base = score_base_len(X, GO, GE, len + 1);
+    if (sop) return emu_fast_stream2_sc<true, ScoreGen<true>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, make_score_gen<true>(M, X, GO, GE), &chk);
+    return emu_fast_stream2_sc<true, ScoreGen<false>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, make_score_gen<false>(M, X, GO, GE), &chk);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -171,6 +171,38 @@ def test_stream2_kernel_choreography(emu, ob, ln, n, ppc):
         assert out.tolist() == want, seed
 
 
+@pytest.mark.parametrize("sc", [None, (2, -1, 2, 1, 0), (1, -1, 2, 1, 1), (4, -4, 8, 2, 1), (2, 0, 0, 0, 0)])
+def test_stream2_kernel_checked_and_with_runtime_scoring(emu, ob, sc):
+    """The range-checked form (sc None: the RTL's constants, every 8th plane sampled) and the run-time-scoring form of the
+    two-planes-per-step kernel: triples the check clears must carry the oracle's score, nothing is flagged at 16 bits."""
+    emu.emu_fast_stream2_ex.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_int, C.c_int, i32p, C.POINTER(C.c_int)]
+    M, X, GO, GE, rule = sc if sc else (1, -1, 2, 1, -1)
+    rng = np.random.default_rng(99 + (sum(abs(v) for v in sc) if sc else 0))
+    for ln, n, ppc in [(131, 4, 2), (70, 3, 1)]:
+        a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+        a[0], b[0], c[0] = ob.mutated_triple(rng, ln)
+        for w, seed in [(16, 4), (9, 0)]:
+            out = np.full(n, -99999, np.int32)
+            flags = np.zeros((n + 1) // 2, np.int32)
+            rc = emu.emu_fast_stream2_ex(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, ppc, seed,
+                                         M, X, GO, GE, rule, w, out.ctypes.data_as(i32p),
+                                         flags.ctypes.data_as(C.POINTER(C.c_int)))
+            assert rc == 0
+            want = ([ob.score_ex(a[t], b[t], c[t], w, sc)[0] for t in range(n)] if sc
+                    else ob.score_batch(a, b, c, w).tolist())
+            flagged = [bool(flags[t // 2] >> (t & 1) & 1) for t in range(n)]
+            if w == 16:
+                assert not any(flagged), (sc, ln, flags)
+            elif ln > 100 and M > 0:
+                assert flagged[0], (sc, ln, flags)  # the mutated copy of length 131 scores far beyond 9 bits
+            for t in range(n):
+                if not flagged[t]:
+                    assert out[t] == want[t], (sc, ln, w, t, out.tolist(), want)
+
+
 # ---- K2L: one long triple on the K1/K2S step engine (fast_long.cuh) ----
 @pytest.fixture(scope="module")
 def emu_long2(emu):
