@@ -243,6 +243,8 @@ int traceback_run_t(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, int la,
     size_t budget;
     if (opt_int("kt_budget_mb", 0) > 0) {
         budget = (size_t)opt_int("kt_budget_mb", 0) << 20;
+    } else if (traceback_dir_bytes(la, lb, lc) <= ctx->dirs.bytes) {
+        budget = ctx->dirs.bytes;  // the whole cube fits what an earlier call reserved: no need to ask the driver
     } else {
         size_t free_b = 0, total_b = 0;
         TA_CUDA(cudaMemGetInfo(&free_b, &total_b));

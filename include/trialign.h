@@ -101,7 +101,7 @@ int trialign_device_count(void);            /* 0 when no driver / no device; nev
 
 /* Run-time options: the experiment switches of the kernels (A/B variants, gate intervals, multi-GPU decomposition).
  * Nothing in the library reads the environment; a caller that wants a non-default kernel says so explicitly.
- * Names: debug, k1, k2_lag, k2_pp, k2_gatetid, k2_early, k2_gate, k2_rgate, k2_cols_order, multi ("slab" | "cols";
+ * Names: debug, k1, k2s, k2_lag, k2_pp, k2_gatetid, k2_early, k2_gate, k2_rgate, k2_cols_order, multi ("slab" | "cols";
  * default: chosen by trialign_multi_plan), multi_min, kt_seg, kt_budget_mb (traceback, see trialign_align).
  * value NULL or "" restores the default.  Unknown names give TRIALIGN_EINVAL.  Process-wide, thread-safe. */
 int trialign_set_option(const char *name, const char *value);
