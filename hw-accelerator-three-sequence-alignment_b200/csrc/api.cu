@@ -76,7 +76,7 @@ NvtxRange::~NvtxRange() { nvtxRangePop(); }
 // Every experiment switch of the kernels is an explicit option of the library; nothing is read from the environment.
 static const char *const kOptionNames[] = {
     "debug",       // 1: launch geometry of the fast kernels on stderr
-    "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l | 256p2 (default) | stream (K2S on len <= 64)
+    "k1",          // K1 variant for A/B runs: 256 | 256m | 512 | 512m | 256l | 256p2 (default) | 256r2 | stream (K2S on len <= 64)
     "k2_lag", "k2_pp", "k2_gatetid", "k2_early", "k2_gate", "k2_rgate", "k2_cols_order",  // K2L experiment parameters (fast_long.cu)
     "k2s",         // K2S variant for A/B runs: "p1" = one plane per step, duties on the edge threads; "dist" = one plane
                    // per step, duties dealt to all threads (default: two planes per step, fast_stream2.cu)

@@ -169,6 +169,54 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2_kernel(fast::BatchArgs
         bar_wait(&step_bar[0], s & 1);  // everybody has finished step s
     }
 }
+// Two planes per step with neighbour-only synchronisation (fast_batch.cuh: batch2_write_borders_warp): warp w arrives on
+// its own barrier (two per warp, even / odd steps, so that a neighbour one step ahead cannot alias the phase parity)
+// and waits for warps w-1 and w+1 only.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2r_kernel(fast::BatchArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    fast::BatchSmem<Cfg> &S = *reinterpret_cast<fast::BatchSmem<Cfg> *>(smem_raw);
+    __shared__ __align__(8) uint64_t ring_bar[Cfg::NT / 32][2];
+    const int tid = threadIdx.x, w = tid >> 5;
+    const long long pair_base = (long long)blockIdx.x * A.pairs_per_cta;
+    long long left = A.pairs_total - pair_base;
+    if (left <= 0) return;
+    const int P = left < A.pairs_per_cta ? (int)left : A.pairs_per_cta;
+    int tj, tk;
+    fast::thread_pos<Cfg>(tid, tj, tk);
+    if (tid < 2 * (Cfg::NT / 32)) bar_init(&ring_bar[tid >> 1][tid & 1], 1);
+    for (int fill = 1; fill < Cfg::NBUF; ++fill) {
+        for (int e = tid; e < 64; e += Cfg::NT) {
+            S.acode[fill][e] = 0;
+            S.bpk[fill][e] = 0;
+            S.cpk[fill][e] = 0;
+        }
+        for (int e = tid; e < 3 * 2 * 64; e += Cfg::NT) (&S.seq[fill][0][0][0])[e] = 0;
+    }
+    fast::load_pair_sequences<Cfg>(S, A, tid, pair_base, 0);
+    __syncthreads();
+    fast::build_pair_tables<Cfg>(S, tid, 0);
+    fast::batch2_write_borders_warp<Cfg>(S, A, tid, 0);
+    __syncthreads();
+    fast::BatchRegs<Cfg> R, R2;
+    fast::BatchConsts<Cfg> K0, K1;
+    uint32_t codes = fast::batch2_fetch_codes<Cfg>(S, tj, tk, 0);
+    fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, 0, codes);
+    const int steps = fast::batch2_total_steps<Cfg>(P);
+    uint64_t *const mine = &ring_bar[w][0], *const left_bar = &ring_bar[(w + Cfg::NT / 32 - 1) % (Cfg::NT / 32)][0],
+                   *const right_bar = &ring_bar[(w + 1) % (Cfg::NT / 32)][0];
+#pragma unroll 1
+    for (int s = 0; s <= steps; ++s) {
+        fast::batch2_write_borders_warp<Cfg>(S, A, tid, s + 1);  // read by this warp's own edge threads at step s+1
+        fast::batch2_thread_step<Cfg>(R, R2, K0, K1, S, A, tj, tk, s, P, pair_base);
+        bar_arrive_warp(mine + (s & 1));
+        fast::batch2_uniform_actions<Cfg, true>(S, A, tid, s, P, pair_base);
+        fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, s + 1, codes);
+        bar_wait(left_bar + (s & 1), (s >> 1) & 1);   // warp w-1 has finished step s: its edges are there
+        bar_wait(right_bar + (s & 1), (s >> 1) & 1);  // warp w+1 has finished step s: it has read what step s+1 overwrites
+    }
+}
 template <class Cfg, bool SPLIT>
 __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch_kernel_checked(fast::BatchArgs A, fast::BatchCheck chk)
 {
@@ -224,12 +272,15 @@ int launch_batch(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, int variant
     return TRIALIGN_OK;
 }
 
-int launch_batch2(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A)
+int launch_batch2(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A, bool ring)
 {
     using Cfg = Cfg256L;  // its shared-memory layout: four edge slots, three pair buffers
     const size_t smem = sizeof(fast::BatchSmem<Cfg>);
     static bool attr_set[kMaxDevices] = {};
     if (!attr_set[ctx->device]) {
+        TA_CUDA(cudaFuncSetAttribute(fast_batch2r_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        TA_CUDA(cudaFuncSetAttribute(fast_batch2r_kernel<Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     (int)cudaSharedmemCarveoutMaxShared));
         TA_CUDA(cudaFuncSetAttribute(fast_batch2_kernel<Cfg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         TA_CUDA(cudaFuncSetAttribute(fast_batch2_kernel<Cfg>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      (int)cudaSharedmemCarveoutMaxShared));
@@ -242,7 +293,8 @@ int launch_batch2(DeviceCtx *ctx, cudaStream_t st, fast::BatchArgs A)
     const long long grid = (A.pairs_total + ppc - 1) / ppc;
     if (opt_debug())
         std::fprintf(stderr, "[trialign] K1 P2: grid=%lld pairs/cta=%lld smem=%zu\n", grid, ppc, smem);
-    fast_batch2_kernel<Cfg><<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
+    if (ring) fast_batch2r_kernel<Cfg><<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
+    else fast_batch2_kernel<Cfg><<<(unsigned)grid, Cfg::NT, smem, st>>>(A);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TRIALIGN_OK;
@@ -315,6 +367,7 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
             if (e[1] && e[2] && e[3] == 'm') variant |= 1;
             if (e[1] && e[2] && e[3] == 'l') variant |= 4;
             if (e[1] && e[2] && e[3] == 'p' && e[4] == '2') variant = 16; // 256p2: two planes per step
+            if (e[1] && e[2] && e[3] == 'r' && e[4] == '2') variant = 32; // 256r2: the same with neighbour-only synchronisation
         }
     }
     fast::BatchArgs A;
@@ -333,7 +386,7 @@ int fast_batch_run(DeviceCtx *ctx, cudaStream_t st, const uint8_t *d_a, const ui
         chk.pair_flags = d_pair_flags;
         return launch_batch<Cfg256L, true, 1, true>(ctx, st, A, 100, chk);
     }
-    if (variant == 16) return launch_batch2(ctx, st, A);
+    if (variant == 16 || variant == 32) return launch_batch2(ctx, st, A, variant == 32);
     switch (variant) {
     case 1: return launch_batch<Cfg256, true>(ctx, st, A, variant);
     case 2: return launch_batch<Cfg512, false>(ctx, st, A, variant);

@@ -138,8 +138,18 @@ struct BatchSmem {
     // every reduced value equals the potential): thread (0,tk) / (tj,0) writes it for itself, one plane ahead
     // (batch_write_borders), so that every thread loads its halos with the same instructions -- no border branches, no
     // per-lane register shuffling in the step (5 of 8 warps used to run the border code on top of the common path).
-    uint32_t row[C::NSLOT][4][C::TJ + 1][C::ROW_STRIDE];  // [slot][wY,u2,u1(old),all(old)][tj+1][k]   bottom rows
-    uint32_t col[C::NSLOT][4][C::TK + 1][C::COL_STRIDE];  // [slot][wZ,u2,u3(old),all(old)][tk+1][j]   right columns
+    // Every [slot][array] plane is followed by four padding words: plane strides of 4 / 12 (mod 32) words put the eight
+    // (array, plane-of-step) groups that one access group of the border writers touches into distinct banks.
+    struct RowPlane {
+        uint32_t v[C::TJ + 1][C::ROW_STRIDE];
+        uint32_t pad[4];
+    };
+    struct ColPlane {
+        uint32_t v[C::TK + 1][C::COL_STRIDE];
+        uint32_t pad[4];
+    };
+    RowPlane row[C::NSLOT][4];  // [slot][wY,u2,u1(old),all(old)].v[tj+1][k]   bottom rows
+    ColPlane col[C::NSLOT][4];  // [slot][wZ,u2,u3(old),all(old)].v[tk+1][j]   right columns
     uint32_t corner[C::NSLOT][2][C::CORNER_ROWS][C::CORNER_STRIDE];  // [slot][u2,all(old)] x (tj, tk+1), see corner_at: relay of the cell above-right of a tile
     uint32_t tabAB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  pair constant {4,2}
     uint32_t tabMB[C::NBUF][16][C::TABJ_STRIDE];     // [buf][a code][j]  triple row constant {9,3}
@@ -256,10 +266,10 @@ TA_HD void batch_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tj, int 
 #pragma unroll
         for (int c = 0; c < RK; ++c) {
             const uint32_t now = e + (uint32_t)c * 0x00020002u, old = now - 0x00020002u;
-            S.row[slot][0][0][k0 + c] = now;
-            S.row[slot][1][0][k0 + c] = now;
-            S.row[slot][2][0][k0 + c] = old;
-            S.row[slot][3][0][k0 + c] = old;
+            S.row[slot][0].v[0][k0 + c] = now;
+            S.row[slot][1].v[0][k0 + c] = now;
+            S.row[slot][2].v[0][k0 + c] = old;
+            S.row[slot][3].v[0][k0 + c] = old;
         }
     }
     if (tk == 0) {  // k = 0 border plane (src/TriAlign_1cyc.v:166-174); the corner cell (j0, 0) lies on it too
@@ -270,10 +280,10 @@ TA_HD void batch_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tj, int 
 #pragma unroll
         for (int r = 0; r < RJ; ++r) {
             const uint32_t now = e + (uint32_t)(r + 1) * 0x00020002u, old = now - 0x00020002u;
-            S.col[slot][0][0][j0 + r] = now;
-            S.col[slot][1][0][j0 + r] = now;
-            S.col[slot][2][0][j0 + r] = old;
-            S.col[slot][3][0][j0 + r] = old;
+            S.col[slot][0].v[0][j0 + r] = now;
+            S.col[slot][1].v[0][j0 + r] = now;
+            S.col[slot][2].v[0][j0 + r] = old;
+            S.col[slot][3].v[0][j0 + r] = old;
         }
     }
 }
@@ -344,7 +354,7 @@ TA_HD void batch_write_borders_all(BatchSmem<C> &S, const BatchArgs &A, int tid,
     if (tid < 128) {
         const int arr = (tid >> 4) & 3, col = tid >> 6;
         const uint32_t e = rep((uint32_t)(A.base + (int)sc.pi() * (i + 4 * t + 1 - (arr >> 1)))), d = sc.pi2();
-        uint32_t *dst = col ? &S.col[slot][arr][0][4 * t] : &S.row[slot][arr][0][4 * t];
+        uint32_t *dst = col ? &S.col[slot][arr].v[0][4 * t] : &S.row[slot][arr].v[0][4 * t];
 #if defined(__CUDA_ARCH__)
         *reinterpret_cast<uint4 *>(dst) = make_uint4(e, e + d, e + 2 * d, e + 3 * d);
 #else
@@ -387,22 +397,22 @@ TA_HD void batch_load_halos(BatchHalo<C> &H, const BatchSmem<C> &S, const BatchA
     (void)i;
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
-        T_wY[c] = S.row[rs][0][tj][k0 + c];
-        T_u1[c] = S.row[rs][2][tj][k0 + c];
-        T_u2[c + 1] = S.row[rs][1][tj][k0 + c];
-        T_all[c + 1] = S.row[rs][3][tj][k0 + c];
+        T_wY[c] = S.row[rs][0].v[tj][k0 + c];
+        T_u1[c] = S.row[rs][2].v[tj][k0 + c];
+        T_u2[c + 1] = S.row[rs][1].v[tj][k0 + c];
+        T_all[c + 1] = S.row[rs][3].v[tj][k0 + c];
     }
     T_u2[0] = corner_at<C>(S, rs, 0, tj, tk);
     T_all[0] = corner_at<C>(S, rs, 1, tj, tk);
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
-        L_wZ[r] = S.col[rs][0][tk][j0 + r];
-        L_u3[r] = S.col[rs][2][tk][j0 + r];
+        L_wZ[r] = S.col[rs][0].v[tk][j0 + r];
+        L_u3[r] = S.col[rs][2].v[tk][j0 + r];
     }
 #pragma unroll
     for (int r = 1; r < RJ; ++r) {
-        L_u2[r] = S.col[rs][1][tk][j0 + r - 1];
-        L_all[r] = S.col[rs][3][tk][j0 + r - 1];
+        L_u2[r] = S.col[rs][1].v[tk][j0 + r - 1];
+        L_all[r] = S.col[rs][3].v[tk][j0 + r - 1];
     }
     L_u2[0] = T_u2[0];
     L_all[0] = T_all[0];
@@ -424,13 +434,13 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
     // the plane i-1 half of this thread's own edges is already known
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
-        S.row[ws][2][tj + 1][k0 + c] = R.u1[RJ - 1][c];
-        S.row[ws][3][tj + 1][k0 + c] = R.all[RJ - 1][c];
+        S.row[ws][2].v[tj + 1][k0 + c] = R.u1[RJ - 1][c];
+        S.row[ws][3].v[tj + 1][k0 + c] = R.all[RJ - 1][c];
     }
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
-        S.col[ws][2][tk + 1][j0 + r] = R.u3[r][RK - 1];
-        S.col[ws][3][tk + 1][j0 + r] = R.all[r][RK - 1];
+        S.col[ws][2].v[tk + 1][j0 + r] = R.u3[r][RK - 1];
+        S.col[ws][3].v[tk + 1][j0 + r] = R.all[r][RK - 1];
     }
 
     // the tile, row-major (within a plane a cell needs its j-1, k-1 and (j-1,k-1) neighbours)
@@ -455,13 +465,13 @@ TA_HD void batch_thread_step_halo(const BatchRegs<C> &R, BatchRegs<C> &Rn, const
     // publish the plane-i half of the tile's bottom row and right column for the neighbours' step s+1
 #pragma unroll
     for (int c = 0; c < RK; ++c) {
-        S.row[ws][0][tj + 1][k0 + c] = n_wY[RJ - 1][c];
-        S.row[ws][1][tj + 1][k0 + c] = n_u2[RJ - 1][c];
+        S.row[ws][0].v[tj + 1][k0 + c] = n_wY[RJ - 1][c];
+        S.row[ws][1].v[tj + 1][k0 + c] = n_u2[RJ - 1][c];
     }
 #pragma unroll
     for (int r = 0; r < RJ; ++r) {
-        S.col[ws][0][tk + 1][j0 + r] = n_wZ[r][RK - 1];
-        S.col[ws][1][tk + 1][j0 + r] = n_u2[r][RK - 1];
+        S.col[ws][0].v[tk + 1][j0 + r] = n_wZ[r][RK - 1];
+        S.col[ws][1].v[tk + 1][j0 + r] = n_u2[r][RK - 1];
     }
 
     if (CHECK) {
@@ -567,6 +577,35 @@ TA_HD uint32_t batch2_fetch_codes(const BatchSmem<C> &S, int tj, int tk, int s)
     return (uint32_t)src[0] | ((uint32_t)src[1] << 8);
 }
 
+// Neighbour-only synchronisation ("ring", option k1=256r2).  With the anti-diagonal thread layout warp w holds the wrapped
+// diagonals 2w and 2w+1: it reads the edges of diagonal 2w-1 (warp w-1) and its own, and the slots it writes were last
+// read by diagonal 2w+2 (warp w+1) -- a warp only needs "warps w-1 and w+1 finished step s" before step s+1, not the
+// whole CTA.  The border halos must then be warp-local too: lane l of warp w writes, for the edge threads of its own
+// warp -- (0,t) [rows] and (t,0) [columns], t = 2w, 2w+1 -- array (l >> 1) & 3 of plane l & 1; the eight lanes of an
+// access group hit distinct banks thanks to the plane padding of BatchSmem.
+template <class C>
+TA_HD void batch2_write_borders_warp(BatchSmem<C> &S, const BatchArgs &A, int tid, int st)
+{
+    static_assert(C::DIAG && C::NT == 256 && C::RJ == 4 && C::RK == 4, "one 128-bit group per thread");
+    const int rs = ((st - 1) & 1) << 1, w = tid >> 5, l = tid & 31;
+    {
+        const int e = l >> 3, col = e >> 1, t = 2 * w + (e & 1), arr = (l >> 1) & 3, pl = l & 1;
+        const int i = 2 * ((st - t) & 31) + 1 + pl;
+        const uint32_t v = rep((uint32_t)(A.base + 2 * (i + 4 * t + 1 - (arr >> 1))));
+        uint32_t *dst = col ? &S.col[rs + pl][arr].v[0][4 * t] : &S.row[rs + pl][arr].v[0][4 * t];
+#if defined(__CUDA_ARCH__)
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(v, v + 0x00020002u, v + 0x00040004u, v + 0x00060006u);
+#else
+        for (int c = 0; c < 4; ++c) dst[c] = v + (uint32_t)c * 0x00020002u;
+#endif
+    }
+    if (l < 8) {  // the corner cell (j0, 0) of the k = 0 border plane
+        const int t = 2 * w + (l & 1), arr = (l >> 1) & 1, pl = l >> 2;
+        const int i = 2 * ((st - t) & 31) + 1 + pl;
+        corner_at<C>(S, rs + pl, arr, t, 0) = rep((uint32_t)(A.base + 2 * (i + 4 * t - arr)));
+    }
+}
+
 // codes: batch2_fetch_codes(s), fetched one step ahead (the pair's codes are staged long before its first plane enters
 // thread (0,0)), so that the table look-ups below do not wait for a shared-memory round trip; on return it holds the
 // codes of step s + 1.
@@ -597,7 +636,7 @@ TA_HD void batch2_write_borders(BatchSmem<C> &S, const BatchArgs &A, int tid, in
         const int t = tid & 15, arr = (tid >> 4) & 3, pl = (tid >> 6) & 1, col = tid >> 7;
         const int i = 2 * ((st - t) & 31) + 1 + pl;
         const uint32_t e = rep((uint32_t)(A.base + 2 * (i + 4 * t + 1 - (arr >> 1))));
-        uint32_t *dst = col ? &S.col[rs + pl][arr][0][4 * t] : &S.row[rs + pl][arr][0][4 * t];
+        uint32_t *dst = col ? &S.col[rs + pl][arr].v[0][4 * t] : &S.row[rs + pl][arr].v[0][4 * t];
 #if defined(__CUDA_ARCH__)
         *reinterpret_cast<uint4 *>(dst) = make_uint4(e, e + 0x00020002u, e + 0x00040004u, e + 0x00060006u);
 #else
@@ -646,13 +685,15 @@ TA_HD void prefetch_pair_sequences(const BatchArgs &A, int tid, long long pair)
 #endif
 }
 
-template <class C>
+// RING (neighbour-only synchronisation, see batch2_write_borders_warp): a warp sees another warp's step s - d - 1 for
+// ring distance d <= 4, so the byte loads run six steps before the table build instead of four.
+template <class C, bool RING = false>
 TA_HD void batch2_uniform_actions(BatchSmem<C> &S, const BatchArgs &A, int tid, int s, int P, long long pair_base)
 {
     const int q = s / kBatch2Steps + 1;  // pair that starts entering the array at step 32*q
     if (q < P) {
-        if (s % kBatch2Steps == kBatch2PrefetchAt) prefetch_pair_sequences<C>(A, tid, pair_base + q);
-        if (s % kBatch2Steps == kBatch2LoadAt) load_pair_sequences<C>(S, A, tid, pair_base + q, q % C::NBUF);
+        if (s % kBatch2Steps == (RING ? 0 : kBatch2PrefetchAt)) prefetch_pair_sequences<C>(A, tid, pair_base + q);
+        if (s % kBatch2Steps == (RING ? kBatch2LoadAt - 2 : kBatch2LoadAt)) load_pair_sequences<C>(S, A, tid, pair_base + q, q % C::NBUF);
         if (s % kBatch2Steps == kBatch2BuildAt) build_pair_tables<C>(S, tid, q % C::NBUF);
     }
 }

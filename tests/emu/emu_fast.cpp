@@ -183,6 +183,82 @@ extern "C" int emu_fast_batch_ex(const uint8_t *a, const uint8_t *b, const uint8
     return emu_fast_batch_cfg<C, ScoreGen<false>>(a, b, c, n, len, base, pairs_per_cta, schedule_seed, scores, make_score_gen<false>(M, X, GO, GE), &chk);
 }
 
+// K1 "P2" with neighbour-only synchronisation (fast_batch2r_kernel).  A warp's step has two parts: A = border halos of
+// step s+1, step s, ARRIVE; B = uniform actions, prepare s+1.  Warp w may start part A of step s+1 once its own part B of
+// step s is done and warps w-1 and w+1 have ARRIVED for step s -- their part B may still be pending, exactly as on the
+// GPU, where the staging stores after the arrive are only released by the next one.  Warps advance in a pseudo-random
+// order; poisoned shared memory.
+extern "C" int emu_fast_batch2_ring(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,
+                                    int pairs_per_cta, int schedule_seed, int32_t *scores)
+{
+    using C = BatchCfg<4, 4, 16, 16, 2>;
+    constexpr int NW = C::NT / 32;
+    if (len < 1 || len > 64 || n < 0) return -1;
+    BatchArgs A;
+    A.a = a; A.b = b; A.c = c; A.n = n; A.len = len; A.scores = scores;
+    A.pairs_total = (n + 1) / 2;
+    A.pairs_per_cta = pairs_per_cta;
+    A.base = base;
+    auto S = std::make_unique<BatchSmem<C>>();
+    std::vector<BatchRegs<C>> R(C::NT), R2(C::NT);
+    std::vector<BatchConsts<C>> K0(C::NT), K1(C::NT);
+    std::vector<uint32_t> codes(C::NT);
+    for (long long pair_base = 0; pair_base < A.pairs_total; pair_base += pairs_per_cta) {
+        const int P = (int)std::min<long long>(pairs_per_cta, A.pairs_total - pair_base);
+        std::memset(S.get(), 0xA5, sizeof(BatchSmem<C>));
+        std::memset(R.data(), 0x5A, R.size() * sizeof(BatchRegs<C>));
+        std::memset(R2.data(), 0x5A, R2.size() * sizeof(BatchRegs<C>));
+        for (int fill = 1; fill < C::NBUF; ++fill) {
+            std::memset(S->acode[fill], 0, sizeof S->acode[fill]);
+            std::memset(S->seq[fill], 0, sizeof S->seq[fill]);
+            std::memset(S->bpk[fill], 0, sizeof S->bpk[fill]);
+            std::memset(S->cpk[fill], 0, sizeof S->cpk[fill]);
+        }
+        for (int tid = 0; tid < C::NT; ++tid) load_pair_sequences<C>(*S, A, tid, pair_base, 0);
+        for (int tid = 0; tid < C::NT; ++tid) build_pair_tables<C>(*S, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) batch2_write_borders_warp<C>(*S, A, tid, 0);
+        for (int tid = 0; tid < C::NT; ++tid) {
+            int tj, tk;
+            thread_pos<C>(tid, tj, tk);
+            codes[tid] = batch2_fetch_codes<C>(*S, tj, tk, 0);
+            batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, 0, codes[tid]);
+        }
+        const int steps = batch2_total_steps<C>(P);
+        std::vector<int> arrived(NW, -1), prepared(NW, -1);  // last step with part A / part B done
+        uint64_t rng = 0x9E3779B97F4A7C15ull ^ (uint64_t)schedule_seed ^ ((uint64_t)pair_base << 17);
+        int finished = 0;
+        while (finished < NW) {
+            rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+            const int w = (int)((rng >> 33) % NW);
+            if (prepared[w] < arrived[w]) {  // part B of step arrived[w]
+                const int s = arrived[w];
+                for (int lane = 0; lane < 32; ++lane) {
+                    const int tid = w * 32 + lane;
+                    int tj, tk;
+                    thread_pos<C>(tid, tj, tk);
+                    batch2_uniform_actions<C, true>(*S, A, tid, s, P, pair_base);
+                    batch2_thread_prepare<C>(R[tid], K0[tid], K1[tid], *S, A, tj, tk, s + 1, codes[tid]);
+                }
+                prepared[w] = s;
+                if (s == steps) ++finished;
+                continue;
+            }
+            const int s = arrived[w] + 1;
+            if (s > steps) continue;
+            if (arrived[(w + NW - 1) % NW] < s - 1 || arrived[(w + 1) % NW] < s - 1) continue;  // the two waits would block
+            for (int lane = 0; lane < 32; ++lane) batch2_write_borders_warp<C>(*S, A, w * 32 + lane, s + 1);
+            for (int lane = 0; lane < 32; ++lane) {
+                const int tid = w * 32 + lane;
+                int tj, tk;
+                thread_pos<C>(tid, tj, tk);
+                batch2_thread_step<C>(R[tid], R2[tid], K0[tid], K1[tid], *S, A, tj, tk, s, P, pair_base);
+            }
+            arrived[w] = s;
+        }
+    }
+    return 0;
+}
+
 // threads = 256: 16x16 threads x 4x4 cells; threads = 512: 16x32 threads x 4x2 cells; lag = 1 / 2 (see BatchCfg);
 // schedule_seed != 0 (lag 2 only): warps advance in a pseudo-random order with bursts
 extern "C" int emu_fast_batch(const uint8_t *a, const uint8_t *b, const uint8_t *c, long long n, int len, int base,

@@ -39,6 +39,14 @@ def _run(L, a, b, c, pairs_per_cta):
                            pairs_per_cta, out.ctypes.data_as(i32p))
     assert rc == 0
     outs.append(out)
+    # the same with neighbour-only synchronisation (fast_batch2r_kernel), warps in pseudo-random order
+    L.emu_fast_batch2_ring.argtypes = [u8p, u8p, u8p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, i32p]
+    for seed in (1, 8, 23):
+        out = np.full(n, -99999, np.int32)
+        rc = L.emu_fast_batch2_ring(a.ctypes.data_as(u8p), b.ctypes.data_as(u8p), c.ctypes.data_as(u8p), n, ln, 2 * 64 + 32,
+                                    pairs_per_cta, seed, out.ctypes.data_as(i32p))
+        assert rc == 0
+        outs.append(out)
     assert all(o.tolist() == outs[0].tolist() for o in outs)
     return outs[0]
 

@@ -330,6 +330,25 @@ def test_fast_kernels_agree_with_literal_kernel_beyond_oracle_sizes(gpu_ta):
     assert gpu_ta.TriAlign(16).align(x, x, x) == 3 * 4096
 
 
+@pytest.mark.parametrize("variant", ["256r2", "256l", "256m", "512m"])
+def test_batch_kernel_variants_match_the_oracle(gpu_ta, ob, variant):
+    """The A/B forms of K1 (option k1): neighbour-only synchronisation, lagged barrier, LAG-1 forms."""
+    rng = np.random.default_rng(len(variant) * 7 + ord(variant[-2]))
+    try:
+        gpu_ta.set_option("k1", variant)
+        for n, ln in ((1301, 64), (77, 41), (5, 1)):
+            a = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+            b = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+            c = rng.integers(0, 4, (n, ln), dtype=np.uint8)
+            for t in range(0, n, 3):
+                a[t], b[t], c[t] = ob.mutated_triple(rng, ln)
+            got = gpu_ta.TriAlign(12).align_batch(a, b, c)
+            assert gpu_ta.last_path() == "fast_batch"
+            assert got.tolist() == ob.score_batch(a, b, c, 12).tolist(), (variant, n, ln)
+    finally:
+        gpu_ta.set_option("k1", None)
+
+
 def test_stream_kernel_with_duties_dealt_to_all_threads(gpu_ta, ob):
     """Option k2s=dist (A/B form of K2S: face fetches, border halos and face stores by thread id) against the oracle."""
     rng = np.random.default_rng(2718)
