@@ -125,6 +125,14 @@ __global__ void __launch_bounds__(Cfg::NT, MINB) fast_batch_kernel(fast::BatchAr
     fast_batch_body<Cfg, SPLIT, MINB, false>(A, nullptr);
 }
 
+// The staging of the next pair runs at 2 of every 32 steps: out of line, so that the hot loop body stays small
+// (instruction cache) -- the calls sit on the rarely taken side of their branches.
+template <class Cfg>
+__device__ __noinline__ void stage_pair_cold(fast::BatchSmem<Cfg> &S, const fast::BatchArgs &A, int tid, int s, int P, long long pair_base)
+{
+    fast::batch2_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
+}
+
 // Two planes per step (fast_batch.cuh, "P2"): the lagged-barrier layout's four edge slots and three pair buffers, one
 // split-phase barrier per TWO planes.
 template <class Cfg>
@@ -164,7 +172,11 @@ __global__ void __launch_bounds__(Cfg::NT, 1) fast_batch2_kernel(fast::BatchArgs
         fast::batch2_write_borders<Cfg>(S, A, tid, s + 1);  // everybody has finished step s-1, the slots' last reader
         fast::batch2_thread_step<Cfg>(R, R2, K0, K1, S, A, tj, tk, s, P, pair_base);
         bar_arrive_warp(&step_bar[0]);
-        fast::batch2_uniform_actions<Cfg>(S, A, tid, s, P, pair_base);
+        {
+            const int m = s % fast::kBatch2Steps;
+            if (m == fast::kBatch2PrefetchAt || m == fast::kBatch2LoadAt || m == fast::kBatch2BuildAt)
+                stage_pair_cold<Cfg>(S, A, tid, s, P, pair_base);
+        }
         fast::batch2_thread_prepare<Cfg>(R, K0, K1, S, A, tj, tk, s + 1, codes);
         bar_wait(&step_bar[0], s & 1);  // everybody has finished step s
     }

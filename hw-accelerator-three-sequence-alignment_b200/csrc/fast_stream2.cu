@@ -37,6 +37,15 @@ __device__ __forceinline__ void bar_wait(uint64_t *bar, int parity)
         "}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
 }
 
+// The staging of the next task runs at 2 of every L2 steps: out of line, so that the hot loop body stays small
+// (instruction cache) -- the call sits on the rarely taken side of its branch.
+template <class SC>
+__device__ __noinline__ void stage_task_cold(fast::StreamSmem<C2> &S, const fast::StreamArgs &A, int tid, int cta, int P,
+                                             long long pair_base, int g_t, int g_off, const SC &sc)
+{
+    fast::stream2_uniform_actions<C2, SC>(S, A, tid, cta, P, pair_base, g_t, g_off, sc);
+}
+
 template <bool CHECK, class SC = fast::ScoreRtl>
 __device__ __forceinline__ void fast_stream2_body(const fast::StreamArgs &A, const fast::RangeCheck *chk, const SC &sc = SC())
 {
@@ -89,7 +98,8 @@ __device__ __forceinline__ void fast_stream2_body(const fast::StreamArgs &A, con
         fast::stream2_thread_step<C, CHECK, SC>(R, R2, K0, K1, S, A, tj, tk, s, pos, &viol, chk, sc);
         fast::ta_copy_wait();
         bar_arrive_warp(&step_bar[0]);
-        if (g_t < tasks) fast::stream2_uniform_actions<C, SC>(S, A, tid, cta, P, pair_base, g_t, g_off, sc);
+        if (g_t < tasks && (g_off == C::LOAD_AT || g_off == C::BUILD_AT))
+            stage_task_cold<SC>(S, A, tid, cta, P, pair_base, g_t, g_off, sc);
         if (++g_off == L2) {
             g_off = 0;
             ++g_t;
