@@ -6,7 +6,7 @@
 //   * the plane-(i-1) state of those cells (all, wX, u1, u3 -- see fast_core.cuh) lives in registers;
 //   * thread (tj,tk) works on plane i at global step s = i + LAG*(tj + tk) (wavefront skew, like PE(j,k) at step
 //     i+j+k; LAG: see BatchCfg);
-//   * neighbours exchange tile edges through shared memory, double buffered, one CTA barrier per step
+//   * neighbours exchange tile edges through shared memory (2 * LAG edge slots), one CTA barrier per step
 //     (the counterpart of the PE-to-PE wires; the RTL's _d1/_d2 delay registers are the "old" values published
 //     one step late -- measured: keeping them in the consumer's registers instead, so that half of the halo loads
 //     leave the critical path, is slower, because it moves all stores to the end of the step);
@@ -135,9 +135,11 @@ constexpr int kBatchCheckEvery = 8;  // steps between two range samples: `all` m
 template <class C>
 struct BatchSmem {
     // Index 0 of the tj / tk dimension is the zero BORDER plane (src/TriAlign_1cyc.v:156-181: all 7 states are 0, i.e.
-    // every reduced value equals the potential): thread (0,tk) / (tj,0) writes it for itself, one plane ahead
-    // (batch_write_borders), so that every thread loads its halos with the same instructions -- no border branches, no
-    // per-lane register shuffling in the step (5 of 8 warps used to run the border code on top of the common path).
+    // every reduced value equals the potential), written ahead of the step that reads it, so that every thread loads its
+    // halos with the same instructions -- no border branches, no per-lane register shuffling in the step (5 of 8 warps
+    // used to run the border code on top of the common path).  Writers: all threads of the CTA, one 128-bit group each
+    // (batch2_write_borders, batch_write_borders_all: the default kernels); the edge threads for themselves
+    // (batch_write_borders: the LAG 1 A/B variants); the lanes of the reader's own warp (batch2_write_borders_warp).
     // Every [slot][array] plane is followed by four padding words: plane strides of 4 / 12 (mod 32) words put the eight
     // (array, plane-of-step) groups that one access group of the border writers touches into distinct banks.
     struct RowPlane {
